@@ -289,20 +289,20 @@ enum vicgpu_hru_scalar {
   HR_NSCALAR
 };
 enum vicgpu_hru_layer {
-#define X(n, p, c) HRL_##n,
-  VICGPU_HRU_LAYER(X)
+#define X(n, p, c) n,
+  VICGPU_HRU_LAYER(X, HRL_)
 #undef X
   HRL_N
 };
 enum vicgpu_hru_front {
-#define X(n, p, c) HRF_##n,
-  VICGPU_HRU_FRONT(X)
+#define X(n, p, c) n,
+  VICGPU_HRU_FRONT(X, HRF_)
 #undef X
   HRF_N
 };
 enum vicgpu_hru_node {
-#define X(n, p, c) HRN_##n,
-  VICGPU_HRU_NODE(X)
+#define X(n, p, c) n,
+  VICGPU_HRU_NODE(X, HRN_)
 #undef X
   HRN_N
 };

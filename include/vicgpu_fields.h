@@ -34,161 +34,173 @@
 
 /* ------------------------------------------------------------------ HRU record */
 /* scalars: X(column, reference member relative to HRU, class) */
+/* Scalar columns, one list per sub-structure of the HRU.  X(P##name, reference member, class):
+ * invoke with a prefix (E_, S_, C_, V_, G_) to get the column name, with an empty prefix to get the
+ * bare member name used by the device-side structs (vic_b200/csrc/vic_types.cuh). */
+#define VICGPU_HRU_ENERGY(X, P) \
+  X(P##AlbedoLake, energy.AlbedoLake, VG_U) \
+  X(P##AlbedoOver, energy.AlbedoOver, VG_C) \
+  X(P##AlbedoUnder, energy.AlbedoUnder, VG_C) \
+  X(P##Cs0, energy.Cs[0], VG_C) \
+  X(P##Cs1, energy.Cs[1], VG_C) \
+  X(P##frozen, energy.frozen, VG_C) \
+  X(P##kappa0, energy.kappa[0], VG_C) \
+  X(P##kappa1, energy.kappa[1], VG_C) \
+  X(P##Nfrost, energy.Nfrost, VG_C) \
+  X(P##Nthaw, energy.Nthaw, VG_C) \
+  X(P##T1_index, energy.T1_index, VG_U) \
+  X(P##Tcanopy, energy.Tcanopy, VG_C) \
+  X(P##Tcanopy_fbflag, energy.Tcanopy_fbflag, VG_C) \
+  X(P##Tcanopy_fbcount, energy.Tcanopy_fbcount, VG_C) \
+  X(P##Tfoliage, energy.Tfoliage, VG_C) \
+  X(P##Tfoliage_fbflag, energy.Tfoliage_fbflag, VG_C) \
+  X(P##Tfoliage_fbcount, energy.Tfoliage_fbcount, VG_C) \
+  X(P##Tsurf, energy.Tsurf, VG_C) \
+  X(P##Tsurf_fbflag, energy.Tsurf_fbflag, VG_C) \
+  X(P##Tsurf_fbcount, energy.Tsurf_fbcount, VG_C) \
+  X(P##unfrozen, energy.unfrozen, VG_U) \
+  X(P##advected_sensible, energy.advected_sensible, VG_C) \
+  X(P##advection, energy.advection, VG_C) \
+  X(P##AtmosError, energy.AtmosError, VG_C) \
+  X(P##AtmosLatent, energy.AtmosLatent, VG_C) \
+  X(P##AtmosLatentSub, energy.AtmosLatentSub, VG_C) \
+  X(P##AtmosSensible, energy.AtmosSensible, VG_C) \
+  X(P##canopy_advection, energy.canopy_advection, VG_C) \
+  X(P##canopy_latent, energy.canopy_latent, VG_C) \
+  X(P##canopy_latent_sub, energy.canopy_latent_sub, VG_C) \
+  X(P##canopy_refreeze, energy.canopy_refreeze, VG_C) \
+  X(P##canopy_sensible, energy.canopy_sensible, VG_C) \
+  X(P##deltaCC, energy.deltaCC, VG_C) \
+  X(P##deltaH, energy.deltaH, VG_C) \
+  X(P##error, energy.error, VG_C) \
+  X(P##fusion, energy.fusion, VG_C) \
+  X(P##grnd_flux, energy.grnd_flux, VG_C) \
+  X(P##latent, energy.latent, VG_C) \
+  X(P##latent_sub, energy.latent_sub, VG_C) \
+  X(P##longwave, energy.longwave, VG_C) \
+  X(P##LongOverIn, energy.LongOverIn, VG_C) \
+  X(P##LongUnderIn, energy.LongUnderIn, VG_C) \
+  X(P##LongUnderOut, energy.LongUnderOut, VG_C) \
+  X(P##melt_energy, energy.melt_energy, VG_C) \
+  X(P##NetLongAtmos, energy.NetLongAtmos, VG_C) \
+  X(P##NetLongOver, energy.NetLongOver, VG_C) \
+  X(P##NetLongUnder, energy.NetLongUnder, VG_C) \
+  X(P##NetShortAtmos, energy.NetShortAtmos, VG_C) \
+  X(P##NetShortGrnd, energy.NetShortGrnd, VG_C) \
+  X(P##NetShortOver, energy.NetShortOver, VG_C) \
+  X(P##NetShortUnder, energy.NetShortUnder, VG_C) \
+  X(P##out_long_canopy, energy.out_long_canopy, VG_C) \
+  X(P##out_long_surface, energy.out_long_surface, VG_C) \
+  X(P##refreeze_energy, energy.refreeze_energy, VG_C) \
+  X(P##sensible, energy.sensible, VG_C) \
+  X(P##shortwave, energy.shortwave, VG_C) \
+  X(P##ShortOverIn, energy.ShortOverIn, VG_C) \
+  X(P##ShortUnderIn, energy.ShortUnderIn, VG_C) \
+  X(P##snow_flux, energy.snow_flux, VG_C) \
+  X(P##glacier_flux, energy.glacier_flux, VG_C) \
+  X(P##deltaCC_glac, energy.deltaCC_glac, VG_C) \
+  X(P##glacier_melt_energy, energy.glacier_melt_energy, VG_C)
+
+#define VICGPU_HRU_SNOW(X, P) \
+  X(P##albedo, snow.albedo, VG_C) \
+  X(P##canopy_albedo, snow.canopy_albedo, VG_C) \
+  X(P##coldcontent, snow.coldcontent, VG_C) \
+  X(P##coverage, snow.coverage, VG_C) \
+  X(P##density, snow.density, VG_C) \
+  X(P##depth, snow.depth, VG_C) \
+  X(P##last_snow, snow.last_snow, VG_C) \
+  X(P##max_swq, snow.max_swq, VG_C) \
+  X(P##MELTING, snow.MELTING, VG_C) \
+  X(P##pack_temp, snow.pack_temp, VG_C) \
+  X(P##pack_water, snow.pack_water, VG_C) \
+  X(P##snow, snow.snow, VG_C) \
+  X(P##snow_canopy, snow.snow_canopy, VG_C) \
+  X(P##store_coverage, snow.store_coverage, VG_C) \
+  X(P##store_snow, snow.store_snow, VG_C) \
+  X(P##store_swq, snow.store_swq, VG_C) \
+  X(P##surf_temp, snow.surf_temp, VG_C) \
+  X(P##surf_temp_fbcount, snow.surf_temp_fbcount, VG_C) \
+  X(P##surf_temp_fbflag, snow.surf_temp_fbflag, VG_C) \
+  X(P##surf_water, snow.surf_water, VG_C) \
+  X(P##swq, snow.swq, VG_C) \
+  X(P##swq_slope, snow.swq_slope, VG_C) \
+  X(P##tmp_int_storage, snow.tmp_int_storage, VG_C) \
+  X(P##blowing_flux, snow.blowing_flux, VG_C) \
+  X(P##canopy_vapor_flux, snow.canopy_vapor_flux, VG_C) \
+  X(P##mass_error, snow.mass_error, VG_C) \
+  X(P##melt, snow.melt, VG_C) \
+  X(P##Qnet, snow.Qnet, VG_C) \
+  X(P##surface_flux, snow.surface_flux, VG_C) \
+  X(P##transport, snow.transport, VG_C) \
+  X(P##vapor_flux, snow.vapor_flux, VG_C)
+
+#define VICGPU_HRU_CELL(X, P) \
+  X(P##aero_surface, cell[0].aero_resist.surface, VG_C) \
+  X(P##aero_overstory, cell[0].aero_resist.overstory, VG_C) \
+  X(P##asat, cell[0].asat, VG_C) \
+  X(P##baseflow, cell[0].baseflow, VG_C) \
+  X(P##inflow, cell[0].inflow, VG_C) \
+  X(P##excess_moist, cell[0].excess_moist, VG_C) \
+  X(P##runoff, cell[0].runoff, VG_C) \
+  X(P##rootmoist, cell[0].rootmoist, VG_C) \
+  X(P##wetness, cell[0].wetness, VG_C) \
+  X(P##zwt, cell[0].zwt, VG_C) \
+  X(P##zwt2, cell[0].zwt2, VG_C) \
+  X(P##zwt3, cell[0].zwt3, VG_C)
+
+#define VICGPU_HRU_VEG(X, P) \
+  X(P##canopyevap, veg_var[0].canopyevap, VG_C) \
+  X(P##throughfall, veg_var[0].throughfall, VG_C) \
+  X(P##Wdew, veg_var[0].Wdew, VG_C)
+
+#define VICGPU_HRU_GLAC(X, P) \
+  X(P##cold_content, glacier.cold_content, VG_C) \
+  X(P##surf_temp, glacier.surf_temp, VG_C) \
+  X(P##surf_temp_fbcount, glacier.surf_temp_fbcount, VG_C) \
+  X(P##surf_temp_fbflag, glacier.surf_temp_fbflag, VG_C) \
+  X(P##Qnet, glacier.Qnet, VG_C) \
+  X(P##mass_balance, glacier.mass_balance, VG_C) \
+  X(P##ice_mass_balance, glacier.ice_mass_balance, VG_C) \
+  X(P##cum_mass_balance, glacier.cum_mass_balance, VG_C) \
+  X(P##accumulation, glacier.accumulation, VG_C) \
+  X(P##melt, glacier.melt, VG_C) \
+  X(P##vapor_flux, glacier.vapor_flux, VG_C) \
+  X(P##water_storage, glacier.water_storage, VG_C) \
+  X(P##outflow, glacier.outflow, VG_C) \
+  X(P##outflow_coef, glacier.outflow_coef, VG_C) \
+  X(P##inflow, glacier.inflow, VG_C)
+
 #define VICGPU_HRU_SCALARS(X) \
-  X(E_AlbedoLake, energy.AlbedoLake, VG_U) \
-  X(E_AlbedoOver, energy.AlbedoOver, VG_C) \
-  X(E_AlbedoUnder, energy.AlbedoUnder, VG_C) \
-  X(E_Cs0, energy.Cs[0], VG_C) \
-  X(E_Cs1, energy.Cs[1], VG_C) \
-  X(E_frozen, energy.frozen, VG_C) \
-  X(E_kappa0, energy.kappa[0], VG_C) \
-  X(E_kappa1, energy.kappa[1], VG_C) \
-  X(E_Nfrost, energy.Nfrost, VG_C) \
-  X(E_Nthaw, energy.Nthaw, VG_C) \
-  X(E_T1_index, energy.T1_index, VG_U) \
-  X(E_Tcanopy, energy.Tcanopy, VG_C) \
-  X(E_Tcanopy_fbflag, energy.Tcanopy_fbflag, VG_C) \
-  X(E_Tcanopy_fbcount, energy.Tcanopy_fbcount, VG_C) \
-  X(E_Tfoliage, energy.Tfoliage, VG_C) \
-  X(E_Tfoliage_fbflag, energy.Tfoliage_fbflag, VG_C) \
-  X(E_Tfoliage_fbcount, energy.Tfoliage_fbcount, VG_C) \
-  X(E_Tsurf, energy.Tsurf, VG_C) \
-  X(E_Tsurf_fbflag, energy.Tsurf_fbflag, VG_C) \
-  X(E_Tsurf_fbcount, energy.Tsurf_fbcount, VG_C) \
-  X(E_unfrozen, energy.unfrozen, VG_U) \
-  X(E_advected_sensible, energy.advected_sensible, VG_C) \
-  X(E_advection, energy.advection, VG_C) \
-  X(E_AtmosError, energy.AtmosError, VG_C) \
-  X(E_AtmosLatent, energy.AtmosLatent, VG_C) \
-  X(E_AtmosLatentSub, energy.AtmosLatentSub, VG_C) \
-  X(E_AtmosSensible, energy.AtmosSensible, VG_C) \
-  X(E_canopy_advection, energy.canopy_advection, VG_C) \
-  X(E_canopy_latent, energy.canopy_latent, VG_C) \
-  X(E_canopy_latent_sub, energy.canopy_latent_sub, VG_C) \
-  X(E_canopy_refreeze, energy.canopy_refreeze, VG_C) \
-  X(E_canopy_sensible, energy.canopy_sensible, VG_C) \
-  X(E_deltaCC, energy.deltaCC, VG_C) \
-  X(E_deltaH, energy.deltaH, VG_C) \
-  X(E_error, energy.error, VG_C) \
-  X(E_fusion, energy.fusion, VG_C) \
-  X(E_grnd_flux, energy.grnd_flux, VG_C) \
-  X(E_latent, energy.latent, VG_C) \
-  X(E_latent_sub, energy.latent_sub, VG_C) \
-  X(E_longwave, energy.longwave, VG_C) \
-  X(E_LongOverIn, energy.LongOverIn, VG_C) \
-  X(E_LongUnderIn, energy.LongUnderIn, VG_C) \
-  X(E_LongUnderOut, energy.LongUnderOut, VG_C) \
-  X(E_melt_energy, energy.melt_energy, VG_C) \
-  X(E_NetLongAtmos, energy.NetLongAtmos, VG_C) \
-  X(E_NetLongOver, energy.NetLongOver, VG_C) \
-  X(E_NetLongUnder, energy.NetLongUnder, VG_C) \
-  X(E_NetShortAtmos, energy.NetShortAtmos, VG_C) \
-  X(E_NetShortGrnd, energy.NetShortGrnd, VG_C) \
-  X(E_NetShortOver, energy.NetShortOver, VG_C) \
-  X(E_NetShortUnder, energy.NetShortUnder, VG_C) \
-  X(E_out_long_canopy, energy.out_long_canopy, VG_C) \
-  X(E_out_long_surface, energy.out_long_surface, VG_C) \
-  X(E_refreeze_energy, energy.refreeze_energy, VG_C) \
-  X(E_sensible, energy.sensible, VG_C) \
-  X(E_shortwave, energy.shortwave, VG_C) \
-  X(E_ShortOverIn, energy.ShortOverIn, VG_C) \
-  X(E_ShortUnderIn, energy.ShortUnderIn, VG_C) \
-  X(E_snow_flux, energy.snow_flux, VG_C) \
-  X(E_glacier_flux, energy.glacier_flux, VG_C) \
-  X(E_deltaCC_glac, energy.deltaCC_glac, VG_C) \
-  X(E_glacier_melt_energy, energy.glacier_melt_energy, VG_C) \
-  X(S_albedo, snow.albedo, VG_C) \
-  X(S_canopy_albedo, snow.canopy_albedo, VG_C) \
-  X(S_coldcontent, snow.coldcontent, VG_C) \
-  X(S_coverage, snow.coverage, VG_C) \
-  X(S_density, snow.density, VG_C) \
-  X(S_depth, snow.depth, VG_C) \
-  X(S_last_snow, snow.last_snow, VG_C) \
-  X(S_max_swq, snow.max_swq, VG_C) \
-  X(S_MELTING, snow.MELTING, VG_C) \
-  X(S_pack_temp, snow.pack_temp, VG_C) \
-  X(S_pack_water, snow.pack_water, VG_C) \
-  X(S_snow, snow.snow, VG_C) \
-  X(S_snow_canopy, snow.snow_canopy, VG_C) \
-  X(S_store_coverage, snow.store_coverage, VG_C) \
-  X(S_store_snow, snow.store_snow, VG_C) \
-  X(S_store_swq, snow.store_swq, VG_C) \
-  X(S_surf_temp, snow.surf_temp, VG_C) \
-  X(S_surf_temp_fbcount, snow.surf_temp_fbcount, VG_C) \
-  X(S_surf_temp_fbflag, snow.surf_temp_fbflag, VG_C) \
-  X(S_surf_water, snow.surf_water, VG_C) \
-  X(S_swq, snow.swq, VG_C) \
-  X(S_swq_slope, snow.swq_slope, VG_C) \
-  X(S_tmp_int_storage, snow.tmp_int_storage, VG_C) \
-  X(S_blowing_flux, snow.blowing_flux, VG_C) \
-  X(S_canopy_vapor_flux, snow.canopy_vapor_flux, VG_C) \
-  X(S_mass_error, snow.mass_error, VG_C) \
-  X(S_melt, snow.melt, VG_C) \
-  X(S_Qnet, snow.Qnet, VG_C) \
-  X(S_surface_flux, snow.surface_flux, VG_C) \
-  X(S_transport, snow.transport, VG_C) \
-  X(S_vapor_flux, snow.vapor_flux, VG_C) \
-  X(C_aero_surface, cell[0].aero_resist.surface, VG_C) \
-  X(C_aero_overstory, cell[0].aero_resist.overstory, VG_C) \
-  X(C_asat, cell[0].asat, VG_C) \
-  X(C_baseflow, cell[0].baseflow, VG_C) \
-  X(C_inflow, cell[0].inflow, VG_C) \
-  X(C_excess_moist, cell[0].excess_moist, VG_C) \
-  X(C_runoff, cell[0].runoff, VG_C) \
-  X(C_rootmoist, cell[0].rootmoist, VG_C) \
-  X(C_wetness, cell[0].wetness, VG_C) \
-  X(C_zwt, cell[0].zwt, VG_C) \
-  X(C_zwt2, cell[0].zwt2, VG_C) \
-  X(C_zwt3, cell[0].zwt3, VG_C) \
-  X(V_canopyevap, veg_var[0].canopyevap, VG_C) \
-  X(V_throughfall, veg_var[0].throughfall, VG_C) \
-  X(V_Wdew, veg_var[0].Wdew, VG_C) \
-  X(G_cold_content, glacier.cold_content, VG_C) \
-  X(G_surf_temp, glacier.surf_temp, VG_C) \
-  X(G_surf_temp_fbcount, glacier.surf_temp_fbcount, VG_C) \
-  X(G_surf_temp_fbflag, glacier.surf_temp_fbflag, VG_C) \
-  X(G_Qnet, glacier.Qnet, VG_C) \
-  X(G_mass_balance, glacier.mass_balance, VG_C) \
-  X(G_ice_mass_balance, glacier.ice_mass_balance, VG_C) \
-  X(G_cum_mass_balance, glacier.cum_mass_balance, VG_C) \
-  X(G_accumulation, glacier.accumulation, VG_C) \
-  X(G_melt, glacier.melt, VG_C) \
-  X(G_vapor_flux, glacier.vapor_flux, VG_C) \
-  X(G_water_storage, glacier.water_storage, VG_C) \
-  X(G_outflow, glacier.outflow, VG_C) \
-  X(G_outflow_coef, glacier.outflow_coef, VG_C) \
-  X(G_inflow, glacier.inflow, VG_C) \
-  X(H_mu, mu, VG_C)
+  VICGPU_HRU_ENERGY(X, E_) VICGPU_HRU_SNOW(X, S_) VICGPU_HRU_CELL(X, C_) VICGPU_HRU_VEG(X, V_) \
+  VICGPU_HRU_GLAC(X, G_) X(H_mu, mu, VG_C)
 
 /* per-soil-layer columns: index i in [0, VICGPU_NLAYER) */
-#define VICGPU_HRU_LAYER(X) \
-  X(L_Cs, cell[0].layer[i].Cs, VG_C) \
-  X(L_T, cell[0].layer[i].T, VG_C) \
-  X(L_evap, cell[0].layer[i].evap, VG_C) \
-  X(L_soil_ice, cell[0].layer[i].soil_ice, VG_C) \
-  X(L_kappa, cell[0].layer[i].kappa, VG_C) \
-  X(L_moist, cell[0].layer[i].moist, VG_C) \
-  X(L_phi, cell[0].layer[i].phi, VG_C) \
-  X(L_zwt, cell[0].layer[i].zwt, VG_C)
+#define VICGPU_HRU_LAYER(X, P) \
+  X(P##Cs, cell[0].layer[i].Cs, VG_C) \
+  X(P##T, cell[0].layer[i].T, VG_C) \
+  X(P##evap, cell[0].layer[i].evap, VG_C) \
+  X(P##soil_ice, cell[0].layer[i].soil_ice, VG_C) \
+  X(P##kappa, cell[0].layer[i].kappa, VG_C) \
+  X(P##moist, cell[0].layer[i].moist, VG_C) \
+  X(P##phi, cell[0].layer[i].phi, VG_C) \
+  X(P##zwt, cell[0].layer[i].zwt, VG_C)
 
 /* freeze/thaw front columns: index i in [0, VICGPU_NFRONTS) */
-#define VICGPU_HRU_FRONT(X) \
-  X(F_fdepth, energy.fdepth[i], VG_C) \
-  X(F_tdepth, energy.tdepth[i], VG_C)
+#define VICGPU_HRU_FRONT(X, P) \
+  X(P##fdepth, energy.fdepth[i], VG_C) \
+  X(P##tdepth, energy.tdepth[i], VG_C)
 
-/* potential-evaporation columns: index i in [0, VICGPU_NPET) */
-#define VICGPU_HRU_PET(X) \
-  X(P_pot_evap, cell[0].pot_evap[i], VG_C)
+/* potential-evaporation columns cell[0].pot_evap[i], i in [0, VICGPU_NPET): handled explicitly */
 
 /* per-thermal-node columns: index i in [0, Nnode) */
-#define VICGPU_HRU_NODE(X) \
-  X(N_Cs, energy.Cs_node[i], VG_C) \
-  X(N_ice, energy.ice_content[i], VG_C) \
-  X(N_kappa, energy.kappa_node[i], VG_C) \
-  X(N_moist, energy.moist[i], VG_C) \
-  X(N_T, energy.T[i], VG_C) \
-  X(N_T_fbflag, energy.T_fbflag[i], VG_C) \
-  X(N_T_fbcount, energy.T_fbcount[i], VG_C)
+#define VICGPU_HRU_NODE(X, P) \
+  X(P##Cs, energy.Cs_node[i], VG_C) \
+  X(P##ice, energy.ice_content[i], VG_C) \
+  X(P##kappa, energy.kappa_node[i], VG_C) \
+  X(P##moist, energy.moist[i], VG_C) \
+  X(P##T, energy.T[i], VG_C) \
+  X(P##T_fbflag, energy.T_fbflag[i], VG_C) \
+  X(P##T_fbcount, energy.T_fbcount[i], VG_C)
 
 /* ------------------------------------------------------------------ HRU parameters (constant) */
 #define VICGPU_HPAR_SCALARS(X) \

@@ -1,0 +1,118 @@
+// vic_common.cuh -- constants, math wrappers and small helpers shared by every physics
+// header of the vic-b200 step kernels.
+//
+// All physics headers are written once and compiled twice:
+//   * by nvcc for sm_100a into libvicgpu.so (the product; vicgpu_kernels.cu), and
+//   * by g++ into oracle/_ref/libvicport.so (the CPU restatement used ONLY by tests/ to
+//     check the algorithm against the reference build without a GPU).
+// FP64 throughout; no fast-math: NaN is the reference's INVALID sentinel
+// (vicNl_def.h:150-159) and its tests (IS_VALID / IS_INVALID) must keep working.
+#ifndef VIC_COMMON_CUH
+#define VIC_COMMON_CUH
+
+#include <math.h>
+#include <limits.h>
+#include "vicgpu.h"
+
+#if defined(__CUDACC__)
+#define VIC_HD __host__ __device__ __forceinline__
+#define VIC_HDN __host__ __device__ __noinline__
+#define VIC_HDI __host__ __device__
+#else
+#define VIC_HD inline
+#define VIC_HDN
+#define VIC_HDI
+#endif
+
+namespace vic {
+
+// ---- model constants (vicNl_def.h:138-302, snow.h:33-79) -------------------------------
+constexpr double HUGE_RESIST = 1.e20;
+constexpr double SMALL = 1.e-12;
+constexpr int ERROR_I = -999;
+constexpr double ERROR_D = -999.0;
+constexpr int INVALID_INT = INT_MIN;
+constexpr double ice_density = 917.0;
+constexpr double von_K = 0.40;
+constexpr double KELVIN = 273.15;
+constexpr double STEFAN_B = 5.6696e-8;
+constexpr double Lf = 3.337e5;
+constexpr double RHO_W = 999.842594;
+constexpr double Cp = 1013.0;
+constexpr double CH_ICE = 2100.0e3;
+constexpr double CH_WATER = 4186.8e3;
+constexpr double K_SNOW = 2.9302e-6;
+constexpr double EPS = 0.62196351;
+constexpr double G_GRAV = 9.81;
+constexpr double JOULESPCAL = 4.1868;
+constexpr double GRAMSPKG = 1000.0;
+constexpr double SEC_PER_DAY = 86400.;
+constexpr int SECPHOUR = 3600;
+constexpr double GLAC_TEMP = 0.0;
+constexpr double GLAC_K_ICE = 2.14;
+constexpr double SNOW_SURF_DENSITY = 350;
+constexpr double CUTOFF_DENSITY = 830;
+constexpr double A_SVP = 0.61078;
+constexpr double B_SVP = 17.269;
+constexpr double C_SVP = 237.3;
+constexpr double CP_PM = 1013;
+constexpr double PS_PM = 101300;
+constexpr double LAPSE_PM = -0.006;
+constexpr double SNOW_DT = 5.0;
+constexpr double SURF_DT = 1.0;
+constexpr double SOIL_DT = 0.25;
+constexpr double CANOPY_DT = 1.0;
+// snow.h
+constexpr double LIQUID_WATER_CAPACITY = 0.035;
+constexpr double LAI_SNOW_MULTIPLIER = 0.0005;
+constexpr double MIN_INTERCEPTION_STORAGE = 0.005;
+constexpr double MAX_SURFACE_SWE = 0.125;
+constexpr double NEW_SNOW_DENSITY = 50.;
+constexpr double SNDENS_DMLIMIT = 100.;
+constexpr double SNDENS_ETA0 = 3.6e6;
+constexpr double SNDENS_C1 = 0.04;
+constexpr double SNDENS_C2 = 2.778e-6;
+constexpr double SNDENS_C5 = 0.08;
+constexpr double SNDENS_C6 = 0.021;
+constexpr double SNDENS_F = 0.6;
+constexpr double MIN_SWQ_EB_THRES = 0.0010;
+constexpr double TraceSnow = 0.03;
+
+// option codes (vicNl_def.h:166-214)
+enum { AR_406 = 0, AR_406_LS, AR_406_FULL, AR_410, AR_COMBO };
+enum { GF_406 = 0, GF_410, GF_FULL };
+enum { USACE = 0, SUN1999 };
+enum { DENS_BRAS = 0, DENS_SNTHRM };
+enum { VIC_412 = 0, KIENZLE };
+enum { N_PET_TYPES = 6, N_PET_TYPES_NON_NAT = 4, PET_VEGNOCR = 5 };
+
+// surface types of the aerodynamic tables (VegConditions.h)
+enum Surf { SNOW_FREE = 0, CANOPY_OVER = 1, SNOW_COVERED = 2, GLACIER_SURF = 3, SURF_UNSET = 4 };
+
+VIC_HD double vnan() {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(0x7ff8000000000000LL);
+#else
+  return NAN;
+#endif
+}
+VIC_HD bool is_invalid(double a) { return a != a; }
+VIC_HD bool is_valid(double a) { return a == a; }
+VIC_HD double vmin(double a, double b) { return (b < a) ? b : a; }   // std::min semantics
+VIC_HD double vmax(double a, double b) { return (a < b) ? b : a; }   // std::max semantics
+VIC_HD bool result_is_error(double r) { return r <= -998; }           // root_brent.h:11
+
+// Four quantities per surface type (snow-free ground / canopy / snow / glacier ice).
+struct Surf4 {
+  double v[4];
+  VIC_HD double& operator[](int i) { return v[i]; }
+  VIC_HD const double& operator[](int i) const { return v[i]; }
+  VIC_HD void set_invalid() { v[0] = v[1] = v[2] = v[3] = vnan(); }
+};
+
+struct RaUsed {  // AeroResistUsed, vicNl_def.h:602-606
+  double surface, overstory;
+};
+
+}  // namespace vic
+#endif

@@ -1,0 +1,136 @@
+// vic_engine.cuh -- the per-HRU and per-cell work items of one model record, written once and
+// called from the CUDA kernels (vicgpu.cu: one thread per HRU / per cell) and from the
+// host-compiled port used only by the tests (oracle/vicport.cpp: a loop).
+//
+// A record of the reference's time loop (vicNl.c:506-610) is, per cell:
+//   [rec 0 only] put_data(rec = -nrecs)    -> cell_output(rec = -1)
+//   dist_prec: full_energy + put_data       -> hru_work for every HRU, then cell_output(rec)
+//   accumulateGlacierMassBalance            -> folded into hru_work (it only touches the HRU's
+//                                              own glacier.cum_mass_balance, which put_data never reads)
+#ifndef VIC_ENGINE_CUH
+#define VIC_ENGINE_CUH
+#include "vic_step.cuh"
+#include "vic_output.cuh"
+
+namespace vic {
+
+// device-resident tables (column-major, see vic_types.cuh)
+struct Tables {
+  int ncell, nhru, nclass;
+  const double* veglib;   // [nclass][vl_stride]
+  const double* cellpar;  // [cp_stride][ncell]
+  const double* hrupar;   // [HP_N][nhru]
+  double* hrurec;         // [hr_stride][nhru]
+  double* hdiag;          // [3][nhru]  Cv-weighted out_prec / out_rain / out_snow of the step
+  const int* cell_h0;     // [ncell+1] first HRU of each cell
+  int* status;            // [ncell] 0 or -999
+  double* carry;          // [CC_N][ncell]
+  double* out;            // [nout][ncell]  OutputData::data of the current record
+  double* agg;            // [nout][ncell]  OutputData::aggdata
+  const int* aggtype;     // [N_OUTVARS]
+};
+
+// what accumulateGlacierMassBalance does at this record (decided on the host from the calendar,
+// accumulateGlacierMassBalance.c:15-66; integer bookkeeping, bit-exact)
+struct GlacAccum {
+  int enabled, reset_first, accumulate, reset_after;
+};
+
+template <int NN>
+VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec /* [f_stride][ncell] */, int h, Dmy dmy, int rec, GlacAccum ga) {
+  const size_t nh = (size_t)t.nhru;
+  Col hpc{t.hrupar + h, nh};
+  const int cell = (int)hpc(HP_cell);
+  double* dg = t.hdiag + h;
+  if (t.status[cell] != 0) {
+    dg[0] = dg[nh] = dg[2 * nh] = 0;
+    return;
+  }
+  Ctx cx;
+  cx.o = o;
+  cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L};
+  cx.vl = VegLib{t.veglib, &o->L};
+  cx.hp = hpc;
+  cx.f = Forcing{Col{forcing_rec + cell, (size_t)t.ncell}, o->L.f_nslot};
+  cx.dmy = dmy;
+  cx.rec = rec;
+  const HruPar hp = load_hrupar(hpc);
+  Hru<NN> hru;
+  load_hru<NN>(hru, t.hrurec + h, nh, &o->L);
+  HruStepDiag d;
+  int e = hru_step<NN>(hru, hp, cx, d);
+  if (e == ERROR_I) {
+    t.status[cell] = ERROR_I;  // benign race: every writer stores the same value
+    dg[0] = dg[nh] = dg[2 * nh] = 0;
+    return;
+  }
+  if (ga.enabled && hp.isGlacier) {
+    if (ga.reset_first) hru.glac.cum_mass_balance = 0;
+    if (ga.accumulate && is_valid(hru.glac.mass_balance)) hru.glac.cum_mass_balance += hru.glac.mass_balance;
+    if (ga.reset_after) hru.glac.cum_mass_balance = 0;
+  }
+  store_hru<NN>(hru, t.hrurec + h, nh, &o->L);
+  dg[0] = d.out_prec * hp.Cv;
+  dg[nh] = d.out_rain * hp.Cv;
+  dg[2 * nh] = d.out_snow * hp.Cv;
+}
+
+VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count) {
+  if (t.status[cell] != 0 && rec >= 0) {
+    // the reference stops touching an invalid cell (vicNl.c:521); its data row keeps the last values
+    return;
+  }
+  const size_t nc = (size_t)t.ncell;
+  CellPar cp{Col{t.cellpar + cell, nc}, &o->L};
+  VegLib vl{t.veglib, &o->L};
+  Forcing f{Col{forcing_rec ? forcing_rec + cell : nullptr, nc}, o->L.f_nslot};
+  put_data_cell(*o, cp, vl, &f, t.hrurec, t.hrupar, t.hdiag, (size_t)t.nhru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count, t.aggtype,
+                RowRW{t.carry + cell, nc}, RowRW{t.out + cell, nc}, RowRW{t.agg + cell, nc});
+}
+
+// options as the kernels want them
+inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
+  *why = "";
+  if (a.abi_version != VICGPU_ABI_VERSION) { *why = "abi_version mismatch"; return VICGPU_EINVAL; }
+  if (a.Nlayer != VICGPU_NLAYER) { *why = "Nlayer must be 3"; return VICGPU_EUNSUPPORTED; }
+  if (a.Nnode < 3 || a.Nnode > VICGPU_MAX_NODES) { *why = "Nnode out of range"; return VICGPU_EUNSUPPORTED; }
+  if (a.Nbands < 1 || a.Nbands > VICGPU_MAX_BANDS) { *why = "Nbands out of range"; return VICGPU_EUNSUPPORTED; }
+  if (a.DIST_PRCP) { *why = "DIST_PRCP is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.BLOWING) { *why = "BLOWING is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.CORRPREC) { *why = "CORRPREC is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.LAKES) { *why = "LAKES is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.IMPLICIT) { *why = "IMPLICIT is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.QUICK_SOLVE) { *why = "QUICK_SOLVE is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.GLACIER_DYNAMICS) { *why = "GLACIER_DYNAMICS is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.COMPUTE_TREELINE) { *why = "COMPUTE_TREELINE is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  if (a.dt < 1 || a.SNOW_STEP < 1 || a.NF < 1 || a.out_step_ratio < 1) { *why = "bad time-step options"; return VICGPU_EINVAL; }
+  o.Nnode = a.Nnode; o.Nbands = a.Nbands; o.dt = a.dt; o.SNOW_STEP = a.SNOW_STEP; o.NR = a.NR; o.NF = a.NF; o.nrecs = a.nrecs;
+  o.out_step_ratio = a.out_step_ratio; o.FULL_ENERGY = a.FULL_ENERGY; o.FROZEN_SOIL = a.FROZEN_SOIL; o.QUICK_FLUX = a.QUICK_FLUX;
+  o.QUICK_SOLVE = a.QUICK_SOLVE; o.IMPLICIT = a.IMPLICIT; o.EXP_TRANS = a.EXP_TRANS; o.NOFLUX = a.NOFLUX; o.GRND_FLUX_TYPE = a.GRND_FLUX_TYPE;
+  o.AERO_RESIST_CANSNOW = a.AERO_RESIST_CANSNOW; o.SNOW_ALBEDO = a.SNOW_ALBEDO; o.SNOW_DENSITY = a.SNOW_DENSITY; o.TEMP_TH_TYPE = a.TEMP_TH_TYPE;
+  o.TFALLBACK = a.TFALLBACK; o.GLACIER_ID = a.GLACIER_ID; o.GLACIER_DYNAMICS = a.GLACIER_DYNAMICS; o.MOISTFRACT = a.MOISTFRACT;
+  o.ALMA_OUTPUT = a.ALMA_OUTPUT; o.NVegLibTypes = a.NVegLibTypes; o.gaYear = a.glacierAccumStartYear; o.gaMonth = a.glacierAccumStartMonth;
+  o.gaDay = a.glacierAccumStartDay; o.gaInterval = a.glacierAccumInterval; o.wind_h = a.wind_h;
+  vicgpu_layout_init(&o.L, &a);
+  return VICGPU_OK;
+}
+
+// accumulateGlacierMassBalance.c:13-66 calendar logic; `started` persists between records
+inline GlacAccum glacier_accum_flags(const Opts& o, const int* dmy_rec, const int* dmy_next, int rec, bool* started) {
+  GlacAccum g = {0, 0, 0, 0};
+  if (o.gaYear == INT_MIN || o.gaMonth == INT_MIN || o.gaDay == INT_MIN || o.gaInterval == INT_MIN) return g;
+  if (rec == o.nrecs) return g;
+  g.enabled = 1;
+  if (rec == 0) g.reset_first = 1;
+  if (dmy_rec[4] == o.gaYear && dmy_rec[3] == o.gaMonth && dmy_rec[0] == o.gaDay) *started = true;
+  if (*started) g.accumulate = 1;
+  const int ny = dmy_next[4], nm = dmy_next[3], nd = dmy_next[0], nhour = dmy_next[2];
+  int dy = ny - o.gaYear;
+  if (dy < 0) dy = -dy;
+  if ((ny > o.gaYear) && (dy % o.gaInterval == 0) && nm == o.gaMonth && nd == o.gaDay && (((o.dt <= 12) && (nhour == 0)) || (o.dt == 24)))
+    g.reset_after = 1;
+  return g;
+}
+
+}  // namespace vic
+#endif

@@ -1,0 +1,156 @@
+// vic_frozen.cuh -- soil thermal-node profile for QUICK_FLUX = FALSE:
+//   explicit finite-difference heat equation, Gauss-Seidel sweeps to 0.01 C (<= 1000 sweeps),
+//   per-node Brent solve where the node is below freezing and frozen soil is active.
+//   solve_T_profile            frozen_soil.c:105-225
+//   calc_soil_thermal_fluxes   frozen_soil.c:305-505
+//   SoilThermalEqn::calculate  soil_thermal_eqn.c:8-92
+//
+// Two reference behaviours are reproduced on purpose (the oracle is the reference build):
+//  (1) the coefficient arrays A..E (frozen_soil.c:150-154) are only filled on the first solve of a
+//      surface-temperature search; they depend only on quantities that are constant during that
+//      search, so this code recomputes them on every call (same values).
+//  (2) calc_soil_thermal_fluxes is handed the per-LAYER arrays soil_con->max_moist / bubble / expt
+//      (frozen_soil.c:219) but indexes them per NODE; with MAX_LAYERS == 3 element j >= 3 of those
+//      arrays is element j-3 of the member that follows them in soil_con_struct
+//      (vicNl_def.h:920-941: bubble -> bubble_node, expt -> expt_node, max_moist -> max_moist_node).
+#ifndef VIC_FROZEN_CUH
+#define VIC_FROZEN_CUH
+#include "vic_brent.cuh"
+#include "vic_leaf.cuh"
+
+namespace vic {
+
+struct SoilThermalEqn {
+  double TL, TU, T0, moist, max_moist, bubble, expt, ice0, A, B, C, D, E;
+  int EXP_TRANS, node;
+  VIC_HDI double operator()(double T) {
+    double ice;
+    if (T < 0.) {
+      ice = moist - maximum_unfrozen_water(T, max_moist, bubble, expt);
+      if (ice < 0.) ice = 0.;
+      if (ice > max_moist) ice = max_moist;
+    } else ice = 0.;
+    double value;
+    if (!EXP_TRANS) {
+      value = -A * (T - T0) + B * (TL - TU) + C * (TL - T) - D * (T - TU) + E * (ice - ice0);
+      const double flux_term1 = B * (TL - TU);
+      const double flux_term2 = C * (TL - T) - D * (T - TU);
+      if (node == 1 && fabs(TL - TU) > 5. && (T < TL && T < TU) && (flux_term1 < 0 && flux_term2 > 0) && fabs(flux_term1) > fabs(flux_term2))
+        value = -A * (T - T0) + C * (TL - T) - D * (T - TU) + E * (ice - ice0);  // cold-nose fix
+    } else {
+      value = -A * (T - T0) + B * (TL - TU) + C * (TL - 2. * T + TU) - D * (TL - TU) + E * (ice - ice0);
+      const double flux_term1 = B * (TL - TU);
+      const double flux_term2 = C * (TL - 2. * T + TU) - D * (TL - TU);
+      if (node == 1 && fabs(TL - TU) > 5. && (T < TL && T < TU) && (flux_term1 < 0 && flux_term2 > 0) && fabs(flux_term1) > fabs(flux_term2))
+        value = -A * (T - T0) + C * (TL - 2. * T + TU) - D * (TL - TU) + E * (ice - ice0);
+    }
+    return value;
+  }
+};
+
+// the three mis-indexed per-layer arrays, see (2) above
+VIC_HD double layer_array_as_node(const CellPar& cp, int layer_field, int node_field, int j) {
+  return (j < VICGPU_NLAYER) ? cp.layer(layer_field, j) : cp.node(node_field, j - VICGPU_NLAYER);
+}
+
+// Returns 0 or ERROR_I.  T (out) and T0 (in) have Nnodes entries; T0[0] is the trial surface
+// temperature.  Tfbflag / Tfbcount are reset on every call, as in the reference.
+template <int NN>
+VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double* Tfbcount, const double* kappa, const double* Cs,
+                            const double* moist, double deltat, const double* ice, double Dp, int Nnodes, int* FIRST_SOLN, int NOFLUX,
+                            int EXP_TRANS, const CellPar& cp, const Opts& o) {
+  const int MAXIT = 1000;
+  double A[NN], B[NN], C[NN], D[NN], E[NN], Tlast[NN];
+  FIRST_SOLN[0] = 0;
+  {
+    double Bexp = 0;
+    if (EXP_TRANS) Bexp = log(Dp + 1.) / (double)(Nnodes - 1);
+    const int jend = NOFLUX ? Nnodes : Nnodes - 1;
+    for (int j = 1; j < jend; j++) {
+      const double kup = (j == Nnodes - 1) ? kappa[j] : kappa[j + 1];
+      if (!EXP_TRANS) {
+        const double al = cp.node(CN_alpha, j - 1);
+        A[j] = Cs[j] * al * al;
+        B[j] = (kup - kappa[j - 1]) * deltat;
+        C[j] = 2 * deltat * kappa[j] * al / cp.node(CN_gamma, j - 1);
+        D[j] = 2 * deltat * kappa[j] * al / cp.node(CN_beta, j - 1);
+        E[j] = ice_density * Lf * al * al;
+      } else {
+        const double z1 = (cp.node(CN_Zsum_node, j) + 1);
+        A[j] = 4 * Bexp * Bexp * Cs[j] * z1 * z1;
+        B[j] = (kup - kappa[j - 1]) * deltat;
+        C[j] = 4 * deltat * kappa[j];
+        D[j] = 2 * deltat * kappa[j] * Bexp;
+        E[j] = 4 * Bexp * Bexp * ice_density * Lf * z1 * z1;
+      }
+    }
+  }
+  for (int j = 0; j < Nnodes; j++) T[j] = T0[j];
+
+  // ---- calc_soil_thermal_fluxes
+  const bool frozen_on = (cp(CP_FS_ACTIVE) != 0.0) && o.FROZEN_SOIL;
+  bool Done = false;
+  int ItCount = 0;
+  const double threshold = 1.e-2;
+  for (int j = 0; j < Nnodes; j++) {
+    Tlast[j] = T[j];
+    Tfbflag[j] = 0;
+    Tfbcount[j] = 0;
+  }
+  while (!Done && ItCount < MAXIT) {
+    ItCount++;
+    double maxdiff = threshold;
+    const int jend = NOFLUX ? Nnodes : Nnodes - 1;
+    for (int j = 1; j < jend; j++) {
+      const bool bottom = (j == Nnodes - 1);  // only reached with NOFLUX: the node below is the node itself
+      const double oldT = T[j];
+      const double Tdn = bottom ? T[j] : T[j + 1];
+      if (T[j] >= 0 || !frozen_on) {
+        if (!EXP_TRANS) T[j] = (A[j] * T0[j] + B[j] * (Tdn - T[j - 1]) + C[j] * Tdn + D[j] * T[j - 1] + E[j] * (0. - ice[j])) / (A[j] + C[j] + D[j]);
+        else T[j] = (A[j] * T0[j] + B[j] * (Tdn - T[j - 1]) + C[j] * (Tdn + T[j - 1]) - D[j] * (Tdn - T[j - 1]) + E[j] * (0. - ice[j])) / (A[j] + 2. * C[j]);
+      } else {
+        SoilThermalEqn eq;
+        eq.TL = Tdn; eq.TU = T[j - 1]; eq.T0 = T0[j]; eq.moist = moist[j];
+        eq.max_moist = layer_array_as_node(cp, CL_max_moist, CN_max_moist_node, j);
+        eq.bubble = layer_array_as_node(cp, CL_bubble, CN_bubble_node, j);
+        eq.expt = layer_array_as_node(cp, CL_expt, CN_expt_node, j);
+        eq.ice0 = ice[j]; eq.A = A[j]; eq.B = B[j]; eq.C = C[j]; eq.D = D[j]; eq.E = E[j]; eq.EXP_TRANS = EXP_TRANS; eq.node = j;
+        T[j] = root_brent(T0[j] - (SOIL_DT), T0[j] + (SOIL_DT), eq);
+        if (result_is_error(T[j])) {
+          if (o.TFALLBACK) {
+            T[j] = T0[j];
+            Tfbflag[j] = 1;
+            Tfbcount[j] += 1;
+          } else return ERROR_I;
+        }
+      }
+      const double diff = fabs(oldT - T[j]);
+      if (diff > maxdiff) maxdiff = diff;
+    }
+    if (maxdiff <= threshold) Done = true;
+  }
+  if (o.TFALLBACK) {
+    // "cold nose" repair (frozen_soil.c:470-484)
+    for (int j = 1; j < Nnodes - 1; j++) {
+      if (Tlast[j - 1] - Tlast[j] > 0 && Tlast[j + 1] - T[j] > 0 && (T[j - 1] - T[j]) - (Tlast[j - 1] - Tlast[j]) > 0 &&
+          (T[j + 1] - T[j]) - (Tlast[j + 1] - Tlast[j]) > 0) {
+        T[j] = 0.5 * (T[j - 1] + T[j + 1]);
+        Tfbflag[j] = 1;
+        Tfbcount[j] += 1;
+      }
+    }
+  }
+  if (!Done) {
+    if (o.TFALLBACK) {
+      for (int j = 0; j < Nnodes; j++) {
+        T[j] = T0[j];
+        Tfbflag[j] = 1;
+        Tfbcount[j] += 1;
+      }
+    } else return ERROR_I;
+  }
+  return 0;
+}
+
+}  // namespace vic
+#endif

@@ -133,19 +133,19 @@ inline void vicgpu_pack_hrurec(const HRU &hru, const vicgpu_layout *L, double *r
   VICGPU_HRU_SCALARS(X)
 #undef X
   for (int i = 0; i < VICGPU_NLAYER; i++) {
-#define X(n, p, c) r[VICGPU_HR_LAYER(L, HRL_##n, i)] = (double)hru.p;
-    VICGPU_HRU_LAYER(X)
+#define X(n, p, c) r[VICGPU_HR_LAYER(L, n, i)] = (double)hru.p;
+    VICGPU_HRU_LAYER(X, HRL_)
 #undef X
   }
   for (int i = 0; i < VICGPU_NFRONTS; i++) {
-#define X(n, p, c) r[VICGPU_HR_FRONT(L, HRF_##n, i)] = (double)hru.p;
-    VICGPU_HRU_FRONT(X)
+#define X(n, p, c) r[VICGPU_HR_FRONT(L, n, i)] = (double)hru.p;
+    VICGPU_HRU_FRONT(X, HRF_)
 #undef X
   }
   for (int i = 0; i < VICGPU_NPET; i++) r[VICGPU_HR_PET(L, i)] = hru.cell[0].pot_evap[i];
   for (int i = 0; i < L->nnode; i++) {
-#define X(n, p, c) r[VICGPU_HR_NODE(L, HRN_##n, i)] = (double)hru.p;
-    VICGPU_HRU_NODE(X)
+#define X(n, p, c) r[VICGPU_HR_NODE(L, n, i)] = (double)hru.p;
+    VICGPU_HRU_NODE(X, HRN_)
 #undef X
   }
 }
@@ -160,19 +160,19 @@ inline void vicgpu_unpack_hrurec(HRU &hru, const vicgpu_layout *L, const double 
   VICGPU_HRU_SCALARS(X)
 #undef X
   for (int i = 0; i < VICGPU_NLAYER; i++) {
-#define X(n, p, c) vicgpu_assign_(hru.p, r[VICGPU_HR_LAYER(L, HRL_##n, i)]);
-    VICGPU_HRU_LAYER(X)
+#define X(n, p, c) vicgpu_assign_(hru.p, r[VICGPU_HR_LAYER(L, n, i)]);
+    VICGPU_HRU_LAYER(X, HRL_)
 #undef X
   }
   for (int i = 0; i < VICGPU_NFRONTS; i++) {
-#define X(n, p, c) vicgpu_assign_(hru.p, r[VICGPU_HR_FRONT(L, HRF_##n, i)]);
-    VICGPU_HRU_FRONT(X)
+#define X(n, p, c) vicgpu_assign_(hru.p, r[VICGPU_HR_FRONT(L, n, i)]);
+    VICGPU_HRU_FRONT(X, HRF_)
 #undef X
   }
   for (int i = 0; i < VICGPU_NPET; i++) hru.cell[0].pot_evap[i] = r[VICGPU_HR_PET(L, i)];
   for (int i = 0; i < L->nnode; i++) {
-#define X(n, p, c) vicgpu_assign_(hru.p, r[VICGPU_HR_NODE(L, HRN_##n, i)]);
-    VICGPU_HRU_NODE(X)
+#define X(n, p, c) vicgpu_assign_(hru.p, r[VICGPU_HR_NODE(L, n, i)]);
+    VICGPU_HRU_NODE(X, HRN_)
 #undef X
   }
 }
