@@ -461,6 +461,9 @@ int vicgpu_set_forcing(vicgpu_handle *h, int rec0, int nrec, const double *forci
  *            interval inside the block, nout = number of records with step_count == out_step_ratio */
 int vicgpu_step(vicgpu_handle *h, int rec0, int nrec, const int *dmy, double *out_data, double *out_agg);
 
+/* mark cells invalid before the run (cells whose initialisation failed on the host, vicNl.c:420-427);
+ * status [ncell]: 0 = valid, -999 = skip */
+int vicgpu_set_cell_status(vicgpu_handle *h, const int *status);
 /* per-cell status: 0 = valid, -999 = the reference would have returned ERROR from dist_prec for
  * that cell (vicNl.c:545-559); such cells are skipped for the rest of the run. */
 int vicgpu_get_cell_status(vicgpu_handle *h, int *status /* [ncell] */);
@@ -469,6 +472,12 @@ int vicgpu_get_cell_status(vicgpu_handle *h, int *status /* [ncell] */);
 int vicgpu_get_balance_errors(vicgpu_handle *h, double *err);
 /* device time (ms) spent in kernels during the last vicgpu_step call, and number of kernel launches */
 int vicgpu_get_last_step_timing(vicgpu_handle *h, double *kernel_ms, long long *launches);
+
+/* measurement aid: with profiling on, every launch of the per-HRU step kernel inside vicgpu_step is bracketed
+ * by CUDA events on the library's stream; get_kernel_profile returns the summed duration and the launch count
+ * since profiling was switched on. */
+int vicgpu_set_profiling(vicgpu_handle *h, int on);
+int vicgpu_get_kernel_profile(vicgpu_handle *h, double *hru_step_ms_total, long long *hru_step_launches);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@
 // It is also the CPU baseline of bench.py (--time-only: OpenMP cell loop exactly as vicNl.c:514-517).
 //
 // Usage: vic_ref_harness -g global.txt [-o case.bin] [--nrec N] [--dump-every K] [--threads T]
-//                        [--forcing-bin forcing.bin] [--time-only] [--no-run] [--verbose]
+//                        [--forcing-bin forcing.bin] [--time-only] [--time-from REC] [--no-run] [--verbose]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -63,7 +63,7 @@ static int init_cell(cell_info_struct &cell, filep_struct filep, dmy_struct *dmy
 
 int main(int argc, char **argv) {
   const char *global_file = NULL, *out_path = NULL, *forcing_path = NULL;
-  int nrec_limit = -1, dump_every = 0, threads = 1;
+  int nrec_limit = -1, dump_every = 0, threads = 1, time_from = 0;
   bool time_only = false, no_run = false, verbose = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -74,6 +74,7 @@ int main(int argc, char **argv) {
     else if (a == "--threads" && i + 1 < argc) threads = atoi(argv[++i]);
     else if (a == "--forcing-bin" && i + 1 < argc) forcing_path = argv[++i];
     else if (a == "--time-only") time_only = true;
+    else if (a == "--time-from" && i + 1 < argc) time_from = atoi(argv[++i]);
     else if (a == "--no-run") no_run = true;
     else if (a == "--verbose") verbose = true;
     else die("bad argument");
@@ -215,6 +216,7 @@ int main(int argc, char **argv) {
   auto t2 = std::chrono::steady_clock::now();
   size_t nd = 0;
   for (int rec = 0; rec < nrec; rec++) {
+    if (rec == time_from) t2 = std::chrono::steady_clock::now();  // warm-up records are not timed
     state.step_count++;
 #if PARALLEL_AVAILABLE
 #pragma omp parallel for
@@ -261,7 +263,7 @@ int main(int argc, char **argv) {
   int nvalid = 0;
   for (int c = 0; c < ncell; c++) nvalid += cells[c].isValid ? 1 : 0;
   fprintf(log, "run_seconds %.6f threads %d cell_steps %lld cell_steps_per_s %.1f valid_cells %d\n", secs, threads,
-          (long long)ncell * nrec, (double)ncell * nrec / secs, nvalid);
+          (long long)ncell * (nrec - time_from), (double)ncell * (nrec - time_from) / secs, nvalid);
 
   if (cw) {
     std::vector<int32_t> dr(dump_recs.begin(), dump_recs.end());

@@ -1,0 +1,100 @@
+"""CPU-only tests (-m "not gpu"): the oracle against the golden vectors, the host-side layout logic, and that
+libvicgpu.so loads, exports every symbol of include/vicgpu.h and refuses to run without a device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from vic_b200 import api
+from vic_b200.casefile import read_case, write_case
+from vic_b200.layout import TABLES, layout_from_options, parse_options
+from vic_b200.parity import column_report, integer_mismatches
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+INPUT_KEYS = ("options_raw", "meta", "veglib", "cellpar", "hrupar", "hrurec0", "aggtype", "valid0", "dmy", "forcing", "dump_recs")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_layout_matches_c_header(name):
+    """strides computed in Python == strides vicgpu_layout_init computed inside the reference harness"""
+    g = load_golden(name)
+    L = layout_from_options(parse_options(g["options_raw"]))
+    ncell, nhru, nrec, nout, hr_stride, cp_stride, f_stride, _ = [int(x) for x in g["meta"]]
+    assert (L.nout, L.hr_stride, L.cp_stride, L.f_stride) == (nout, hr_stride, cp_stride, f_stride)
+    assert g["hrurec0"].shape == (nhru, hr_stride) and g["cellpar"].shape == (ncell, cp_stride)
+    assert g["forcing"].shape == (nrec, ncell, f_stride)
+    assert len(TABLES["outvars"]) == api.N_OUTVARS
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_port_reproduces_reference_golden(name, vicport, tmp_path):
+    """the host-compiled restatement (same headers as the CUDA kernels) against the reference's own answers:
+    same compiler, same libm, no contraction => bit-identical state, aggregates and balance errors"""
+    g = load_golden(name)
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "res.bin")
+    write_case(case, {k: g[k] for k in INPUT_KEYS})
+    subprocess.run([vicport, case, out], check=True)
+    res = read_case(out)
+    L = layout_from_options(parse_options(g["options_raw"]))
+    assert res["hrurec"].shape == g["hrurec_ref"].shape
+    for k, kr, names in (("hrurec", "hrurec_ref", L.hru_names), ("agg", "agg_ref", L.out_names)):
+        worst = column_report(res[k], g[kr], names)[0]
+        assert worst[1] == 0.0, (k, worst)
+    assert column_report(res["out"][:24], g["out_ref_head"], L.out_names)[0][1] == 0.0
+    assert column_report(res["out"][-24:], g["out_ref_tail"], L.out_names)[0][1] == 0.0
+    assert integer_mismatches(res["hrurec"], g["hrurec_ref"], L.hru_names) == {}
+    assert np.array_equal(res["status"], g["status_ref"])
+    assert np.array_equal(res["balance"], g["balance_ref"], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN if n.startswith("fe_") or n.startswith("wb_")])
+def test_golden_water_balance_closes(name):
+    """known-answer check the reference itself prints: |water balance error| < 1e-5 mm per step, cumulative ~ 0
+    (calc_water_energy_balance_errors.c:33-43)"""
+    g = load_golden(name)
+    assert np.all(np.abs(g["balance_ref"][:, 2]) < 1e-5 + 1e-12)  # water_max_error only records |err| > 1e-5
+    assert np.all(np.abs(g["balance_ref"][:, 1]) < 1e-6)
+
+
+def test_library_exports_every_declared_symbol(root):
+    hdr = open(os.path.join(root, "include", "vicgpu.h")).read()
+    declared = set(re.findall(r"\b(vicgpu_[a-z_]+)\s*\(", hdr)) - {"vicgpu_layout_init", "vicgpu_default_aggtypes"}
+    assert declared == set(api.SYMBOLS)
+    lib = api.load_library()
+    for s in declared:
+        assert getattr(lib, s) is not None
+    assert lib.vicgpu_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    """the product path must fail loudly when there is no GPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    g = load_golden(GOLDEN[0])
+    with pytest.raises(api.VicGpuError) as e:
+        api.VicGpu(g["options_raw"])
+    assert e.value.code == -2
+
+
+def test_unsupported_options_are_rejected():
+    """option combinations that are not implemented on the device are errors, never silently approximated"""
+    g = load_golden(GOLDEN[0])
+    opt = parse_options(g["options_raw"])
+    assert api.parse_options(api.options_to_raw(opt)) == opt
+    lib = api.load_library()
+    for key in ("DIST_PRCP", "BLOWING", "LAKES", "IMPLICIT", "CORRPREC"):
+        o = dict(opt)
+        o[key] = 1
+        raw = api.options_to_raw(o)
+        h = ctypes.c_void_p()
+        rc = lib.vicgpu_create(ctypes.byref(h), raw.ctypes.data_as(ctypes.c_void_p), 0)
+        assert rc in (-3, -2), (key, rc)  # EUNSUPPORTED (or ENODEV when the device check comes first)

@@ -1,0 +1,83 @@
+"""GPU parity tests (-m gpu): the CUDA library, called through its C-ABI, against (1) the committed golden
+vectors generated from the reference and (2) the reference build itself (oracle/_ref/vic_ref_harness travels
+to the GPU box) on freshly generated, larger synthetic domains.
+
+Tolerance (BASELINE.json north_star): per-step state and outputs within 1e-9 relative; integer bookkeeping
+(flags, counters, last_snow, cell status) bit-exact.  Relative error is measured against
+max(|ref|, 1e-6 * column magnitude) -- see vic_b200/parity.py."""
+import dataclasses
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from vic_b200 import api, synth
+from vic_b200.casefile import read_case
+from vic_b200.layout import layout_from_options, parse_options
+from vic_b200.parity import column_report, integer_mismatches
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-9
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def _check(res, ref, keys, L, tol=TOL_STEP):
+    for k, kr, names in keys:
+        n = min(res[k].shape[0], ref[kr].shape[0])
+        worst = column_report(res[k][:n], ref[kr][:n], names)[:3]
+        assert worst[0][1] < tol, (k, worst)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_case(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    L = layout_from_options(parse_options(g["options_raw"]))
+    res = api.run_case(g, device=0)
+    _check(res, g, (("hrurec", "hrurec_ref", L.hru_names), ("agg", "agg_ref", L.out_names)), L)
+    assert column_report(res["out"][:24], g["out_ref_head"], L.out_names)[0][1] < TOL_STEP
+    assert column_report(res["out"][-24:], g["out_ref_tail"], L.out_names)[0][1] < TOL_STEP
+    assert integer_mismatches(res["hrurec"], g["hrurec_ref"], L.hru_names) == {}
+    assert np.array_equal(res["status"], g["status_ref"])
+    # balance errors: cumulative sums of per-step residuals that are ~1e-13 each; compare absolutely
+    assert np.nanmax(np.abs(res["balance"][:, 1:] - g["balance_ref"][:, 1:])) < 1e-6
+
+
+@pytest.mark.parametrize("cfgname,nlat,nlon,ndays,seed", [("fe_hourly", 6, 6, 60, 101), ("wb_daily", 5, 5, 365, 102)])
+def test_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref_harness, tmp_path):
+    cfg = dataclasses.replace(synth.CONFIGS[cfgname], ndays=ndays)
+    r = synth.generate(str(tmp_path / "in"), cfg, nlat, nlon, seed)
+    case = str(tmp_path / "case.bin")
+    subprocess.run([ref_harness, "-g", r["global_file"], "-o", case, "--dump-every", "240"], check=True, stdout=subprocess.DEVNULL)
+    c = read_case(case)
+    L = layout_from_options(parse_options(c["options_raw"]))
+    res = api.run_case(c, device=0)
+    _check(res, c, (("out", "out_ref", L.out_names), ("hrurec", "hrurec_ref", L.hru_names)), L)
+    assert integer_mismatches(res["hrurec"], c["hrurec_ref"], L.hru_names) == {}
+    assert np.array_equal(res["status"], c["status_ref"])
+
+
+def test_state_roundtrip_and_restart():
+    """set_state/get_state are exact, and stepping 48 records at once == 24 + get_state/set_state + 24"""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "fe_hourly_winter.npz")))
+    a = api.run_case({**g, "dump_recs": np.array([47], dtype=np.int32)}, nrec=48)
+    b = api.run_case({**g, "dump_recs": np.array([23, 47], dtype=np.int32)}, nrec=48)
+    assert np.array_equal(a["hrurec"][-1], b["hrurec"][-1], equal_nan=True)
+    assert np.array_equal(a["out"], b["out"], equal_nan=True)
+    gp = api.VicGpu(g["options_raw"])
+    gp.set_veglib(g["veglib"]); gp.set_cells(g["cellpar"], g["hrupar"]); gp.set_state(g["hrurec0"])
+    assert np.array_equal(gp.get_state(), g["hrurec0"], equal_nan=True)
+    gp.close()
+
+
+def test_call_order_errors():
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "fe_hourly_winter.npz")))
+    gp = api.VicGpu(g["options_raw"])
+    with pytest.raises(api.VicGpuError):
+        gp.set_state(g["hrurec0"])  # before set_cells
+    gp.set_veglib(g["veglib"]); gp.set_cells(g["cellpar"], g["hrupar"]); gp.set_state(g["hrurec0"])
+    with pytest.raises(api.VicGpuError):
+        gp.step(0, 4, g["dmy"][:5])  # no forcing resident
+    gp.close()

@@ -1,0 +1,243 @@
+"""ctypes binding of libvicgpu.so (include/vicgpu.h) for the tests and bench.py.
+
+The product's host side is C (the reference's own vicNl + vic_b200/host/vicgpu_pack.h, see
+INTEGRATION.md); this module only lets Python drive the same C-ABI.  There is no fallback of
+any kind: if the shared library is missing, or no CUDA device is present, it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .layout import OPTION_INT_FIELDS, layout_from_options, parse_options
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvicgpu.so")
+
+N_OUTVARS = 184
+
+ERRORS = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "EUNSUPPORTED", -4: "ECUDA", -5: "ESTATE"}
+
+# every symbol include/vicgpu.h declares
+SYMBOLS = [
+    "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
+    "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
+    "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
+    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile",
+]
+
+
+class VicGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvicgpu: {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen libvicgpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)")
+    lib = C.CDLL(path)
+    dp = C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int)
+    vp = C.c_void_p
+    lib.vicgpu_abi_version.restype = C.c_int
+    lib.vicgpu_last_error.restype = C.c_char_p
+    lib.vicgpu_create.argtypes = [C.POINTER(vp), vp, C.c_int]
+    lib.vicgpu_destroy.argtypes = [vp]
+    lib.vicgpu_get_layout.argtypes = [vp, vp]
+    lib.vicgpu_set_veglib.argtypes = [vp, C.c_int, dp]
+    lib.vicgpu_set_cells.argtypes = [vp, C.c_int, dp, C.c_int, dp]
+    lib.vicgpu_set_output_spec.argtypes = [vp, ip]
+    lib.vicgpu_set_cell_status.argtypes = [vp, ip]
+    lib.vicgpu_set_state.argtypes = [vp, dp]
+    lib.vicgpu_get_state.argtypes = [vp, dp]
+    lib.vicgpu_set_forcing.argtypes = [vp, C.c_int, C.c_int, dp]
+    lib.vicgpu_step.argtypes = [vp, C.c_int, C.c_int, ip, dp, dp]
+    lib.vicgpu_get_cell_status.argtypes = [vp, ip]
+    lib.vicgpu_get_balance_errors.argtypes = [vp, dp]
+    lib.vicgpu_get_last_step_timing.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
+    lib.vicgpu_set_profiling.argtypes = [vp, C.c_int]
+    lib.vicgpu_get_kernel_profile.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
+    for s in SYMBOLS:
+        getattr(lib, s)
+    _lib = lib
+    return lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _as_f64(a):
+    """contiguous float64 view without copying when already so (torch pinned tensors come in through .numpy())"""
+    a = np.asarray(a)
+    if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def options_to_raw(opt: dict) -> np.ndarray:
+    """dict -> int32 view of struct vicgpu_options"""
+    n = len(OPTION_INT_FIELDS)
+    npad = n + n % 2
+    raw = np.zeros(npad + 4, dtype=np.int32)
+    for i, k in enumerate(OPTION_INT_FIELDS):
+        raw[i] = int(opt[k])
+    raw[npad:npad + 4] = np.array([opt["wind_h"], opt["MIN_WIND_SPEED"]], dtype=np.float64).view(np.int32)
+    return raw
+
+
+class VicGpu:
+    """One model domain resident on one GPU (mirrors the calls a patched runModel() makes)."""
+
+    def __init__(self, options_raw, device=0):
+        self.lib = load_library()
+        self.options_raw = np.ascontiguousarray(options_raw, dtype=np.int32)
+        self.opt = parse_options(self.options_raw)
+        self.L = layout_from_options(self.opt)
+        self.h = C.c_void_p()
+        self._chk(self.lib.vicgpu_create(C.byref(self.h), self.options_raw.ctypes.data_as(C.c_void_p), int(device)))
+        self.ncell = self.nhru = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise VicGpuError(rc, (self.lib.vicgpu_last_error() or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.lib.vicgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_veglib(self, veglib):
+        v = _as_f64(veglib)
+        self._chk(self.lib.vicgpu_set_veglib(self.h, int(v.shape[0]), _dptr(v)))
+
+    def set_cells(self, cellpar, hrupar):
+        c, p = _as_f64(cellpar), _as_f64(hrupar)
+        assert c.shape[1] == self.L.cp_stride, (c.shape, self.L.cp_stride)
+        self.ncell, self.nhru = int(c.shape[0]), int(p.shape[0])
+        self._chk(self.lib.vicgpu_set_cells(self.h, self.ncell, _dptr(c), self.nhru, _dptr(p)))
+
+    def set_output_spec(self, aggtype=None):
+        if aggtype is None:
+            self._chk(self.lib.vicgpu_set_output_spec(self.h, None))
+        else:
+            a = np.ascontiguousarray(aggtype, dtype=np.int32)
+            assert a.size == N_OUTVARS
+            self._chk(self.lib.vicgpu_set_output_spec(self.h, _iptr(a)))
+
+    def set_cell_status(self, status):
+        s = np.ascontiguousarray(status, dtype=np.int32)
+        self._chk(self.lib.vicgpu_set_cell_status(self.h, _iptr(s)))
+
+    def set_state(self, hrurec):
+        r = _as_f64(hrurec)
+        assert r.shape == (self.nhru, self.L.hr_stride), (r.shape, self.nhru, self.L.hr_stride)
+        self._chk(self.lib.vicgpu_set_state(self.h, _dptr(r)))
+
+    def get_state(self):
+        r = np.empty((self.nhru, self.L.hr_stride), dtype=np.float64)
+        self._chk(self.lib.vicgpu_get_state(self.h, _dptr(r)))
+        return r
+
+    def set_forcing(self, rec0, forcing):
+        f = _as_f64(forcing)
+        assert f.shape[1:] == (self.ncell, self.L.f_stride), f.shape
+        self._chk(self.lib.vicgpu_set_forcing(self.h, int(rec0), int(f.shape[0]), _dptr(f)))
+
+    def n_output_steps(self, nrec, step_count0=0):
+        return (step_count0 + nrec) // self.opt["out_step_ratio"]
+
+    def step(self, rec0, nrec, dmy, out_data=None, out_agg=None):
+        """dmy: int32 [nrec+1][5].  out_data / out_agg: preallocated float64 arrays or None."""
+        d = np.ascontiguousarray(dmy, dtype=np.int32)
+        assert d.shape[0] >= nrec + 1 and d.shape[1] == 5
+        od = _dptr(out_data) if out_data is not None else None
+        oa = _dptr(out_agg) if out_agg is not None else None
+        self._chk(self.lib.vicgpu_step(self.h, int(rec0), int(nrec), _iptr(d), od, oa))
+
+    def cell_status(self):
+        s = np.empty(self.ncell, dtype=np.int32)
+        self._chk(self.lib.vicgpu_get_cell_status(self.h, _iptr(s)))
+        return s
+
+    def balance_errors(self):
+        e = np.empty((self.ncell, 5), dtype=np.float64)
+        self._chk(self.lib.vicgpu_get_balance_errors(self.h, _dptr(e)))
+        return e
+
+    def set_profiling(self, on=True):
+        self._chk(self.lib.vicgpu_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_profile(self):
+        ms = C.c_double()
+        n = C.c_longlong()
+        self._chk(self.lib.vicgpu_get_kernel_profile(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def last_step_timing(self):
+        ms = C.c_double()
+        n = C.c_longlong()
+        self._chk(self.lib.vicgpu_get_last_step_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def run_case(case, device=0, nrec=None, want_out=True, block=None):
+    """Run a case file's inputs through the CUDA library; returns arrays named like the host port's result file."""
+    g = VicGpu(case["options_raw"], device)
+    try:
+        L = g.L
+        g.set_veglib(case["veglib"])
+        g.set_cells(case["cellpar"], case["hrupar"])
+        g.set_output_spec(case["aggtype"])
+        if "valid0" in case:
+            g.set_cell_status(np.where(case["valid0"] != 0, 0, -999).astype(np.int32))
+        g.set_state(case["hrurec0"])
+        ntot = int(case["forcing"].shape[0])
+        nrec = ntot if nrec is None else min(nrec, ntot)
+        g.set_forcing(0, case["forcing"][:nrec])
+        dmy = case["dmy"]
+        dump_recs = [int(r) for r in case.get("dump_recs", []) if r < nrec]
+        ratio = g.opt["out_step_ratio"]
+        out = np.zeros((nrec, g.ncell, L.nout)) if want_out else None
+        agg = np.zeros((nrec // ratio, g.ncell, L.nout))
+        hru = []
+        # advance from dump record to dump record so that the state can be read back in between
+        cuts = sorted(set([r + 1 for r in dump_recs] + [nrec]))
+        r0 = 0
+        nagg = 0
+        for c in cuts:
+            n = c - r0
+            if n <= 0:
+                continue
+            na = ((r0 % ratio) + n) // ratio
+            g.step(r0, n, dmy[r0:r0 + n + 1], out[r0:c] if want_out else None, agg[nagg:nagg + na] if na else None)
+            nagg += na
+            if (c - 1) in dump_recs:
+                hru.append(g.get_state())
+            r0 = c
+        res = {"agg": agg, "hrurec": np.array(hru), "balance": g.balance_errors(), "status": g.cell_status()}
+        if want_out:
+            res["out"] = out
+        return res
+    finally:
+        g.close()

@@ -14,14 +14,17 @@
 #include <limits.h>
 #include "vicgpu.h"
 
+// VIC_HD : small leaf relations, always inlined.
+// VIC_HDI: the larger routines and the residual functors' operator(): real calls (one copy of
+//          each in the kernel), because the Brent solver evaluates a residual from a dozen call
+//          sites and residuals nest (surface -> soil profile -> per-node solve); inlining all of
+//          that multiplies code size and compile time by orders of magnitude.
 #if defined(__CUDACC__)
 #define VIC_HD __host__ __device__ __forceinline__
-#define VIC_HDN __host__ __device__ __noinline__
-#define VIC_HDI __host__ __device__
+#define VIC_HDI inline __host__ __device__ __noinline__
 #else
 #define VIC_HD inline
-#define VIC_HDN
-#define VIC_HDI
+#define VIC_HDI inline
 #endif
 
 namespace vic {

@@ -1,0 +1,428 @@
+// vicgpu.cu -- libvicgpu.so: CUDA kernels (sm_100a, FP64) and the C-ABI declared in include/vicgpu.h.
+//
+// Device data layout: every table is column-major ("structure of arrays") so that consecutive
+// threads (= consecutive HRUs, the HRUs of one cell being adjacent) read consecutive addresses:
+//   cellpar [cp_stride][ncell]   hrupar [HP_N][nhru]   hrurec [hr_stride][nhru]
+//   forcing [nrec][f_stride][ncell]   out / agg [nout][ncell]
+// The C-ABI speaks row-major records (what a host packer naturally produces); the conversion is
+// a tiled transpose ON THE DEVICE after a straight host->device copy, never a host loop.
+//
+// There is no CPU path in this file: without a CUDA device vicgpu_create fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "vicgpu_kernels.h"
+
+using namespace vic;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(VICGPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- kernels ---------------------------------------------------------------------------------
+// in: [batch][rows][cols] row-major  ->  out: [batch][cols][rows]
+__global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int rows, int cols) {
+  __shared__ double tile[32][33];
+  const size_t boff = (size_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[boff + (size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[boff + (size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
+                                                     int step_count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= t.ncell) return;
+  cell_output(o, t, forcing_rec, c, rec, step_count);
+}
+
+// ---- handle ----------------------------------------------------------------------------------
+struct vicgpu_handle {
+  int device = 0;
+  vicgpu_options abi;
+  Opts o;
+  Opts* d_o = nullptr;
+  Tables t;
+  int nout = 0;
+  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_hrupar = nullptr, *d_hrurec = nullptr, *d_hdiag = nullptr, *d_carry = nullptr,
+         *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr, *d_forcing = nullptr, *d_fstage = nullptr;
+  size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
+  int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
+  int frec0 = 0, fnrec = 0;
+  bool have_cells = false, have_state = false, glac_started = false;
+  int step_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0;
+  long long last_launches = 0;
+  // optional per-launch timing of the per-HRU step kernel (vicgpu_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> pev;
+  double prof_hru_ms = 0;
+  long long prof_hru_launches = 0;
+};
+
+static int transpose_to(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch) {
+  dim3 b(32, 8), g((cols + 31) / 32, (rows + 31) / 32, batch);
+  k_transpose<<<g, b, 0, h->stream>>>(d_in, d_out, rows, cols);
+  h->last_launches++;
+  CK(cudaGetLastError());
+  return VICGPU_OK;
+}
+
+static int ensure_stage(vicgpu_handle* h, size_t elems) {
+  if (elems <= h->stage_elems) return VICGPU_OK;
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_stage = nullptr;
+  h->stage_elems = 0;
+  CK(cudaMalloc(&h->d_stage, elems * sizeof(double)));
+  h->stage_elems = elems;
+  return VICGPU_OK;
+}
+
+// host row-major [rows][cols] -> device column-major [cols][rows]
+static int upload_transposed(vicgpu_handle* h, const double* host, double* d_dst, int rows, int cols) {
+  int rc = ensure_stage(h, (size_t)rows * cols);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_stage, host, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  rc = transpose_to(h, h->d_stage, d_dst, rows, cols, 1);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return VICGPU_OK;
+}
+// device column-major [cols][rows] -> host row-major [rows][cols]
+static int download_transposed(vicgpu_handle* h, const double* d_src, double* host, int rows, int cols, bool sync) {
+  int rc = ensure_stage(h, (size_t)rows * cols);
+  if (rc) return rc;
+  rc = transpose_to(h, d_src, h->d_stage, cols, rows, 1);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(host, h->d_stage, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (sync) CK(cudaStreamSynchronize(h->stream));
+  return VICGPU_OK;
+}
+
+extern "C" {
+
+int vicgpu_abi_version(void) { return VICGPU_ABI_VERSION; }
+const char* vicgpu_last_error(void) { return g_err.c_str(); }
+
+int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
+  if (!out || !opt) return fail(VICGPU_EINVAL, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return fail(VICGPU_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(VICGPU_ENODEV, "device ordinal out of range");
+  Opts o;
+  const char* why = "";
+  int rc = opts_from_abi(*opt, o, &why);
+  if (rc != VICGPU_OK) return fail(rc, why);
+  CK(cudaSetDevice(device));
+  vicgpu_handle* h = new vicgpu_handle();
+  h->device = device;
+  h->abi = *opt;
+  h->o = o;
+  h->nout = o.L.out_off[VICGPU_N_OUTVARS];
+  memset(&h->t, 0, sizeof(h->t));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  CK(cudaMalloc(&h->d_o, sizeof(Opts)));
+  CK(cudaMemcpy(h->d_o, &h->o, sizeof(Opts), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_aggtype, VICGPU_N_OUTVARS * sizeof(int)));
+  int agg[VICGPU_N_OUTVARS];
+  vicgpu_default_aggtypes(agg);
+  CK(cudaMemcpy(h->d_aggtype, agg, sizeof(agg), cudaMemcpyHostToDevice));
+  // the step kernel keeps one HRU (about 2 KB) plus its working copies in thread-local memory
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
+  *out = h;
+  return VICGPU_OK;
+}
+
+int vicgpu_destroy(vicgpu_handle* h) {
+  if (!h) return VICGPU_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_hrupar); cudaFree(h->d_hrurec); cudaFree(h->d_hdiag);
+  cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_forcing); cudaFree(h->d_fstage);
+  cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return VICGPU_OK;
+}
+
+int vicgpu_get_layout(const vicgpu_handle* h, vicgpu_layout* L) {
+  if (!h || !L) return fail(VICGPU_EINVAL, "null argument");
+  *L = h->o.L;
+  return VICGPU_OK;
+}
+
+int vicgpu_set_veglib(vicgpu_handle* h, int nclass, const double* veglib) {
+  if (!h || !veglib || nclass < h->o.NVegLibTypes + 4) return fail(VICGPU_EINVAL, "veglib must hold NVegLibTypes + 4 rows");
+  CK(cudaSetDevice(h->device));
+  cudaFree(h->d_veglib);
+  const size_t n = (size_t)nclass * h->o.L.vl_stride;
+  CK(cudaMalloc(&h->d_veglib, n * sizeof(double)));
+  CK(cudaMemcpy(h->d_veglib, veglib, n * sizeof(double), cudaMemcpyHostToDevice));
+  h->t.veglib = h->d_veglib;
+  h->t.nclass = nclass;
+  return VICGPU_OK;
+}
+
+int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhru, const double* hrupar) {
+  if (!h || !cellpar || !hrupar || ncell <= 0 || nhru <= 0) return fail(VICGPU_EINVAL, "bad argument");
+  CK(cudaSetDevice(h->device));
+  const vicgpu_layout& L = h->o.L;
+  // HRU -> cell map must be ascending (hruList order grouped by cell)
+  std::vector<int> h0(ncell + 1, 0);
+  int prev = 0;
+  for (int k = 0; k < nhru; k++) {
+    const double cd = hrupar[(size_t)k * HP_N + HP_cell];
+    const int c = (int)cd;
+    if (cd != (double)c || c < prev || c >= ncell) return fail(VICGPU_EINVAL, "hrupar[HP_cell] must be ascending cell indices in [0, ncell)");
+    const int vi = (int)hrupar[(size_t)k * HP_N + HP_vegIndex], b = (int)hrupar[(size_t)k * HP_N + HP_band];
+    if (vi < 0 || (h->t.nclass && vi >= h->t.nclass)) return fail(VICGPU_EINVAL, "hrupar[HP_vegIndex] out of range");
+    if (b < 0 || b >= h->o.Nbands) return fail(VICGPU_EINVAL, "hrupar[HP_band] out of range");
+    prev = c;
+    h0[c + 1]++;
+  }
+  for (int c = 0; c < ncell; c++) h0[c + 1] += h0[c];
+  cudaFree(h->d_cellpar); cudaFree(h->d_hrupar); cudaFree(h->d_hrurec); cudaFree(h->d_hdiag); cudaFree(h->d_carry); cudaFree(h->d_out);
+  cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
+  h->d_cellpar = h->d_hrupar = h->d_hrurec = h->d_hdiag = h->d_carry = h->d_out = h->d_agg = nullptr;
+  h->d_cell_h0 = h->d_status = nullptr;
+  CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
+  CK(cudaMalloc(&h->d_hrupar, (size_t)nhru * HP_N * sizeof(double)));
+  CK(cudaMalloc(&h->d_hrurec, (size_t)nhru * L.hr_stride * sizeof(double)));
+  CK(cudaMalloc(&h->d_hdiag, (size_t)nhru * 3 * sizeof(double)));
+  CK(cudaMalloc(&h->d_carry, (size_t)ncell * CC_N * sizeof(double)));
+  CK(cudaMalloc(&h->d_out, (size_t)ncell * h->nout * sizeof(double)));
+  CK(cudaMalloc(&h->d_agg, (size_t)ncell * h->nout * sizeof(double)));
+  CK(cudaMalloc(&h->d_cell_h0, (size_t)(ncell + 1) * sizeof(int)));
+  CK(cudaMalloc(&h->d_status, (size_t)ncell * sizeof(int)));
+  CK(cudaMemset(h->d_hdiag, 0, (size_t)nhru * 3 * sizeof(double)));
+  CK(cudaMemset(h->d_carry, 0, (size_t)ncell * CC_N * sizeof(double)));
+  CK(cudaMemset(h->d_out, 0, (size_t)ncell * h->nout * sizeof(double)));
+  CK(cudaMemset(h->d_agg, 0, (size_t)ncell * h->nout * sizeof(double)));
+  CK(cudaMemset(h->d_status, 0, (size_t)ncell * sizeof(int)));
+  CK(cudaMemcpy(h->d_cell_h0, h0.data(), (size_t)(ncell + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  int rc = upload_transposed(h, cellpar, h->d_cellpar, ncell, L.cp_stride);
+  if (rc) return rc;
+  rc = upload_transposed(h, hrupar, h->d_hrupar, nhru, HP_N);
+  if (rc) return rc;
+  h->t.ncell = ncell; h->t.nhru = nhru;
+  h->t.cellpar = h->d_cellpar; h->t.hrupar = h->d_hrupar; h->t.hrurec = h->d_hrurec; h->t.hdiag = h->d_hdiag; h->t.cell_h0 = h->d_cell_h0;
+  h->t.status = h->d_status; h->t.carry = h->d_carry; h->t.out = h->d_out; h->t.agg = h->d_agg; h->t.aggtype = h->d_aggtype;
+  h->have_cells = true;
+  h->have_state = false;
+  h->step_count = 0;
+  h->glac_started = false;
+  return VICGPU_OK;
+}
+
+int vicgpu_set_output_spec(vicgpu_handle* h, const int* aggtype) {
+  if (!h) return fail(VICGPU_EINVAL, "null handle");
+  CK(cudaSetDevice(h->device));
+  int agg[VICGPU_N_OUTVARS];
+  if (aggtype) memcpy(agg, aggtype, sizeof(agg));
+  else vicgpu_default_aggtypes(agg);
+  for (int v = 0; v < VICGPU_N_OUTVARS; v++)
+    if (agg[v] != VICGPU_AGG_AVG && agg[v] != VICGPU_AGG_END && agg[v] != VICGPU_AGG_SUM)
+      return fail(VICGPU_EUNSUPPORTED, "only AVG / END / SUM aggregation is implemented (as in put_data.c:664-680)");
+  CK(cudaMemcpy(h->d_aggtype, agg, sizeof(agg), cudaMemcpyHostToDevice));
+  return VICGPU_OK;
+}
+
+int vicgpu_set_cell_status(vicgpu_handle* h, const int* status) {
+  if (!h || !status || !h->have_cells) return fail(VICGPU_ESTATE, "set_cells first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(h->d_status, status, (size_t)h->t.ncell * sizeof(int), cudaMemcpyHostToDevice));
+  return VICGPU_OK;
+}
+
+int vicgpu_set_state(vicgpu_handle* h, const double* hrurec) {
+  if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
+  if (!h->have_cells) return fail(VICGPU_ESTATE, "set_cells before set_state");
+  CK(cudaSetDevice(h->device));
+  int rc = upload_transposed(h, hrurec, h->d_hrurec, h->t.nhru, h->o.L.hr_stride);
+  if (rc) return rc;
+  h->have_state = true;
+  return VICGPU_OK;
+}
+
+int vicgpu_get_state(vicgpu_handle* h, double* hrurec) {
+  if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
+  if (!h->have_state) return fail(VICGPU_ESTATE, "no state set");
+  CK(cudaSetDevice(h->device));
+  return download_transposed(h, h->d_hrurec, hrurec, h->t.nhru, h->o.L.hr_stride, true);
+}
+
+int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forcing) {
+  if (!h || !forcing || nrec <= 0 || rec0 < 0) return fail(VICGPU_EINVAL, "bad argument");
+  if (!h->have_cells) return fail(VICGPU_ESTATE, "set_cells before set_forcing");
+  CK(cudaSetDevice(h->device));
+  const size_t per = (size_t)h->t.ncell * h->o.L.f_stride;
+  const size_t need = per * nrec;
+  if (need > h->forcing_cap) {
+    cudaFree(h->d_forcing);
+    h->d_forcing = nullptr;
+    h->forcing_cap = 0;
+    CK(cudaMalloc(&h->d_forcing, need * sizeof(double)));
+    h->forcing_cap = need;
+  }
+  // staged in chunks of at most 256 MiB so that the staging buffer stays small next to the window
+  const size_t chunk_recs = std::min<size_t>(65535, std::max<size_t>(1, (size_t)(256u << 20) / (per * sizeof(double))));
+  const size_t stage_need = per * std::min<size_t>(chunk_recs, (size_t)nrec);
+  if (stage_need > h->fstage_cap) {
+    cudaFree(h->d_fstage);
+    h->d_fstage = nullptr;
+    h->fstage_cap = 0;
+    CK(cudaMalloc(&h->d_fstage, stage_need * sizeof(double)));
+    h->fstage_cap = stage_need;
+  }
+  for (size_t r = 0; r < (size_t)nrec; r += chunk_recs) {
+    const int nr = (int)std::min<size_t>(chunk_recs, (size_t)nrec - r);
+    CK(cudaMemcpyAsync(h->d_fstage, forcing + r * per, per * nr * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dim3 b(32, 8), g((h->o.L.f_stride + 31) / 32, (h->t.ncell + 31) / 32, nr);
+    k_transpose<<<g, b, 0, h->stream>>>(h->d_fstage, h->d_forcing + r * per, h->t.ncell, h->o.L.f_stride);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->frec0 = rec0;
+  h->fnrec = nrec;
+  return VICGPU_OK;
+}
+
+int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* out_data, double* out_agg) {
+  if (!h || !dmy || nrec <= 0) return fail(VICGPU_EINVAL, "bad argument");
+  if (!h->have_cells || !h->have_state || !h->d_veglib) return fail(VICGPU_ESTATE, "set_veglib, set_cells and set_state before step");
+  if (rec0 < h->frec0 || rec0 + nrec > h->frec0 + h->fnrec) return fail(VICGPU_ESTATE, "records outside the resident forcing window");
+  CK(cudaSetDevice(h->device));
+  const size_t per = (size_t)h->t.ncell * h->o.L.f_stride;
+  const size_t rowsz = (size_t)h->t.ncell * h->nout;
+  const int B = 128;
+  const int cgrid = (h->t.ncell + B - 1) / B;
+  h->last_launches = 0;
+  int nagg = 0;
+  if (out_data || out_agg) {
+    int rc = ensure_stage(h, rowsz);
+    if (rc) return rc;
+  }
+  if (h->profiling) {
+    while ((int)h->pev.size() < 2 * nrec) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      h->pev.push_back(e);
+    }
+  }
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < nrec; i++) {
+    const int rec = rec0 + i;
+    const double* frec = h->d_forcing + (size_t)(rec - h->frec0) * per;
+    h->step_count++;
+    if (rec == 0) {
+      k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, h->t, nullptr, -1, h->step_count);
+      h->last_launches++;
+    }
+    Dmy d = {dmy[i * 5 + 0], dmy[i * 5 + 1], dmy[i * 5 + 2], dmy[i * 5 + 3], dmy[i * 5 + 4]};
+    GlacAccum ga = glacier_accum_flags(h->o, &dmy[i * 5], &dmy[(i + 1) * 5], rec, &h->glac_started);
+    if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
+    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, h->t, frec, d, rec, ga, h->stream);
+    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, h->t, frec, d, rec, ga, h->stream);
+    else vicgpu_launch_hru_step_nn32(h->d_o, h->t, frec, d, rec, ga, h->stream);
+    if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));
+    k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, h->t, frec, rec, h->step_count);
+    h->last_launches += 2;
+    if (out_data) {
+      int rc = transpose_to(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(out_data + (size_t)i * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (h->step_count == h->o.out_step_ratio) {
+      if (out_agg) {
+        int rc = transpose_to(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      }
+      nagg++;
+      CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), h->stream));
+      h->step_count = 0;
+    }
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  if (h->profiling) {
+    for (int i = 0; i < nrec; i++) {
+      float k = 0;
+      CK(cudaEventElapsedTime(&k, h->pev[2 * i], h->pev[2 * i + 1]));
+      h->prof_hru_ms += k;
+      h->prof_hru_launches++;
+    }
+  }
+  return VICGPU_OK;
+}
+
+int vicgpu_get_cell_status(vicgpu_handle* h, int* status) {
+  if (!h || !status || !h->have_cells) return fail(VICGPU_ESTATE, "set_cells first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(status, h->d_status, (size_t)h->t.ncell * sizeof(int), cudaMemcpyDeviceToHost));
+  return VICGPU_OK;
+}
+
+int vicgpu_get_balance_errors(vicgpu_handle* h, double* err) {
+  if (!h || !err || !h->have_cells) return fail(VICGPU_ESTATE, "set_cells first");
+  CK(cudaSetDevice(h->device));
+  std::vector<double> c((size_t)CC_N * h->t.ncell);
+  CK(cudaMemcpy(c.data(), h->d_carry, c.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < h->t.ncell; i++)
+    for (int k = 0; k < 5; k++) err[(size_t)i * 5 + k] = c[(size_t)(CC_water_last_storage + k) * h->t.ncell + i];
+  return VICGPU_OK;
+}
+
+int vicgpu_set_profiling(vicgpu_handle* h, int on) {
+  if (!h) return fail(VICGPU_EINVAL, "null handle");
+  h->profiling = on != 0;
+  h->prof_hru_ms = 0;
+  h->prof_hru_launches = 0;
+  return VICGPU_OK;
+}
+
+int vicgpu_get_kernel_profile(vicgpu_handle* h, double* hru_step_ms_total, long long* hru_step_launches) {
+  if (!h) return fail(VICGPU_EINVAL, "null handle");
+  if (hru_step_ms_total) *hru_step_ms_total = h->prof_hru_ms;
+  if (hru_step_launches) *hru_step_launches = h->prof_hru_launches;
+  return VICGPU_OK;
+}
+
+int vicgpu_get_last_step_timing(vicgpu_handle* h, double* kernel_ms, long long* launches) {
+  if (!h) return fail(VICGPU_EINVAL, "null handle");
+  if (kernel_ms) *kernel_ms = h->last_ms;
+  if (launches) *launches = h->last_launches;
+  return VICGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,15 @@
+// vicgpu_kernels.h -- launchers of the per-record kernels; one translation unit per thermal-node
+// template width (vicgpu_step_nn*.cu) so that they compile in parallel.
+#ifndef VICGPU_KERNELS_H
+#define VICGPU_KERNELS_H
+#include <cuda_runtime.h>
+#include "vic_engine.cuh"
+
+// thread block of the per-HRU kernels
+#define VICGPU_HRU_BLOCK 128
+
+void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, cudaStream_t s);
+void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, cudaStream_t s);
+void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, cudaStream_t s);
+
+#endif

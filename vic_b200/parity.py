@@ -26,6 +26,13 @@ def rel_err(a, b, floor):
     return d / den
 
 
+# Columns that ARE residuals of a balance (root-finder residuals, closure errors): their own magnitude is
+# rounding noise of the terms they are the sum of, so they are judged against the size of those terms
+# (energy fluxes O(100) W/m2 -> 1 W/m2 is a conservative unit; water storages O(100) mm -> 1 mm; SWE -> 1e-3 m).
+RESIDUAL_FLOORS = {"E_error": 1.0, "ENERGY_ERROR": 1.0, "WATER_ERROR": 1.0, "S_mass_error": 1e-3, "S_Qnet": 1.0, "G_Qnet": 1.0,
+                   "E_AtmosError": 1.0}
+
+
 def column_report(got, ref, names, scale_floor=1e-6, abs_floor=1e-9):
     """got/ref: [..., ncol]; returns list of (name, max_rel_err, argmax index) sorted worst first."""
     got = np.asarray(got)
@@ -37,7 +44,7 @@ def column_report(got, ref, names, scale_floor=1e-6, abs_floor=1e-9):
     for c in range(ncol):
         fin = r[:, c][np.isfinite(r[:, c])]
         mag = np.max(np.abs(fin)) if fin.size else 0.0
-        floor = max(mag * scale_floor, abs_floor)
+        floor = max(mag * scale_floor, abs_floor, RESIDUAL_FLOORS.get(names[c].split("[")[0], 0.0))
         e = rel_err(g[:, c], r[:, c], floor)
         k = int(np.argmax(e)) if e.size else 0
         out.append((names[c], float(e[k]) if e.size else 0.0, k))

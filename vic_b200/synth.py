@@ -43,6 +43,8 @@ class Config:
     implicit: bool = False
     exp_trans: bool = False
     noflux: bool = False
+    out_step: int = 0  # OUT_STEP [h]; 0 = every model step
+    startday: int = 1  # day of January the run (and the forcing files) start on
     extra_global: list = field(default_factory=list)
 
 
@@ -226,7 +228,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
             # --- daily forcing
             if forcing:
                 nd = cfg.ndays
-                doy = np.arange(nd)
+                doy = np.arange(nd) + (cfg.startday - 1)
                 tmean = avg_temp + 2.0 - 0.0065 * 0.0 + 12.0 * np.sin(2 * np.pi * (doy - 105) / 365.0) \
                     - 0.004 * (elev - 1000.0) + rng.normal(0.0, 2.0, nd)
                 dtr = rng.uniform(6.0, 12.0, nd)
@@ -250,7 +252,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
 
     # --- end date
     import datetime
-    d0 = datetime.date(cfg.startyear, 1, 1)
+    d0 = datetime.date(cfg.startyear, 1, 1) + datetime.timedelta(days=cfg.startday - 1)
     d1 = d0 + datetime.timedelta(days=cfg.ndays - 1)
 
     def tf(b):
@@ -277,7 +279,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
         g += [f"GLACIER_ID {GLACIER_ID}"]
     g += [f"FORCING1 {fdir}/f_", "FORCE_FORMAT ASCII", "FORCE_ENDIAN LITTLE", "N_TYPES 4",
           "FORCE_TYPE PREC", "FORCE_TYPE TMAX", "FORCE_TYPE TMIN", "FORCE_TYPE WIND",
-          "FORCE_DT 24", f"FORCEYEAR {d0.year}", "FORCEMONTH 1", "FORCEDAY 1", "FORCEHOUR 0",
+          "FORCE_DT 24", f"FORCEYEAR {d0.year}", f"FORCEMONTH {d0.month}", f"FORCEDAY {d0.day}", "FORCEHOUR 0",
           f"GRID_DECIMAL {grid_decimal}", "WIND_H 10.0", "MEASURE_H 2.0", "ALMA_INPUT FALSE"]
     if cfg.output_force:
         g += ["OUTPUT_FORCE TRUE"]
@@ -288,7 +290,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
         g += [f"SNOW_BAND {cfg.nbands} {outdir}/snowband.txt"]
     else:
         g += ["SNOW_BAND 1"]
-    g += [f"RESULT_DIR {rdir}", "OUT_STEP 0", "SKIPYEAR 0", "COMPRESS FALSE", "OUTPUT_FORMAT BINARY",
+    g += [f"RESULT_DIR {rdir}", f"OUT_STEP {cfg.out_step}", "SKIPYEAR 0", "COMPRESS FALSE", "OUTPUT_FORMAT BINARY",
           "ALMA_OUTPUT FALSE", "MOISTFRACT FALSE", "PRT_HEADER FALSE", "PRT_SNOW_BAND FALSE"]
     g += cfg.extra_global
     gpath = os.path.join(outdir, "global.txt")
