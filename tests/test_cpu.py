@@ -45,8 +45,10 @@ def test_port_reproduces_reference_golden(name, vicport, tmp_path):
     res = read_case(out)
     L = layout_from_options(parse_options(g["options_raw"]))
     assert res["hrurec"].shape == g["hrurec_ref"].shape
-    for k, kr, names in (("hrurec", "hrurec_ref", L.hru_names), ("agg", "agg_ref", L.out_names)):
-        worst = column_report(res[k], g[kr], names)[0]
+    # the reference never initialises aggdata before its first output step (output_list_utils.c:20-24 allocates it
+    # with new[]), so the first aggregate of AVG/SUM variables holds heap garbage: compare from the second on
+    for k, kr, names, first in (("hrurec", "hrurec_ref", L.hru_names, 0), ("agg", "agg_ref", L.out_names, 1)):
+        worst = column_report(res[k][first:], g[kr][first:], names)[0]
         assert worst[1] == 0.0, (k, worst)
     assert column_report(res["out"][:24], g["out_ref_head"], L.out_names)[0][1] == 0.0
     assert column_report(res["out"][-24:], g["out_ref_tail"], L.out_names)[0][1] == 0.0

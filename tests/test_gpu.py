@@ -36,7 +36,9 @@ def test_golden_case(name):
     g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
     L = layout_from_options(parse_options(g["options_raw"]))
     res = api.run_case(g, device=0)
-    _check(res, g, (("hrurec", "hrurec_ref", L.hru_names), ("agg", "agg_ref", L.out_names)), L)
+    _check(res, g, (("hrurec", "hrurec_ref", L.hru_names),), L)
+    # the reference's first aggregate holds uninitialised heap memory (see tests/test_cpu.py): compare from the second on
+    _check({"agg": res["agg"][1:]}, {"agg_ref": g["agg_ref"][1:]}, (("agg", "agg_ref", L.out_names),), L)
     assert column_report(res["out"][:24], g["out_ref_head"], L.out_names)[0][1] < TOL_STEP
     assert column_report(res["out"][-24:], g["out_ref_tail"], L.out_names)[0][1] < TOL_STEP
     assert integer_mismatches(res["hrurec"], g["hrurec_ref"], L.hru_names) == {}
@@ -45,7 +47,7 @@ def test_golden_case(name):
     assert np.nanmax(np.abs(res["balance"][:, 1:] - g["balance_ref"][:, 1:])) < 1e-6
 
 
-@pytest.mark.parametrize("cfgname,nlat,nlon,ndays,seed", [("fe_hourly", 6, 6, 60, 101), ("wb_daily", 5, 5, 365, 102)])
+@pytest.mark.parametrize("cfgname,nlat,nlon,ndays,seed", [("fe_hourly", 6, 6, 60, 101), ("wb_daily", 5, 5, 365, 102), ("glacier", 4, 4, 200, 103), ("frozen_bands", 2, 3, 20, 104)])
 def test_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref_harness, tmp_path):
     cfg = dataclasses.replace(synth.CONFIGS[cfgname], ndays=ndays)
     r = synth.generate(str(tmp_path / "in"), cfg, nlat, nlon, seed)

@@ -21,8 +21,8 @@ VIC_HDI int calc_aerodynamic(bool OverStory, double Height, double Trunk, double
   if (!OverStory) {
     Z0_Lower = roughness[SNOW_FREE];
     d_Lower = displacement[SNOW_FREE];
-    const double l2 = log((2. + Z0_Lower) / Z0_Lower);
-    const double lr = log((ref_height[SNOW_FREE] - d_Lower) / Z0_Lower);
+    const double l2 = vlog((2. + Z0_Lower) / Z0_Lower);
+    const double lr = vlog((ref_height[SNOW_FREE] - d_Lower) / Z0_Lower);
     wind_speed[SNOW_FREE] = l2 / lr;
     aero_resist[SNOW_FREE] = l2 * lr / K2;
     ref_height[CANOPY_OVER] = ref_height[SNOW_FREE];
@@ -33,15 +33,15 @@ VIC_HDI int calc_aerodynamic(bool OverStory, double Height, double Trunk, double
     ref_height[SNOW_COVERED] = ref_height[SNOW_FREE];
     roughness[SNOW_COVERED] = Z0_SNOW;
     displacement[SNOW_COVERED] = 0.;
-    const double s2 = log((2. + Z0_SNOW) / Z0_SNOW);
-    const double sr = log(ref_height[SNOW_COVERED] / Z0_SNOW);
+    const double s2 = vlog((2. + Z0_SNOW) / Z0_SNOW);
+    const double sr = vlog(ref_height[SNOW_COVERED] / Z0_SNOW);
     wind_speed[SNOW_COVERED] = s2 / sr;
     aero_resist[SNOW_COVERED] = s2 * sr / K2;
     ref_height[SNOW_COVERED] = 2. + Z0_SNOW;
     ref_height[GLACIER_SURF] = ref_height[SNOW_FREE];
     roughness[GLACIER_SURF] = Z0_Lower;
     displacement[GLACIER_SURF] = 0.;
-    const double gr = log(ref_height[GLACIER_SURF] / Z0_Lower);
+    const double gr = vlog(ref_height[GLACIER_SURF] / Z0_Lower);
     wind_speed[GLACIER_SURF] = l2 / gr;
     aero_resist[GLACIER_SURF] = l2 * gr / K2;
     ref_height[GLACIER_SURF] = 2. + Z0_Lower;
@@ -53,31 +53,31 @@ VIC_HDI int calc_aerodynamic(bool OverStory, double Height, double Trunk, double
     Zw = 1.5 * Height - 0.5 * d_Upper;
     Zt = Trunk * Height;
     if (Zt < (Z0_Lower + d_Lower)) return ERROR_I;
-    const double lru = log((ref_height[SNOW_FREE] - d_Upper) / Z0_Upper);
+    const double lru = vlog((ref_height[SNOW_FREE] - d_Upper) / Z0_Upper);
     aero_resist[CANOPY_OVER] = lru / K2 *
-        (Height / (n * (Zw - d_Upper)) * (exp(n * (1 - (d_Upper + Z0_Upper) / Height)) - 1) + (Zw - Height) / (Zw - d_Upper) +
-         log((ref_height[SNOW_FREE] - d_Upper) / (Zw - d_Upper)));
-    Uw = log((Zw - d_Upper) / Z0_Upper) / lru;
+        (Height / (n * (Zw - d_Upper)) * (vexp(n * (1 - (d_Upper + Z0_Upper) / Height)) - 1) + (Zw - Height) / (Zw - d_Upper) +
+         vlog((ref_height[SNOW_FREE] - d_Upper) / (Zw - d_Upper)));
+    Uw = vlog((Zw - d_Upper) / Z0_Upper) / lru;
     Uh = Uw - (1 - (Height - d_Upper) / (Zw - d_Upper)) / lru;
-    wind_speed[CANOPY_OVER] = Uh * exp(n * ((Z0_Upper + d_Upper) / Height - 1.));
-    Ut = Uh * exp(n * (Zt / Height - 1.));
-    const double l2 = log((2. + Z0_Lower) / Z0_Lower);
-    const double lt = log(Zt / Z0_Lower);
+    wind_speed[CANOPY_OVER] = Uh * vexp(n * ((Z0_Upper + d_Upper) / Height - 1.));
+    Ut = Uh * vexp(n * (Zt / Height - 1.));
+    const double l2 = vlog((2. + Z0_Lower) / Z0_Lower);
+    const double lt = vlog(Zt / Z0_Lower);
     wind_speed[SNOW_FREE] = Ut * l2 / lt;
     aero_resist[SNOW_FREE] = l2 * lt / (K2 * Ut);
     if (Zt > (2. + Z0_SNOW)) {
-      const double s2 = log((2. + Z0_SNOW) / Z0_SNOW), st = log(Zt / Z0_SNOW);
+      const double s2 = vlog((2. + Z0_SNOW) / Z0_SNOW), st = vlog(Zt / Z0_SNOW);
       wind_speed[SNOW_COVERED] = Ut * s2 / st;
       aero_resist[SNOW_COVERED] = s2 * st / (K2 * Ut);
     } else if (Height > (2. + Z0_SNOW)) {
-      const double st = log(Zt / Z0_SNOW);
-      wind_speed[SNOW_COVERED] = Uh * exp(n * ((2. + Z0_SNOW) / Height - 1.));
+      const double st = vlog(Zt / Z0_SNOW);
+      wind_speed[SNOW_COVERED] = Uh * vexp(n * ((2. + Z0_SNOW) / Height - 1.));
       aero_resist[SNOW_COVERED] = st * st / (K2 * Ut) +
-          Height * lru / (n * K2 * (Zw - d_Upper)) * (exp(n * (1 - Zt / Height)) - exp(n * (1 - (Z0_SNOW + 2.) / Height)));
+          Height * lru / (n * K2 * (Zw - d_Upper)) * (vexp(n * (1 - Zt / Height)) - vexp(n * (1 - (Z0_SNOW + 2.) / Height)));
     } else {
-      const double st = log(Zt / Z0_SNOW);
+      const double st = vlog(Zt / Z0_SNOW);
       wind_speed[SNOW_COVERED] = Uh;
-      aero_resist[SNOW_COVERED] = st * st / (K2 * Ut) + Height * lru / (n * K2 * (Zw - d_Upper)) * (exp(n * (1 - Zt / Height)) - 1);
+      aero_resist[SNOW_COVERED] = st * st / (K2 * Ut) + Height * lru / (n * K2 * (Zw - d_Upper)) * (vexp(n * (1 - Zt / Height)) - 1);
     }
     ref_height[CANOPY_OVER] = ref_height[SNOW_FREE];
     roughness[CANOPY_OVER] = roughness[SNOW_FREE];

@@ -92,6 +92,14 @@ enum { N_PET_TYPES = 6, N_PET_TYPES_NON_NAT = 4, PET_VEGNOCR = 5 };
 // surface types of the aerodynamic tables (VegConditions.h)
 enum Surf { SNOW_FREE = 0, CANOPY_OVER = 1, SNOW_COVERED = 2, GLACIER_SURF = 3, SURF_UNSET = 4 };
 
+// libm entry points as real calls on the device: each of pow / exp / log expands to hundreds of
+// instructions, and the step kernel has dozens of call sites; one shared copy keeps the kernel's
+// code closer to the instruction cache.  (The host build inlines them as usual.)
+VIC_HDI double vpow(double a, double b) { return pow(a, b); }
+VIC_HDI double vexp(double a) { return exp(a); }
+VIC_HDI double vlog(double a) { return log(a); }
+VIC_HDI double vlog10(double a) { return log10(a); }
+
 VIC_HD double vnan() {
 #if defined(__CUDA_ARCH__)
   return __longlong_as_double(0x7ff8000000000000LL);

@@ -60,7 +60,7 @@ VIC_HDI void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doub
   }
   const double moist2 = layer[NL - 1].moist - layer[NL - 1].soil_ice;
   avail_moist[NL - 1] = moist2;
-  const double wet_canopy = 1.0 - f * pow((Wdew / veg.Wdmax), (2.0 / 3.0));
+  const double wet_canopy = 1.0 - f * vpow((Wdew / veg.Wdmax), (2.0 / 3.0));
   // (1 - root) is evaluated in single precision by the reference (float operand)
   const double one_minus_rootN = (double)(1.0f - s.root[NL - 1]);
   if ((moist1 >= Wcr1 && moist2 >= s.Wcr[NL - 1] && Wcr1 > 0.) || (moist1 >= Wcr1 && one_minus_rootN >= 0.5) ||
@@ -124,7 +124,7 @@ VIC_HDI double canopy_evap(SoilLayer* layer, VegVar& vv, bool CALC_EVAP, const V
     tmp_Wdew = veg.Wdmax;
   }
   double rc = calc_rc(0.0, net_short, veg.RGL, air_temp, vpd, veg.LAI, 1.0, false);
-  double canopyevap = pow((tmp_Wdew / veg.Wdmax), (2.0 / 3.0)) * penman(air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t / SEC_PER_DAY;
+  double canopyevap = vpow((tmp_Wdew / veg.Wdmax), (2.0 / 3.0)) * penman(air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t / SEC_PER_DAY;
   double f;
   if (canopyevap > 0.0 && delta_t == SEC_PER_DAY) f = vmin(1.0, ((tmp_Wdew + ppt) / canopyevap));
   else if (canopyevap > 0.0) f = vmin(1.0, ((tmp_Wdew) / canopyevap));
@@ -162,7 +162,7 @@ VIC_HDI double arno_evap(SoilLayer* layer, double rad, double air_temp, double v
     ratio = 1.0 - (moist) / (max_moist);
     if (ratio > 1.0) return ERROR_D;
     else if (ratio < 0.0) return ERROR_D;
-    else ratio = pow(ratio, (1.0 / (b_infilt + 1.0)));
+    else ratio = vpow(ratio, (1.0 / (b_infilt + 1.0)));
     tmp = max_infil * (1.0 - ratio);
   }
   if (tmp >= max_infil) evap = Epot;
@@ -171,9 +171,9 @@ VIC_HDI double arno_evap(SoilLayer* layer, double rad, double air_temp, double v
     ratio = 1.0 - ratio;
     if (ratio > 1.0) return ERROR_D;
     else if (ratio < 0.0) return ERROR_D;
-    else if (ratio != 0.0) ratio = pow(ratio, b_infilt);
+    else if (ratio != 0.0) ratio = vpow(ratio, b_infilt);
     as = 1 - ratio;
-    ratio = pow(ratio, (1.0 / b_infilt));
+    ratio = vpow(ratio, (1.0 / b_infilt));
     // 30-term series; the running power reproduces the reference's repeated product
     // tmpsum = ratio * ratio * ... (left to right), so the partial products are identical
     double dummy = 1.0, tmpsum = 1.0;

@@ -64,7 +64,7 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
   FIRST_SOLN[0] = 0;
   {
     double Bexp = 0;
-    if (EXP_TRANS) Bexp = log(Dp + 1.) / (double)(Nnodes - 1);
+    if (EXP_TRANS) Bexp = vlog(Dp + 1.) / (double)(Nnodes - 1);
     const int jend = NOFLUX ? Nnodes : Nnodes - 1;
     for (int j = 1; j < jend; j++) {
       const double kup = (j == Nnodes - 1) ? kappa[j] : kappa[j + 1];

@@ -10,7 +10,7 @@ namespace vic {
 
 // saturated vapour pressure [Pa], svp.c:7-23 (Handbook of Hydrology 4.2.2)
 VIC_HD double svp(double temp) {
-  double SVP = A_SVP * exp((B_SVP * temp) / (C_SVP + temp));
+  double SVP = A_SVP * vexp((B_SVP * temp) / (C_SVP + temp));
   if (temp < 0) SVP *= 1.0 + .00972 * temp + .000042 * temp * temp;
   return SVP * 1000.;
 }
@@ -27,7 +27,7 @@ VIC_HD double linear_interp(double x, double lx, double ux, double ly, double uy
 // vegetation height from displacement, calc_veg_params.c:26-37 (COEF_DRAG 0.2)
 VIC_HD double calc_veg_height(double displacement, double lai) {
   double X = 0.2 * lai;
-  return displacement / (1.1 * log(1 + pow(X, 0.25)));
+  return displacement / (1.1 * vlog(1 + vpow(X, 0.25)));
 }
 
 // canopy resistance, penman.c:44-90 (Wigmosta et al. 1994)
@@ -61,7 +61,7 @@ VIC_HD double calc_rc(double rs, double net_short, float RGL, double tair, doubl
 VIC_HD double penman(double tair, double elevation, double rad, double vpd, double ra, double rc, double rarc) {
   double slope = svp_slope(tair);
   double h = 287 / 9.81 * ((tair + 273.15) + 0.5 * (double)elevation * LAPSE_PM);
-  double pz = PS_PM * exp(-(double)elevation / h);
+  double pz = PS_PM * vexp(-(double)elevation / h);
   double lv = 2501000 - 2361 * tair;
   double gamma = 1628.6 * pz / lv;
   double r_air = 0.003486 * pz / (275 + tair);
@@ -76,7 +76,7 @@ VIC_HD double stability_correction(double Z, double d, double TSurf, double Tair
   const double RiCr = 0.2;
   if (TSurf != Tair) {
     double Ri = G_GRAV * (Tair - TSurf) * (Z - d) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * Wind * Wind);
-    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (log((Z - d) / Z0) + 5));
+    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (vlog((Z - d) / Z0) + 5));
     if (Ri > RiLimit) Ri = RiLimit;
     if (Ri > 0.0) Correction = (1 - Ri / RiCr) * (1 - Ri / RiCr);
     else {
@@ -99,8 +99,8 @@ VIC_HD double calc_rainonly(double air_temp, double prec, double MAX_SNOW_TEMP, 
     double rfrac;
     double TT = MIN_RAIN_TEMP, TR = MAX_SNOW_TEMP;
     double D = 1.4 * TR;
-    double E1 = 5. * pow((air_temp - TT) / D, 3.0);
-    double E2 = 6.76 * pow((air_temp - TT) / D, 2.0);
+    double E1 = 5. * vpow((air_temp - TT) / D, 3.0);
+    double E2 = 6.76 * vpow((air_temp - TT) / D, 2.0);
     double E3 = 3.19 * (air_temp - TT) / D;
     if (air_temp <= TT) rfrac = E1 + E2 + E3 + 0.5;
     else rfrac = E1 - E2 + E3 + 0.5;
@@ -118,7 +118,7 @@ VIC_HD double calc_rainonly(double air_temp, double prec, double MAX_SNOW_TEMP, 
 VIC_HD double new_snow_density(double air_temp, int SNOW_DENSITY) {
   double density_new;
   if (SNOW_DENSITY == DENS_SNTHRM) {
-    density_new = 67.9 + 51.3 * exp(air_temp / 2.6);
+    density_new = 67.9 + 51.3 * vexp(air_temp / 2.6);
   } else {
     air_temp = air_temp * 9. / 5. + 32.;
     if (air_temp > 0) density_new = (double)NEW_SNOW_DENSITY + 1000. * (air_temp / 100.) * (air_temp / 100.);
@@ -140,13 +140,13 @@ VIC_HD double snow_density(const SnowPack& snow, double new_snow, double sswq, d
       if (snow.depth > 0.0) density = snow.density;
       else density = density_new;
     } else density = snow.density;
-    double dexpf = exp(-SNDENS_C1 * (KELVIN - Tavg));
+    double dexpf = vexp(-SNDENS_C1 * (KELVIN - Tavg));
     double dm;
     if (new_snow > 0.0 && density_new > 0.0) dm = (SNDENS_DMLIMIT > 1.15 * density_new) ? SNDENS_DMLIMIT : 1.15 * density_new;
     else dm = SNDENS_DMLIMIT;
     double c3, c4;
     if (density <= dm) { c3 = 1.0; c4 = 1.0; }
-    else { c3 = exp(-0.046 * (density - dm)); c4 = 1.0; }
+    else { c3 = vexp(-0.046 * (density - dm)); c4 = 1.0; }
     if ((snow.surf_water + snow.pack_water) / snow.depth > 0.01) c4 = 2.0;
     double ddz1 = -SNDENS_C2 * c3 * c4 * dexpf;
     double f = SNDENS_F;
@@ -154,7 +154,7 @@ VIC_HD double snow_density(const SnowPack& snow, double new_snow, double sswq, d
     double ddz2;
     if (new_snow > 0.0) {
       double Ps = 0.5 * G_GRAV * RHO_W * swq;
-      ddz2 = -Ps / SNDENS_ETA0 * exp(-(-SNDENS_C5 * (Tavg - KELVIN) + SNDENS_C6 * density));
+      ddz2 = -Ps / SNDENS_ETA0 * vexp(-(-SNDENS_C5 * (Tavg - KELVIN) + SNDENS_C6 * density));
     } else ddz2 = 0.0;
     double CR = -ddz1 - ddz2;
     density = density * (1 + CR * dt * SECPHOUR);
@@ -163,7 +163,7 @@ VIC_HD double snow_density(const SnowPack& snow, double new_snow, double sswq, d
     swq = sswq;
     if (new_snow > 0) {
       if (depth > 0.) {
-        delta_depth = (((new_snow / 25.4) * (depth / 0.0254)) / (swq / 0.0254) * pow((depth / 0.0254) / 10., 0.35)) * 0.0254;
+        delta_depth = (((new_snow / 25.4) * (depth / 0.0254)) / (swq / 0.0254) * vpow((depth / 0.0254) / 10., 0.35)) * 0.0254;
         if (delta_depth > MAX_CHANGE * depth) delta_depth = MAX_CHANGE * depth;
         depth_new = new_snow / density_new;
         depth = depth - delta_depth + depth_new;
@@ -177,7 +177,7 @@ VIC_HD double snow_density(const SnowPack& snow, double new_snow, double sswq, d
     } else density = 1000. * swq / snow.depth;
     if (depth > 0.) {
       double overburden = 0.5 * G_GRAV * RHO_W * swq;
-      double viscosity = SNDENS_ETA0 * exp(-SNDENS_C5 * (Tavg - KELVIN) + SNDENS_C6 * density);
+      double viscosity = SNDENS_ETA0 * vexp(-SNDENS_C5 * (Tavg - KELVIN) + SNDENS_C6 * density);
       delta_depth = overburden / viscosity * depth * dt * SECPHOUR;
       if (delta_depth > MAX_CHANGE * depth) delta_depth = MAX_CHANGE * depth;
       depth -= delta_depth;
@@ -193,15 +193,15 @@ VIC_HD double snow_albedo(double new_snow, double swq, double depth, double albe
   if (new_snow > TraceSnow && cold_content < 0.0) albedo = cp(CP_NEW_SNOW_ALB);
   else if (swq > 0.0) {
     if (SNOW_ALBEDO == SUN1999) {
-      if (depth > 0.025) albedo = 0.5 + (albedo - 0.5) * exp(-0.01 * dt / 24);
+      if (depth > 0.025) albedo = 0.5 + (albedo - 0.5) * vexp(-0.01 * dt / 24);
       else if (cold_content < 0.0) albedo = albedo - 0.006 * dt / 24;
       else albedo = albedo - 0.071 * dt / 24;
       if (albedo < 0) albedo = 0;
     } else {
       if (cold_content < 0.0 && !MELTING)
-        albedo = cp(CP_NEW_SNOW_ALB) * pow(cp(CP_SNOW_ALB_ACCUM_A), pow((double)last_snow * dt / 24., cp(CP_SNOW_ALB_ACCUM_B)));
+        albedo = cp(CP_NEW_SNOW_ALB) * vpow(cp(CP_SNOW_ALB_ACCUM_A), vpow((double)last_snow * dt / 24., cp(CP_SNOW_ALB_ACCUM_B)));
       else
-        albedo = cp(CP_NEW_SNOW_ALB) * pow(cp(CP_SNOW_ALB_THAW_A), pow((double)last_snow * dt / 24., cp(CP_SNOW_ALB_THAW_B)));
+        albedo = cp(CP_NEW_SNOW_ALB) * vpow(cp(CP_SNOW_ALB_THAW_A), vpow((double)last_snow * dt / 24., cp(CP_SNOW_ALB_THAW_B)));
     }
   } else albedo = 0;
   return albedo;
@@ -236,14 +236,14 @@ VIC_HD double soil_conductivity(double moist, double Wu, double soil_dens_min, d
     double porosity = 1.0 - bulk_density / soil_density;
     double Sr = moist / porosity;
     double Ks_min;
-    if (quartz < .2) Ks_min = pow(7.7, quartz) * pow(3.0, 1.0 - quartz);
-    else Ks_min = pow(7.7, quartz) * pow(2.2, 1.0 - quartz);
+    if (quartz < .2) Ks_min = vpow(7.7, quartz) * vpow(3.0, 1.0 - quartz);
+    else Ks_min = vpow(7.7, quartz) * vpow(2.2, 1.0 - quartz);
     double Ks = (1 - organic) * Ks_min + organic * Ks_org;
     if (Wu == moist) {
-      Ksat = pow(Ks, 1.0 - porosity) * pow(Kw, porosity);
-      Ke = 0.7 * log10(Sr) + 1.0;
+      Ksat = vpow(Ks, 1.0 - porosity) * vpow(Kw, porosity);
+      Ke = 0.7 * vlog10(Sr) + 1.0;
     } else {
-      Ksat = pow(Ks, 1.0 - porosity) * pow(Ki, porosity - Wu) * pow(Kw, Wu);
+      Ksat = vpow(Ks, 1.0 - porosity) * vpow(Ki, porosity - Wu) * vpow(Kw, Wu);
       Ke = Sr;
     }
     K = (Ksat - Kdry) * Ke + Kdry;
@@ -266,7 +266,7 @@ VIC_HD double volumetric_heat_capacity(double soil_fract, double water_fract, do
 VIC_HD double maximum_unfrozen_water(double T, double max_moist, double bubble, double expt) {
   double unfrozen;
   if (T <= 0) {
-    unfrozen = max_moist * pow((-Lf * T) / 273.16 / (9.81 * bubble / 100.), -(2.0 / (expt - 3.0)));
+    unfrozen = max_moist * vpow((-Lf * T) / 273.16 / (9.81 * bubble / 100.), -(2.0 / (expt - 3.0)));
     if (unfrozen > max_moist) unfrozen = max_moist;
     if (unfrozen < 0) unfrozen = 0;
   } else unfrozen = max_moist;
@@ -277,10 +277,10 @@ VIC_HD double maximum_unfrozen_water(double T, double max_moist, double bubble, 
 VIC_HD double estimate_T1(double Ts, double T1_old, double T2, double D1, double D2, double kappa1, double kappa2,
                           double Cs1, double Cs2, double dp, double delta_t) {
   (void)Cs1;
-  double C1 = Cs2 * dp / D2 * (1. - exp(-D2 / dp));
-  double C2 = -(1. - exp(D1 / dp)) * exp(-D2 / dp);
-  double C3 = kappa1 / D1 - kappa2 / D1 + kappa2 / D1 * exp(-D1 / dp);
-  double T1 = (kappa1 / 2. / D1 / D2 * (Ts) + C1 / delta_t * T1_old + (2. * C2 - 1. + exp(-D1 / dp)) * kappa2 / 2. / D1 / D2 * T2) /
+  double C1 = Cs2 * dp / D2 * (1. - vexp(-D2 / dp));
+  double C2 = -(1. - vexp(D1 / dp)) * vexp(-D2 / dp);
+  double C3 = kappa1 / D1 - kappa2 / D1 + kappa2 / D1 * vexp(-D1 / dp);
+  double T1 = (kappa1 / 2. / D1 / D2 * (Ts) + C1 / delta_t * T1_old + (2. * C2 - 1. + vexp(-D1 / dp)) * kappa2 / 2. / D1 / D2 * T2) /
               (C1 / delta_t + kappa2 / D1 / D2 * C2 + C3 / 2. / D2);
   return T1;
 }

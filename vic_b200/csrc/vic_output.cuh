@@ -282,7 +282,7 @@ VIC_HDI void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, c
     OUT(SNOW_PACK_TEMP, 0) /= cv_snow;
   }
   if (cv_glacier > 0) OUT(GLAC_SURF_TEMP, 0) /= cv_glacier;
-  OUT(RAD_TEMP, 0) = pow(OUT(RAD_TEMP, 0), 0.25);
+  OUT(RAD_TEMP, 0) = vpow(OUT(RAD_TEMP, 0), 0.25);
   OUT(AERO_RESIST1, 0) = (OUT(AERO_COND1, 0) > SMALL) ? 1 / OUT(AERO_COND1, 0) : HUGE_RESIST;
   OUT(AERO_RESIST2, 0) = (OUT(AERO_COND2, 0) > SMALL) ? 1 / OUT(AERO_COND2, 0) : HUGE_RESIST;
   OUT(AERO_RESIST, 0) = (OUT(AERO_COND, 0) > SMALL) ? 1 / OUT(AERO_COND, 0) : HUGE_RESIST;

@@ -64,7 +64,7 @@ struct SnowMeltOut {
 VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy, double Tgrnd, double Z0_snow, double aero_resist,
                       RaUsed& aero_resist_used, double air_temp, double delta_t, double density, double grnd_flux, double LongSnowIn,
                       double pressure, double rainfall, double snowfall, double vp, double vpd, double wind, double z2, bool UNSTABLE_SNOW,
-                      SnowPack& snow, const Opts& o, SnowMeltOut& out) {
+                      SnowPack& snow, const Opts& o, SnowMeltOut& out, bool GLAC = false, double* firn_to_ice = nullptr) {
   double DeltaPackCC, DeltaPackSwq, SnowMelt = 0, RefrozenWater;
   double advection = 0, deltaCC = 0, latent_heat = 0, latent_heat_sub = 0, sensible_heat = 0, advected_sensible_heat = 0, RefreezeEnergy = 0;
   double melt_energy = 0.;
@@ -91,7 +91,31 @@ VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy
     SurfaceCC += SnowFallCC;
   }
   snow.surf_temp = (SurfaceSwq > 0.0) ? SurfaceCC / (CH_ICE * SurfaceSwq) : 0.0;
-  snow.pack_temp = (PackSwq > 0.0) ? PackCC / (CH_ICE * PackSwq) : 0.0;
+  if (!GLAC) {
+    snow.pack_temp = (PackSwq > 0.0) ? PackCC / (CH_ICE * PackSwq) : 0.0;
+  } else {
+    // snow on glacier ice (snow_melt_glac.c:110-132): the part of the pack denser than the firn/ice
+    // cut-off becomes glacier ice.  When the whole pack converts, pack_temp is 0/0 for a moment, as in
+    // the reference (it is reassigned below before anything reads it).
+    double FirnToIce = 0.;
+    if (PackSwq > 0.0) {
+      if (snow.density > SNOW_SURF_DENSITY) {
+        const double zco = (CUTOFF_DENSITY - SNOW_SURF_DENSITY) * (snow.depth / 2) / (snow.density - SNOW_SURF_DENSITY);
+        if (zco < snow.depth) {
+          const double density_zsnow = SNOW_SURF_DENSITY + 2 * (snow.density - SNOW_SURF_DENSITY);
+          FirnToIce = (density_zsnow + CUTOFF_DENSITY) / (2 * RHO_W) * (snow.depth - zco);
+          if (FirnToIce >= PackSwq) {
+            FirnToIce = PackSwq;
+            PackSwq = 0.0;
+            snow.pack_temp = 0.0;
+            PackCC = 0.0;
+          } else PackSwq -= FirnToIce;
+        }
+      }
+      snow.pack_temp = PackCC / (CH_ICE * PackSwq);
+    } else snow.pack_temp = 0.0;
+    *firn_to_ice = FirnToIce;
+  }
   Ice += SnowFall;
   snow.surf_water += RainFall;
 
@@ -159,7 +183,7 @@ VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy
       }
     } else {
       // pack surface below freezing: solve for its temperature
-      if (SurfaceSwq > MIN_SWQ_EB_THRES) {
+      if (GLAC || SurfaceSwq > MIN_SWQ_EB_THRES) {
         snow.surf_temp = root_brent((double)(snow.surf_temp - SNOW_DT), (double)(snow.surf_temp + SNOW_DT), eb);
         if (result_is_error(snow.surf_temp)) {
           if (o.TFALLBACK) {
@@ -255,7 +279,7 @@ VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy
     snow.pack_temp = 0.0;
   }
   const double MassBalanceError = (InitialSwq - snow.swq) + (RainFall + SnowFall) - melt + snow.vapor_flux;
-  melt *= 1000.;
+  if (!GLAC) melt *= 1000.;  // snow_melt_glac.c:391 leaves the melt in metres
   snow.mass_error = MassBalanceError;
   snow.coldcontent = SurfaceCC;
   snow.vapor_flux *= -1.;

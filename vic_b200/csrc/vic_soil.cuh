@@ -20,15 +20,15 @@ VIC_HDI void compute_runoff_and_asat(const CellPar& cp, const double* moist, dou
   if (top_moist > top_max_moist) top_moist = top_max_moist;
   const double b = cp(CP_b_infilt);
   double ex = b / (1.0 + b);
-  *A = 1.0 - pow((1.0 - top_moist / top_max_moist), ex);
+  *A = 1.0 - vpow((1.0 - top_moist / top_max_moist), ex);
   double max_infil = (1.0 + b) * top_max_moist;
-  double i_0 = max_infil * (1.0 - pow((1.0 - *A), (1.0 / b)));
+  double i_0 = max_infil * (1.0 - vpow((1.0 - *A), (1.0 / b)));
   if (inflow == 0.0) *runoff = 0.0;
   else if (max_infil == 0.0) *runoff = inflow;
   else if ((i_0 + inflow) > max_infil) *runoff = inflow - top_max_moist + top_moist;
   else {
     double basis = 1.0 - (i_0 + inflow) / max_infil;
-    *runoff = (inflow - top_max_moist + top_moist + top_max_moist * pow(basis, 1.0 * (1.0 + b)));
+    *runoff = (inflow - top_max_moist + top_moist + top_max_moist * vpow(basis, 1.0 * (1.0 + b)));
   }
   if (*runoff < 0.) *runoff = 0.;
 }
@@ -135,7 +135,7 @@ VIC_HDI int runoff(SoilCol& cell, EnergyBal<NN>& energy, const CellPar& cp, doub
     for (int l = 0; l < NL - 1; l++) {
       double tmp_liq = liq[l] - evap[l];
       if (tmp_liq < resid_moist[l]) tmp_liq = resid_moist[l];
-      if (liq[l] > resid_moist[l]) Q12[l] = Ksat[l] * pow(((tmp_liq - resid_moist[l]) / (max_moist[l] - resid_moist[l])), expt[l]);
+      if (liq[l] > resid_moist[l]) Q12[l] = Ksat[l] * vpow(((tmp_liq - resid_moist[l]) / (max_moist[l] - resid_moist[l])), expt[l]);
       else Q12[l] = 0.;
     }
     for (int l = 0; l < NL - 1; l++) {
@@ -179,7 +179,7 @@ VIC_HDI int runoff(SoilCol& cell, EnergyBal<NN>& energy, const CellPar& cp, doub
     double dt_baseflow = frac * rel_moist;
     if (rel_moist > Ws) {
       frac = (rel_moist - Ws) / (1 - Ws);
-      dt_baseflow += Dsmax * (1 - Ds / Ws) * pow(frac, c_exp);
+      dt_baseflow += Dsmax * (1 - Ds / Ws) * vpow(frac, c_exp);
     }
     if (dt_baseflow < 0) dt_baseflow = 0;
     liq[l] += Q12[l - 1] - (evap[l] + dt_baseflow);
@@ -259,7 +259,7 @@ VIC_HDI void estimate_layer_ice_content_quick_flux(SoilLayer* layer, double Tsur
   const double avg_temp = cp(CP_avg_temp), dp = cp(CP_dp);
   layer[0].T = 0.5 * (Tsurf + T1);
   for (int l = 1; l < NL; l++)
-    layer[l].T = avg_temp - dp / (cp.layer(CL_depth, l)) * (T1 - avg_temp) * (exp(-(Lsum[l + 1] - Lsum[1]) / dp) - exp(-(Lsum[l] - Lsum[1]) / dp));
+    layer[l].T = avg_temp - dp / (cp.layer(CL_depth, l)) * (T1 - avg_temp) * (vexp(-(Lsum[l + 1] - Lsum[1]) / dp) - vexp(-(Lsum[l] - Lsum[1]) / dp));
   const bool fs = o.FROZEN_SOIL && (cp(CP_FS_ACTIVE) != 0.0);
   for (int l = 0; l < NL; l++) {
     layer[l].soil_ice = 0;

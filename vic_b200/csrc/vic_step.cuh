@@ -58,7 +58,7 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
   const int veg_class = hp.vegIndex;
   const VegNow veg = veg_now(cx.vl, veg_class, month0);
   const double wind_h = veg.wind_h;
-  double surf_atten = exp(-veg.rad_atten * veg.LAI);
+  double surf_atten = vexp(-veg.rad_atten * veg.LAI);
   double moist0 = 0, ice0 = 0;
   prepare_full_energy<NN>(hru, cp, AreaFract, o, &moist0, &ice0);
   const double bare_albedo = hp.isGlacier ? cp(CP_GLAC_ALBEDO) : veg.albedo;
@@ -73,6 +73,8 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
   bool overstory = false;
   const double soil_rough = cp(CP_rough);
   const double wind_NR = cx.f(FV_wind, o.NR);
+  double in_prev[8] = {-1, 0, 0, 0, 0, 0, 0, 0};
+  Surf4 snap_displacement = as.displacement, snap_ref_height = as.ref_height, snap_roughness = as.roughness, snap_wind_speed = as.displacement;
   for (int p = 0; p < N_PET_TYPES + 1; p++) {
     const int pet_class = (p < N_PET_TYPES_NON_NAT) ? o.NVegLibTypes + p : veg_class;
     VegRow r = cx.vl.row(pet_class);
@@ -85,15 +87,29 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
     if (as.displacement[SNOW_FREE] < wind_h) as.ref_height[SNOW_FREE] = wind_h;
     else as.ref_height[SNOW_FREE] = as.displacement[SNOW_FREE] + wind_h + as.roughness[SNOW_FREE];
     // bring the forcing wind from its nominal height to the reference height (log profile over open ground)
-    const double wind_corr = log((as.ref_height[SNOW_FREE] - 0.) / soil_rough) / log((o.wind_h - 0.) / soil_rough);
+    const double wind_corr = vlog((as.ref_height[SNOW_FREE] - 0.) / soil_rough) / vlog((o.wind_h - 0.) / soil_rough);
     as.wind_speed[SNOW_FREE] = wind_NR * wind_corr;
     as.wind_speed[CANOPY_OVER] = vnan();
     as.wind_speed[SNOW_COVERED] = vnan();
     as.wind_speed[GLACIER_SURF] = vnan();
     as.aero_resist[p].set_invalid();
-    int e = calc_aerodynamic(overstory, height, r.s(VL_trunk_ratio), cp(CP_snow_rough), soil_rough, r.s(VL_wind_atten), as.aero_resist[p],
-                             as.wind_speed, as.displacement, as.ref_height, as.roughness);
-    if (e == ERROR_I) return ERROR_I;
+    // calc_aerodynamic is a pure function of the values just set (every shared entry is overwritten), so when
+    // a land cover repeats the previous one (the two bare reference covers; the tile's own cover three times)
+    // the previous results are reused bit for bit instead of being recomputed.
+    const double in_now[8] = {(double)overstory, height, r.s(VL_trunk_ratio), r.s(VL_wind_atten), as.roughness[SNOW_FREE],
+                              as.displacement[SNOW_FREE], as.ref_height[SNOW_FREE], as.wind_speed[SNOW_FREE]};
+    bool same = (p > 0);
+    for (int k = 0; k < 8; k++) same = same && (in_now[k] == in_prev[k]);
+    if (same) {
+      as.aero_resist[p] = as.aero_resist[p - 1];
+      as.displacement = snap_displacement; as.ref_height = snap_ref_height; as.roughness = snap_roughness; as.wind_speed = snap_wind_speed;
+    } else {
+      int e = calc_aerodynamic(overstory, height, r.s(VL_trunk_ratio), cp(CP_snow_rough), soil_rough, r.s(VL_wind_atten), as.aero_resist[p],
+                               as.wind_speed, as.displacement, as.ref_height, as.roughness);
+      if (e == ERROR_I) return ERROR_I;
+      for (int k = 0; k < 8; k++) in_prev[k] = in_now[k];
+      snap_displacement = as.displacement; snap_ref_height = as.ref_height; snap_roughness = as.roughness; snap_wind_speed = as.wind_speed;
+    }
   }
   if (AreaFract > 0) {
     hru.cell.aero_surface = as.aero_resist[N_PET_TYPES][SNOW_FREE];

@@ -52,7 +52,7 @@ struct SurfEB {
     if (o->QUICK_FLUX) {
       *T1 = estimate_T1(TMean, T1_old, T2, D1, D2, kappa1, kappa2, Cs1, Cs2, dp, delta_t);
       if (o->GRND_FLUX_TYPE == GF_406) *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean));
-      else *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean) + (kappa2 / D2 * (1. - exp(-D1 / dp)) * (T2 - (*T1)))) / 2.;
+      else *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean) + (kappa2 / D2 * (1. - vexp(-D1 / dp)) * (T2 - (*T1)))) / 2.;
     } else {
       T_node[0] = TMean;
       int Error = solve_T_profile<NN>(Tnew_node, T_node, Tnew_fbflag, Tnew_fbcount, kappa_node, Cs_node, moist_node, delta_t, ice_node, dp,

@@ -152,7 +152,7 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   vicgpu_default_aggtypes(agg);
   CK(cudaMemcpy(h->d_aggtype, agg, sizeof(agg), cudaMemcpyHostToDevice));
   // the step kernel keeps one HRU (about 2 KB) plus its working copies in thread-local memory
-  CK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024));
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024));
   *out = h;
   return VICGPU_OK;
 }

@@ -69,7 +69,8 @@ def compare_case(case, result, keys=(("out", "out_ref"), ("hrurec", "hrurec_ref"
     return rep, L
 
 
-INT_COLUMNS = ("fbflag", "fbcount", "last_snow", "MELTING", "S_snow", "store_snow", "Nfrost", "Nthaw", "frozen")
+INT_SUBSTR = ("fbflag", "fbcount")
+INT_EXACT = ("S_last_snow", "S_MELTING", "S_snow", "S_store_snow", "E_Nfrost", "E_Nthaw", "E_frozen")
 
 
 def integer_mismatches(got, ref, names):
@@ -79,7 +80,7 @@ def integer_mismatches(got, ref, names):
     g = got.reshape(-1, ncol)
     r = ref.reshape(-1, ncol)
     for c, n in enumerate(names):
-        if any(t in n for t in INT_COLUMNS):
+        if any(t in n for t in INT_SUBSTR) or n in INT_EXACT:
             m = int(np.sum(~((g[:, c] == r[:, c]) | (np.isnan(g[:, c]) & np.isnan(r[:, c])))))
             if m:
                 bad[n] = m
