@@ -29,8 +29,11 @@ def rel_err(a, b, floor):
 # Columns that ARE residuals of a balance (root-finder residuals, closure errors): their own magnitude is
 # rounding noise of the terms they are the sum of, so they are judged against the size of those terms
 # (energy fluxes O(100) W/m2 -> 1 W/m2 is a conservative unit; water storages O(100) mm -> 1 mm; SWE -> 1e-3 m).
+# Runoff is formed as inflow - top_max_moist + top_moist + top_max_moist*basis^(1+b) (runoff.c:808-809), a difference of
+# O(100 mm) storages, and the DEL* outputs are differences of two storages: 1e-3 mm is 1e-5 of the terms.
 RESIDUAL_FLOORS = {"E_error": 1.0, "ENERGY_ERROR": 1.0, "WATER_ERROR": 1.0, "S_mass_error": 1e-3, "S_Qnet": 1.0, "G_Qnet": 1.0,
-                   "E_AtmosError": 1.0}
+                   "E_AtmosError": 1.0, "RUNOFF": 1e-3, "C_runoff": 1e-3, "DELSOILMOIST": 1e-3, "DELSWE": 1e-3, "DELINTERCEPT": 1e-3,
+                   "DELSURFSTOR": 1e-3}
 
 
 def column_report(got, ref, names, scale_floor=1e-6, abs_floor=1e-9):
