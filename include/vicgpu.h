@@ -473,6 +473,27 @@ int vicgpu_get_balance_errors(vicgpu_handle *h, double *err);
 /* device time (ms) spent in kernels during the last vicgpu_step call, and number of kernel launches */
 int vicgpu_get_last_step_timing(vicgpu_handle *h, double *kernel_ms, long long *launches);
 
+/* ---- forcing disaggregation (stands in for initialize_atmos() / mtclim_wrapper(), vicNl.h:362, 390-392) ------------ */
+/* members of global_param_struct / option_struct that only initialize_atmos reads */
+typedef struct vicgpu_disagg_options {
+  int abi_version;        /* VICGPU_ABI_VERSION */
+  int starthour, startyear, startmonth, startday;   /* global_param.start* */
+  int Ndays;              /* number of daily forcing records (initialize_atmos.c:146-149) */
+  int PLAPSE, MTCLIM_SWE_CORR, VP_INTERP, OUTPUT_FORCE;
+  int VP_ITER;            /* VP_ITER_NEVER=0, ALWAYS, ANNUAL, CONVERGE */
+  int LW_TYPE;            /* LW_TVA=0, ANDERSON, BRUTSAERT, SATTERLUND, IDSO, PRATA */
+  int LW_CLOUD;           /* LW_CLOUD_BRAS=0, LW_CLOUD_DEARDORFF */
+  int reserved;
+  double SW_PREC_THRESH;  /* options.SW_PREC_THRESH (float member) */
+} vicgpu_disagg_options;
+
+/* daily [ncell][Ndays][4] = PREC [mm/day], TMAX, TMIN [C], WIND [m/s] (FORCE_DT 24; no other forcing variable supplied).
+ * Fills the device-resident forcing window with records [0, nrecs) -- what initialize_atmos() would have put into
+ * cell->atmos[] for every cell -- and, when forcing_out is not NULL, copies it back as [nrecs][ncell][L.f_stride]
+ * (the OUTPUT_FORCE use).  Needs vicgpu_set_cells (latitude, longitude, time zone, elevation, slope, aspect, horizons,
+ * annual precipitation, band temperature factors, rain/snow thresholds are cell parameters). */
+int vicgpu_disagg(vicgpu_handle *h, const vicgpu_disagg_options *dopt, const double *daily, double *forcing_out);
+
 /* measurement aid: with profiling on, every launch of the per-HRU step kernel inside vicgpu_step is bracketed
  * by CUDA events on the library's stream; get_kernel_profile returns the summed duration and the launch count
  * since profiling was switched on. */

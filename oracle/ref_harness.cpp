@@ -152,6 +152,10 @@ int main(int argc, char **argv) {
     {
       int64_t d[1] = {(int64_t)(sizeof(opt) / sizeof(int32_t))};
       cw->i32("options_raw", (const int32_t *)&opt, 1, d);
+      vicgpu_disagg_options dop;
+      vicgpu_pack_disagg_options(&state, dmy, &dop);
+      int64_t dd1[1] = {(int64_t)(sizeof(dop) / sizeof(int32_t))};
+      cw->i32("disagg_raw", (const int32_t *)&dop, 1, dd1);
       int32_t meta[8] = {ncell, nhru, nrec, nout, L.hr_stride, L.cp_stride, L.f_stride, state.options.OUTPUT_FORCE};
       int64_t dm[1] = {8};
       cw->i32("meta", meta, 1, dm);

@@ -4,7 +4,8 @@ Run in the development container (needs /root/reference, built through oracle/Ma
     python tests/golden/make_golden.py
 For every configuration it writes synthetic inputs with vic_b200.synth (fixed seed), runs
 oracle/_ref/vic_ref_harness (the reference's unmodified physics) and keeps, as a compressed .npz:
-  the flat C-ABI inputs (options_raw, veglib, cellpar, hrupar, hrurec0, aggtype, valid0, dmy, forcing)
+  the flat C-ABI inputs (options_raw, veglib, cellpar, hrupar, hrurec0, aggtype, valid0, dmy, forcing; disagg_raw + daily:
+  the daily PREC/TMAX/TMIN/WIND the reference read, of which `forcing` is ITS disaggregation = the answer for vicgpu_disagg)
   the reference's answers: hrurec_ref at dump_recs, agg_ref at agg_recs (daily aggregates of all 184
   output variables), balance_ref, status_ref and out_ref for the first and last 24 records.
 """
@@ -41,9 +42,15 @@ def make(name):
         case = os.path.join(d, "case.bin")
         subprocess.run([HARNESS, "-g", r["global_file"], "-o", case, "--dump-every", str(dump_every)], check=True, stdout=subprocess.DEVNULL)
         c = read_case(case)
+        # the daily forcing the reference read (ASCII PREC TMAX TMIN WIND, one file per cell): input of the disaggregation tests
+        from vic_b200.layout import TABLES
+        lat = c["cellpar"][:, TABLES["cpar"].index("CP_lat")]
+        lng = c["cellpar"][:, TABLES["cpar"].index("CP_lng")]
+        ndays = int(c["disagg_raw"][5])
+        c["daily"] = np.stack([np.loadtxt(os.path.join(d, "forc", f"f_{la:.5f}_{lo:.5f}"))[:ndays] for la, lo in zip(lat, lng)])
     nrec = c["out_ref"].shape[0]
     keep = {k: c[k] for k in ("options_raw", "meta", "veglib", "cellpar", "hrupar", "hrurec0", "aggtype", "valid0", "dmy", "forcing",
-                              "dump_recs", "hrurec_ref", "agg_recs", "agg_ref", "balance_ref", "status_ref")}
+                              "dump_recs", "disagg_raw", "daily", "hrurec_ref", "agg_recs", "agg_ref", "balance_ref", "status_ref")}
     keep["out_ref_head"] = c["out_ref"][:24]
     keep["out_ref_tail"] = c["out_ref"][nrec - 24:]
     # uninitialised aggdata of the reference's very first output step shows up as denormal garbage; not part of the contract

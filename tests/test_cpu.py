@@ -57,6 +57,22 @@ def test_port_reproduces_reference_golden(name, vicport, tmp_path):
     assert np.array_equal(res["balance"], g["balance_ref"], equal_nan=True)
 
 
+@pytest.mark.parametrize("name", GOLDEN)
+def test_disagg_port_reproduces_reference_forcing(name, root, tmp_path):
+    """forcing disaggregation (initialize_atmos + mtclim): the host build of vic_disagg.cuh against the hourly / sub-daily
+    forcing the reference produced from the same daily PREC/TMAX/TMIN/WIND: bit-identical for all 11 variables and slots"""
+    port = os.path.join(root, "oracle", "_ref", "disaggport")
+    if not os.path.exists(port):
+        pytest.skip("oracle/_ref/disaggport not built")
+    g = load_golden(name)
+    case, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    write_case(case, {k: g[k] for k in ("options_raw", "disagg_raw", "meta", "cellpar", "daily")})
+    subprocess.run([port, case, out], check=True)
+    f = read_case(out)["forcing"]
+    assert f.shape == g["forcing"].shape
+    assert np.array_equal(f, g["forcing"])
+
+
 @pytest.mark.parametrize("name", [n for n in GOLDEN if n.startswith("fe_") or n.startswith("wb_")])
 def test_golden_water_balance_closes(name):
     """known-answer check the reference itself prints: |water balance error| < 1e-5 mm per step, cumulative ~ 0

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile",
+    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg",
 ]
 
 
@@ -65,6 +65,7 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_get_cell_status.argtypes = [vp, ip]
     lib.vicgpu_get_balance_errors.argtypes = [vp, dp]
     lib.vicgpu_get_last_step_timing.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
+    lib.vicgpu_disagg.argtypes = [vp, vp, dp, dp]
     lib.vicgpu_set_profiling.argtypes = [vp, C.c_int]
     lib.vicgpu_get_kernel_profile.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     for s in SYMBOLS:
@@ -163,6 +164,16 @@ class VicGpu:
         f = _as_f64(forcing)
         assert f.shape[1:] == (self.ncell, self.L.f_stride), f.shape
         self._chk(self.lib.vicgpu_set_forcing(self.h, int(rec0), int(f.shape[0]), _dptr(f)))
+
+    def disagg(self, disagg_raw, daily, want_host=True):
+        """daily [ncell][Ndays][4] (PREC, TMAX, TMIN, WIND) -> fills the device forcing window [0, nrecs); returns the
+        hourly / sub-daily forcing [nrecs][ncell][f_stride] when want_host (vicgpu_disagg, include/vicgpu.h)."""
+        raw = np.ascontiguousarray(disagg_raw, dtype=np.int32)
+        d = _as_f64(daily)
+        assert d.shape == (self.ncell, int(raw[5]), 4), d.shape
+        out = np.empty((self.opt["nrecs"], self.ncell, self.L.f_stride), dtype=np.float64) if want_host else None
+        self._chk(self.lib.vicgpu_disagg(self.h, raw.ctypes.data_as(C.c_void_p), _dptr(d), _dptr(out) if want_host else None))
+        return out
 
     def n_output_steps(self, nrec, step_count0=0):
         return (step_count0 + nrec) // self.opt["out_step_ratio"]

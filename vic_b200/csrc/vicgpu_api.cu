@@ -15,20 +15,12 @@
 #include <algorithm>
 #include <string>
 #include <vector>
-#include "vicgpu_kernels.h"
+#include "vicgpu_internal.h"
 
 using namespace vic;
 
-static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
-}
-#define CK(call)                                                                                         \
-  do {                                                                                                   \
-    cudaError_t e_ = (call);                                                                             \
-    if (e_ != cudaSuccess) return fail(VICGPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-  } while (0)
+thread_local std::string vicgpu_err;
+#define fail vicgpu_fail
 
 // ---- kernels ---------------------------------------------------------------------------------
 // in: [batch][rows][cols] row-major  ->  out: [batch][cols][rows]
@@ -54,37 +46,22 @@ __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o,
   cell_output(o, t, forcing_rec, c, rec, step_count);
 }
 
-// ---- handle ----------------------------------------------------------------------------------
-struct vicgpu_handle {
-  int device = 0;
-  vicgpu_options abi;
-  Opts o;
-  Opts* d_o = nullptr;
-  Tables t;
-  int nout = 0;
-  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_hrupar = nullptr, *d_hrurec = nullptr, *d_hdiag = nullptr, *d_carry = nullptr,
-         *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr, *d_forcing = nullptr, *d_fstage = nullptr;
-  size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
-  int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
-  int frec0 = 0, fnrec = 0;
-  bool have_cells = false, have_state = false, glac_started = false;
-  int step_count = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double last_ms = 0;
-  long long last_launches = 0;
-  // optional per-launch timing of the per-HRU step kernel (vicgpu_set_profiling)
-  bool profiling = false;
-  std::vector<cudaEvent_t> pev;
-  double prof_hru_ms = 0;
-  long long prof_hru_launches = 0;
-};
-
-static int transpose_to(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch) {
+int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch) {
   dim3 b(32, 8), g((cols + 31) / 32, (rows + 31) / 32, batch);
   k_transpose<<<g, b, 0, h->stream>>>(d_in, d_out, rows, cols);
   h->last_launches++;
   CK(cudaGetLastError());
+  return VICGPU_OK;
+}
+
+int vicgpu_ensure_forcing(vicgpu_handle* h, size_t need) {
+  if (need > h->forcing_cap) {
+    cudaFree(h->d_forcing);
+    h->d_forcing = nullptr;
+    h->forcing_cap = 0;
+    CK(cudaMalloc(&h->d_forcing, need * sizeof(double)));
+    h->forcing_cap = need;
+  }
   return VICGPU_OK;
 }
 
@@ -103,7 +80,7 @@ static int upload_transposed(vicgpu_handle* h, const double* host, double* d_dst
   int rc = ensure_stage(h, (size_t)rows * cols);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->d_stage, host, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  rc = transpose_to(h, h->d_stage, d_dst, rows, cols, 1);
+  rc = vicgpu_transpose(h, h->d_stage, d_dst, rows, cols, 1);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return VICGPU_OK;
@@ -112,7 +89,7 @@ static int upload_transposed(vicgpu_handle* h, const double* host, double* d_dst
 static int download_transposed(vicgpu_handle* h, const double* d_src, double* host, int rows, int cols, bool sync) {
   int rc = ensure_stage(h, (size_t)rows * cols);
   if (rc) return rc;
-  rc = transpose_to(h, d_src, h->d_stage, cols, rows, 1);
+  rc = vicgpu_transpose(h, d_src, h->d_stage, cols, rows, 1);
   if (rc) return rc;
   CK(cudaMemcpyAsync(host, h->d_stage, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (sync) CK(cudaStreamSynchronize(h->stream));
@@ -122,7 +99,7 @@ static int download_transposed(vicgpu_handle* h, const double* d_src, double* ho
 extern "C" {
 
 int vicgpu_abi_version(void) { return VICGPU_ABI_VERSION; }
-const char* vicgpu_last_error(void) { return g_err.c_str(); }
+const char* vicgpu_last_error(void) { return vicgpu_err.c_str(); }
 
 int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   if (!out || !opt) return fail(VICGPU_EINVAL, "null argument");
@@ -283,13 +260,7 @@ int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forci
   CK(cudaSetDevice(h->device));
   const size_t per = (size_t)h->t.ncell * h->o.L.f_stride;
   const size_t need = per * nrec;
-  if (need > h->forcing_cap) {
-    cudaFree(h->d_forcing);
-    h->d_forcing = nullptr;
-    h->forcing_cap = 0;
-    CK(cudaMalloc(&h->d_forcing, need * sizeof(double)));
-    h->forcing_cap = need;
-  }
+  { int rcf = vicgpu_ensure_forcing(h, need); if (rcf) return rcf; }
   // staged in chunks of at most 256 MiB so that the staging buffer stays small next to the window
   const size_t chunk_recs = std::min<size_t>(65535, std::max<size_t>(1, (size_t)(256u << 20) / (per * sizeof(double))));
   const size_t stage_need = per * std::min<size_t>(chunk_recs, (size_t)nrec);
@@ -354,13 +325,13 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
     k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, h->t, frec, rec, h->step_count);
     h->last_launches += 2;
     if (out_data) {
-      int rc = transpose_to(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1);
+      int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1);
       if (rc) return rc;
       CK(cudaMemcpyAsync(out_data + (size_t)i * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     if (h->step_count == h->o.out_step_ratio) {
       if (out_agg) {
-        int rc = transpose_to(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1);
+        int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1);
         if (rc) return rc;
         CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       }

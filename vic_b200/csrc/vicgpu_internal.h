@@ -1,0 +1,50 @@
+// vicgpu_internal.h -- the library handle and small helpers shared by the translation units of libvicgpu.so
+#ifndef VICGPU_INTERNAL_H
+#define VICGPU_INTERNAL_H
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "vicgpu_kernels.h"
+
+extern thread_local std::string vicgpu_err;
+inline int vicgpu_fail(int code, const std::string& msg) {
+  vicgpu_err = msg;
+  return code;
+}
+#define CK(call)                                                                                                \
+  do {                                                                                                          \
+    cudaError_t e_ = (call);                                                                                    \
+    if (e_ != cudaSuccess) return vicgpu_fail(VICGPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct vicgpu_handle {
+  int device = 0;
+  vicgpu_options abi;
+  vic::Opts o;
+  vic::Opts* d_o = nullptr;
+  vic::Tables t;
+  int nout = 0;
+  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_hrupar = nullptr, *d_hrurec = nullptr, *d_hdiag = nullptr, *d_carry = nullptr,
+         *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr, *d_forcing = nullptr, *d_fstage = nullptr;
+  size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
+  int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
+  int frec0 = 0, fnrec = 0;
+  bool have_cells = false, have_state = false, glac_started = false;
+  int step_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0;
+  long long last_launches = 0;
+  // optional per-launch timing of the per-HRU step kernel (vicgpu_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> pev;
+  double prof_hru_ms = 0;
+  long long prof_hru_launches = 0;
+};
+
+
+// in: [batch][rows][cols] row-major  ->  out: [batch][cols][rows]   (vicgpu_api.cu)
+int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch);
+int vicgpu_ensure_forcing(vicgpu_handle* h, size_t elems);
+
+#endif

@@ -63,6 +63,21 @@ inline void vicgpu_pack_options(const ProgramState *state, vicgpu_options *o) {
   o->MIN_WIND_SPEED = op.MIN_WIND_SPEED;
 }
 
+// what initialize_atmos() reads besides the hot-path options (initialize_atmos.c:125-160, 905, 1103, 1274; mtclim_vic.c:1493, 1552-1571, 1698)
+inline void vicgpu_pack_disagg_options(const ProgramState *state, const dmy_struct *dmy, vicgpu_disagg_options *d) {
+  memset(d, 0, sizeof(*d));
+  const option_struct &op = state->options;
+  const global_param_struct &gp = state->global_param;
+  d->abi_version = VICGPU_ABI_VERSION;
+  d->starthour = gp.starthour; d->startyear = gp.startyear; d->startmonth = gp.startmonth; d->startday = gp.startday;
+  const int tmp_starthour = 0, tmp_endhour = 24 - gp.dt;
+  const int tmp_nrecs = gp.nrecs + gp.starthour - tmp_starthour + tmp_endhour - dmy[gp.nrecs - 1].hour;
+  d->Ndays = (tmp_nrecs * gp.dt) / 24;
+  d->PLAPSE = op.PLAPSE; d->MTCLIM_SWE_CORR = op.MTCLIM_SWE_CORR; d->VP_INTERP = op.VP_INTERP; d->OUTPUT_FORCE = op.OUTPUT_FORCE;
+  d->VP_ITER = op.VP_ITER; d->LW_TYPE = op.LW_TYPE; d->LW_CLOUD = op.LW_CLOUD;
+  d->SW_PREC_THRESH = (double)op.SW_PREC_THRESH;
+}
+
 // veg_lib_struct rows incl. the four reference PET classes (read_veglib.c:118-136)
 inline void vicgpu_pack_veglib(const ProgramState *state, const vicgpu_layout *L, std::vector<double> &out) {
   const int nclass = state->veg_lib[0].NVegLibTypes + N_PET_TYPES_NON_NAT;
