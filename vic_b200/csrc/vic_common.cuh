@@ -13,6 +13,7 @@
 #include <math.h>
 #include <limits.h>
 #include "vicgpu.h"
+#include "vic_math.cuh"
 
 // VIC_HD : small leaf relations, always inlined.
 // VIC_HDI: the larger routines and the residual functors' operator(): real calls (one copy of
@@ -92,13 +93,26 @@ enum { N_PET_TYPES = 6, N_PET_TYPES_NON_NAT = 4, PET_VEGNOCR = 5 };
 // surface types of the aerodynamic tables (VegConditions.h)
 enum Surf { SNOW_FREE = 0, CANOPY_OVER = 1, SNOW_COVERED = 2, GLACIER_SURF = 3, SURF_UNSET = 4 };
 
-// libm entry points as real calls on the device: each of pow / exp / log expands to hundreds of
-// instructions, and the step kernel has dozens of call sites; one shared copy keeps the kernel's
-// code closer to the instruction cache.  (The host build inlines them as usual.)
-VIC_HDI double vpow(double a, double b) { return pow(a, b); }
-VIC_HDI double vexp(double a) { return exp(a); }
-VIC_HDI double vlog(double a) { return log(a); }
-VIC_HDI double vlog10(double a) { return log10(a); }
+// Elementary functions: the portable implementations of vic_math.cuh, identical on device and host (see there).
+// -DVIC_USE_LIBM swaps in the platform's libm; it exists only so that the host port can ALSO be compared bit for
+// bit with the glibc-linked reference build (oracle/Makefile builds both flavours); libvicgpu.so never uses it.
+#if defined(VIC_USE_LIBM) && !defined(__CUDACC__)
+inline double vpow(double a, double b) { return pow(a, b); }
+inline double vexp(double a) { return exp(a); }
+inline double vlog(double a) { return log(a); }
+inline double vlog10(double a) { return log10(a); }
+inline double vsin(double a) { return sin(a); }
+inline double vcos(double a) { return cos(a); }
+inline double vacos(double a) { return acos(a); }
+#else
+VIC_HD double vpow(double a, double b) { return dl::pow(a, b); }
+VIC_HD double vexp(double a) { return dl::exp(a); }
+VIC_HD double vlog(double a) { return dl::log(a); }
+VIC_HD double vlog10(double a) { return dl::log10(a); }
+VIC_HD double vsin(double a) { return dl::sin(a); }
+VIC_HD double vcos(double a) { return dl::cos(a); }
+VIC_HD double vacos(double a) { return dl::acos(a); }
+#endif
 
 VIC_HD double vnan() {
 #if defined(__CUDA_ARCH__)

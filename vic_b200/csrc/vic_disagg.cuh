@@ -120,19 +120,19 @@ VIC_HDI void disagg_solar(const CellPar& cp, const DisaggOpts& d, const DisaggSc
   lat *= RADPERDEG;
   if (lat > 1.5707) lat = 1.5707;
   if (lat < -1.5707) lat = -1.5707;
-  const double coslat = cos(lat), sinlat = sin(lat);
+  const double coslat = vcos(lat), sinlat = vsin(lat);
   const double slp = cp(CP_slope), asp = cp(CP_aspect);
-  const double cosslp = cos(slp * RADPERDEG), sinslp = sin(slp * RADPERDEG), cosasp = cos(asp * RADPERDEG), sinasp = sin(asp * RADPERDEG);
-  const double coszeh = cos(1.570796 - (cp(CP_ehoriz) * RADPERDEG));
-  const double coszwh = cos(1.570796 - (cp(CP_whoriz) * RADPERDEG));
+  const double cosslp = vcos(slp * RADPERDEG), sinslp = vsin(slp * RADPERDEG), cosasp = vcos(asp * RADPERDEG), sinasp = vsin(asp * RADPERDEG);
+  const double coszeh = vcos(1.570796 - (cp(CP_ehoriz) * RADPERDEG));
+  const double coszwh = vcos(1.570796 - (cp(CP_whoriz) * RADPERDEG));
   const double dt = SRADDT;
   const double dh = dt / SECPERRAD;
   const int tinystepspday = (int)(86400 / SRADDT);
   const int tinystepsphour = (int)(3600 / SRADDT);
   const int tiny_offset = (int)((float)tinystepsphour * lt.hour_offset);
 
-  const double decl = MINDECL * cos(((double)i + DAYSOFF) * RADPERDAY);
-  const double cosdecl = cos(decl), sindecl = sin(decl);
+  const double decl = MINDECL * vcos(((double)i + DAYSOFF) * RADPERDAY);
+  const double cosdecl = vcos(decl), sindecl = vsin(decl);
   const double bsg1 = -sinslp * sinasp * cosdecl;
   const double bsg2 = (-cosasp * sinslp * sinlat + cosslp * coslat) * cosdecl;
   const double bsg3 = (cosasp * sinslp * coslat + cosslp * sinlat) * sindecl;
@@ -141,22 +141,22 @@ VIC_HDI void disagg_solar(const CellPar& cp, const DisaggOpts& d, const DisaggSc
   double coshss = -(sinegeom) / cosegeom;
   if (coshss < -1.0) coshss = -1.0;
   if (coshss > 1.0) coshss = 1.0;
-  const double hss = acos(coshss);
+  const double hss = vacos(coshss);
   double daylength = 2.0 * hss * SECPERRAD;
   if (daylength > 86400) daylength = 86400;
-  const double sc = 1368.0 + 45.5 * sin((2.0 * PI_M * (double)i / 365.25) + 1.7);
+  const double sc = 1368.0 + 45.5 * vsin((2.0 * PI_M * (double)i / 365.25) + 1.7);
   const double dir_beam_topa = sc * dt;
   double sum_trans = 0.0, sum_flat_potrad = 0.0, sum_slope_potrad = 0.0;
   // pass 1: the day's sums
   for (double h = -hss; h < hss; h += dh) {
-    const double cosh_ = cos(h), sinh_ = sin(h);
+    const double cosh_ = vcos(h), sinh_ = vsin(h);
     const double cza = cosegeom * cosh_ + sinegeom;
     const double cbsa = sinh_ * bsg1 + cosh_ * bsg2 + bsg3;
     if (cza > 0.0) {
       const double dir_flat_topa = dir_beam_topa * cza;
       double am = 1.0 / (cza + 0.0000001);
       if (am > 2.9) {
-        int ami = (int)(acos(cza) / RADPERDEG) - 69;
+        int ami = (int)(vacos(cza) / RADPERDEG) - 69;
         if (ami < 0) ami = 0;
         if (ami > 20) ami = 20;
         am = optam[ami];
@@ -180,7 +180,7 @@ VIC_HDI void disagg_solar(const CellPar& cp, const DisaggOpts& d, const DisaggSc
   int cur = -1;
   double curv = 0;
   for (double h = -hss; h < hss; h += dh) {
-    const double cza = cosegeom * cos(h) + sinegeom;
+    const double cza = cosegeom * vcos(h) + sinegeom;
     const double dir_flat_topa = (cza > 0.0) ? dir_beam_topa * cza : -1;
     int tinystep = (int)((12L * 3600L + h * SECPERRAD) / SRADDT);
     if (tinystep < 0) tinystep = 0;
@@ -405,7 +405,7 @@ VIC_HDI void disagg_daily(const CellPar& cp, const DisaggOpts& d, const DisaggSc
   // sky view
   const double slp = cp(CP_slope), eh = cp(CP_ehoriz), wh = cp(CP_whoriz);
   const double avg_horizon = (eh + wh) / 2.0;
-  const double horizon_scalar = 1.0 - sin(avg_horizon * RADPERDEG);
+  const double horizon_scalar = 1.0 - vsin(avg_horizon * RADPERDEG);
   const double slope_excess = (slp > avg_horizon) ? slp - avg_horizon : 0.0;
   double slope_scalar;
   if (2.0 * avg_horizon > 180.0) slope_scalar = 0.0;

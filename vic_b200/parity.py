@@ -1,8 +1,8 @@
 """Parity metrics between a result (CUDA library or host port) and the reference's answers of a case file.
 
 Tolerances follow BASELINE.json north_star: per-step state 1e-9 relative, annual totals 1e-6 relative.
-Relative error of a column is |a-b| / max(|b|, floor) with a per-column floor derived from the column's
-typical magnitude, so that values that are sums of cancelling terms (balance errors, fluxes near zero)
+Relative error of a column is |a-b| / max(|b|, floor) with a per-column floor of 1e-3 x the column's largest
+magnitude (so an entry that happens to be near zero must still agree to 1e-12 of the column's scale), so that values that are sums of cancelling terms (balance errors, fluxes near zero)
 are judged against the size of their terms and not against their own near-zero value.
 """
 from __future__ import annotations
@@ -36,7 +36,7 @@ RESIDUAL_FLOORS = {"E_error": 1.0, "ENERGY_ERROR": 1.0, "WATER_ERROR": 1.0, "S_m
                    "DELSURFSTOR": 1e-3}
 
 
-def column_report(got, ref, names, scale_floor=1e-6, abs_floor=1e-9):
+def column_report(got, ref, names, scale_floor=1e-3, abs_floor=1e-9):
     """got/ref: [..., ncol]; returns list of (name, max_rel_err, argmax index) sorted worst first."""
     got = np.asarray(got)
     ref = np.asarray(ref)
@@ -53,6 +53,19 @@ def column_report(got, ref, names, scale_floor=1e-6, abs_floor=1e-9):
         out.append((names[c], float(e[k]) if e.size else 0.0, k))
     out.sort(key=lambda x: -x[1])
     return out
+
+
+def row_errors(got, ref, names, scale_floor=1e-3, abs_floor=1e-9):
+    """got/ref: [nrec, nrow, ncol] -> [nrec, nrow] largest relative error of each row, same floors as column_report"""
+    got = np.asarray(got)
+    ref = np.asarray(ref)
+    worst = np.zeros(ref.shape[:-1])
+    for c in range(ref.shape[-1]):
+        fin = ref[..., c][np.isfinite(ref[..., c])]
+        mag = np.max(np.abs(fin)) if fin.size else 0.0
+        floor = max(mag * scale_floor, abs_floor, RESIDUAL_FLOORS.get(names[c].split("[")[0], 0.0))
+        worst = np.maximum(worst, rel_err(got[..., c], ref[..., c], floor))
+    return worst
 
 
 def compare_case(case, result, keys=(("out", "out_ref"), ("hrurec", "hrurec_ref"), ("agg", "agg_ref"))):
