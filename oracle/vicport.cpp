@@ -25,21 +25,25 @@ static void run_record(const Opts* o, Tables& t, const double* frec, Dmy d, int 
   for (int h = 0; h < t.nhru; h++) hru_work<NN>(o, t, frec, h, d, rec, ga);
 }
 
-static void to_colmajor(const std::vector<double>& rm, int nrow, int ncol, std::vector<double>& cm) {
+// row-major record r -> column-major row (slot ? slot[r] : r)
+static void to_colmajor(const std::vector<double>& rm, int nrow, int ncol, std::vector<double>& cm, const int* slot = nullptr) {
   cm.resize(rm.size());
   for (int r = 0; r < nrow; r++)
-    for (int c = 0; c < ncol; c++) cm[(size_t)c * nrow + r] = rm[(size_t)r * ncol + c];
+    for (int c = 0; c < ncol; c++) cm[(size_t)c * nrow + (slot ? slot[r] : r)] = rm[(size_t)r * ncol + c];
 }
-static void to_rowmajor(const double* cm, int nrow, int ncol, double* rm) {
+static void to_rowmajor(const double* cm, int nrow, int ncol, double* rm, const int* slot = nullptr) {
   for (int r = 0; r < nrow; r++)
-    for (int c = 0; c < ncol; c++) rm[(size_t)r * ncol + c] = cm[(size_t)c * nrow + r];
+    for (int c = 0; c < ncol; c++) rm[(size_t)r * ncol + c] = cm[(size_t)c * nrow + (slot ? slot[r] : r)];
 }
 
 int main(int argc, char** argv) {
-  if (argc < 3) die("usage: vicport case.bin result.bin [--nrec N]");
+  if (argc < 3) die("usage: vicport case.bin result.bin [--nrec N] [--binned]");
   int nrec_limit = -1;
-  for (int i = 3; i < argc; i++)
+  bool binned = false;  // keep the HRU tables in the device's binned row order (bin_hrus) instead of the caller's
+  for (int i = 3; i < argc; i++) {
     if (!strcmp(argv[i], "--nrec") && i + 1 < argc) nrec_limit = atoi(argv[++i]);
+    if (!strcmp(argv[i], "--binned")) binned = true;
+  }
   std::map<std::string, CaseArray> cs;
   if (!case_read(argv[1], cs)) die("cannot read case file");
   vicgpu_options abi;
@@ -56,20 +60,27 @@ int main(int argc, char** argv) {
 
   std::vector<double> cellpar, hrupar, hrurec;
   to_colmajor(cs["cellpar"].f64, ncell, L.cp_stride, cellpar);
-  to_colmajor(cs["hrupar"].f64, nhru, HP_N, hrupar);
-  to_colmajor(cs["hrurec0"].f64, nhru, L.hr_stride, hrurec);
+  std::vector<int> hru_of_slot, slot_of_hru;
+  if (binned) bin_hrus(cs["hrupar"].f64.data(), nhru, hru_of_slot, slot_of_hru);
+  const int* slot = binned ? slot_of_hru.data() : nullptr;
+  to_colmajor(cs["hrupar"].f64, nhru, HP_N, hrupar, slot);
+  to_colmajor(cs["hrurec0"].f64, nhru, L.hr_stride, hrurec, slot);
   std::vector<double> hdiag((size_t)3 * nhru, 0.0), carry((size_t)CC_N * ncell, 0.0), out((size_t)nout * ncell, 0.0), agg((size_t)nout * ncell, 0.0);
-  std::vector<int> cell_h0(ncell + 1, 0), status(ncell, 0);
+  std::vector<int> cell_h0(ncell + 1, 0), status(ncell, 0), fail_rec(ncell, INT_MAX);
   for (int h = 0; h < nhru; h++) cell_h0[(int)cs["hrupar"].f64[(size_t)h * HP_N + HP_cell] + 1]++;
   for (int c = 0; c < ncell; c++) cell_h0[c + 1] += cell_h0[c];
   if (cs.count("valid0"))
-    for (int c = 0; c < ncell; c++) status[c] = cs["valid0"].i32[c] ? 0 : ERROR_I;
+    for (int c = 0; c < ncell; c++) {
+      status[c] = cs["valid0"].i32[c] ? 0 : ERROR_I;
+      if (status[c] != 0) fail_rec[c] = -1;
+    }
 
   Tables t;
   t.ncell = ncell; t.nhru = nhru; t.nclass = (int)cs["veglib"].dims[0];
-  t.veglib = cs["veglib"].f64.data(); t.cellpar = cellpar.data(); t.hrupar = hrupar.data(); t.hrurec = hrurec.data(); t.hdiag = hdiag.data();
-  t.cell_h0 = cell_h0.data(); t.status = status.data(); t.carry = carry.data(); t.out = out.data(); t.agg = agg.data();
+  t.veglib = cs["veglib"].f64.data(); t.cellpar = cellpar.data(); t.hrupar = hrupar.data(); t.hrurec = hrurec.data(); t.hrurec_out = hrurec.data(); t.hdiag_out = hdiag.data();
+  t.cell_h0 = cell_h0.data(); t.status = status.data(); t.fail_rec = fail_rec.data(); t.carry = carry.data(); t.out = out.data(); t.agg = agg.data();
   t.aggtype = cs["aggtype"].i32.data();
+  t.slot_of_hru = slot;
 
   const std::vector<double>& forcing = cs["forcing"].f64;  // [nrec][ncell][f_stride]
   const std::vector<int32_t>& dmy = cs["dmy"].i32;
@@ -98,7 +109,7 @@ int main(int argc, char** argv) {
     if (nd < dump_recs.size() && dump_recs[nd] == rec) {
       size_t base = hru_all.size();
       hru_all.resize(base + (size_t)nhru * L.hr_stride);
-      to_rowmajor(hrurec.data(), nhru, L.hr_stride, &hru_all[base]);
+      to_rowmajor(hrurec.data(), nhru, L.hr_stride, &hru_all[base], slot);
       nd++;
     }
     if (step_count == o.out_step_ratio) {

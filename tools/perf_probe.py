@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Quick device-time probe of the hot path on the bench domain (development tool; bench.py is the measurement of record).
+
+    python tools/perf_probe.py [--cells C] [--steps K] [--warmup W] [--tag NAME]
+Prints one line: tag, cells, ms per 24-record step, average step-kernel launch in us, cell-timesteps/s.
+Tuning knobs are read by libvicgpu.so from the environment (VICGPU_BLOCK, VICGPU_NOBIN, ...)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from vic_b200 import api  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--cells", type=int, default=10000)
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--start-day", type=int, default=0)
+ap.add_argument("--tag", default="")
+a = ap.parse_args()
+dom = bench.build_domain(a.cells, 1)
+g = api.VicGpu(dom["options_raw"], device=0)
+g.set_veglib(dom["veglib"]); g.set_output_spec(dom["aggtype"]); g.set_cells(dom["cellpar"], dom["hrupar"]); g.set_state(dom["hrurec0"])
+nd = a.warmup + a.steps
+f = np.empty((nd * 24, a.cells, g.L.f_stride))
+for d in range(nd):
+    bench.forcing_day(dom, a.start_day + d, 1, f[d * 24:(d + 1) * 24])
+g.set_forcing(0, f)
+dmy = bench.make_dmy(nd * 24)
+for s in range(a.warmup):
+    g.step(s * 24, 24, dmy[s * 24:s * 24 + 25])
+g.set_profiling(True)
+ms = 0.0
+for s in range(a.warmup, nd):
+    g.step(s * 24, 24, dmy[s * 24:s * 24 + 25])
+    ms += g.last_step_timing()[0]
+kms, kn = g.kernel_profile()
+env = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("VICGPU_"))
+print(f"PROBE {a.tag} [{env}] cells={a.cells} hrus={g.nhru} ms_per_step={ms / a.steps:.3f} hru_kernel_us={kms / max(kn, 1) * 1e3:.1f} "
+      f"cell_steps_per_s={a.cells * 24 * a.steps / (ms / 1e3):.4g} state_sum={np.nansum(g.get_state()):.17g}", flush=True)
+g.close()

@@ -9,6 +9,8 @@
 //                                              own glacier.cum_mass_balance, which put_data never reads)
 #ifndef VIC_ENGINE_CUH
 #define VIC_ENGINE_CUH
+#include <algorithm>
+#include <vector>
 #include "vic_step.cuh"
 #include "vic_output.cuh"
 
@@ -20,10 +22,15 @@ struct Tables {
   const double* veglib;   // [nclass][vl_stride]
   const double* cellpar;  // [cp_stride][ncell]
   const double* hrupar;   // [HP_N][nhru]
-  double* hrurec;         // [hr_stride][nhru]
-  double* hdiag;          // [3][nhru]  Cv-weighted out_prec / out_rain / out_snow of the step
-  const int* cell_h0;     // [ncell+1] first HRU of each cell
+  const double* hrurec;   // [hr_stride][nhru]  state at the start of the record (read by hru_work)
+  double* hrurec_out;     // [hr_stride][nhru]  state at the end of the record (written by hru_work, read by cell_output);
+                          //                    the CUDA library ping-pongs two buffers so that cell_output of record r runs
+                          //                    beside hru_work of record r+1; the host port passes hrurec_out == hrurec
+  double* hdiag_out;      // [3][nhru]  Cv-weighted out_prec / out_rain / out_snow of the step (same ping-pong)
+  const int* cell_h0;     // [ncell+1] first HRU of each cell (caller's HRU numbering: hruList order grouped by cell)
+  const int* slot_of_hru; // [nhru] row of the HRU tables an HRU occupies (null = identity); threads of hru_work run over rows
   int* status;            // [ncell] 0 or -999
+  int* fail_rec;          // [ncell] first record at which the cell is invalid (INT_MAX: never; -1: from the start)
   double* carry;          // [CC_N][ncell]
   double* out;            // [nout][ncell]  OutputData::data of the current record
   double* agg;            // [nout][ncell]  OutputData::aggdata
@@ -36,14 +43,23 @@ struct GlacAccum {
   int enabled, reset_first, accumulate, reset_after;
 };
 
+// an HRU that is not stepped (its cell is invalid) keeps its state: copy the record to the output buffer when there are two
+VIC_HDI void carry_hru_record(const Tables& t, int h, int hr_stride) {
+  if (t.hrurec_out == t.hrurec) return;
+  const size_t nh = (size_t)t.nhru;
+  for (int k = 0; k < hr_stride; k++) t.hrurec_out[(size_t)k * nh + h] = t.hrurec[(size_t)k * nh + h];
+}
+
+// h: row of the HRU tables
 template <int NN>
 VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec /* [f_stride][ncell] */, int h, Dmy dmy, int rec, GlacAccum ga) {
   const size_t nh = (size_t)t.nhru;
   Col hpc{t.hrupar + h, nh};
   const int cell = (int)hpc(HP_cell);
-  double* dg = t.hdiag + h;
+  double* dg = t.hdiag_out + h;
   if (t.status[cell] != 0) {
     dg[0] = dg[nh] = dg[2 * nh] = 0;
+    carry_hru_record(t, h, o->L.hr_stride);
     return;
   }
   Ctx cx;
@@ -61,7 +77,13 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   int e = hru_step<NN>(hru, hp, cx, d);
   if (e == ERROR_I) {
     t.status[cell] = ERROR_I;  // benign race: every writer stores the same value
+#if defined(__CUDA_ARCH__)
+    atomicMin(&t.fail_rec[cell], rec);
+#else
+    if (rec < t.fail_rec[cell]) t.fail_rec[cell] = rec;
+#endif
     dg[0] = dg[nh] = dg[2 * nh] = 0;
+    carry_hru_record(t, h, o->L.hr_stride);
     return;
   }
   if (ga.enabled && hp.isGlacier) {
@@ -69,14 +91,14 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
     if (ga.accumulate && is_valid(hru.glac.mass_balance)) hru.glac.cum_mass_balance += hru.glac.mass_balance;
     if (ga.reset_after) hru.glac.cum_mass_balance = 0;
   }
-  store_hru<NN>(hru, t.hrurec + h, nh, &o->L);
+  store_hru<NN>(hru, t.hrurec_out + h, nh, &o->L);
   dg[0] = d.out_prec * hp.Cv;
   dg[nh] = d.out_rain * hp.Cv;
   dg[2 * nh] = d.out_snow * hp.Cv;
 }
 
 VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count) {
-  if (t.status[cell] != 0 && rec >= 0) {
+  if (rec >= 0 && t.fail_rec[cell] <= rec) {
     // the reference stops touching an invalid cell (vicNl.c:521); its data row keeps the last values
     return;
   }
@@ -84,7 +106,7 @@ VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_r
   CellPar cp{Col{t.cellpar + cell, nc}, &o->L};
   VegLib vl{t.veglib, &o->L};
   Forcing f{Col{forcing_rec ? forcing_rec + cell : nullptr, nc}, o->L.f_nslot};
-  put_data_cell(*o, cp, vl, &f, t.hrurec, t.hrupar, t.hdiag, (size_t)t.nhru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count, t.aggtype,
+  put_data_cell(*o, cp, vl, &f, t.hrurec_out, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count, t.aggtype,
                 RowRW{t.carry + cell, nc}, RowRW{t.out + cell, nc}, RowRW{t.agg + cell, nc});
 }
 
@@ -113,6 +135,26 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   o.gaDay = a.glacierAccumStartDay; o.gaInterval = a.glacierAccumInterval; o.wind_h = a.wind_h;
   vicgpu_layout_init(&o.L, &a);
   return VICGPU_OK;
+}
+
+// Binning (host): the rows of the HRU tables are ordered by kind -- glacier / artificial bare soil / vegetation class --
+// and by cell within a kind, so that the threads of a warp (consecutive rows) take the same branches of the step
+// (surface_fluxes vs surface_fluxes_glac, overstory canopy balance, transpiration vs bare-soil evaporation) and the warps
+// of a block run through the same code.  hrupar_rm: the caller's row-major HRU parameter records.
+inline void bin_hrus(const double* hrupar_rm, int nhru, std::vector<int>& hru_of_slot, std::vector<int>& slot_of_hru) {
+  std::vector<long long> key((size_t)nhru);
+  for (int k = 0; k < nhru; k++) {
+    const double* p = hrupar_rm + (size_t)k * HP_N;
+    long long kind = (long long)p[HP_vegIndex];
+    if (p[HP_isArtBare] != 0.0) kind += 1000000;
+    if (p[HP_isGlacier] != 0.0) kind += 2000000;
+    key[k] = kind;
+  }
+  hru_of_slot.resize((size_t)nhru);
+  for (int k = 0; k < nhru; k++) hru_of_slot[k] = k;
+  std::stable_sort(hru_of_slot.begin(), hru_of_slot.end(), [&](int a, int b) { return key[a] < key[b]; });
+  slot_of_hru.resize((size_t)nhru);
+  for (int s = 0; s < nhru; s++) slot_of_hru[hru_of_slot[s]] = s;
 }
 
 // accumulateGlacierMassBalance.c:13-66 calendar logic; `started` persists between records

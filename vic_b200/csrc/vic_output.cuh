@@ -24,10 +24,11 @@ struct RowRW {
 };
 
 // out: the cell's row of OutputData::data; agg: its row of aggdata (may be null when rec < 0).
-// hrec/hpar/hdiag are the column-major HRU tables, [h0, h1) the cell's HRUs.
+// hrec/hpar/hdiag are the column-major HRU tables, [h0, h1) the cell's HRUs in hruList order; slot (may be null = identity)
+// maps an HRU to the table row it currently occupies (the device keeps HRUs binned by kind, not by cell).
 // rec < 0 reproduces the storage initialisation call put_data(rec = -nrecs) (vicNl.c:524-541).
 VIC_HDI void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, const Forcing* f, const double* hrec, const double* hpar,
-                           const double* hdiag, size_t nhru, int h0, int h1, int rec, int step_count, const int* aggtype, RowRW carry,
+                           const double* hdiag, size_t nhru, const int* slot, int h0, int h1, int rec, int step_count, const int* aggtype, RowRW carry,
                            RowRW out, RowRW agg) {
   const vicgpu_layout& L = o.L;
   const int NL = VICGPU_NLAYER;
@@ -38,7 +39,8 @@ VIC_HDI void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, c
 #define HP(k) hpar[(size_t)(k) * nhru + h]
   double bandCv[VICGPU_MAX_BANDS], TreeAdjustFactor[VICGPU_MAX_BANDS];
   for (int b = 0; b < VICGPU_MAX_BANDS; b++) bandCv[b] = 0;
-  for (int h = h0; h < h1; h++) {
+  for (int hh = h0; hh < h1; hh++) {
+    const int h = slot ? slot[hh] : hh;
     if (vl.row((int)HP(HP_vegIndex)).overstory()) bandCv[(int)HP(HP_band)] += HP(HP_Cv);
   }
   for (int b = 0; b < Nbands; b++) {
@@ -50,7 +52,8 @@ VIC_HDI void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, c
   double out_prec = 0, out_rain = 0, out_snow = 0;
   if (rec >= 0) {
     // atmos->out_prec etc. (full_energy.c:425-427): Cv-weighted sums over the HRUs that were stepped
-    for (int h = h0; h < h1; h++) {
+    for (int hh = h0; hh < h1; hh++) {
+    const int h = slot ? slot[hh] : hh;
       out_prec += hdiag[(size_t)0 * nhru + h];
       out_rain += hdiag[(size_t)1 * nhru + h];
       out_snow += hdiag[(size_t)2 * nhru + h];
@@ -72,7 +75,8 @@ VIC_HDI void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, c
     OUT(VPD, 0) = (*f)(FV_vpd, NR) / 1000.;
     OUT(WIND, 0) = (*f)(FV_wind, NR);
   }
-  for (int h = h0; h < h1; h++) {
+  for (int hh = h0; hh < h1; hh++) {
+    const int h = slot ? slot[hh] : hh;
     const double Cv = HP(HP_Cv);
     const bool isArtBare = HP(HP_isArtBare) != 0.0, HasGlac = HP(HP_isGlacier) != 0.0;
     const bool HasVeg = !(isArtBare || HasGlac);

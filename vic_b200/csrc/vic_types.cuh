@@ -138,90 +138,106 @@ struct Hru {
 };
 
 // HRU record (column-major in memory, stride n) -> working set
-template <int NN>
-VIC_HDI void load_hru(Hru<NN>& h, const double* rec, size_t n, const vicgpu_layout* L) {
-#define LD(k) rec[(size_t)(k) * n]
-#define X(nm, p, c) h.energy.nm = LD(HR_E_##nm);
-  VICGPU_HRU_ENERGY(X, )
-#undef X
-#define X(nm, p, c) h.snow.nm = LD(HR_S_##nm);
-  VICGPU_HRU_SNOW(X, )
-#undef X
-#define X(nm, p, c) h.cell.nm = LD(HR_C_##nm);
-  VICGPU_HRU_CELL(X, )
-#undef X
-#define X(nm, p, c) h.veg.nm = LD(HR_V_##nm);
-  VICGPU_HRU_VEG(X, )
-#undef X
-#define X(nm, p, c) h.glac.nm = LD(HR_G_##nm);
-  VICGPU_HRU_GLAC(X, )
-#undef X
-  h.mu = LD(HR_H_mu);
-  for (int i = 0; i < VICGPU_NLAYER; i++) {
-#define X(nm, p, c) h.cell.layer[i].nm = LD(VICGPU_HR_LAYER(L, HRL_##nm, i));
-    VICGPU_HRU_LAYER(X, )
-#undef X
-  }
-  for (int i = 0; i < VICGPU_NFRONTS; i++) {
-    h.energy.fdepth[i] = LD(VICGPU_HR_FRONT(L, HRF_fdepth, i));
-    h.energy.tdepth[i] = LD(VICGPU_HR_FRONT(L, HRF_tdepth, i));
-  }
-  for (int i = 0; i < VICGPU_NPET; i++) h.cell.pot_evap[i] = LD(VICGPU_HR_PET(L, i));
-  for (int i = 0; i < NN; i++) {
-    if (i < L->nnode) {
-      h.energy.Cs_node[i] = LD(VICGPU_HR_NODE(L, HRN_Cs, i));
-      h.energy.ice[i] = LD(VICGPU_HR_NODE(L, HRN_ice, i));
-      h.energy.kappa_node[i] = LD(VICGPU_HR_NODE(L, HRN_kappa, i));
-      h.energy.moist[i] = LD(VICGPU_HR_NODE(L, HRN_moist, i));
-      h.energy.T[i] = LD(VICGPU_HR_NODE(L, HRN_T, i));
-      h.energy.T_fbflag[i] = LD(VICGPU_HR_NODE(L, HRN_T_fbflag, i));
-      h.energy.T_fbcount[i] = LD(VICGPU_HR_NODE(L, HRN_T_fbcount, i));
+// ---- record <-> working set ------------------------------------------------------------------------------------------
+// The scalar columns of the HRU record (include/vicgpu_fields.h) and the members of EnergyBal / SnowPack / SoilCol / VegVar /
+// Glacier are generated from the same X-macro tables in the same order, and every member is a double: a group of columns is
+// a run of consecutive doubles of the working set.  The transfer is written as chunked loops -- a chunk of independent loads
+// first, then the chunk's stores -- so that the memory round trips of a chunk overlap (a member-by-member copy compiles to
+// load, store, load, store ... and pays one round trip per column).
+#include <stddef.h>
+#define VIC_XFER_CHUNK 16
+
+// columns col0 .. col0+count-1 of my record row  ->  dst[0 .. count)
+VIC_HD void cols_to_local(const double* __restrict__ rec, size_t n, int col0, int count, double* __restrict__ dst) {
+  int k = 0;
+  for (; k + VIC_XFER_CHUNK <= count; k += VIC_XFER_CHUNK) {
+    double r[VIC_XFER_CHUNK];
+#pragma unroll
+    for (int j = 0; j < VIC_XFER_CHUNK; j++) {
+#if defined(__CUDA_ARCH__)
+      r[j] = __ldg(rec + (size_t)(col0 + k + j) * n);
+#else
+      r[j] = rec[(size_t)(col0 + k + j) * n];
+#endif
     }
+#pragma unroll
+    for (int j = 0; j < VIC_XFER_CHUNK; j++) dst[k + j] = r[j];
   }
-#undef LD
+  for (; k < count; k++) dst[k] = rec[(size_t)(col0 + k) * n];
+}
+VIC_HD void local_to_cols(const double* __restrict__ src, double* __restrict__ rec, size_t n, int col0, int count) {
+  int k = 0;
+  for (; k + VIC_XFER_CHUNK <= count; k += VIC_XFER_CHUNK) {
+    double r[VIC_XFER_CHUNK];
+#pragma unroll
+    for (int j = 0; j < VIC_XFER_CHUNK; j++) r[j] = src[k + j];
+#pragma unroll
+    for (int j = 0; j < VIC_XFER_CHUNK; j++) rec[(size_t)(col0 + k + j) * n] = r[j];
+  }
+  for (; k < count; k++) rec[(size_t)(col0 + k) * n] = src[k];
 }
 
 template <int NN>
-VIC_HDI void store_hru(const Hru<NN>& h, double* rec, size_t n, const vicgpu_layout* L) {
-#define ST(k) rec[(size_t)(k) * n]
-#define X(nm, p, c) ST(HR_E_##nm) = h.energy.nm;
-  VICGPU_HRU_ENERGY(X, )
-#undef X
-#define X(nm, p, c) ST(HR_S_##nm) = h.snow.nm;
-  VICGPU_HRU_SNOW(X, )
-#undef X
-#define X(nm, p, c) ST(HR_C_##nm) = h.cell.nm;
-  VICGPU_HRU_CELL(X, )
-#undef X
-#define X(nm, p, c) ST(HR_V_##nm) = h.veg.nm;
-  VICGPU_HRU_VEG(X, )
-#undef X
-#define X(nm, p, c) ST(HR_G_##nm) = h.glac.nm;
-  VICGPU_HRU_GLAC(X, )
-#undef X
-  ST(HR_H_mu) = h.mu;
-  for (int i = 0; i < VICGPU_NLAYER; i++) {
-#define X(nm, p, c) ST(VICGPU_HR_LAYER(L, HRL_##nm, i)) = h.cell.layer[i].nm;
-    VICGPU_HRU_LAYER(X, )
-#undef X
-  }
-  for (int i = 0; i < VICGPU_NFRONTS; i++) {
-    ST(VICGPU_HR_FRONT(L, HRF_fdepth, i)) = h.energy.fdepth[i];
-    ST(VICGPU_HR_FRONT(L, HRF_tdepth, i)) = h.energy.tdepth[i];
-  }
-  for (int i = 0; i < VICGPU_NPET; i++) ST(VICGPU_HR_PET(L, i)) = h.cell.pot_evap[i];
-  for (int i = 0; i < NN; i++) {
-    if (i < L->nnode) {
-      ST(VICGPU_HR_NODE(L, HRN_Cs, i)) = h.energy.Cs_node[i];
-      ST(VICGPU_HR_NODE(L, HRN_ice, i)) = h.energy.ice[i];
-      ST(VICGPU_HR_NODE(L, HRN_kappa, i)) = h.energy.kappa_node[i];
-      ST(VICGPU_HR_NODE(L, HRN_moist, i)) = h.energy.moist[i];
-      ST(VICGPU_HR_NODE(L, HRN_T, i)) = h.energy.T[i];
-      ST(VICGPU_HR_NODE(L, HRN_T_fbflag, i)) = h.energy.T_fbflag[i];
-      ST(VICGPU_HR_NODE(L, HRN_T_fbcount, i)) = h.energy.T_fbcount[i];
+struct HruGroups {
+  static constexpr int nE = (int)(offsetof(EnergyBal<NN>, fdepth) / sizeof(double));
+  static constexpr int nS = (int)(sizeof(SnowPack) / sizeof(double));
+  static constexpr int nC = (int)(offsetof(SoilCol, layer) / sizeof(double));
+  static constexpr int nV = (int)(sizeof(VegVar) / sizeof(double));
+  static constexpr int nG = (int)(sizeof(Glacier) / sizeof(double));
+  static constexpr int nLayerF = (int)(sizeof(SoilLayer) / sizeof(double));
+  static_assert(nE + nS + nC + nV + nG == (int)HR_H_mu && (int)HR_H_mu + 1 == (int)HR_NSCALAR, "HRU scalar columns and working-set members out of step");
+  static_assert(nLayerF == (int)HRL_N, "soil-layer columns and SoilLayer members out of step");
+  static_assert(offsetof(EnergyBal<NN>, tdepth) == offsetof(EnergyBal<NN>, fdepth) + VICGPU_NFRONTS * sizeof(double), "fronts");
+  static_assert(offsetof(EnergyBal<NN>, T_fbcount) == offsetof(EnergyBal<NN>, Cs_node) + 6 * NN * sizeof(double) && (int)HRN_N == 7, "nodes");
+};
+
+// HRU record (column-major in memory, stride n) -> working set
+template <int NN>
+VIC_HDI void load_hru(Hru<NN>& h, const double* __restrict__ rec, size_t n, const vicgpu_layout* Lg) {
+  typedef HruGroups<NN> G;
+  const int hr_layer0 = Lg->hr_layer0, hr_front0 = Lg->hr_front0, hr_pet0 = Lg->hr_pet0, hr_node0 = Lg->hr_node0, nnode = Lg->nnode;
+  cols_to_local(rec, n, 0, G::nE, reinterpret_cast<double*>(&h.energy));
+  cols_to_local(rec, n, G::nE, G::nS, reinterpret_cast<double*>(&h.snow));
+  cols_to_local(rec, n, G::nE + G::nS, G::nC, reinterpret_cast<double*>(&h.cell));
+  cols_to_local(rec, n, G::nE + G::nS + G::nC, G::nV, reinterpret_cast<double*>(&h.veg));
+  cols_to_local(rec, n, G::nE + G::nS + G::nC + G::nV, G::nG, reinterpret_cast<double*>(&h.glac));
+  h.mu = rec[(size_t)HR_H_mu * n];
+  // layers: record [field][layer], working set layer[i].field
+  {
+    double r[HRL_N * VICGPU_NLAYER];
+    cols_to_local(rec, n, hr_layer0, HRL_N * VICGPU_NLAYER, r);
+    for (int i = 0; i < VICGPU_NLAYER; i++) {
+      double* li = reinterpret_cast<double*>(&h.cell.layer[i]);
+      for (int f = 0; f < HRL_N; f++) li[f] = r[f * VICGPU_NLAYER + i];
     }
   }
-#undef ST
+  cols_to_local(rec, n, hr_front0, 2 * VICGPU_NFRONTS, h.energy.fdepth);  // fdepth[], tdepth[] are adjacent
+  cols_to_local(rec, n, hr_pet0, VICGPU_NPET, h.cell.pot_evap);
+  // nodes: record [field][nnode], working set field[NN]
+  for (int f = 0; f < HRN_N; f++) cols_to_local(rec, n, hr_node0 + f * nnode, nnode < NN ? nnode : NN, h.energy.Cs_node + f * NN);
+}
+
+template <int NN>
+VIC_HDI void store_hru(const Hru<NN>& h, double* __restrict__ rec, size_t n, const vicgpu_layout* Lg) {
+  typedef HruGroups<NN> G;
+  const int hr_layer0 = Lg->hr_layer0, hr_front0 = Lg->hr_front0, hr_pet0 = Lg->hr_pet0, hr_node0 = Lg->hr_node0, nnode = Lg->nnode;
+  local_to_cols(reinterpret_cast<const double*>(&h.energy), rec, n, 0, G::nE);
+  local_to_cols(reinterpret_cast<const double*>(&h.snow), rec, n, G::nE, G::nS);
+  local_to_cols(reinterpret_cast<const double*>(&h.cell), rec, n, G::nE + G::nS, G::nC);
+  local_to_cols(reinterpret_cast<const double*>(&h.veg), rec, n, G::nE + G::nS + G::nC, G::nV);
+  local_to_cols(reinterpret_cast<const double*>(&h.glac), rec, n, G::nE + G::nS + G::nC + G::nV, G::nG);
+  rec[(size_t)HR_H_mu * n] = h.mu;
+  {
+    double r[HRL_N * VICGPU_NLAYER];
+    for (int i = 0; i < VICGPU_NLAYER; i++) {
+      const double* li = reinterpret_cast<const double*>(&h.cell.layer[i]);
+      for (int f = 0; f < HRL_N; f++) r[f * VICGPU_NLAYER + i] = li[f];
+    }
+    local_to_cols(r, rec, n, hr_layer0, HRL_N * VICGPU_NLAYER);
+  }
+  local_to_cols(h.energy.fdepth, rec, n, hr_front0, 2 * VICGPU_NFRONTS);
+  local_to_cols(h.cell.pot_evap, rec, n, hr_pet0, VICGPU_NPET);
+  for (int f = 0; f < HRN_N; f++) local_to_cols(h.energy.Cs_node + f * NN, rec, n, hr_node0 + f * nnode, nnode < NN ? nnode : NN);
 }
 
 // everything a physics routine needs to know about "where am I"

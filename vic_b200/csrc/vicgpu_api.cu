@@ -39,6 +39,23 @@ __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ 
   }
 }
 
+// The same conversions when the device row of record r is not r (HRU tables are kept binned by kind, vic_engine.cuh bin_hrus):
+// host record r (row-major) <-> device row row_of[r] (column-major).  One thread per element, coalesced on the device side.
+__global__ void k_scatter_rows(const double* __restrict__ in /* [rows][cols] */, double* __restrict__ out /* [cols][rows] */, int rows, int cols,
+                               const int* __restrict__ rec_of_row) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int c = (int)(i / rows), r = (int)(i % rows);
+  out[i] = in[(size_t)rec_of_row[r] * cols + c];
+}
+__global__ void k_gather_rows(const double* __restrict__ in /* [cols][rows] */, double* __restrict__ out /* [rows][cols] */, int rows, int cols,
+                              const int* __restrict__ row_of_rec) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  out[i] = in[(size_t)c * rows + row_of_rec[r]];
+}
+
 __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
                                                      int step_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,9 +63,10 @@ __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o,
   cell_output(o, t, forcing_rec, c, rec, step_count);
 }
 
-int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch) {
+int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch, cudaStream_t st) {
+  if (!st) st = h->stream;
   dim3 b(32, 8), g((cols + 31) / 32, (rows + 31) / 32, batch);
-  k_transpose<<<g, b, 0, h->stream>>>(d_in, d_out, rows, cols);
+  k_transpose<<<g, b, 0, st>>>(d_in, d_out, rows, cols);
   h->last_launches++;
   CK(cudaGetLastError());
   return VICGPU_OK;
@@ -75,22 +93,36 @@ static int ensure_stage(vicgpu_handle* h, size_t elems) {
   return VICGPU_OK;
 }
 
-// host row-major [rows][cols] -> device column-major [cols][rows]
-static int upload_transposed(vicgpu_handle* h, const double* host, double* d_dst, int rows, int cols) {
+// host row-major [rows][cols] -> device column-major [cols][rows]; rec_of_row (device, may be null): record held by each device row
+static int upload_transposed(vicgpu_handle* h, const double* host, double* d_dst, int rows, int cols, const int* rec_of_row = nullptr) {
   int rc = ensure_stage(h, (size_t)rows * cols);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->d_stage, host, (size_t)rows * cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  rc = vicgpu_transpose(h, h->d_stage, d_dst, rows, cols, 1);
-  if (rc) return rc;
+  if (rec_of_row) {
+    const size_t n = (size_t)rows * cols;
+    k_scatter_rows<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_stage, d_dst, rows, cols, rec_of_row);
+    h->last_launches++;
+    CK(cudaGetLastError());
+  } else {
+    rc = vicgpu_transpose(h, h->d_stage, d_dst, rows, cols, 1);
+    if (rc) return rc;
+  }
   CK(cudaStreamSynchronize(h->stream));
   return VICGPU_OK;
 }
-// device column-major [cols][rows] -> host row-major [rows][cols]
-static int download_transposed(vicgpu_handle* h, const double* d_src, double* host, int rows, int cols, bool sync) {
+// device column-major [cols][rows] -> host row-major [rows][cols]; row_of_rec (device, may be null): device row of each record
+static int download_transposed(vicgpu_handle* h, const double* d_src, double* host, int rows, int cols, bool sync, const int* row_of_rec = nullptr) {
   int rc = ensure_stage(h, (size_t)rows * cols);
   if (rc) return rc;
-  rc = vicgpu_transpose(h, d_src, h->d_stage, cols, rows, 1);
-  if (rc) return rc;
+  if (row_of_rec) {
+    const size_t n = (size_t)rows * cols;
+    k_gather_rows<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_src, h->d_stage, rows, cols, row_of_rec);
+    h->last_launches++;
+    CK(cudaGetLastError());
+  } else {
+    rc = vicgpu_transpose(h, d_src, h->d_stage, cols, rows, 1);
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(host, h->d_stage, (size_t)rows * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (sync) CK(cudaStreamSynchronize(h->stream));
   return VICGPU_OK;
@@ -122,6 +154,13 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  const char* noov = getenv("VICGPU_NOOVERLAP");  // A/B knob: run the cell output in the step's stream
+  h->overlap = !(noov && atoi(noov) != 0);
+  if (h->overlap) CK(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+  else h->stream_out = h->stream;
+  CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_out[0], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_out[1], cudaEventDisableTiming));
   CK(cudaMalloc(&h->d_o, sizeof(Opts)));
   CK(cudaMemcpy(h->d_o, &h->o, sizeof(Opts), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_aggtype, VICGPU_N_OUTVARS * sizeof(int)));
@@ -130,6 +169,8 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   CK(cudaMemcpy(h->d_aggtype, agg, sizeof(agg), cudaMemcpyHostToDevice));
   // the step kernel keeps one HRU (about 2 KB) plus its working copies in thread-local memory
   CK(cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024));
+  const char* blk = getenv("VICGPU_BLOCK");  // threads per block of the per-HRU step kernel (tuning knob; multiple of 32, <= VICGPU_HRU_BLOCK_MAX)
+  if (blk && atoi(blk) >= 32 && atoi(blk) <= VICGPU_HRU_BLOCK_MAX && atoi(blk) % 32 == 0) h->hru_block = atoi(blk);
   *out = h;
   return VICGPU_OK;
 }
@@ -137,9 +178,14 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
 int vicgpu_destroy(vicgpu_handle* h) {
   if (!h) return VICGPU_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_hrupar); cudaFree(h->d_hrurec); cudaFree(h->d_hdiag);
+  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_hrupar);
+  for (int b = 0; b < 2; b++) { cudaFree(h->d_hrurec2[b]); cudaFree(h->d_hdiag2[b]); }
+  cudaFree(h->d_fail_rec);
   cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_forcing); cudaFree(h->d_fstage);
-  cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype);
+  cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype); cudaFree(h->d_slot_of_hru); cudaFree(h->d_hru_of_slot);
+  if (h->ev_step) cudaEventDestroy(h->ev_step);
+  for (int b = 0; b < 2; b++) if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
+  if (h->overlap && h->stream_out) cudaStreamDestroy(h->stream_out);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
@@ -184,20 +230,42 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     h0[c + 1]++;
   }
   for (int c = 0; c < ncell; c++) h0[c + 1] += h0[c];
-  cudaFree(h->d_cellpar); cudaFree(h->d_hrupar); cudaFree(h->d_hrurec); cudaFree(h->d_hdiag); cudaFree(h->d_carry); cudaFree(h->d_out);
-  cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
-  h->d_cellpar = h->d_hrupar = h->d_hrurec = h->d_hdiag = h->d_carry = h->d_out = h->d_agg = nullptr;
-  h->d_cell_h0 = h->d_status = nullptr;
+  // rows of the HRU tables: binned by kind (VICGPU_NOBIN=1 keeps the caller's order; for A/B measurements only)
+  std::vector<int> hru_of_slot, slot_of_hru;
+  const char* nobin = getenv("VICGPU_NOBIN");
+  h->binned = !(nobin && atoi(nobin) != 0);
+  if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru);
+  cudaFree(h->d_slot_of_hru); cudaFree(h->d_hru_of_slot);
+  h->d_slot_of_hru = h->d_hru_of_slot = nullptr;
+  if (h->binned) {
+    CK(cudaMalloc(&h->d_slot_of_hru, (size_t)nhru * sizeof(int)));
+    CK(cudaMalloc(&h->d_hru_of_slot, (size_t)nhru * sizeof(int)));
+    CK(cudaMemcpy(h->d_slot_of_hru, slot_of_hru.data(), (size_t)nhru * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_hru_of_slot, hru_of_slot.data(), (size_t)nhru * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  cudaFree(h->d_cellpar); cudaFree(h->d_hrupar); cudaFree(h->d_carry); cudaFree(h->d_out);
+  cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_fail_rec);
+  for (int b = 0; b < 2; b++) { cudaFree(h->d_hrurec2[b]); cudaFree(h->d_hdiag2[b]); h->d_hrurec2[b] = h->d_hdiag2[b] = nullptr; }
+  h->d_cellpar = h->d_hrupar = h->d_carry = h->d_out = h->d_agg = nullptr;
+  h->d_cell_h0 = h->d_status = h->d_fail_rec = nullptr;
+  h->cur = 0;
   CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
   CK(cudaMalloc(&h->d_hrupar, (size_t)nhru * HP_N * sizeof(double)));
-  CK(cudaMalloc(&h->d_hrurec, (size_t)nhru * L.hr_stride * sizeof(double)));
-  CK(cudaMalloc(&h->d_hdiag, (size_t)nhru * 3 * sizeof(double)));
+  for (int b = 0; b < 2; b++) {
+    CK(cudaMalloc(&h->d_hrurec2[b], (size_t)nhru * L.hr_stride * sizeof(double)));
+    CK(cudaMalloc(&h->d_hdiag2[b], (size_t)nhru * 3 * sizeof(double)));
+    CK(cudaMemset(h->d_hdiag2[b], 0, (size_t)nhru * 3 * sizeof(double)));
+  }
+  CK(cudaMalloc(&h->d_fail_rec, (size_t)ncell * sizeof(int)));
+  {
+    std::vector<int> never((size_t)ncell, INT_MAX);
+    CK(cudaMemcpy(h->d_fail_rec, never.data(), (size_t)ncell * sizeof(int), cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc(&h->d_carry, (size_t)ncell * CC_N * sizeof(double)));
   CK(cudaMalloc(&h->d_out, (size_t)ncell * h->nout * sizeof(double)));
   CK(cudaMalloc(&h->d_agg, (size_t)ncell * h->nout * sizeof(double)));
   CK(cudaMalloc(&h->d_cell_h0, (size_t)(ncell + 1) * sizeof(int)));
   CK(cudaMalloc(&h->d_status, (size_t)ncell * sizeof(int)));
-  CK(cudaMemset(h->d_hdiag, 0, (size_t)nhru * 3 * sizeof(double)));
   CK(cudaMemset(h->d_carry, 0, (size_t)ncell * CC_N * sizeof(double)));
   CK(cudaMemset(h->d_out, 0, (size_t)ncell * h->nout * sizeof(double)));
   CK(cudaMemset(h->d_agg, 0, (size_t)ncell * h->nout * sizeof(double)));
@@ -205,10 +273,12 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   CK(cudaMemcpy(h->d_cell_h0, h0.data(), (size_t)(ncell + 1) * sizeof(int), cudaMemcpyHostToDevice));
   int rc = upload_transposed(h, cellpar, h->d_cellpar, ncell, L.cp_stride);
   if (rc) return rc;
-  rc = upload_transposed(h, hrupar, h->d_hrupar, nhru, HP_N);
+  rc = upload_transposed(h, hrupar, h->d_hrupar, nhru, HP_N, h->d_hru_of_slot);
   if (rc) return rc;
   h->t.ncell = ncell; h->t.nhru = nhru;
-  h->t.cellpar = h->d_cellpar; h->t.hrupar = h->d_hrupar; h->t.hrurec = h->d_hrurec; h->t.hdiag = h->d_hdiag; h->t.cell_h0 = h->d_cell_h0;
+  h->t.slot_of_hru = h->d_slot_of_hru;
+  h->t.cellpar = h->d_cellpar; h->t.hrupar = h->d_hrupar; h->t.hrurec = h->d_hrurec2[0]; h->t.hrurec_out = h->d_hrurec2[1];
+  h->t.hdiag_out = h->d_hdiag2[1]; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
   h->t.status = h->d_status; h->t.carry = h->d_carry; h->t.out = h->d_out; h->t.agg = h->d_agg; h->t.aggtype = h->d_aggtype;
   h->have_cells = true;
   h->have_state = false;
@@ -234,6 +304,9 @@ int vicgpu_set_cell_status(vicgpu_handle* h, const int* status) {
   if (!h || !status || !h->have_cells) return fail(VICGPU_ESTATE, "set_cells first");
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpy(h->d_status, status, (size_t)h->t.ncell * sizeof(int), cudaMemcpyHostToDevice));
+  std::vector<int> fr((size_t)h->t.ncell);
+  for (int c = 0; c < h->t.ncell; c++) fr[c] = status[c] != 0 ? -1 : INT_MAX;
+  CK(cudaMemcpy(h->d_fail_rec, fr.data(), fr.size() * sizeof(int), cudaMemcpyHostToDevice));
   return VICGPU_OK;
 }
 
@@ -241,7 +314,7 @@ int vicgpu_set_state(vicgpu_handle* h, const double* hrurec) {
   if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
   if (!h->have_cells) return fail(VICGPU_ESTATE, "set_cells before set_state");
   CK(cudaSetDevice(h->device));
-  int rc = upload_transposed(h, hrurec, h->d_hrurec, h->t.nhru, h->o.L.hr_stride);
+  int rc = upload_transposed(h, hrurec, h->d_hrurec2[h->cur], h->t.nhru, h->o.L.hr_stride, h->d_hru_of_slot);
   if (rc) return rc;
   h->have_state = true;
   return VICGPU_OK;
@@ -251,7 +324,7 @@ int vicgpu_get_state(vicgpu_handle* h, double* hrurec) {
   if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
   if (!h->have_state) return fail(VICGPU_ESTATE, "no state set");
   CK(cudaSetDevice(h->device));
-  return download_transposed(h, h->d_hrurec, hrurec, h->t.nhru, h->o.L.hr_stride, true);
+  return download_transposed(h, h->d_hrurec2[h->cur], hrurec, h->t.nhru, h->o.L.hr_stride, true, h->d_slot_of_hru);
 }
 
 int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forcing) {
@@ -306,43 +379,67 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
       h->pev.push_back(e);
     }
   }
+  // Two streams: the HRU step of record r (stream) reads state buffer `cur` and writes `cur ^ 1`; the cell output of record r
+  // (stream_out) reads `cur ^ 1` while the step of record r + 1 already runs -- that step writes buffer `cur`, which was last read
+  // by the output of record r - 1 (ev_out[cur]).
+  cudaStream_t so = h->stream_out;
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < nrec; i++) {
     const int rec = rec0 + i;
     const double* frec = h->d_forcing + (size_t)(rec - h->frec0) * per;
     h->step_count++;
+    const int cur = h->cur, nxt = h->cur ^ 1;
+    Tables t = h->t;
+    t.hrurec = h->d_hrurec2[cur];
+    t.hrurec_out = h->d_hrurec2[nxt];
+    t.hdiag_out = h->d_hdiag2[nxt];
     if (rec == 0) {
-      k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, h->t, nullptr, -1, h->step_count);
+      Tables t0 = t;
+      t0.hrurec_out = h->d_hrurec2[cur];  // storage terms of the initial state
+      k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t0, nullptr, -1, h->step_count);
       h->last_launches++;
+      if (h->overlap) {
+        CK(cudaEventRecord(h->ev_out[cur], so));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_out[cur], 0));
+      }
     }
     Dmy d = {dmy[i * 5 + 0], dmy[i * 5 + 1], dmy[i * 5 + 2], dmy[i * 5 + 3], dmy[i * 5 + 4]};
     GlacAccum ga = glacier_accum_flags(h->o, &dmy[i * 5], &dmy[(i + 1) * 5], rec, &h->glac_started);
+    if (h->overlap) CK(cudaStreamWaitEvent(h->stream, h->ev_out[nxt], 0));  // the output that last read buffer nxt
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, h->t, frec, d, rec, ga, h->stream);
-    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, h->t, frec, d, rec, ga, h->stream);
-    else vicgpu_launch_hru_step_nn32(h->d_o, h->t, frec, d, rec, ga, h->stream);
+    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream);
+    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream);
+    else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream);
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));
-    k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, h->t, frec, rec, h->step_count);
+    if (h->overlap) {
+      CK(cudaEventRecord(h->ev_step, h->stream));
+      CK(cudaStreamWaitEvent(so, h->ev_step, 0));
+    }
+    k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t, frec, rec, h->step_count);
     h->last_launches += 2;
     if (out_data) {
-      int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1);
+      int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1, so);
       if (rc) return rc;
-      CK(cudaMemcpyAsync(out_data + (size_t)i * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(out_data + (size_t)i * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
     }
     if (h->step_count == h->o.out_step_ratio) {
       if (out_agg) {
-        int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1);
+        int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1, so);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
       }
       nagg++;
-      CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), h->stream));
+      CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), so));
       h->step_count = 0;
     }
+    if (h->overlap) CK(cudaEventRecord(h->ev_out[nxt], so));
+    h->cur = nxt;
   }
+  if (h->overlap) CK(cudaStreamWaitEvent(h->stream, h->ev_out[h->cur], 0));
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
+  if (h->overlap) CK(cudaStreamSynchronize(so));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;

@@ -24,10 +24,19 @@ struct vicgpu_handle {
   vic::Opts* d_o = nullptr;
   vic::Tables t;
   int nout = 0;
-  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_hrupar = nullptr, *d_hrurec = nullptr, *d_hdiag = nullptr, *d_carry = nullptr,
+  // HRU state and step diagnostics are double-buffered: record r reads buffer `cur` and writes `cur ^ 1` (vicgpu_step)
+  double *d_hrurec2[2] = {nullptr, nullptr}, *d_hdiag2[2] = {nullptr, nullptr};
+  int cur = 0;
+  int* d_fail_rec = nullptr;
+  cudaStream_t stream_out = nullptr;  // cell output (put_data) of record r runs here, beside the HRU step of record r + 1
+  cudaEvent_t ev_step = nullptr, ev_out[2] = {nullptr, nullptr};
+  bool overlap = true;
+  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_hrupar = nullptr, *d_carry = nullptr,
          *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr, *d_forcing = nullptr, *d_fstage = nullptr;
   size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
-  int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
+  int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr, *d_slot_of_hru = nullptr, *d_hru_of_slot = nullptr;
+  bool binned = true;
+  int hru_block = VICGPU_HRU_BLOCK;
   int frec0 = 0, fnrec = 0;
   bool have_cells = false, have_state = false, glac_started = false;
   int step_count = 0;
@@ -44,7 +53,7 @@ struct vicgpu_handle {
 
 
 // in: [batch][rows][cols] row-major  ->  out: [batch][cols][rows]   (vicgpu_api.cu)
-int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch);
+int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch, cudaStream_t st = nullptr);
 int vicgpu_ensure_forcing(vicgpu_handle* h, size_t elems);
 
 #endif

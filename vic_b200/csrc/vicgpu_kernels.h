@@ -5,11 +5,12 @@
 #include <cuda_runtime.h>
 #include "vic_engine.cuh"
 
-// thread block of the per-HRU kernels
-#define VICGPU_HRU_BLOCK 64
+// thread block of the per-HRU kernels: default and the largest the kernels are compiled for
+#define VICGPU_HRU_BLOCK 128
+#define VICGPU_HRU_BLOCK_MAX 384
 
-void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, cudaStream_t s);
-void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, cudaStream_t s);
-void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, cudaStream_t s);
+void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s);
+void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s);
+void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s);
 
 #endif
