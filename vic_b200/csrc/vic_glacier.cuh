@@ -18,13 +18,14 @@ struct GlacierEB {
   double Dt, Ra, Z, Z0_snow, AirDens, EactAir, LongSnowIn, Lv, Press, Rain, NetShortUnder, Vpd, Wind, OldTSurf, IceDepth, Tair, TGrnd;
   RaUsed* Ra_used;
   double *AdvectedEnergy, *DeltaColdContent, *GroundFlux, *LatentHeat, *LatentHeatSub, *NetLongUnder, *SensibleHeat, *vapor_flux;
+  StabLog stab;
 
   VIC_HDI double operator()(double TSurf) {
     const double TMean = (TSurf + TGrnd) / 2;
     const double OldTMean = (OldTSurf + TGrnd) / 2;
     const double Density = RHO_W;
     const double temp_IceDepth = IceDepth / 1000.;
-    if (Wind > 0.0) Ra_used->surface = Ra / stability_correction(Z, 0., TSurf, Tair, Wind, Z0_snow);
+    if (Wind > 0.0) Ra_used->surface = Ra / stab.correction(Z, 0., TSurf, Tair, Wind, Z0_snow);
     else Ra_used->surface = HUGE_RESIST;
     const double Tmp = TSurf + KELVIN;
     (*NetLongUnder) = LongSnowIn - STEFAN_B * Tmp * Tmp * Tmp * Tmp;
@@ -68,6 +69,7 @@ VIC_HDI int glacier_melt(double Le, double NetShort, double Tgrnd, double Z0_sno
   const double RainFall = rainfall / 1000.;
   (*OldTSurf) = glacier.surf_temp;
   GlacierEB eb;
+  eb.stab.reset();
   eb.Dt = delta_t; eb.Ra = aero_resist; eb.Z = z2; eb.Z0_snow = Z0_snow; eb.AirDens = density; eb.EactAir = vp; eb.LongSnowIn = LongIn; eb.Lv = Le;
   eb.Press = pressure; eb.Rain = RainFall; eb.NetShortUnder = NetShort; eb.Vpd = vpd; eb.Wind = wind; eb.OldTSurf = *OldTSurf;
   eb.IceDepth = cp(CP_GLAC_SURF_THICK); eb.Tair = air_temp; eb.TGrnd = Tgrnd; eb.Ra_used = &aero_resist_used;

@@ -57,26 +57,38 @@ VIC_HD double calc_rc(double rs, double net_short, float RGL, double tair, doubl
   return rc;
 }
 
-// Penman-Monteith evaporation [mm/day], penman.c:96-144
-VIC_HD double penman(double tair, double elevation, double rad, double vpd, double ra, double rc, double rarc) {
-  double slope = svp_slope(tair);
+// Penman-Monteith evaporation [mm/day], penman.c:96-144.  The terms that depend on air temperature and elevation only are
+// split off (PenmanPre) so that a root finder that re-evaluates the evaporation with a new net radiation does not recompute
+// them: the same operations in the same order, hence the same bits.
+struct PenmanPre {
+  double slope, lv, gamma, r_air;
+};
+VIC_HD PenmanPre penman_pre(double tair, double elevation) {
+  PenmanPre p;
+  p.slope = svp_slope(tair);
   double h = 287 / 9.81 * ((tair + 273.15) + 0.5 * (double)elevation * LAPSE_PM);
   double pz = PS_PM * vexp(-(double)elevation / h);
-  double lv = 2501000 - 2361 * tair;
-  double gamma = 1628.6 * pz / lv;
-  double r_air = 0.003486 * pz / (275 + tair);
-  double evap = (slope * rad + r_air * CP_PM * vpd / ra) / (lv * (slope + gamma * (1 + (rc + rarc) / ra))) * SEC_PER_DAY;
+  p.lv = 2501000 - 2361 * tair;
+  p.gamma = 1628.6 * pz / p.lv;
+  p.r_air = 0.003486 * pz / (275 + tair);
+  return p;
+}
+VIC_HD double penman_eval(const PenmanPre& p, double rad, double vpd, double ra, double rc, double rarc) {
+  double evap = (p.slope * rad + p.r_air * CP_PM * vpd / ra) / (p.lv * (p.slope + p.gamma * (1 + (rc + rarc) / ra))) * SEC_PER_DAY;
   if (vpd >= 0.0 && evap < 0.0) evap = 0.0;
   return evap;
 }
+VIC_HD double penman(double tair, double elevation, double rad, double vpd, double ra, double rc, double rarc) {
+  return penman_eval(penman_pre(tair, elevation), rad, vpd, ra, rc, rarc);
+}
 
-// Richardson-number stability multiplier, StabilityCorrection.c:44-81
-VIC_HD double stability_correction(double Z, double d, double TSurf, double Tair, double Wind, double Z0) {
+// Richardson-number stability multiplier, StabilityCorrection.c:44-81; lg = log((Z - d) / Z0)
+VIC_HD double stability_correction_lg(double Z, double d, double TSurf, double Tair, double Wind, double lg) {
   double Correction = 1.0;
   const double RiCr = 0.2;
   if (TSurf != Tair) {
     double Ri = G_GRAV * (Tair - TSurf) * (Z - d) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * Wind * Wind);
-    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (vlog((Z - d) / Z0) + 5));
+    double RiLimit = (Tair + 273.15) / (((Tair + 273.15) + (TSurf + 273.15)) / 2.0 * (lg + 5));
     if (Ri > RiLimit) Ri = RiLimit;
     if (Ri > 0.0) Correction = (1 - Ri / RiCr) * (1 - Ri / RiCr);
     else {
@@ -86,6 +98,24 @@ VIC_HD double stability_correction(double Z, double d, double TSurf, double Tair
   }
   return Correction;
 }
+VIC_HD double stability_correction(double Z, double d, double TSurf, double Tair, double Wind, double Z0) {
+  if (TSurf == Tair) return 1.0;
+  return stability_correction_lg(Z, d, TSurf, Tair, Wind, vlog((Z - d) / Z0));
+}
+// log((Z - d) / Z0) does not change between the evaluations of one solve: computed at the first evaluation that needs it
+struct StabLog {
+  double lg;
+  int ok;
+  VIC_HD void reset() { lg = 0; ok = 0; }
+  VIC_HD double correction(double Z, double d, double TSurf, double Tair, double Wind, double Z0) {
+    if (TSurf == Tair) return 1.0;
+    if (!ok) {
+      lg = vlog((Z - d) / Z0);
+      ok = 1;
+    }
+    return stability_correction_lg(Z, d, TSurf, Tair, Wind, lg);
+  }
+};
 
 // rain / snow partition, calc_rainonly.c:12-103 (mu == 1 on this path)
 VIC_HD double calc_rainonly(double air_temp, double prec, double MAX_SNOW_TEMP, double MIN_RAIN_TEMP, double mu, int TEMP_TH_TYPE) {

@@ -1,6 +1,8 @@
 // vic_math.cuh -- the elementary functions of the hot path (exp, log, log10, pow, sin, cos, acos) written in
-// plain IEEE-754 double arithmetic (+, -, *, /, sqrt, no fused multiply-add, no tables), so that the SAME
-// sequence of roundings runs on the device (nvcc --fmad=false) and on the host (g++ -ffp-contract=off).
+// plain IEEE-754 double arithmetic (+, -, *, /, sqrt and EXPLICIT fused multiply-adds, no tables), so that the SAME
+// sequence of roundings runs on the device (nvcc --fmad=false: no contraction; dl::fma is the DFMA instruction) and on the
+// host (g++ -ffp-contract=off; dl::fma is __builtin_fma: the FMA instruction, or glibc's exact fma() where the CPU has
+// none -- both are the correctly rounded a*b+c, so the results do not depend on which is used).
 //
 // Why: the reference model is full of exact comparisons on computed values (surface temperature == 0, snow
 // store < threshold, first sunlit 30-second slot of a day, Brent branch tests).  A last-ulp difference between
@@ -46,6 +48,13 @@ VM_IN double from_bits(uint64_t u) {
   return x;
 #endif
 }
+VM_IN double fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
 VM_IN double qnan() { return from_bits(0x7ff8000000000000ULL); }
 VM_IN double pinf() { return from_bits(0x7ff0000000000000ULL); }
 
@@ -80,25 +89,24 @@ VM_IN double exp_ext(double x, double xl) {
   if (x < -745.1332191019412) return 0.0;
   const double kd = rint52(x * inv_ln2);
   const int k = (int)kd;
-  const double hi = x - kd * ln2_hi;  // exact: kd * ln2_hi has <= 43 significant bits and cancels the leading bits of x
-  const double lo = kd * ln2_lo;
-  const double r = hi - lo;  // |r| <= 0.3466
-  const double rl = ((hi - r) - lo) + xl;  // what the rounding of r dropped, plus the caller's low part
+  const double hi = dl::fma(-kd, ln2_hi, x);  // exact: kd * ln2_hi has <= 43 significant bits and cancels the leading bits of x
+  const double r = dl::fma(-kd, ln2_lo, hi);  // |r| <= 0.3466
+  const double rl = dl::fma(-kd, ln2_lo, hi - r) + xl;  // what the rounding of r dropped, plus the caller's low part
   // e^r = 1 + r + r^2/2! + ... + r^13/13!
   double p = 1.0 / 6227020800.0;
-  p = p * r + 1.0 / 479001600.0;
-  p = p * r + 1.0 / 39916800.0;
-  p = p * r + 1.0 / 3628800.0;
-  p = p * r + 1.0 / 362880.0;
-  p = p * r + 1.0 / 40320.0;
-  p = p * r + 1.0 / 5040.0;
-  p = p * r + 1.0 / 720.0;
-  p = p * r + 1.0 / 120.0;
-  p = p * r + 1.0 / 24.0;
-  p = p * r + 1.0 / 6.0;
-  p = p * r + 0.5;
+  p = dl::fma(p, r, 1.0 / 479001600.0);
+  p = dl::fma(p, r, 1.0 / 39916800.0);
+  p = dl::fma(p, r, 1.0 / 3628800.0);
+  p = dl::fma(p, r, 1.0 / 362880.0);
+  p = dl::fma(p, r, 1.0 / 40320.0);
+  p = dl::fma(p, r, 1.0 / 5040.0);
+  p = dl::fma(p, r, 1.0 / 720.0);
+  p = dl::fma(p, r, 1.0 / 120.0);
+  p = dl::fma(p, r, 1.0 / 24.0);
+  p = dl::fma(p, r, 1.0 / 6.0);
+  p = dl::fma(p, r, 0.5);
   const double q = (r * r) * p;
-  const double e = 1.0 + (r + (q + (rl + rl * (r + q))));  // e^(r + rl) = e^r (1 + rl)
+  const double e = 1.0 + (r + (q + dl::fma(rl, r + q, rl)));  // e^(r + rl) = e^r (1 + rl)
   return scale2(e, k);
 }
 VM_FN double exp(double x) { return exp_ext(x, 0.0); }
@@ -129,20 +137,20 @@ VM_FN double log(double x) {
   const double s = f / (2.0 + f);
   const double z = s * s;
   double R = 2.0 / 23.0;
-  R = R * z + 2.0 / 21.0;
-  R = R * z + 2.0 / 19.0;
-  R = R * z + 2.0 / 17.0;
-  R = R * z + 2.0 / 15.0;
-  R = R * z + 2.0 / 13.0;
-  R = R * z + 2.0 / 11.0;
-  R = R * z + 2.0 / 9.0;
-  R = R * z + 2.0 / 7.0;
-  R = R * z + 2.0 / 5.0;
-  R = R * z + 2.0 / 3.0;
+  R = dl::fma(R, z, 2.0 / 21.0);
+  R = dl::fma(R, z, 2.0 / 19.0);
+  R = dl::fma(R, z, 2.0 / 17.0);
+  R = dl::fma(R, z, 2.0 / 15.0);
+  R = dl::fma(R, z, 2.0 / 13.0);
+  R = dl::fma(R, z, 2.0 / 11.0);
+  R = dl::fma(R, z, 2.0 / 9.0);
+  R = dl::fma(R, z, 2.0 / 7.0);
+  R = dl::fma(R, z, 2.0 / 5.0);
+  R = dl::fma(R, z, 2.0 / 3.0);
   R = R * z;
   const double hfsq = 0.5 * f * f;
   const double dk = (double)k;
-  return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+  return dl::fma(dk, ln2_hi, -((hfsq - dl::fma(s, hfsq + R, dk * ln2_lo)) - f));
 }
 
 VM_FN double log10(double x) {
@@ -150,7 +158,7 @@ VM_FN double log10(double x) {
   return dl::log(x) * inv_ln10;
 }
 
-// ---- extended-precision helpers for pow (no FMA: Veltkamp / Dekker splitting) ----
+// ---- extended-precision helpers for pow ----
 VM_IN void two_sum(double a, double b, double* s, double* e) {
   const double t = a + b;
   const double bb = t - a;
@@ -158,12 +166,8 @@ VM_IN void two_sum(double a, double b, double* s, double* e) {
   *s = t;
 }
 VM_IN void two_prod(double a, double b, double* p, double* e) {
-  const double split = 134217729.0;  // 2^27 + 1
-  const double ca = split * a, cb = split * b;
-  const double ah = ca - (ca - a), bh = cb - (cb - b);
-  const double al = a - ah, bl = b - bh;
   const double t = a * b;
-  *e = ((ah * bh - t) + ah * bl + al * bh) + al * bl;
+  *e = dl::fma(a, b, -t);
   *p = t;
 }
 // log(x) = *hi + *lo to ~2^-60 relative, x positive and finite
@@ -187,42 +191,40 @@ VM_IN void log_ext(double x, double* hi, double* lo) {
   double dh, dl_;
   two_sum(2.0, f, &dh, &dl_);  // 2 + f = dh + dl_
   const double sh = f / dh;
-  double ph, pl;
-  two_prod(sh, dh, &ph, &pl);
-  const double sl = (((f - ph) - pl) - sh * dl_) / dh;  // s = f / (2 + f) = sh + sl
+  const double sl = dl::fma(-sh, dl_, dl::fma(-sh, dh, f)) / dh;  // s = f / (2 + f) = sh + sl
   const double z = sh * sh;
   // 2 atanh(s) = 2 s + s R,  R = 2 z/3 + 2 z^2/5 + ...
   double R = 2.0 / 25.0;
-  R = R * z + 2.0 / 23.0;
-  R = R * z + 2.0 / 21.0;
-  R = R * z + 2.0 / 19.0;
-  R = R * z + 2.0 / 17.0;
-  R = R * z + 2.0 / 15.0;
-  R = R * z + 2.0 / 13.0;
-  R = R * z + 2.0 / 11.0;
-  R = R * z + 2.0 / 9.0;
-  R = R * z + 2.0 / 7.0;
-  R = R * z + 2.0 / 5.0;
-  R = R * z + 2.0 / 3.0;
+  R = dl::fma(R, z, 2.0 / 23.0);
+  R = dl::fma(R, z, 2.0 / 21.0);
+  R = dl::fma(R, z, 2.0 / 19.0);
+  R = dl::fma(R, z, 2.0 / 17.0);
+  R = dl::fma(R, z, 2.0 / 15.0);
+  R = dl::fma(R, z, 2.0 / 13.0);
+  R = dl::fma(R, z, 2.0 / 11.0);
+  R = dl::fma(R, z, 2.0 / 9.0);
+  R = dl::fma(R, z, 2.0 / 7.0);
+  R = dl::fma(R, z, 2.0 / 5.0);
+  R = dl::fma(R, z, 2.0 / 3.0);
   R = R * z;
   const double dk = (double)k;
   // k ln2_hi is exact (ln2_hi has 33 significant bits); sum the two leading terms exactly, the rest in double
   double h, e;
   two_sum(dk * ln2_hi, 2.0 * sh, &h, &e);
-  const double tail = e + ((sh * R + 2.0 * sl) + dk * ln2_lo);
+  const double tail = e + dl::fma(dk, ln2_lo, dl::fma(sh, R, 2.0 * sl));
   const double hh = h + tail;
   *lo = (h - hh) + tail;
   *hi = hh;
 }
 
 // pow(x, y) = exp(y log x) with the logarithm and the product carried in two doubles: ~1 ulp
-VM_IN double pow_pos(double x, double y) {
+VM_FN double pow_pos(double x, double y) {
   double lh, ll;
   log_ext(x, &lh, &ll);
   double ph, pl;
   two_prod(y, lh, &ph, &pl);
   if (!(ph > -1.0e300 && ph < 1.0e300)) return dl::exp(ph);  // overflow / underflow / NaN: plain path
-  return exp_ext(ph, pl + y * ll);
+  return exp_ext(ph, dl::fma(y, ll, pl));
 }
 
 VM_FN double pow(double x, double y) {
@@ -259,38 +261,38 @@ VM_IN double reduce_pio2(double x, int* q) {
   const double p3t = 8.47842766036889956997e-32;
   const double n = rint52(x * two_over_pi);
   *q = (int)((long long)n & 3);
-  double r = x - n * p1;
-  r = r - n * p2;
-  r = r - n * p3;
-  r = r - n * p3t;
+  double r = dl::fma(-n, p1, x);
+  r = dl::fma(-n, p2, r);
+  r = dl::fma(-n, p3, r);
+  r = dl::fma(-n, p3t, r);
   return r;
 }
 VM_IN double sin_kernel(double r) {  // |r| <= pi/4: r - r^3/3! + ... - r^19/19!
   const double z = r * r;
   double p = -1.0 / 121645100408832000.0;
-  p = p * z + 1.0 / 355687428096000.0;
-  p = p * z - 1.0 / 1307674368000.0;
-  p = p * z + 1.0 / 6227020800.0;
-  p = p * z - 1.0 / 39916800.0;
-  p = p * z + 1.0 / 362880.0;
-  p = p * z - 1.0 / 5040.0;
-  p = p * z + 1.0 / 120.0;
-  p = p * z - 1.0 / 6.0;
-  return r + r * (z * p);
+  p = dl::fma(p, z, 1.0 / 355687428096000.0);
+  p = dl::fma(p, z, -(1.0 / 1307674368000.0));
+  p = dl::fma(p, z, 1.0 / 6227020800.0);
+  p = dl::fma(p, z, -(1.0 / 39916800.0));
+  p = dl::fma(p, z, 1.0 / 362880.0);
+  p = dl::fma(p, z, -(1.0 / 5040.0));
+  p = dl::fma(p, z, 1.0 / 120.0);
+  p = dl::fma(p, z, -(1.0 / 6.0));
+  return dl::fma(r, z * p, r);
 }
 VM_IN double cos_kernel(double r) {  // 1 - r^2/2! + ... + r^20/20!
   const double z = r * r;
   double p = 1.0 / 2432902008176640000.0;
-  p = p * z - 1.0 / 6402373705728000.0;
-  p = p * z + 1.0 / 20922789888000.0;
-  p = p * z - 1.0 / 87178291200.0;
-  p = p * z + 1.0 / 479001600.0;
-  p = p * z - 1.0 / 3628800.0;
-  p = p * z + 1.0 / 40320.0;
-  p = p * z - 1.0 / 720.0;
-  p = p * z + 1.0 / 24.0;
+  p = dl::fma(p, z, -(1.0 / 6402373705728000.0));
+  p = dl::fma(p, z, 1.0 / 20922789888000.0);
+  p = dl::fma(p, z, -(1.0 / 87178291200.0));
+  p = dl::fma(p, z, 1.0 / 479001600.0);
+  p = dl::fma(p, z, -(1.0 / 3628800.0));
+  p = dl::fma(p, z, 1.0 / 40320.0);
+  p = dl::fma(p, z, -(1.0 / 720.0));
+  p = dl::fma(p, z, 1.0 / 24.0);
   const double hz = 0.5 * z;
-  return (1.0 - hz) + z * (z * p);
+  return dl::fma(z, z * p, 1.0 - hz);
 }
 VM_FN double sin(double x) {
   if (x != x || x == pinf() || x == -pinf()) return qnan();

@@ -22,11 +22,12 @@ struct SnowPackEB {
   RaUsed* Ra_used;
   double *AdvectedEnergy, *AdvectedSensibleHeat, *DeltaColdContent, *GroundFlux, *LatentHeat, *LatentHeatSub, *NetLongUnder,
       *RefreezeEnergy, *SensibleHeat, *vapor_flux, *blowing_flux, *surface_flux;
+  StabLog stab;
 
   VIC_HDI double operator()(double TSurf) {
     const double TMean = TSurf;
     const double Density = RHO_W;
-    if (Wind > 0.0) Ra_used->surface = Ra / stability_correction(Z, 0., TMean, Tair, Wind, Z0_snow);
+    if (Wind > 0.0) Ra_used->surface = Ra / stab.correction(Z, 0., TMean, Tair, Wind, Z0_snow);
     else Ra_used->surface = HUGE_RESIST;
     const double Tmp = TMean + KELVIN;
     *NetLongUnder = LongSnowIn - STEFAN_B * Tmp * Tmp * Tmp * Tmp;
@@ -120,6 +121,7 @@ VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy
   snow.surf_water += RainFall;
 
   SnowPackEB eb;
+  eb.stab.reset();
   eb.Dt = delta_t; eb.Ra = aero_resist; eb.Z = z2; eb.Z0_snow = Z0_snow; eb.AirDens = density; eb.EactAir = vp;
   eb.LongSnowIn = LongSnowIn; eb.Lv = latent_heat_Le; eb.Press = pressure; eb.Rain = RainFall; eb.NetShortUnder = NetShortSnow;
   eb.Vpd = vpd; eb.Wind = wind; eb.OldTSurf = out.OldTSurf; eb.SnowDepth = snow.depth; eb.SnowDensity = snow.density;
@@ -311,6 +313,8 @@ struct CanopyEB {
   SoilLayer* layer;
   VegVar* vv;
   double *Evap, *AdvectedEnergy, *LatentHeat, *LatentHeatSub, *LongOverOut, *NetLongOver, *NetRadiation, *RefreezeEnergy, *SensibleHeat, *VaporMassFlux;
+  StabLog stab;
+  EvapMemo memo;
 
   VIC_HDI double operator()(double Tfoliage) {
     const double Tmp = Tfoliage + KELVIN;
@@ -325,7 +329,7 @@ struct CanopyEB {
       const double EsSnow = svp(Tfoliage);
       if (ar == AR_COMBO || ar == AR_410) {
         if ((*wind_speed)[CANOPY_OVER] > 0.0)
-          Ra_used->overstory /= stability_correction((*ref_height)[CANOPY_OVER], (*displacement)[CANOPY_OVER], Tfoliage, Tcanopy,
+          Ra_used->overstory /= stab.correction((*ref_height)[CANOPY_OVER], (*displacement)[CANOPY_OVER], Tfoliage, Tcanopy,
                                                      (*wind_speed)[CANOPY_OVER], (*roughness)[CANOPY_OVER]);
         else Ra_used->overstory = HUGE_RESIST;
       }
@@ -351,7 +355,7 @@ struct CanopyEB {
       // same object (snow_intercept is handed &veg_var_wet->Wdew), so the write-back below is the
       // division the reference applies to that object.
       *Evap = canopy_evap(layer, *vv, false, *veg, *Wdew, delta_t, *NetRadiation, Vpd, NetShortOver, Tcanopy, Ra_used->overstory, elevation,
-                          prec, *soil);
+                          prec, *soil, &memo);
       *Wdew = vv->Wdew / 1000.;
       vv->Wdew = *Wdew;
       *LatentHeat = latent_heat_Le * *Evap * RHO_W;
@@ -483,6 +487,8 @@ VIC_HDI int snow_intercept(double Dt, double LAI, double latent_heat_Le, double 
 
   // canopy energy balance
   CanopyEB eb;
+  eb.stab.reset();
+  eb.memo.reset();
   eb.delta_t = Dt; eb.elevation = cp(CP_elevation); eb.AirDens = AirDens; eb.EactAir = EactAir; eb.Press = Press;
   eb.latent_heat_Le = latent_heat_Le; eb.Tcanopy = Tcanopy; eb.Vpd = Vpd; eb.IntRain = IntRainOrg; eb.LongOverIn = LongOverIn;
   eb.LongUnderOut = LongUnderOut; eb.AERO_RESIST_CANSNOW = o.AERO_RESIST_CANSNOW;

@@ -39,6 +39,31 @@ struct SurfEB {
   VegVar* vv;
   int* FIRST_SOLN;
   double *NetLongBare, *NetLongSnow, *T1, *deltaH, *fusion, *grnd_flux, *latent_heat, *latent_heat_sub, *sensible_heat, *snow_flux, *store_error;
+  // sub-expressions of the residual that do not depend on the trial temperature, evaluated once per solve (same operations,
+  // same order as func_surf_energy_bal.c / estimate_T1.c evaluate them at every trial)
+  double t1_k1, t1_b, t1_c, t1_den, gf_k1, gf_k2e, sc_lg;
+  int sc_lg_ok;
+  EvapMemo memo;
+
+  VIC_HD void prepare() {
+    memo.reset();
+    sc_lg_ok = 0;
+    sc_lg = 0;
+    t1_k1 = t1_b = t1_c = t1_den = gf_k1 = gf_k2e = 0;
+    if (o->QUICK_FLUX) {
+      // estimate_T1.c:8-47 with Ts factored out
+      const double e_mD1 = vexp(-D1 / dp);
+      const double C1 = Cs2 * dp / D2 * (1. - vexp(-D2 / dp));
+      const double C2 = -(1. - vexp(D1 / dp)) * vexp(-D2 / dp);
+      const double C3 = kappa1 / D1 - kappa2 / D1 + kappa2 / D1 * e_mD1;
+      t1_k1 = kappa1 / 2. / D1 / D2;
+      t1_b = C1 / delta_t * T1_old;
+      t1_c = (2. * C2 - 1. + e_mD1) * kappa2 / 2. / D1 / D2 * T2;
+      t1_den = (C1 / delta_t + kappa2 / D1 / D2 * C2 + C3 / 2. / D2);
+      gf_k1 = kappa1 / D1;
+      gf_k2e = kappa2 / D2 * (1. - e_mD1);
+    }
+  }
 
   VIC_HDI double operator()(double Ts) {
     const double TMean = Ts;
@@ -50,9 +75,9 @@ struct SurfEB {
     } else *snow_flux = 0;
     const double cover = (snow_coverage + (1. - snow_coverage) * surf_atten);
     if (o->QUICK_FLUX) {
-      *T1 = estimate_T1(TMean, T1_old, T2, D1, D2, kappa1, kappa2, Cs1, Cs2, dp, delta_t);
-      if (o->GRND_FLUX_TYPE == GF_406) *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean));
-      else *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean) + (kappa2 / D2 * (1. - vexp(-D1 / dp)) * (T2 - (*T1)))) / 2.;
+      *T1 = (t1_k1 * (TMean) + t1_b + t1_c) / t1_den;
+      if (o->GRND_FLUX_TYPE == GF_406) *grnd_flux = cover * (gf_k1 * ((*T1) - TMean));
+      else *grnd_flux = cover * (gf_k1 * ((*T1) - TMean) + (gf_k2e * (T2 - (*T1)))) / 2.;
     } else {
       T_node[0] = TMean;
       int Error = solve_T_profile<NN>(Tnew_node, T_node, Tnew_fbflag, Tnew_fbcount, kappa_node, Cs_node, moist_node, delta_t, ice_node, dp,
@@ -85,19 +110,22 @@ struct SurfEB {
     (*NetLongBare) = (LongBareIn - (1. - snow_coverage) * LongBareOut);
     const double NetBareRad = (NetShortBare + (*NetLongBare) + *grnd_flux + *deltaH + *fusion);
     const double ws = (*wind_speed)[UnderStory];
-    if (ws > 0.0 && overstory && SNOWING)
-      aero_resist_used->surface = (*aero_resist)[UnderStory] / stability_correction((*ref_height)[UnderStory], 0., TMean, Tair, ws, (*roughness)[UnderStory]);
-    else if (ws > 0.0)
-      aero_resist_used->surface = (*aero_resist)[UnderStory] /
-                                  stability_correction((*ref_height)[UnderStory], (*displacement)[UnderStory], TMean, Tair, ws, (*roughness)[UnderStory]);
-    else aero_resist_used->surface = HUGE_RESIST;
+    if (ws > 0.0) {
+      // the displacement height is dropped under a snowing overstory (func_surf_energy_bal.c:280-296); which case applies is fixed for the solve
+      const double Zr = (*ref_height)[UnderStory], dr = (overstory && SNOWING) ? 0. : (*displacement)[UnderStory];
+      if (!sc_lg_ok && TMean != Tair) {
+        sc_lg = vlog((Zr - dr) / (*roughness)[UnderStory]);
+        sc_lg_ok = 1;
+      }
+      aero_resist_used->surface = (*aero_resist)[UnderStory] / stability_correction_lg(Zr, dr, TMean, Tair, ws, sc_lg);
+    } else aero_resist_used->surface = HUGE_RESIST;
     double Evap;
     if (VEG && !SNOWING && veg->LAI > 0) {
       Evap = canopy_evap(layer, *vv, true, *veg, Wdew, delta_t, NetBareRad, vpd, NetShortBare, Tair, aero_resist_used->overstory,
-                         (*cp)(CP_elevation), rainfall, *soil);
+                         (*cp)(CP_elevation), rainfall, *soil, &memo);
     } else if (!SNOWING) {
       Evap = arno_evap(layer, NetBareRad, Tair, vpd, cp->layer(CL_depth, 0), max_moist * cp->layer(CL_depth, 0) * 1000., (*cp)(CP_elevation),
-                       (*cp)(CP_b_infilt), aero_resist_used->surface, delta_t, cp->layer(CL_resid_moist, 0));
+                       (*cp)(CP_b_infilt), aero_resist_used->surface, delta_t, cp->layer(CL_resid_moist, 0), &memo);
     } else Evap = 0.;
     *latent_heat = -RHO_W * latent_heat_Le * Evap;
     *latent_heat_sub = 0.;
@@ -196,6 +224,7 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   eb.NetLongBare = &NetLongBare; eb.NetLongSnow = &TmpNetLongSnow; eb.T1 = &T1; eb.deltaH = &energy.deltaH; eb.fusion = &energy.fusion;
   eb.grnd_flux = &energy.grnd_flux; eb.latent_heat = &energy.latent; eb.latent_heat_sub = &energy.latent_sub; eb.sensible_heat = &energy.sensible;
   eb.snow_flux = &energy.snow_flux; eb.store_error = &energy.error;
+  eb.prepare();
 
   if (o.FULL_ENERGY) {
     double T_lower, T_upper;
