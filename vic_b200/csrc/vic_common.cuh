@@ -114,6 +114,11 @@ VIC_HD double vcos(double a) { return dl::cos(a); }
 VIC_HD double vacos(double a) { return dl::acos(a); }
 #endif
 
+// a / b where b is known to be positive and finite (a time step, a density, a count of sub-steps, a resistance).  The device's
+// IEEE double division branches to a ~70-instruction subroutine when the numerator is zero or tiny; 0 / b is the numerator itself
+// (sign included), so that case is returned directly -- the same value the division gives.
+VIC_HD double div_pos(double a, double b) { return (a == 0.0) ? a : a / b; }
+
 VIC_HD double vnan() {
 #if defined(__CUDA_ARCH__)
   return __longlong_as_double(0x7ff8000000000000LL);

@@ -141,7 +141,7 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
 // and by cell within a kind, so that the threads of a warp (consecutive rows) take the same branches of the step
 // (surface_fluxes vs surface_fluxes_glac, overstory canopy balance, transpiration vs bare-soil evaporation) and the warps
 // of a block run through the same code.  hrupar_rm: the caller's row-major HRU parameter records.
-inline void bin_hrus(const double* hrupar_rm, int nhru, std::vector<int>& hru_of_slot, std::vector<int>& slot_of_hru) {
+inline void bin_hrus(const double* hrupar_rm, int nhru, std::vector<int>& hru_of_slot, std::vector<int>& slot_of_hru, int deal_blocks = 0) {
   std::vector<long long> key((size_t)nhru);
   for (int k = 0; k < nhru; k++) {
     const double* p = hrupar_rm + (size_t)k * HP_N;
@@ -153,6 +153,20 @@ inline void bin_hrus(const double* hrupar_rm, int nhru, std::vector<int>& hru_of
   hru_of_slot.resize((size_t)nhru);
   for (int k = 0; k < nhru; k++) hru_of_slot[k] = k;
   std::stable_sort(hru_of_slot.begin(), hru_of_slot.end(), [&](int a, int b) { return key[a] < key[b]; });
+  // deal_blocks > 0: the full warps (32 consecutive rows) of the kind-sorted order are dealt round-robin into that many piles and
+  // the piles concatenated, so that every thread block holds a similar mix of cheap and expensive kinds (a block of bare-soil
+  // HRUs finishes long before a block of forest HRUs; with one block per SM the slowest block is the kernel's duration) while a
+  // warp still holds one kind.
+  if (deal_blocks > 1) {
+    const int nfull = nhru / 32;
+    std::vector<int> dealt;
+    dealt.reserve((size_t)nhru);
+    for (int p = 0; p < deal_blocks; p++)
+      for (int w = p; w < nfull; w += deal_blocks)
+        for (int l = 0; l < 32; l++) dealt.push_back(hru_of_slot[(size_t)w * 32 + l]);
+    for (int k = nfull * 32; k < nhru; k++) dealt.push_back(hru_of_slot[k]);
+    hru_of_slot.swap(dealt);
+  }
   slot_of_hru.resize((size_t)nhru);
   for (int s = 0; s < nhru; s++) slot_of_hru[hru_of_slot[s]] = s;
 }

@@ -187,7 +187,7 @@ VIC_HDI double canopy_evap(SoilLayer* layer, VegVar& vv, bool CALC_EVAP, const V
     layer[i].evap = layerevap[i];
     tmp_Evap += layerevap[i];
   }
-  return 0 + tmp_Evap * 1.0 / (1000. * delta_t);
+  return 0 + div_pos(tmp_Evap * 1.0, (1000. * delta_t));
 }
 
 // arno_evap.c:61-228; returns evaporation [m/s] or ERROR_D.  Only Epot depends on the net radiation and the resistance: the
@@ -246,7 +246,7 @@ VIC_HDI double arno_evap(SoilLayer* layer, double rad, double air_temp, double v
     } else evap = 0.0;
   }
   layer[0].evap = evap;
-  return 0 + evap / 1000. / delta_t * 1.0;
+  return 0 + div_pos(div_pos(evap, 1000.), delta_t) * 1.0;
 }
 
 // compute_pot_evap.c:8-78.  aero[p] = {surface, overstory} resistances already corrected for

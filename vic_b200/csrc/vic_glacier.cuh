@@ -31,7 +31,7 @@ struct GlacierEB {
     (*NetLongUnder) = LongSnowIn - STEFAN_B * Tmp * Tmp * Tmp * Tmp;
     const double NetRad = NetShortUnder + (*NetLongUnder);
     *SensibleHeat = AirDens * Cp * (Tair - TSurf) / Ra_used->surface;
-    double VaporMassFlux = *vapor_flux * Density / Dt;
+    double VaporMassFlux = div_pos(*vapor_flux * Density, Dt);
     // latent_heat_from_glacier.c
     {
       const double EsSnow = svp(TSurf);
@@ -47,9 +47,9 @@ struct GlacierEB {
       }
     }
     *vapor_flux = VaporMassFlux * Dt / Density;
-    if (TSurf == 0) *AdvectedEnergy = (CH_WATER * (Tair)*Rain) / (Dt);
+    if (TSurf == 0) *AdvectedEnergy = div_pos((CH_WATER * (Tair)*Rain), (Dt));
     else *AdvectedEnergy = 0.;
-    *DeltaColdContent = CH_ICE * temp_IceDepth * (TMean - OldTMean) / (Dt);
+    *DeltaColdContent = div_pos(CH_ICE * temp_IceDepth * (TMean - OldTMean), (Dt));
     *GroundFlux = (GLAC_K_ICE + TSurf * (-0.0142)) * (TGrnd - TSurf) / temp_IceDepth;
     const double Fbal = NetRad + *SensibleHeat + *LatentHeat + *LatentHeatSub + *AdvectedEnergy;
     double RestTerm = Fbal - *DeltaColdContent + *GroundFlux;
@@ -387,23 +387,23 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
   hru.glac.ice_mass_balance = hru.glac.accumulation - hru.glac.melt - hru.glac.vapor_flux;
   hru.energy = step_energy;
   hru.energy.AlbedoOver = 0 / N;
-  hru.energy.AlbedoUnder = st_AlbedoUnder / N;
-  hru.energy.AtmosLatent = st_AtmosLatent / N;
-  hru.energy.AtmosLatentSub = st_AtmosLatentSub / N;
-  hru.energy.AtmosSensible = st_AtmosSensible / N;
+  hru.energy.AlbedoUnder = div_pos(st_AlbedoUnder, N);
+  hru.energy.AtmosLatent = div_pos(st_AtmosLatent, N);
+  hru.energy.AtmosLatentSub = div_pos(st_AtmosLatentSub, N);
+  hru.energy.AtmosSensible = div_pos(st_AtmosSensible, N);
   hru.energy.LongOverIn = 0 / N;
-  hru.energy.LongUnderIn = st_LongUnderIn / N;
-  hru.energy.LongUnderOut = st_LongUnderOut / N;
-  hru.energy.NetLongAtmos = st_NetLongAtmos / N;
+  hru.energy.LongUnderIn = div_pos(st_LongUnderIn, N);
+  hru.energy.LongUnderOut = div_pos(st_LongUnderOut, N);
+  hru.energy.NetLongAtmos = div_pos(st_NetLongAtmos, N);
   hru.energy.NetLongOver = 0 / N;
-  hru.energy.NetLongUnder = st_NetLongUnder / N;
-  hru.energy.NetShortAtmos = st_NetShortAtmos / N;
+  hru.energy.NetLongUnder = div_pos(st_NetLongUnder, N);
+  hru.energy.NetShortAtmos = div_pos(st_NetShortAtmos, N);
   hru.energy.NetShortGrnd = 0 / N;
   hru.energy.NetShortOver = 0 / N;
-  hru.energy.NetShortUnder = st_NetShortUnder / N;
+  hru.energy.NetShortUnder = div_pos(st_NetShortUnder, N);
   hru.energy.ShortOverIn = 0 / N;
-  hru.energy.ShortUnderIn = st_ShortUnderIn / N;
-  hru.energy.advected_sensible = st_advected_sensible / N;
+  hru.energy.ShortUnderIn = div_pos(st_ShortUnderIn, N);
+  hru.energy.advected_sensible = div_pos(st_advected_sensible, N);
   hru.energy.canopy_advection = 0 / N;
   hru.energy.canopy_latent = 0 / N;
   hru.energy.canopy_latent_sub = 0 / N;
@@ -411,18 +411,18 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
   hru.energy.canopy_sensible = 0 / N;
   hru.energy.deltaH = 0 / N;
   hru.energy.fusion = 0 / N;
-  hru.energy.grnd_flux = st_grnd_flux / N;
-  hru.energy.latent = st_latent / N;
-  hru.energy.latent_sub = st_latent_sub / N;
-  hru.energy.melt_energy = st_melt_energy / N;
-  hru.energy.sensible = st_sensible / N;
-  hru.energy.glacier_flux = st_glacier_flux / N;
-  hru.energy.deltaCC_glac = st_deltaCC_glac / N;
-  hru.energy.glacier_melt_energy = st_glacier_melt_energy / N;
-  hru.energy.advection = st_advection / N;
-  hru.energy.deltaCC = st_deltaCC / N;
-  hru.energy.refreeze_energy = st_refreeze_energy / N;
-  hru.energy.snow_flux = st_snow_flux / N;
+  hru.energy.grnd_flux = div_pos(st_grnd_flux, N);
+  hru.energy.latent = div_pos(st_latent, N);
+  hru.energy.latent_sub = div_pos(st_latent_sub, N);
+  hru.energy.melt_energy = div_pos(st_melt_energy, N);
+  hru.energy.sensible = div_pos(st_sensible, N);
+  hru.energy.glacier_flux = div_pos(st_glacier_flux, N);
+  hru.energy.deltaCC_glac = div_pos(st_deltaCC_glac, N);
+  hru.energy.glacier_melt_energy = div_pos(st_glacier_melt_energy, N);
+  hru.energy.advection = div_pos(st_advection, N);
+  hru.energy.deltaCC = div_pos(st_deltaCC, N);
+  hru.energy.refreeze_energy = div_pos(st_refreeze_energy, N);
+  hru.energy.snow_flux = div_pos(st_snow_flux, N);
   hru.energy.Tcanopy = Tcanopy;
   // the canopy stores of a glacier tile are never touched by the sub-steps
   hru.veg.throughfall = 0.;

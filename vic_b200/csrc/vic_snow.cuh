@@ -34,21 +34,21 @@ struct SnowPackEB {
     const double NetRad = NetShortUnder + (*NetLongUnder);
     *SensibleHeat = AirDens * Cp * (Tair - TMean) / Ra_used->surface;
     *AdvectedSensibleHeat = 0;
-    double VaporMassFlux = *vapor_flux * Density / Dt;
-    double BlowingMassFlux = *blowing_flux * Density / Dt;
-    double SurfaceMassFlux = *surface_flux * Density / Dt;
+    double VaporMassFlux = div_pos(*vapor_flux * Density, Dt);
+    double BlowingMassFlux = div_pos(*blowing_flux * Density, Dt);
+    double SurfaceMassFlux = div_pos(*surface_flux * Density, Dt);
     latent_heat_from_snow(AirDens, EactAir, Lv, Press, Ra_used->surface, TMean, Vpd, LatentHeat, LatentHeatSub, &VaporMassFlux,
                           &BlowingMassFlux, &SurfaceMassFlux);
-    *vapor_flux = VaporMassFlux * Dt / Density;
-    *blowing_flux = BlowingMassFlux * Dt / Density;
-    *surface_flux = SurfaceMassFlux * Dt / Density;
-    if (TMean == 0) *AdvectedEnergy = (CH_WATER * (Tair)*Rain) / (Dt);
+    *vapor_flux = div_pos(VaporMassFlux * Dt, Density);
+    *blowing_flux = div_pos(BlowingMassFlux * Dt, Density);
+    *surface_flux = div_pos(SurfaceMassFlux * Dt, Density);
+    if (TMean == 0) *AdvectedEnergy = div_pos((CH_WATER * (Tair)*Rain), (Dt));
     else *AdvectedEnergy = 0.;
-    *DeltaColdContent = CH_ICE * SweSurfaceLayer * (TSurf - OldTSurf) / (Dt);
+    *DeltaColdContent = div_pos(CH_ICE * SweSurfaceLayer * (TSurf - OldTSurf), (Dt));
     if (SnowDepth > 0.) *GroundFlux = K_SNOW * SnowDensity * SnowDensity * (TGrnd - TMean) / SnowDepth / (Dt);
     else *GroundFlux = 0;
     double RestTerm = NetRad + *SensibleHeat + *LatentHeat + *LatentHeatSub + *AdvectedEnergy + *AdvectedSensibleHeat - *DeltaColdContent + *GroundFlux;
-    *RefreezeEnergy = (SurfaceLiquidWater * Lf * Density) / (Dt);
+    *RefreezeEnergy = div_pos((SurfaceLiquidWater * Lf * Density), (Dt));
     if (TSurf == 0.0 && RestTerm > -(*RefreezeEnergy)) {
       *RefreezeEnergy = -RestTerm;
       RestTerm = 0.0;
@@ -356,16 +356,16 @@ struct CanopyEB {
       // division the reference applies to that object.
       *Evap = canopy_evap(layer, *vv, false, *veg, *Wdew, delta_t, *NetRadiation, Vpd, NetShortOver, Tcanopy, Ra_used->overstory, elevation,
                           prec, *soil, &memo);
-      *Wdew = vv->Wdew / 1000.;
+      *Wdew = div_pos(vv->Wdew, 1000.);
       vv->Wdew = *Wdew;
       *LatentHeat = latent_heat_Le * *Evap * RHO_W;
       *LatentHeatSub = 0;
     }
     *SensibleHeat = AirDens * Cp * (Tcanopy - Tfoliage) / Ra_used->overstory;
-    *AdvectedEnergy = (4186.8 * Tcanopy * Rainfall[0]) / (delta_t);
+    *AdvectedEnergy = div_pos((4186.8 * Tcanopy * Rainfall[0]), (delta_t));
     double RestTerm = *SensibleHeat + *LatentHeat + *LatentHeatSub + *NetRadiation + *AdvectedEnergy;
     if (IntSnow > 0) {
-      *RefreezeEnergy = (IntRain * Lf * RHO_W) / (delta_t);
+      *RefreezeEnergy = div_pos((IntRain * Lf * RHO_W), (delta_t));
       if (Tfoliage == 0.0 && RestTerm > -(*RefreezeEnergy)) {
         *RefreezeEnergy = -RestTerm;
         RestTerm = 0.0;

@@ -87,8 +87,8 @@ struct SurfEB {
       if (o->GRND_FLUX_TYPE == GF_406) *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean));
       else *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean) + (kappa2 / D2 * (Tnew_node[2] - (*T1)))) / 2.;
     }
-    if (o->GRND_FLUX_TYPE == GF_FULL) *deltaH = cover * (Cs1 * ((Ts_old + T1_old) - (TMean + *T1)) * D1 / delta_t / 2.);
-    else *deltaH = (Cs1 * ((Ts_old + T1_old) - (TMean + *T1)) * D1 / delta_t / 2.);
+    if (o->GRND_FLUX_TYPE == GF_FULL) *deltaH = cover * (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + *T1)) * D1, delta_t) / 2.);
+    else *deltaH = (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + *T1)) * D1, delta_t) / 2.);
     if (((*cp)(CP_FS_ACTIVE) != 0.0) && o->FROZEN_SOIL) {
       double ice;
       if ((TMean + *T1) / 2. < 0.) {
@@ -99,9 +99,9 @@ struct SurfEB {
       else *fusion = (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
     }
     if (INCLUDE_SNOW) {
-      if (TMean > 0) *deltaCC = CH_ICE * (snow_swq - snow_water) * (0 - OldTSurf) / delta_t;
-      else *deltaCC = CH_ICE * (snow_swq - snow_water) * (TMean - OldTSurf) / delta_t;
-      *refreeze_energy = (snow_water * Lf * snow_density) / delta_t;
+      if (TMean > 0) *deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (0 - OldTSurf), delta_t);
+      else *deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (TMean - OldTSurf), delta_t);
+      *refreeze_energy = div_pos((snow_water * Lf * snow_density), delta_t);
       *deltaCC *= snow_coverage;
       *refreeze_energy *= snow_coverage;
     }
@@ -130,17 +130,17 @@ struct SurfEB {
     *latent_heat = -RHO_W * latent_heat_Le * Evap;
     *latent_heat_sub = 0.;
     if (INCLUDE_SNOW) {
-      double VaporMassFlux = *vapor_flux * ice_density / delta_t;
-      double BlowingMassFlux = *blowing_flux * ice_density / delta_t;
-      double SurfaceMassFlux = *surface_flux * ice_density / delta_t;
+      double VaporMassFlux = div_pos(*vapor_flux * ice_density, delta_t);
+      double BlowingMassFlux = div_pos(*blowing_flux * ice_density, delta_t);
+      double SurfaceMassFlux = div_pos(*surface_flux * ice_density, delta_t);
       double tl, tls;
       latent_heat_from_snow(atmos_density, vp, latent_heat_Le, atmos_pressure, aero_resist_used->surface, TMean, vpd, &tl, &tls, &VaporMassFlux,
                             &BlowingMassFlux, &SurfaceMassFlux);
       *latent_heat += tl * snow_coverage;
       *latent_heat_sub = tls * snow_coverage;
-      *vapor_flux = VaporMassFlux * delta_t / ice_density;
-      *blowing_flux = BlowingMassFlux * delta_t / ice_density;
-      *surface_flux = SurfaceMassFlux * delta_t / ice_density;
+      *vapor_flux = div_pos(VaporMassFlux * delta_t, ice_density);
+      *blowing_flux = div_pos(BlowingMassFlux * delta_t, ice_density);
+      *surface_flux = div_pos(SurfaceMassFlux * delta_t, ice_density);
     } else *latent_heat *= (1. - snow_coverage);
     if (snow_coverage < 1 || INCLUDE_SNOW) {
       *sensible_heat = atmos_density * Cp * (Tair - (TMean)) / aero_resist_used->surface;
@@ -575,16 +575,19 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
   else snow_flux = -(energy.grnd_flux + energy.deltaH + energy.fusion);
   energy.refreeze_energy = 0;
   double coverage = snow.coverage;
-  // working copies: snow-side and ground-side energy records, snow pack, layers, canopy stores
+  // The reference works on copies (snow-side and ground-side energy records, snow pack, layers, canopy stores) and copies
+  // them back at the end of the step.  Here the ground-side energy record, the snow pack and the layers ARE the HRU's own
+  // records: nothing reads the HRU's originals once the sub-steps have started except the ground temperature handed to
+  // solve_snow (surface_fluxes.c:433 reads energy->T[0], which the reference only updates after the last sub-step), saved below.
+  // Only the snow-side energy record, which evolves separately, is a copy.  A failed step returns ERROR_I and the caller
+  // drops the whole working set, so the in-place updates never reach the stored state.
   EnergyBal<NN> snow_energy = energy;
-  EnergyBal<NN> soil_energy = energy;
+  EnergyBal<NN>& soil_energy = energy;
+  const double Tgrnd_step = energy.T[0];
   VegVar snow_vv = hru.veg, soil_vv = hru.veg;
-  SnowPack step_snow = snow;
-  SoilLayer step_layer[NL];
-  for (int l = 0; l < NL; l++) {
-    step_layer[l] = cell.layer[l];
-    step_layer[l].evap = 0;
-  }
+  SnowPack& step_snow = snow;
+  SoilLayer* step_layer = cell.layer;
+  for (int l = 0; l < NL; l++) step_layer[l].evap = 0;
   soil_vv.canopyevap = 0;
   snow_vv.canopyevap = 0;
   soil_vv.throughfall = 0;
@@ -623,7 +626,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
   do {
     const double Tair = f(FV_air_temp, hidx) + Tfactor;
     const double step_prec = f(FV_prec, hidx) / hru.mu * Pfactor;
-    const double Tgrnd = energy.T[0];
+    const double Tgrnd = Tgrnd_step;
     const double Tcanopy = Tair;
     const double VPcanopy = f(FV_vp, hidx);
     const double VPDcanopy = f(FV_vpd, hidx);
@@ -796,7 +799,6 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
 
   // ---- store the step's results
   const double N = (double)N_steps;
-  snow = step_snow;
   snow.vapor_flux = st_vapor_flux;
   snow.blowing_flux = st_blowing_flux;
   snow.surface_flux = st_surface_flux;
@@ -804,42 +806,41 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
   out.Melt = st_melt;
   snow.melt = st_melt;
   double ppt = st_ppt;
-  energy = soil_energy;
-  energy.AlbedoOver = st_AlbedoOver / N;
-  energy.AlbedoUnder = st_AlbedoUnder / N;
-  energy.AtmosLatent = st_AtmosLatent / N;
-  energy.AtmosLatentSub = st_AtmosLatentSub / N;
-  energy.AtmosSensible = st_AtmosSensible / N;
-  energy.LongOverIn = st_LongOverIn / N;
-  energy.LongUnderIn = st_LongUnderIn / N;
-  energy.LongUnderOut = st_LongUnderOut / N;
-  energy.NetLongAtmos = st_NetLongAtmos / N;
-  energy.NetLongOver = st_NetLongOver / N;
-  energy.NetLongUnder = st_NetLongUnder / N;
-  energy.NetShortAtmos = st_NetShortAtmos / N;
-  energy.NetShortGrnd = st_NetShortGrnd / N;
-  energy.NetShortOver = st_NetShortOver / N;
-  energy.NetShortUnder = st_NetShortUnder / N;
-  energy.ShortOverIn = st_ShortOverIn / N;
-  energy.ShortUnderIn = st_ShortUnderIn / N;
-  energy.advected_sensible = st_advected_sensible / N;
-  energy.canopy_advection = st_canopy_advection / N;
-  energy.canopy_latent = st_canopy_latent / N;
-  energy.canopy_latent_sub = st_canopy_latent_sub / N;
-  energy.canopy_refreeze = st_canopy_refreeze / N;
-  energy.canopy_sensible = st_canopy_sensible / N;
-  energy.deltaH = st_deltaH / N;
-  energy.fusion = st_fusion / N;
-  energy.grnd_flux = st_grnd_flux / N;
-  energy.latent = st_latent / N;
-  energy.latent_sub = st_latent_sub / N;
-  energy.melt_energy = st_melt_energy / N;
-  energy.sensible = st_sensible / N;
+  energy.AlbedoOver = div_pos(st_AlbedoOver, N);
+  energy.AlbedoUnder = div_pos(st_AlbedoUnder, N);
+  energy.AtmosLatent = div_pos(st_AtmosLatent, N);
+  energy.AtmosLatentSub = div_pos(st_AtmosLatentSub, N);
+  energy.AtmosSensible = div_pos(st_AtmosSensible, N);
+  energy.LongOverIn = div_pos(st_LongOverIn, N);
+  energy.LongUnderIn = div_pos(st_LongUnderIn, N);
+  energy.LongUnderOut = div_pos(st_LongUnderOut, N);
+  energy.NetLongAtmos = div_pos(st_NetLongAtmos, N);
+  energy.NetLongOver = div_pos(st_NetLongOver, N);
+  energy.NetLongUnder = div_pos(st_NetLongUnder, N);
+  energy.NetShortAtmos = div_pos(st_NetShortAtmos, N);
+  energy.NetShortGrnd = div_pos(st_NetShortGrnd, N);
+  energy.NetShortOver = div_pos(st_NetShortOver, N);
+  energy.NetShortUnder = div_pos(st_NetShortUnder, N);
+  energy.ShortOverIn = div_pos(st_ShortOverIn, N);
+  energy.ShortUnderIn = div_pos(st_ShortUnderIn, N);
+  energy.advected_sensible = div_pos(st_advected_sensible, N);
+  energy.canopy_advection = div_pos(st_canopy_advection, N);
+  energy.canopy_latent = div_pos(st_canopy_latent, N);
+  energy.canopy_latent_sub = div_pos(st_canopy_latent_sub, N);
+  energy.canopy_refreeze = div_pos(st_canopy_refreeze, N);
+  energy.canopy_sensible = div_pos(st_canopy_sensible, N);
+  energy.deltaH = div_pos(st_deltaH, N);
+  energy.fusion = div_pos(st_fusion, N);
+  energy.grnd_flux = div_pos(st_grnd_flux, N);
+  energy.latent = div_pos(st_latent, N);
+  energy.latent_sub = div_pos(st_latent_sub, N);
+  energy.melt_energy = div_pos(st_melt_energy, N);
+  energy.sensible = div_pos(st_sensible, N);
   if ((snow.snow != 0.0) || INCLUDE_SNOW) {
-    energy.advection = st_advection / N;
-    energy.deltaCC = st_deltaCC / N;
-    energy.refreeze_energy = st_refreeze_energy / N;
-    energy.snow_flux = st_snow_flux / N;
+    energy.advection = div_pos(st_advection, N);
+    energy.deltaCC = div_pos(st_deltaCC, N);
+    energy.refreeze_energy = div_pos(st_refreeze_energy, N);
+    energy.snow_flux = div_pos(st_snow_flux, N);
   }
   energy.Tfoliage = snow_energy.Tfoliage;
   energy.Tfoliage_fbflag = snow_energy.Tfoliage_fbflag;
@@ -850,10 +851,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     if (snow.snow != 0.0) hru.veg.Wdew = snow_vv.Wdew;
     else hru.veg.Wdew = soil_vv.Wdew;
   }
-  for (int l = 0; l < NL; l++) {
-    cell.layer[l] = step_layer[l];
-    cell.layer[l].evap = st_layerevap[l];
-  }
+  for (int l = 0; l < NL; l++) cell.layer[l].evap = st_layerevap[l];
   if (st_aero_cond_used.surface > 0 && st_aero_cond_used.surface < HUGE_RESIST) cell.aero_surface = 1 / (st_aero_cond_used.surface / N);
   else if (st_aero_cond_used.surface >= HUGE_RESIST) cell.aero_surface = 0;
   else cell.aero_surface = HUGE_RESIST;

@@ -149,32 +149,33 @@ struct Hru {
 
 // columns col0 .. col0+count-1 of my record row  ->  dst[0 .. count)
 VIC_HD void cols_to_local(const double* __restrict__ rec, size_t n, int col0, int count, double* __restrict__ dst) {
-  int k = 0;
-  for (; k + VIC_XFER_CHUNK <= count; k += VIC_XFER_CHUNK) {
+  for (int k = 0; k < count; k += VIC_XFER_CHUNK) {
     double r[VIC_XFER_CHUNK];
 #pragma unroll
     for (int j = 0; j < VIC_XFER_CHUNK; j++) {
+      if (k + j < count) {
 #if defined(__CUDA_ARCH__)
-      r[j] = __ldg(rec + (size_t)(col0 + k + j) * n);
+        r[j] = __ldg(rec + (size_t)(col0 + k + j) * n);
 #else
-      r[j] = rec[(size_t)(col0 + k + j) * n];
+        r[j] = rec[(size_t)(col0 + k + j) * n];
 #endif
+      }
     }
 #pragma unroll
-    for (int j = 0; j < VIC_XFER_CHUNK; j++) dst[k + j] = r[j];
+    for (int j = 0; j < VIC_XFER_CHUNK; j++)
+      if (k + j < count) dst[k + j] = r[j];
   }
-  for (; k < count; k++) dst[k] = rec[(size_t)(col0 + k) * n];
 }
 VIC_HD void local_to_cols(const double* __restrict__ src, double* __restrict__ rec, size_t n, int col0, int count) {
-  int k = 0;
-  for (; k + VIC_XFER_CHUNK <= count; k += VIC_XFER_CHUNK) {
+  for (int k = 0; k < count; k += VIC_XFER_CHUNK) {
     double r[VIC_XFER_CHUNK];
 #pragma unroll
-    for (int j = 0; j < VIC_XFER_CHUNK; j++) r[j] = src[k + j];
+    for (int j = 0; j < VIC_XFER_CHUNK; j++)
+      if (k + j < count) r[j] = src[k + j];
 #pragma unroll
-    for (int j = 0; j < VIC_XFER_CHUNK; j++) rec[(size_t)(col0 + k + j) * n] = r[j];
+    for (int j = 0; j < VIC_XFER_CHUNK; j++)
+      if (k + j < count) rec[(size_t)(col0 + k + j) * n] = r[j];
   }
-  for (; k < count; k++) rec[(size_t)(col0 + k) * n] = src[k];
 }
 
 template <int NN>
@@ -214,7 +215,9 @@ VIC_HDI void load_hru(Hru<NN>& h, const double* __restrict__ rec, size_t n, cons
   cols_to_local(rec, n, hr_front0, 2 * VICGPU_NFRONTS, h.energy.fdepth);  // fdepth[], tdepth[] are adjacent
   cols_to_local(rec, n, hr_pet0, VICGPU_NPET, h.cell.pot_evap);
   // nodes: record [field][nnode], working set field[NN]
-  for (int f = 0; f < HRN_N; f++) cols_to_local(rec, n, hr_node0 + f * nnode, nnode < NN ? nnode : NN, h.energy.Cs_node + f * NN);
+  if (nnode == NN) cols_to_local(rec, n, hr_node0, HRN_N * NN, h.energy.Cs_node);  // both sides contiguous
+  else
+    for (int f = 0; f < HRN_N; f++) cols_to_local(rec, n, hr_node0 + f * nnode, nnode < NN ? nnode : NN, h.energy.Cs_node + f * NN);
 }
 
 template <int NN>
@@ -237,7 +240,9 @@ VIC_HDI void store_hru(const Hru<NN>& h, double* __restrict__ rec, size_t n, con
   }
   local_to_cols(h.energy.fdepth, rec, n, hr_front0, 2 * VICGPU_NFRONTS);
   local_to_cols(h.cell.pot_evap, rec, n, hr_pet0, VICGPU_NPET);
-  for (int f = 0; f < HRN_N; f++) local_to_cols(h.energy.Cs_node + f * NN, rec, n, hr_node0 + f * nnode, nnode < NN ? nnode : NN);
+  if (nnode == NN) local_to_cols(h.energy.Cs_node, rec, n, hr_node0, HRN_N * NN);
+  else
+    for (int f = 0; f < HRN_N; f++) local_to_cols(h.energy.Cs_node + f * NN, rec, n, hr_node0 + f * nnode, nnode < NN ? nnode : NN);
 }
 
 // everything a physics routine needs to know about "where am I"

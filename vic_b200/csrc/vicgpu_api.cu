@@ -234,7 +234,9 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   std::vector<int> hru_of_slot, slot_of_hru;
   const char* nobin = getenv("VICGPU_NOBIN");
   h->binned = !(nobin && atoi(nobin) != 0);
-  if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru);
+  const char* deal = getenv("VICGPU_DEAL");  // A/B knob: 1 deals the warps of a kind over all blocks (measured slower: same-kind blocks share the instruction cache)
+  const bool dealing = deal && atoi(deal) != 0;
+  if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru, dealing ? (nhru + h->hru_block - 1) / h->hru_block : 0);
   cudaFree(h->d_slot_of_hru); cudaFree(h->d_hru_of_slot);
   h->d_slot_of_hru = h->d_hru_of_slot = nullptr;
   if (h->binned) {
