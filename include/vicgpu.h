@@ -499,6 +499,12 @@ int vicgpu_disagg(vicgpu_handle *h, const vicgpu_disagg_options *dopt, const dou
  * since profiling was switched on. */
 int vicgpu_set_profiling(vicgpu_handle *h, int on);
 int vicgpu_get_kernel_profile(vicgpu_handle *h, double *hru_step_ms_total, long long *hru_step_launches);
+/* measurement aid: per-warp start and end times (globaltimer, ns relative to the earliest start) of the LAST launch of the
+ * per-HRU step kernel made while profiling was on; times[2*w] / times[2*w+1] for warp w of the launch, kind[w] the binning kind
+ * of the warp's first row (vegetation class, + 1e6 bare soil, + 2e6 glacier).  Returns the number of warps (<= max_warps
+ * are written).  Shows the load balance between warps and thread blocks.  The timers are only compiled into the launch when
+ * the environment variable VICGPU_WARPTIME=1 was set at vicgpu_create (they cost ~15 % of the kernel). */
+int vicgpu_get_warp_times(vicgpu_handle *h, double *times, double *kind, int max_warps);
 
 #ifdef __cplusplus
 }

@@ -42,4 +42,15 @@ kms, kn = g.kernel_profile()
 env = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("VICGPU_"))
 print(f"PROBE {a.tag} [{env}] cells={a.cells} hrus={g.nhru} ms_per_step={ms / a.steps:.3f} hru_kernel_us={kms / max(kn, 1) * 1e3:.1f} "
       f"cell_steps_per_s={a.cells * 24 * a.steps / (ms / 1e3):.4g} state_sum={np.nansum(g.get_state()):.17g}", flush=True)
+if os.environ.get("VICGPU_WARPTIME"):
+    t0, t1, kind = g.warp_times()
+    dur = (t1 - t0) / 1e3
+    B = int(os.environ.get("VICGPU_BLOCK", "384")) // 32
+    nb = (len(dur) + B - 1) // B
+    blk = np.array([t1[b * B:(b + 1) * B].max() - t0[b * B:(b + 1) * B].min() for b in range(nb)]) / 1e3
+    print(f"WARPS n={len(dur)} dur us: min {dur.min():.0f} mean {dur.mean():.0f} p50 {np.median(dur):.0f} p90 {np.percentile(dur, 90):.0f} max {dur.max():.0f}; "
+          f"kernel span {(t1.max() - t0.min()) / 1e3:.0f}; blocks n={nb} mean {blk.mean():.0f} max {blk.max():.0f} min {blk.min():.0f}")
+    for kd in np.unique(kind):
+        m = kind == kd
+        print(f"  kind {int(kd):8d}: warps {m.sum():4d} mean {dur[m].mean():6.0f} max {dur[m].max():6.0f} us")
 g.close()

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg",
+    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times",
 ]
 
 
@@ -68,6 +68,7 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_disagg.argtypes = [vp, vp, dp, dp]
     lib.vicgpu_set_profiling.argtypes = [vp, C.c_int]
     lib.vicgpu_get_kernel_profile.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
+    lib.vicgpu_get_warp_times.argtypes = [vp, dp, dp, C.c_int]
     for s in SYMBOLS:
         getattr(lib, s)
     _lib = lib
@@ -204,6 +205,16 @@ class VicGpu:
         n = C.c_longlong()
         self._chk(self.lib.vicgpu_get_kernel_profile(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def warp_times(self):
+        """(start_ns, end_ns, kind) per warp of the last profiled launch of the step kernel"""
+        nw = (self.nhru + 31) // 32
+        t = np.zeros((nw, 2))
+        k = np.zeros(nw)
+        n = self.lib.vicgpu_get_warp_times(self.h, _dptr(t), _dptr(k), nw)
+        if n < 0:
+            self._chk(n)
+        return t[:, 0], t[:, 1], k
 
     def last_step_timing(self):
         ms = C.c_double()

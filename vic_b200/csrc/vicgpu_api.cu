@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <string>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 #include "vicgpu_internal.h"
 
 using namespace vic;
@@ -54,6 +55,38 @@ __global__ void k_gather_rows(const double* __restrict__ in /* [cols][rows] */, 
   if (i >= (size_t)rows * cols) return;
   const int r = (int)(i / cols), c = (int)(i % cols);
   out[i] = in[(size_t)c * rows + row_of_rec[r]];
+}
+
+// ---- dynamic binning: rows of the HRU tables re-ordered by (kind, snow on the ground or in the canopy, cell) ----------------
+// The step's control flow differs most between glacier / bare / vegetated HRUs (static: bin_hrus) and between HRUs with and
+// without snow (dynamic: solve_snow's pack and canopy balances, sub-stepping, evaporation switched off under snow).  Every
+// `rebin_interval` records the rows are re-sorted on the device so that the 32 HRUs of a warp share both.
+__global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __restrict__ hrurec, int nhru, const int* __restrict__ hru_of_slot,
+                           unsigned long long* __restrict__ keys, int* __restrict__ old_slot) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nhru) return;
+  const size_t n = (size_t)nhru;
+  unsigned long long kind = (unsigned long long)(long long)hrupar[(size_t)HP_vegIndex * n + s] & 0xfffffull;
+  if (hrupar[(size_t)HP_isArtBare * n + s] != 0.0) kind |= 1ull << 20;
+  if (hrupar[(size_t)HP_isGlacier * n + s] != 0.0) kind |= 1ull << 21;
+  const bool snowy = hrurec[(size_t)HR_S_swq * n + s] > 0.0 || hrurec[(size_t)HR_S_snow_canopy * n + s] > 0.0;
+  // low 32 bits: the HRU's own index, i.e. cell order within a bin (and a total order: the sort is deterministic)
+  keys[s] = (kind << 33) | ((unsigned long long)(snowy ? 1 : 0) << 32) | (unsigned long long)(unsigned)hru_of_slot[s];
+  old_slot[s] = s;
+}
+// out[c][s] = in[c][src[s]]
+__global__ void k_permute_rows(const double* __restrict__ in, double* __restrict__ out, int rows, int cols, const int* __restrict__ src) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int c = (int)(i / rows), r = (int)(i % rows);
+  out[i] = in[(size_t)c * rows + src[r]];
+}
+__global__ void k_slot_maps(const unsigned long long* __restrict__ keys, int nhru, int* __restrict__ hru_of_slot, int* __restrict__ slot_of_hru) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nhru) return;
+  const int hru = (int)(unsigned)(keys[s] & 0xffffffffull);
+  hru_of_slot[s] = hru;
+  slot_of_hru[hru] = s;
 }
 
 __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
@@ -128,6 +161,36 @@ static int download_transposed(vicgpu_handle* h, const double* d_src, double* ho
   return VICGPU_OK;
 }
 
+// Re-sort the rows of the HRU tables (state buffer `cur`, hrupar) by (kind, snow, HRU); all earlier work must be complete on
+// both streams (the caller orders that).  Runs on h->stream.
+static int rebin_rows(vicgpu_handle* h) {
+  const int nhru = h->t.nhru;
+  const vicgpu_layout& L = h->o.L;
+  const int T = 256, G = (nhru + T - 1) / T;
+  k_bin_keys<<<G, T, 0, h->stream>>>(h->d_hrupar, h->d_hrurec2[h->cur], nhru, h->d_hru_of_slot, h->d_keys[0], h->d_oldslot[0]);
+  size_t need = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
+  if (need > h->sort_tmp_bytes) {
+    cudaFree(h->d_sort_tmp);
+    h->d_sort_tmp = nullptr;
+    h->sort_tmp_bytes = 0;
+    CK(cudaMalloc(&h->d_sort_tmp, need));
+    h->sort_tmp_bytes = need;
+  }
+  CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
+  const size_t ns = (size_t)nhru * L.hr_stride, np = (size_t)nhru * HP_N;
+  k_permute_rows<<<(unsigned)((ns + T - 1) / T), T, 0, h->stream>>>(h->d_hrurec2[h->cur], h->d_hrurec2[h->cur ^ 1], nhru, L.hr_stride, h->d_oldslot[1]);
+  k_permute_rows<<<(unsigned)((np + T - 1) / T), T, 0, h->stream>>>(h->d_hrupar, h->d_hrupar_alt, nhru, HP_N, h->d_oldslot[1]);
+  k_slot_maps<<<G, T, 0, h->stream>>>(h->d_keys[1], nhru, h->d_hru_of_slot, h->d_slot_of_hru);
+  h->last_launches += 5 + 2;  // + the radix sort's own passes (counted as two)
+  CK(cudaGetLastError());
+  std::swap(h->d_hrupar, h->d_hrupar_alt);
+  h->t.hrupar = h->d_hrupar;
+  h->cur ^= 1;
+  h->recs_since_bin = 0;
+  return VICGPU_OK;
+}
+
 extern "C" {
 
 int vicgpu_abi_version(void) { return VICGPU_ABI_VERSION; }
@@ -151,12 +214,18 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   h->o = o;
   h->nout = o.L.out_off[VICGPU_N_OUTVARS];
   memset(&h->t, 0, sizeof(h->t));
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  // the HRU step owns the machine: its stream has the highest priority, the cell-output stream the lowest, so that an output
+  // kernel still running when the next step starts never holds back a step block (measured: up to 0.2 ms of late block starts)
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  const char* wt = getenv("VICGPU_WARPTIME");  // per-warp timers in profiled launches (vicgpu_get_warp_times); they slow the kernel
+  h->warp_timing = wt && atoi(wt) != 0;
   const char* noov = getenv("VICGPU_NOOVERLAP");  // A/B knob: run the cell output in the step's stream
   h->overlap = !(noov && atoi(noov) != 0);
-  if (h->overlap) CK(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+  if (h->overlap) CK(cudaStreamCreateWithPriority(&h->stream_out, cudaStreamNonBlocking, prio_lo));
   else h->stream_out = h->stream;
   CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_out[0], cudaEventDisableTiming));
@@ -180,9 +249,11 @@ int vicgpu_destroy(vicgpu_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_hrupar);
   for (int b = 0; b < 2; b++) { cudaFree(h->d_hrurec2[b]); cudaFree(h->d_hdiag2[b]); }
-  cudaFree(h->d_fail_rec);
+  cudaFree(h->d_fail_rec); cudaFree(h->d_hrupar_alt); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]);
+  cudaFree(h->d_sort_tmp);
   cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_forcing); cudaFree(h->d_fstage);
   cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype); cudaFree(h->d_slot_of_hru); cudaFree(h->d_hru_of_slot);
+  cudaFree(h->d_warp_ns);
   if (h->ev_step) cudaEventDestroy(h->ev_step);
   for (int b = 0; b < 2; b++) if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
   if (h->overlap && h->stream_out) cudaStreamDestroy(h->stream_out);
@@ -258,6 +329,21 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     CK(cudaMalloc(&h->d_hdiag2[b], (size_t)nhru * 3 * sizeof(double)));
     CK(cudaMemset(h->d_hdiag2[b], 0, (size_t)nhru * 3 * sizeof(double)));
   }
+  cudaFree(h->d_hrupar_alt); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]);
+  h->d_hrupar_alt = nullptr; h->d_keys[0] = h->d_keys[1] = nullptr; h->d_oldslot[0] = h->d_oldslot[1] = nullptr;
+  {
+    const char* rb = getenv("VICGPU_REBIN");  // records between re-sorts of the rows by (kind, snow); 0 = static binning only
+    h->rebin_interval = rb ? atoi(rb) : 24;
+    if (!h->binned) h->rebin_interval = 0;
+  }
+  if (h->rebin_interval > 0) {
+    CK(cudaMalloc(&h->d_hrupar_alt, (size_t)nhru * HP_N * sizeof(double)));
+    for (int b = 0; b < 2; b++) {
+      CK(cudaMalloc(&h->d_keys[b], (size_t)nhru * sizeof(unsigned long long)));
+      CK(cudaMalloc(&h->d_oldslot[b], (size_t)nhru * sizeof(int)));
+    }
+  }
+  h->recs_since_bin = 1 << 30;  // re-sort before the first record stepped
   CK(cudaMalloc(&h->d_fail_rec, (size_t)ncell * sizeof(int)));
   {
     std::vector<int> never((size_t)ncell, INT_MAX);
@@ -319,6 +405,7 @@ int vicgpu_set_state(vicgpu_handle* h, const double* hrurec) {
   int rc = upload_transposed(h, hrurec, h->d_hrurec2[h->cur], h->t.nhru, h->o.L.hr_stride, h->d_hru_of_slot);
   if (rc) return rc;
   h->have_state = true;
+  h->recs_since_bin = 1 << 30;
   return VICGPU_OK;
 }
 
@@ -390,6 +477,20 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
     const int rec = rec0 + i;
     const double* frec = h->d_forcing + (size_t)(rec - h->frec0) * per;
     h->step_count++;
+    if (h->rebin_interval > 0 && h->recs_since_bin >= h->rebin_interval) {
+      // every output kernel issued so far must have finished with the old row order and both state buffers
+      if (h->overlap) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_out[0], 0));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_out[1], 0));
+      }
+      int rc = rebin_rows(h);
+      if (rc) return rc;
+      if (h->overlap) {  // the initial-storage output of record 0 (below) reads the new order
+        CK(cudaEventRecord(h->ev_step, h->stream));
+        CK(cudaStreamWaitEvent(so, h->ev_step, 0));
+      }
+    }
+    h->recs_since_bin++;
     const int cur = h->cur, nxt = h->cur ^ 1;
     Tables t = h->t;
     t.hrurec = h->d_hrurec2[cur];
@@ -408,10 +509,17 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
     Dmy d = {dmy[i * 5 + 0], dmy[i * 5 + 1], dmy[i * 5 + 2], dmy[i * 5 + 3], dmy[i * 5 + 4]};
     GlacAccum ga = glacier_accum_flags(h->o, &dmy[i * 5], &dmy[(i + 1) * 5], rec, &h->glac_started);
     if (h->overlap) CK(cudaStreamWaitEvent(h->stream, h->ev_out[nxt], 0));  // the output that last read buffer nxt
+    unsigned long long* wns = nullptr;
+    if (h->profiling && h->warp_timing) {
+      const size_t nw = ((size_t)h->t.nhru + 31) / 32;
+      if (!h->d_warp_ns) CK(cudaMalloc(&h->d_warp_ns, 2 * nw * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(h->d_warp_ns, 0, 2 * nw * sizeof(unsigned long long), h->stream));
+      wns = h->d_warp_ns;
+    }
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream);
-    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream);
-    else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream);
+    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream, wns);
+    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream, wns);
+    else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream, wns);
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));
     if (h->overlap) {
       CK(cudaEventRecord(h->ev_step, h->stream));
@@ -486,6 +594,29 @@ int vicgpu_get_kernel_profile(vicgpu_handle* h, double* hru_step_ms_total, long 
   if (hru_step_ms_total) *hru_step_ms_total = h->prof_hru_ms;
   if (hru_step_launches) *hru_step_launches = h->prof_hru_launches;
   return VICGPU_OK;
+}
+
+int vicgpu_get_warp_times(vicgpu_handle* h, double* times, double* kind, int max_warps) {
+  if (!h || !times || !h->have_cells) return fail(VICGPU_EINVAL, "bad argument");
+  if (!h->d_warp_ns) return fail(VICGPU_ESTATE, "no profiled launch yet (vicgpu_set_profiling)");
+  CK(cudaSetDevice(h->device));
+  const int nw = (h->t.nhru + 31) / 32;
+  std::vector<unsigned long long> ns((size_t)2 * nw);
+  CK(cudaMemcpy(ns.data(), h->d_warp_ns, ns.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::vector<double> hp((size_t)h->t.nhru * HP_N);
+  CK(cudaMemcpy(hp.data(), h->d_hrupar, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  for (int w = 0; w < nw; w++) if (ns[2 * w] && ns[2 * w] < t0) t0 = ns[2 * w];
+  const size_t n = (size_t)h->t.nhru;
+  for (int w = 0; w < nw && w < max_warps; w++) {
+    times[2 * w] = (double)(ns[2 * w] - t0);
+    times[2 * w + 1] = (double)(ns[2 * w + 1] - t0);
+    if (kind) {
+      const size_t s = (size_t)w * 32;
+      kind[w] = hp[(size_t)HP_vegIndex * n + s] + (hp[(size_t)HP_isArtBare * n + s] != 0.0 ? 1e6 : 0) + (hp[(size_t)HP_isGlacier * n + s] != 0.0 ? 2e6 : 0);
+    }
+  }
+  return nw;
 }
 
 int vicgpu_get_last_step_timing(vicgpu_handle* h, double* kernel_ms, long long* launches) {

@@ -36,6 +36,13 @@ struct vicgpu_handle {
   size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
   int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr, *d_slot_of_hru = nullptr, *d_hru_of_slot = nullptr;
   bool binned = true;
+  // dynamic re-binning (vicgpu_api.cu rebin_rows)
+  int rebin_interval = 24, recs_since_bin = 1 << 30;
+  double* d_hrupar_alt = nullptr;
+  unsigned long long* d_keys[2] = {nullptr, nullptr};
+  int* d_oldslot[2] = {nullptr, nullptr};
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
   int hru_block = VICGPU_HRU_BLOCK;
   int frec0 = 0, fnrec = 0;
   bool have_cells = false, have_state = false, glac_started = false;
@@ -45,7 +52,8 @@ struct vicgpu_handle {
   double last_ms = 0;
   long long last_launches = 0;
   // optional per-launch timing of the per-HRU step kernel (vicgpu_set_profiling)
-  bool profiling = false;
+  bool profiling = false, warp_timing = false;
+  unsigned long long* d_warp_ns = nullptr;  // [2 * nwarps] start / end of every warp of the last profiled step launch
   std::vector<cudaEvent_t> pev;
   double prof_hru_ms = 0;
   long long prof_hru_launches = 0;
