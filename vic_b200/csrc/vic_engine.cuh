@@ -97,6 +97,80 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   dg[2 * nh] = d.out_snow * hp.Cv;
 }
 
+// ---- a block of consecutive records in one launch ------------------------------------------------------------------------------
+// An HRU's record r + 1 depends on nothing but its own record r (and the forcing); only the cell output needs all HRUs of a cell
+// at the same record.  So the CUDA library advances every HRU through up to VICGPU_RECBLOCK_MAX records in ONE launch, keeping the
+// working set in the thread between records and writing the state after each record to its own snapshot buffer; the cell outputs of
+// those records run afterwards from the snapshots.  Warps no longer wait for the slowest warp of the grid after every record (a
+// forest warp with an unlucky root-finder iteration count is 1.5x the average), only once per block of records.
+#define VICGPU_RECBLOCK_MAX 24
+struct RecBlock {
+  int n, rec0;
+  Dmy dmy[VICGPU_RECBLOCK_MAX];
+  unsigned char ga[VICGPU_RECBLOCK_MAX];  // GlacAccum as bits: 1 enabled, 2 reset_first, 4 accumulate, 8 reset_after
+};
+VIC_HD unsigned char pack_ga(const GlacAccum& g) { return (unsigned char)((g.enabled ? 1 : 0) | (g.reset_first ? 2 : 0) | (g.accumulate ? 4 : 0) | (g.reset_after ? 8 : 0)); }
+
+// t.hrurec: state at the start of the block; snap + i * snap_stride: state after record i; hdiag + i * 3 * nhru: step diagnostics.
+// forcing: record rb.rec0 of the window, records `per` doubles apart.  A cell that fails at record r (fail_rec) is frozen from r on;
+// because sibling HRUs may be ahead of the failing one, k_freeze_failed() afterwards makes the snapshots after r equal to snapshot r.
+template <int NN>
+VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcing, size_t per, const RecBlock& rb, double* snap, size_t snap_stride,
+                            double* hdiag, int h) {
+  const size_t nh = (size_t)t.nhru;
+  Col hpc{t.hrupar + h, nh};
+  const int cell = (int)hpc(HP_cell);
+  Ctx cx;
+  cx.o = o;
+  cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L};
+  cx.vl = VegLib{t.veglib, &o->L};
+  cx.hp = hpc;
+  const HruPar hp = load_hrupar(hpc);
+  Hru<NN> hru;
+  const double* prev = t.hrurec;
+  load_hru<NN>(hru, prev + h, nh, &o->L);
+  for (int i = 0; i < rb.n; i++) {
+    const int rec = rb.rec0 + i;
+    double* out = snap + (size_t)i * snap_stride;
+    double* dg = hdiag + (size_t)i * 3 * nh + h;
+    if (t.fail_rec[cell] <= rec) {
+      dg[0] = dg[nh] = dg[2 * nh] = 0;
+      store_hru<NN>(hru, out + h, nh, &o->L);
+      prev = out;
+      continue;
+    }
+    cx.f = Forcing{Col{forcing + (size_t)i * per + cell, (size_t)t.ncell}, o->L.f_nslot};
+    cx.dmy = rb.dmy[i];
+    cx.rec = rec;
+    HruStepDiag d;
+    const int e = hru_step<NN>(hru, hp, cx, d);
+    if (e == ERROR_I) {
+      t.status[cell] = ERROR_I;
+#if defined(__CUDA_ARCH__)
+      atomicMin(&t.fail_rec[cell], rec);
+#else
+      if (rec < t.fail_rec[cell]) t.fail_rec[cell] = rec;
+#endif
+      dg[0] = dg[nh] = dg[2 * nh] = 0;
+      load_hru<NN>(hru, prev + h, nh, &o->L);  // the failed step left the working set half updated: back to the last good record
+      store_hru<NN>(hru, out + h, nh, &o->L);
+      prev = out;
+      continue;
+    }
+    const unsigned char ga = rb.ga[i];
+    if ((ga & 1) && hp.isGlacier) {
+      if (ga & 2) hru.glac.cum_mass_balance = 0;
+      if ((ga & 4) && is_valid(hru.glac.mass_balance)) hru.glac.cum_mass_balance += hru.glac.mass_balance;
+      if (ga & 8) hru.glac.cum_mass_balance = 0;
+    }
+    store_hru<NN>(hru, out + h, nh, &o->L);
+    dg[0] = d.out_prec * hp.Cv;
+    dg[nh] = d.out_rain * hp.Cv;
+    dg[2 * nh] = d.out_snow * hp.Cv;
+    prev = out;
+  }
+}
+
 VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count) {
   if (rec >= 0 && t.fail_rec[cell] <= rec) {
     // the reference stops touching an invalid cell (vicNl.c:521); its data row keeps the last values

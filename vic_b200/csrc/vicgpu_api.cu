@@ -89,6 +89,22 @@ __global__ void k_slot_maps(const unsigned long long* __restrict__ keys, int nhr
   slot_of_hru[hru] = s;
 }
 
+// After a block of records: the snapshots of an HRU whose cell failed at record fr (inside the block) are made equal to the
+// snapshot of record fr from there on -- a sibling HRU may have run ahead of the failing one (hru_block_work).
+__global__ void k_freeze_failed(Tables t, int rec0, int n, double* snap, size_t snap_stride, int hr_stride) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= t.nhru) return;
+  const size_t nh = (size_t)t.nhru;
+  const int cell = (int)t.hrupar[(size_t)HP_cell * nh + h];
+  const int fr = t.fail_rec[cell];
+  if (fr < rec0 || fr >= rec0 + n - 1) return;
+  const double* good = snap + (size_t)(fr - rec0) * snap_stride;
+  for (int i = fr - rec0 + 1; i < n; i++) {
+    double* out = snap + (size_t)i * snap_stride;
+    for (int k = 0; k < hr_stride; k++) out[(size_t)k * nh + h] = good[(size_t)k * nh + h];
+  }
+}
+
 __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
                                                      int step_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,16 +177,34 @@ static int download_transposed(vicgpu_handle* h, const double* d_src, double* ho
   return VICGPU_OK;
 }
 
-// Re-sort the rows of the HRU tables (state buffer `cur`, hrupar) by (kind, snow, HRU); all earlier work must be complete on
-// both streams (the caller orders that).  Runs on h->stream.
-static int rebin_rows(vicgpu_handle* h) {
+// ---- state halves ------------------------------------------------------------------------------------------------------------
+// A block of up to `recblock` records is advanced by ONE launch of the step kernel (vic_engine.cuh hru_block_work): it reads the
+// block's input state and writes the state after every record to a snapshot buffer of the half it runs in; the cell outputs of
+// those records then run from the snapshots on the second stream while the next block already runs in the other half.  A half
+// also owns the row order its snapshots are in (the rows are re-sorted by kind and snow state before each block) together with
+// the HRU parameter table in that order.
+static void free_half(StateHalf& s) {
+  cudaFree(s.in); cudaFree(s.snap); cudaFree(s.hdiag);
+  s.in = s.snap = s.hdiag = nullptr;
+  s.ord = 0;
+}
+static void free_order(RowOrder& r) {
+  cudaFree(r.hrupar); cudaFree(r.slot_of_hru); cudaFree(r.hru_of_slot);
+  r.hrupar = nullptr;
+  r.slot_of_hru = r.hru_of_slot = nullptr;
+}
+
+// Re-sort the rows by (kind, snow, HRU): state `src_state` in row order S  ->  buffer dst_state in the new row order D (parameter
+// table and maps).  Runs on h->stream; the caller has made sure nothing still reads order D or dst_state.
+static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const double* src_state, double* dst_state) {
   const int nhru = h->t.nhru;
   const vicgpu_layout& L = h->o.L;
   const int T = 256, G = (nhru + T - 1) / T;
-  k_bin_keys<<<G, T, 0, h->stream>>>(h->d_hrupar, h->d_hrurec2[h->cur], nhru, h->d_hru_of_slot, h->d_keys[0], h->d_oldslot[0]);
+  k_bin_keys<<<G, T, 0, h->stream>>>(S.hrupar, src_state, nhru, S.hru_of_slot, h->d_keys[0], h->d_oldslot[0]);
   size_t need = 0;
   CK(cub::DeviceRadixSort::SortPairs(nullptr, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
   if (need > h->sort_tmp_bytes) {
+    CK(cudaStreamSynchronize(h->stream));
     cudaFree(h->d_sort_tmp);
     h->d_sort_tmp = nullptr;
     h->sort_tmp_bytes = 0;
@@ -179,15 +213,11 @@ static int rebin_rows(vicgpu_handle* h) {
   }
   CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
   const size_t ns = (size_t)nhru * L.hr_stride, np = (size_t)nhru * HP_N;
-  k_permute_rows<<<(unsigned)((ns + T - 1) / T), T, 0, h->stream>>>(h->d_hrurec2[h->cur], h->d_hrurec2[h->cur ^ 1], nhru, L.hr_stride, h->d_oldslot[1]);
-  k_permute_rows<<<(unsigned)((np + T - 1) / T), T, 0, h->stream>>>(h->d_hrupar, h->d_hrupar_alt, nhru, HP_N, h->d_oldslot[1]);
-  k_slot_maps<<<G, T, 0, h->stream>>>(h->d_keys[1], nhru, h->d_hru_of_slot, h->d_slot_of_hru);
+  k_permute_rows<<<(unsigned)((ns + T - 1) / T), T, 0, h->stream>>>(src_state, dst_state, nhru, L.hr_stride, h->d_oldslot[1]);
+  k_permute_rows<<<(unsigned)((np + T - 1) / T), T, 0, h->stream>>>(S.hrupar, D.hrupar, nhru, HP_N, h->d_oldslot[1]);
+  k_slot_maps<<<G, T, 0, h->stream>>>(h->d_keys[1], nhru, D.hru_of_slot, D.slot_of_hru);
   h->last_launches += 5 + 2;  // + the radix sort's own passes (counted as two)
   CK(cudaGetLastError());
-  std::swap(h->d_hrupar, h->d_hrupar_alt);
-  h->t.hrupar = h->d_hrupar;
-  h->cur ^= 1;
-  h->recs_since_bin = 0;
   return VICGPU_OK;
 }
 
@@ -214,22 +244,29 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   h->o = o;
   h->nout = o.L.out_off[VICGPU_N_OUTVARS];
   memset(&h->t, 0, sizeof(h->t));
-  // the HRU step owns the machine: its stream has the highest priority, the cell-output stream the lowest, so that an output
-  // kernel still running when the next step starts never holds back a step block (measured: up to 0.2 ms of late block starts)
+  // the HRU step owns the machine: its stream has the highest priority, the cell-output stream the lowest
   int prio_lo = 0, prio_hi = 0;
   CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  // tuning / A-B knobs (environment, read once per handle)
   const char* wt = getenv("VICGPU_WARPTIME");  // per-warp timers in profiled launches (vicgpu_get_warp_times); they slow the kernel
   h->warp_timing = wt && atoi(wt) != 0;
-  const char* noov = getenv("VICGPU_NOOVERLAP");  // A/B knob: run the cell output in the step's stream
+  const char* noov = getenv("VICGPU_NOOVERLAP");  // run the cell output in the step's stream
   h->overlap = !(noov && atoi(noov) != 0);
+  const char* rbk = getenv("VICGPU_RECBLOCK");  // records advanced per launch of the step kernel (1 .. VICGPU_RECBLOCK_MAX)
+  h->recblock = rbk ? std::max(1, std::min(VICGPU_RECBLOCK_MAX, atoi(rbk))) : VICGPU_RECBLOCK_MAX;
+  const char* nobin = getenv("VICGPU_NOBIN");  // keep the caller's row order (no binning at all)
+  h->binned = !(nobin && atoi(nobin) != 0);
+  const char* rb = getenv("VICGPU_REBIN");  // records between re-sorts of the rows by (kind, snow); 0: bin by kind once (set_cells)
+  h->rebin_every = rb ? atoi(rb) : 24;
+  h->rebin = h->binned && h->rebin_every > 0;
+  h->recblock = rbk ? h->recblock : 1;  // default: one record per launch (warps that drift apart lose the shared instruction cache)
   if (h->overlap) CK(cudaStreamCreateWithPriority(&h->stream_out, cudaStreamNonBlocking, prio_lo));
   else h->stream_out = h->stream;
   CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&h->ev_out[0], cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&h->ev_out[1], cudaEventDisableTiming));
+  for (int b = 0; b < 2; b++) CK(cudaEventCreateWithFlags(&h->half[b].ev_out, cudaEventDisableTiming));
   CK(cudaMalloc(&h->d_o, sizeof(Opts)));
   CK(cudaMemcpy(h->d_o, &h->o, sizeof(Opts), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_aggtype, VICGPU_N_OUTVARS * sizeof(int)));
@@ -238,7 +275,7 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   CK(cudaMemcpy(h->d_aggtype, agg, sizeof(agg), cudaMemcpyHostToDevice));
   // the step kernel keeps one HRU (about 2 KB) plus its working copies in thread-local memory
   CK(cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024));
-  const char* blk = getenv("VICGPU_BLOCK");  // threads per block of the per-HRU step kernel (tuning knob; multiple of 32, <= VICGPU_HRU_BLOCK_MAX)
+  const char* blk = getenv("VICGPU_BLOCK");  // threads per block of the per-HRU step kernel (multiple of 32, <= VICGPU_HRU_BLOCK_MAX)
   if (blk && atoi(blk) >= 32 && atoi(blk) <= VICGPU_HRU_BLOCK_MAX && atoi(blk) % 32 == 0) h->hru_block = atoi(blk);
   *out = h;
   return VICGPU_OK;
@@ -247,15 +284,20 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
 int vicgpu_destroy(vicgpu_handle* h) {
   if (!h) return VICGPU_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_hrupar);
-  for (int b = 0; b < 2; b++) { cudaFree(h->d_hrurec2[b]); cudaFree(h->d_hdiag2[b]); }
-  cudaFree(h->d_fail_rec); cudaFree(h->d_hrupar_alt); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->overlap && h->stream_out) cudaStreamSynchronize(h->stream_out);
+  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar);
+  for (int b = 0; b < 2; b++) {
+    free_half(h->half[b]);
+    free_order(h->order[b]);
+    if (h->half[b].ev_out) cudaEventDestroy(h->half[b].ev_out);
+  }
+  cudaFree(h->d_fail_rec); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]);
   cudaFree(h->d_sort_tmp);
   cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_forcing); cudaFree(h->d_fstage);
-  cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype); cudaFree(h->d_slot_of_hru); cudaFree(h->d_hru_of_slot);
+  cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype);
   cudaFree(h->d_warp_ns);
   if (h->ev_step) cudaEventDestroy(h->ev_step);
-  for (int b = 0; b < 2; b++) if (h->ev_out[b]) cudaEventDestroy(h->ev_out[b]);
   if (h->overlap && h->stream_out) cudaStreamDestroy(h->stream_out);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -301,59 +343,69 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     h0[c + 1]++;
   }
   for (int c = 0; c < ncell; c++) h0[c + 1] += h0[c];
-  // rows of the HRU tables: binned by kind (VICGPU_NOBIN=1 keeps the caller's order; for A/B measurements only)
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->overlap) CK(cudaStreamSynchronize(h->stream_out));
+  // initial row order: binned by kind (bin_hrus); VICGPU_DEAL=1 deals the warps of a kind over all blocks (measured slower:
+  // blocks of one kind share the instruction cache)
   std::vector<int> hru_of_slot, slot_of_hru;
-  const char* nobin = getenv("VICGPU_NOBIN");
-  h->binned = !(nobin && atoi(nobin) != 0);
-  const char* deal = getenv("VICGPU_DEAL");  // A/B knob: 1 deals the warps of a kind over all blocks (measured slower: same-kind blocks share the instruction cache)
+  const char* deal = getenv("VICGPU_DEAL");
   const bool dealing = deal && atoi(deal) != 0;
   if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru, dealing ? (nhru + h->hru_block - 1) / h->hru_block : 0);
-  cudaFree(h->d_slot_of_hru); cudaFree(h->d_hru_of_slot);
-  h->d_slot_of_hru = h->d_hru_of_slot = nullptr;
-  if (h->binned) {
-    CK(cudaMalloc(&h->d_slot_of_hru, (size_t)nhru * sizeof(int)));
-    CK(cudaMalloc(&h->d_hru_of_slot, (size_t)nhru * sizeof(int)));
-    CK(cudaMemcpy(h->d_slot_of_hru, slot_of_hru.data(), (size_t)nhru * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_hru_of_slot, hru_of_slot.data(), (size_t)nhru * sizeof(int), cudaMemcpyHostToDevice));
-  }
-  cudaFree(h->d_cellpar); cudaFree(h->d_hrupar); cudaFree(h->d_carry); cudaFree(h->d_out);
-  cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_fail_rec);
-  for (int b = 0; b < 2; b++) { cudaFree(h->d_hrurec2[b]); cudaFree(h->d_hdiag2[b]); h->d_hrurec2[b] = h->d_hdiag2[b] = nullptr; }
-  h->d_cellpar = h->d_hrupar = h->d_carry = h->d_out = h->d_agg = nullptr;
+  cudaFree(h->d_cellpar); cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
+  cudaFree(h->d_fail_rec); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]); cudaFree(h->d_warp_ns);
+  h->d_cellpar = h->d_carry = h->d_out = h->d_agg = nullptr;
   h->d_cell_h0 = h->d_status = h->d_fail_rec = nullptr;
-  h->cur = 0;
-  CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
-  CK(cudaMalloc(&h->d_hrupar, (size_t)nhru * HP_N * sizeof(double)));
+  h->d_keys[0] = h->d_keys[1] = nullptr;
+  h->d_oldslot[0] = h->d_oldslot[1] = nullptr;
+  h->d_warp_ns = nullptr;
   for (int b = 0; b < 2; b++) {
-    CK(cudaMalloc(&h->d_hrurec2[b], (size_t)nhru * L.hr_stride * sizeof(double)));
-    CK(cudaMalloc(&h->d_hdiag2[b], (size_t)nhru * 3 * sizeof(double)));
-    CK(cudaMemset(h->d_hdiag2[b], 0, (size_t)nhru * 3 * sizeof(double)));
+    free_half(h->half[b]);
+    free_order(h->order[b]);
   }
-  cudaFree(h->d_hrupar_alt); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]);
-  h->d_hrupar_alt = nullptr; h->d_keys[0] = h->d_keys[1] = nullptr; h->d_oldslot[0] = h->d_oldslot[1] = nullptr;
-  {
-    const char* rb = getenv("VICGPU_REBIN");  // records between re-sorts of the rows by (kind, snow); 0 = static binning only
-    h->rebin_interval = rb ? atoi(rb) : 24;
-    if (!h->binned) h->rebin_interval = 0;
+  // records per launch: as many as fit in a third of the free memory (two halves of snapshots), at most `recblock`
+  const size_t state_bytes = (size_t)nhru * L.hr_stride * sizeof(double);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  int rbn = h->recblock;
+  while (rbn > 1 && 2 * (size_t)rbn * state_bytes > free_b / 3) rbn--;
+  h->rb = rbn;
+  CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
+  for (int b = 0; b < 2; b++) {
+    StateHalf& s = h->half[b];
+    CK(cudaMalloc(&s.in, state_bytes));
+    CK(cudaMalloc(&s.snap, (size_t)h->rb * state_bytes));
+    CK(cudaMalloc(&s.hdiag, (size_t)h->rb * nhru * 3 * sizeof(double)));
+    CK(cudaMemset(s.hdiag, 0, (size_t)h->rb * nhru * 3 * sizeof(double)));
+    RowOrder& r = h->order[b];
+    if (b == 0 || h->rebin) {
+      CK(cudaMalloc(&r.hrupar, (size_t)nhru * HP_N * sizeof(double)));
+      if (h->binned) {
+        CK(cudaMalloc(&r.slot_of_hru, (size_t)nhru * sizeof(int)));
+        CK(cudaMalloc(&r.hru_of_slot, (size_t)nhru * sizeof(int)));
+      }
+    }
   }
-  if (h->rebin_interval > 0) {
-    CK(cudaMalloc(&h->d_hrupar_alt, (size_t)nhru * HP_N * sizeof(double)));
+  if (h->binned) {
+    CK(cudaMemcpy(h->order[0].slot_of_hru, slot_of_hru.data(), (size_t)nhru * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->order[0].hru_of_slot, hru_of_slot.data(), (size_t)nhru * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  h->recs_since_rebin = 1 << 30;
+  if (h->rebin) {
     for (int b = 0; b < 2; b++) {
       CK(cudaMalloc(&h->d_keys[b], (size_t)nhru * sizeof(unsigned long long)));
       CK(cudaMalloc(&h->d_oldslot[b], (size_t)nhru * sizeof(int)));
     }
-  }
-  h->recs_since_bin = 1 << 30;  // re-sort before the first record stepped
-  CK(cudaMalloc(&h->d_fail_rec, (size_t)ncell * sizeof(int)));
-  {
-    std::vector<int> never((size_t)ncell, INT_MAX);
-    CK(cudaMemcpy(h->d_fail_rec, never.data(), (size_t)ncell * sizeof(int), cudaMemcpyHostToDevice));
   }
   CK(cudaMalloc(&h->d_carry, (size_t)ncell * CC_N * sizeof(double)));
   CK(cudaMalloc(&h->d_out, (size_t)ncell * h->nout * sizeof(double)));
   CK(cudaMalloc(&h->d_agg, (size_t)ncell * h->nout * sizeof(double)));
   CK(cudaMalloc(&h->d_cell_h0, (size_t)(ncell + 1) * sizeof(int)));
   CK(cudaMalloc(&h->d_status, (size_t)ncell * sizeof(int)));
+  CK(cudaMalloc(&h->d_fail_rec, (size_t)ncell * sizeof(int)));
+  {
+    std::vector<int> never((size_t)ncell, INT_MAX);
+    CK(cudaMemcpy(h->d_fail_rec, never.data(), (size_t)ncell * sizeof(int), cudaMemcpyHostToDevice));
+  }
   CK(cudaMemset(h->d_carry, 0, (size_t)ncell * CC_N * sizeof(double)));
   CK(cudaMemset(h->d_out, 0, (size_t)ncell * h->nout * sizeof(double)));
   CK(cudaMemset(h->d_agg, 0, (size_t)ncell * h->nout * sizeof(double)));
@@ -361,13 +413,13 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   CK(cudaMemcpy(h->d_cell_h0, h0.data(), (size_t)(ncell + 1) * sizeof(int), cudaMemcpyHostToDevice));
   int rc = upload_transposed(h, cellpar, h->d_cellpar, ncell, L.cp_stride);
   if (rc) return rc;
-  rc = upload_transposed(h, hrupar, h->d_hrupar, nhru, HP_N, h->d_hru_of_slot);
+  rc = upload_transposed(h, hrupar, h->order[0].hrupar, nhru, HP_N, h->order[0].hru_of_slot);
   if (rc) return rc;
   h->t.ncell = ncell; h->t.nhru = nhru;
-  h->t.slot_of_hru = h->d_slot_of_hru;
-  h->t.cellpar = h->d_cellpar; h->t.hrupar = h->d_hrupar; h->t.hrurec = h->d_hrurec2[0]; h->t.hrurec_out = h->d_hrurec2[1];
-  h->t.hdiag_out = h->d_hdiag2[1]; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
+  h->t.cellpar = h->d_cellpar; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
   h->t.status = h->d_status; h->t.carry = h->d_carry; h->t.out = h->d_out; h->t.agg = h->d_agg; h->t.aggtype = h->d_aggtype;
+  h->cur_half = 0;
+  h->d_state_cur = h->half[0].in;
   h->have_cells = true;
   h->have_state = false;
   h->step_count = 0;
@@ -402,10 +454,12 @@ int vicgpu_set_state(vicgpu_handle* h, const double* hrurec) {
   if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
   if (!h->have_cells) return fail(VICGPU_ESTATE, "set_cells before set_state");
   CK(cudaSetDevice(h->device));
-  int rc = upload_transposed(h, hrurec, h->d_hrurec2[h->cur], h->t.nhru, h->o.L.hr_stride, h->d_hru_of_slot);
+  StateHalf& s = h->half[h->cur_half];
+  int rc = upload_transposed(h, hrurec, s.in, h->t.nhru, h->o.L.hr_stride, h->order[s.ord].hru_of_slot);
   if (rc) return rc;
+  h->d_state_cur = s.in;
   h->have_state = true;
-  h->recs_since_bin = 1 << 30;
+  h->recs_since_rebin = 1 << 30;
   return VICGPU_OK;
 }
 
@@ -413,7 +467,7 @@ int vicgpu_get_state(vicgpu_handle* h, double* hrurec) {
   if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
   if (!h->have_state) return fail(VICGPU_ESTATE, "no state set");
   CK(cudaSetDevice(h->device));
-  return download_transposed(h, h->d_hrurec2[h->cur], hrurec, h->t.nhru, h->o.L.hr_stride, true, h->d_slot_of_hru);
+  return download_transposed(h, h->d_state_cur, hrurec, h->t.nhru, h->o.L.hr_stride, true, h->order[h->half[h->cur_half].ord].slot_of_hru);
 }
 
 int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forcing) {
@@ -451,8 +505,11 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
   if (!h->have_cells || !h->have_state || !h->d_veglib) return fail(VICGPU_ESTATE, "set_veglib, set_cells and set_state before step");
   if (rec0 < h->frec0 || rec0 + nrec > h->frec0 + h->fnrec) return fail(VICGPU_ESTATE, "records outside the resident forcing window");
   CK(cudaSetDevice(h->device));
-  const size_t per = (size_t)h->t.ncell * h->o.L.f_stride;
+  const vicgpu_layout& L = h->o.L;
+  const int nhru = h->t.nhru;
+  const size_t per = (size_t)h->t.ncell * L.f_stride;
   const size_t rowsz = (size_t)h->t.ncell * h->nout;
+  const size_t snap_stride = (size_t)nhru * L.hr_stride;
   const int B = 128;
   const int cgrid = (h->t.ncell + B - 1) / B;
   h->last_launches = 0;
@@ -461,91 +518,119 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
     int rc = ensure_stage(h, rowsz);
     if (rc) return rc;
   }
+  const int nblocks = (nrec + h->rb - 1) / h->rb;
   if (h->profiling) {
-    while ((int)h->pev.size() < 2 * nrec) {
+    while ((int)h->pev.size() < 2 * nblocks) {
       cudaEvent_t e;
       CK(cudaEventCreate(&e));
       h->pev.push_back(e);
     }
   }
-  // Two streams: the HRU step of record r (stream) reads state buffer `cur` and writes `cur ^ 1`; the cell output of record r
-  // (stream_out) reads `cur ^ 1` while the step of record r + 1 already runs -- that step writes buffer `cur`, which was last read
-  // by the output of record r - 1 (ev_out[cur]).
   cudaStream_t so = h->stream_out;
   CK(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < nrec; i++) {
-    const int rec = rec0 + i;
-    const double* frec = h->d_forcing + (size_t)(rec - h->frec0) * per;
-    h->step_count++;
-    if (h->rebin_interval > 0 && h->recs_since_bin >= h->rebin_interval) {
-      // every output kernel issued so far must have finished with the old row order and both state buffers
-      if (h->overlap) {
-        CK(cudaStreamWaitEvent(h->stream, h->ev_out[0], 0));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_out[1], 0));
-      }
-      int rc = rebin_rows(h);
+  for (int blk = 0; blk < nblocks; blk++) {
+    const int i0 = blk * h->rb;
+    const int n = std::min(h->rb, nrec - i0);
+    const int brec0 = rec0 + i0;
+    StateHalf& S = h->half[h->cur_half];
+    StateHalf& D = h->half[h->cur_half ^ 1];
+    // nothing may still read half D (the cell outputs of the block before the previous one)
+    if (h->overlap) CK(cudaStreamWaitEvent(h->stream, D.ev_out, 0));
+    const double* input = h->d_state_cur;
+    if (h->rebin && h->recs_since_rebin >= h->rebin_every) {
+      // the other RowOrder is free: the only work that could still use it reads half D, and that is complete (above)
+      int rc = rebin_rows(h, h->order[S.ord], h->order[S.ord ^ 1], h->d_state_cur, D.in);
       if (rc) return rc;
-      if (h->overlap) {  // the initial-storage output of record 0 (below) reads the new order
+      D.ord = S.ord ^ 1;
+      input = D.in;
+      h->recs_since_rebin = 0;
+    } else {
+      D.ord = S.ord;
+    }
+    h->recs_since_rebin += n;
+    const RowOrder& R = h->order[D.ord];
+    Tables t = h->t;
+    t.hrupar = R.hrupar;
+    t.slot_of_hru = R.slot_of_hru;
+    t.hrurec = input;
+    RecBlock rb;
+    rb.n = n;
+    rb.rec0 = brec0;
+    for (int i = 0; i < n; i++) {
+      const int* d = &dmy[(i0 + i) * 5];
+      rb.dmy[i] = Dmy{d[0], d[1], d[2], d[3], d[4]};
+      rb.ga[i] = pack_ga(glacier_accum_flags(h->o, d, d + 5, brec0 + i, &h->glac_started));
+    }
+    if (brec0 == 0) {
+      // storage terms of the initial state: put_data(rec = -nrecs), vicNl.c:524-541
+      if (h->overlap) {
         CK(cudaEventRecord(h->ev_step, h->stream));
         CK(cudaStreamWaitEvent(so, h->ev_step, 0));
       }
-    }
-    h->recs_since_bin++;
-    const int cur = h->cur, nxt = h->cur ^ 1;
-    Tables t = h->t;
-    t.hrurec = h->d_hrurec2[cur];
-    t.hrurec_out = h->d_hrurec2[nxt];
-    t.hdiag_out = h->d_hdiag2[nxt];
-    if (rec == 0) {
       Tables t0 = t;
-      t0.hrurec_out = h->d_hrurec2[cur];  // storage terms of the initial state
-      k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t0, nullptr, -1, h->step_count);
+      t0.hrurec_out = const_cast<double*>(input);
+      t0.hdiag_out = D.hdiag;
+      k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t0, nullptr, -1, h->step_count + 1);
       h->last_launches++;
-      if (h->overlap) {
-        CK(cudaEventRecord(h->ev_out[cur], so));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_out[cur], 0));
-      }
     }
-    Dmy d = {dmy[i * 5 + 0], dmy[i * 5 + 1], dmy[i * 5 + 2], dmy[i * 5 + 3], dmy[i * 5 + 4]};
-    GlacAccum ga = glacier_accum_flags(h->o, &dmy[i * 5], &dmy[(i + 1) * 5], rec, &h->glac_started);
-    if (h->overlap) CK(cudaStreamWaitEvent(h->stream, h->ev_out[nxt], 0));  // the output that last read buffer nxt
+    const double* frec = h->d_forcing + (size_t)(brec0 - h->frec0) * per;
     unsigned long long* wns = nullptr;
     if (h->profiling && h->warp_timing) {
-      const size_t nw = ((size_t)h->t.nhru + 31) / 32;
+      const size_t nw = ((size_t)nhru + 31) / 32;
       if (!h->d_warp_ns) CK(cudaMalloc(&h->d_warp_ns, 2 * nw * sizeof(unsigned long long)));
       CK(cudaMemsetAsync(h->d_warp_ns, 0, 2 * nw * sizeof(unsigned long long), h->stream));
       wns = h->d_warp_ns;
     }
-    if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream, wns);
-    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream, wns);
-    else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, d, rec, ga, h->hru_block, h->stream, wns);
-    if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));
+    if (h->profiling) CK(cudaEventRecord(h->pev[2 * blk], h->stream));
+    if (n == 1) {
+      // one record per launch: all warps of the grid start the record together (see the note on the instruction cache in DESIGN.md)
+      t.hrurec_out = D.snap;
+      t.hdiag_out = D.hdiag;
+      const GlacAccum ga = {rb.ga[0] & 1, (rb.ga[0] >> 1) & 1, (rb.ga[0] >> 2) & 1, (rb.ga[0] >> 3) & 1};
+      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns);
+      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns);
+      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns);
+      h->last_launches++;
+    } else {
+      if (h->o.Nnode <= 3) vicgpu_launch_hru_steps_nn3(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);
+      else if (h->o.Nnode <= 10) vicgpu_launch_hru_steps_nn10(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);
+      else vicgpu_launch_hru_steps_nn32(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);
+      k_freeze_failed<<<(nhru + 255) / 256, 256, 0, h->stream>>>(t, brec0, n, D.snap, snap_stride, L.hr_stride);
+      h->last_launches += 2;
+    }
+    if (h->profiling) CK(cudaEventRecord(h->pev[2 * blk + 1], h->stream));
     if (h->overlap) {
       CK(cudaEventRecord(h->ev_step, h->stream));
       CK(cudaStreamWaitEvent(so, h->ev_step, 0));
     }
-    k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t, frec, rec, h->step_count);
-    h->last_launches += 2;
-    if (out_data) {
-      int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1, so);
-      if (rc) return rc;
-      CK(cudaMemcpyAsync(out_data + (size_t)i * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
-    }
-    if (h->step_count == h->o.out_step_ratio) {
-      if (out_agg) {
-        int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1, so);
+    // cell outputs of the block's records, from the snapshots
+    for (int i = 0; i < n; i++) {
+      h->step_count++;
+      t.hrurec_out = D.snap + (size_t)i * snap_stride;
+      t.hdiag_out = D.hdiag + (size_t)i * 3 * nhru;
+      k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t, frec + (size_t)i * per, brec0 + i, h->step_count);
+      h->last_launches++;
+      if (out_data) {
+        int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1, so);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(out_data + (size_t)(i0 + i) * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
       }
-      nagg++;
-      CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), so));
-      h->step_count = 0;
+      if (h->step_count == h->o.out_step_ratio) {
+        if (out_agg) {
+          int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1, so);
+          if (rc) return rc;
+          CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
+        }
+        nagg++;
+        CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), so));
+        h->step_count = 0;
+      }
     }
-    if (h->overlap) CK(cudaEventRecord(h->ev_out[nxt], so));
-    h->cur = nxt;
+    if (h->overlap) CK(cudaEventRecord(D.ev_out, so));
+    h->d_state_cur = D.snap + (size_t)(n - 1) * snap_stride;
+    h->cur_half ^= 1;
   }
-  if (h->overlap) CK(cudaStreamWaitEvent(h->stream, h->ev_out[h->cur], 0));
+  if (h->overlap) CK(cudaStreamWaitEvent(h->stream, h->half[h->cur_half].ev_out, 0));
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
@@ -554,9 +639,9 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
   if (h->profiling) {
-    for (int i = 0; i < nrec; i++) {
+    for (int blk = 0; blk < nblocks; blk++) {
       float k = 0;
-      CK(cudaEventElapsedTime(&k, h->pev[2 * i], h->pev[2 * i + 1]));
+      CK(cudaEventElapsedTime(&k, h->pev[2 * blk], h->pev[2 * blk + 1]));
       h->prof_hru_ms += k;
       h->prof_hru_launches++;
     }
@@ -604,7 +689,7 @@ int vicgpu_get_warp_times(vicgpu_handle* h, double* times, double* kind, int max
   std::vector<unsigned long long> ns((size_t)2 * nw);
   CK(cudaMemcpy(ns.data(), h->d_warp_ns, ns.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   std::vector<double> hp((size_t)h->t.nhru * HP_N);
-  CK(cudaMemcpy(hp.data(), h->d_hrupar, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hp.data(), h->order[h->half[h->cur_half].ord].hrupar, hp.size() * sizeof(double), cudaMemcpyDeviceToHost));
   unsigned long long t0 = ~0ull;
   for (int w = 0; w < nw; w++) if (ns[2 * w] && ns[2 * w] < t0) t0 = ns[2 * w];
   const size_t n = (size_t)h->t.nhru;

@@ -17,6 +17,20 @@ inline int vicgpu_fail(int code, const std::string& msg) {
     if (e_ != cudaSuccess) return vicgpu_fail(VICGPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// one half of the double-buffered state (vicgpu_api.cu "state halves")
+struct StateHalf {
+  double* in = nullptr;      // [hr_stride][nhru] input state of a record block, in this half's row order
+  double* snap = nullptr;    // [rb][hr_stride][nhru] state after each record of the block
+  double* hdiag = nullptr;   // [rb][3][nhru] Cv-weighted out_prec / out_rain / out_snow of each record
+  int ord = 0;               // which RowOrder its rows are in
+  cudaEvent_t ev_out = nullptr;  // the last cell-output work that reads this half
+};
+// a row order of the HRU tables: the parameter table in that order and the maps row <-> caller's HRU index (null: identity)
+struct RowOrder {
+  double* hrupar = nullptr;  // [HP_N][nhru]
+  int *slot_of_hru = nullptr, *hru_of_slot = nullptr;
+};
+
 struct vicgpu_handle {
   int device = 0;
   vicgpu_options abi;
@@ -24,34 +38,32 @@ struct vicgpu_handle {
   vic::Opts* d_o = nullptr;
   vic::Tables t;
   int nout = 0;
-  // HRU state and step diagnostics are double-buffered: record r reads buffer `cur` and writes `cur ^ 1` (vicgpu_step)
-  double *d_hrurec2[2] = {nullptr, nullptr}, *d_hdiag2[2] = {nullptr, nullptr};
-  int cur = 0;
+  StateHalf half[2];
+  RowOrder order[2];
+  int rebin_every = 24, recs_since_rebin = 1 << 30;  // records between re-sorts of the rows
+  int cur_half = 0;               // the half whose row order d_state_cur is in
+  double* d_state_cur = nullptr;  // current state: half.in after set_state, else the last snapshot of the last block
+  int recblock = VICGPU_RECBLOCK_MAX, rb = 1;  // records per launch: requested, and what fits in memory
+  bool binned = true, rebin = true, overlap = true;
   int* d_fail_rec = nullptr;
-  cudaStream_t stream_out = nullptr;  // cell output (put_data) of record r runs here, beside the HRU step of record r + 1
-  cudaEvent_t ev_step = nullptr, ev_out[2] = {nullptr, nullptr};
-  bool overlap = true;
-  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_hrupar = nullptr, *d_carry = nullptr,
-         *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr, *d_forcing = nullptr, *d_fstage = nullptr;
+  cudaStream_t stream = nullptr, stream_out = nullptr;  // HRU step / cell output
+  cudaEvent_t ev_step = nullptr, ev0 = nullptr, ev1 = nullptr;
+  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_carry = nullptr, *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr,
+         *d_forcing = nullptr, *d_fstage = nullptr;
   size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
-  int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr, *d_slot_of_hru = nullptr, *d_hru_of_slot = nullptr;
-  bool binned = true;
-  // dynamic re-binning (vicgpu_api.cu rebin_rows)
-  int rebin_interval = 24, recs_since_bin = 1 << 30;
-  double* d_hrupar_alt = nullptr;
+  int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
+  int hru_block = VICGPU_HRU_BLOCK;
+  // re-binning scratch (vicgpu_api.cu rebin_rows)
   unsigned long long* d_keys[2] = {nullptr, nullptr};
   int* d_oldslot[2] = {nullptr, nullptr};
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
-  int hru_block = VICGPU_HRU_BLOCK;
   int frec0 = 0, fnrec = 0;
   bool have_cells = false, have_state = false, glac_started = false;
   int step_count = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0;
   long long last_launches = 0;
-  // optional per-launch timing of the per-HRU step kernel (vicgpu_set_profiling)
+  // optional timing of the step kernel launches (vicgpu_set_profiling)
   bool profiling = false, warp_timing = false;
   unsigned long long* d_warp_ns = nullptr;  // [2 * nwarps] start / end of every warp of the last profiled step launch
   std::vector<cudaEvent_t> pev;
