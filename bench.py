@@ -299,11 +299,9 @@ def main():
             g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
         barrier()
         e2e_wall = time.perf_counter() - t0
-    # max over ranks
-    times = torch.tensor([dev_ms / 1e3, wall, e2e_wall if not a.no_e2e else 0.0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_s, wall_s, e2e_s = [float(x) for x in times.cpu()]
+    # max over ranks (vic_b200/shard.py; covered by the world_size-2 gloo test)
+    from vic_b200.shard import max_over_ranks
+    dev_s, wall_s, e2e_s = max_over_ranks([dev_ms / 1e3, wall, e2e_wall if not a.no_e2e else 0.0], device="cuda")
     units = a.cells * RECS_PER_STEP * K * world
     line = None
     if rank == 0:
@@ -313,21 +311,28 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6544.7))
-        per_launch_bytes = ALGO_BYTES_PER_CELL_STEP * a.cells
+        recs_per_launch = (K * RECS_PER_STEP) / max(hru_n, 1)   # 1 unless VICGPU_RECBLOCK > 1
+        per_launch_bytes = ALGO_BYTES_PER_CELL_STEP * a.cells * recs_per_launch
         hru_avg_s = hru_ms / 1e3 / max(hru_n, 1)
         achieved = per_launch_bytes / hru_avg_s / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_hru_step_nn3"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {"metric": "cell-timesteps/s", "value": units / dev_s, "unit": "cell-timesteps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "cells_per_gpu": a.cells, "hrus_per_gpu": int(g.nhru), "records_per_step": RECS_PER_STEP,
-                           "l2": "no flush: per-step working set (HRU state 75 MB r/w + output rows 33 MB + forcing 21 MB) exceeds the 126 MB L2; "
+                           "l2": "no flush: what a record touches (two 76 MB state buffers, 380 MB of thread-local stack, 33 MB of output rows, forcing) exceeds the 126 MB L2; "
                                  "the persistent model state is legitimately cache/HBM resident between records",
                            "timing": "value: sum of CUDA-event device time of the K timed vicgpu_step calls (max over ranks); wall for the same region "
                                      f"{wall_s:.3f} s", "invalid_cells": int((status != 0).sum())},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": "k_hru_step_nn3", "avg_launch_us": hru_avg_s * 1e6, "launches_timed": int(hru_n),
                              "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6544.7",
-                             "kernel_share_of_step": (hru_ms / 1e3) / dev_s if dev_s > 0 else None},
+                             "kernel_share_of_step": (hru_ms / 1e3) / dev_s if dev_s > 0 else None,
+                             "note": "latency / instruction-cache bound, not bandwidth bound: see profiles/ and DESIGN.md section 6"},
                 "clocks": cs.summary()}
         if not a.no_e2e:
             line["e2e"] = {"value": units / e2e_s, "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(24 * a.cells * L.f_stride * 8),

@@ -20,11 +20,16 @@ for l in elf.splitlines():
         break
     elif on:
         p = l.split()
-        if len(p) >= 7 and p[3] == "0x2":
+        # out-of-line device functions are named $<kernel>$<function>; keep those of the single-record kernel k_hru_step_nn*
+        if len(p) >= 7 and p[3] == "0x2" and p[6].startswith("$") and "k_hru_step_nn" in p[6].split("$")[1]:
             syms.append((int(p[1], 16), int(p[2], 16), p[6]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:k_hru_step", "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr, data = rows[1], rows[2:]
+for k, r in enumerate(data):  # a report with several launches repeats the two header rows: keep the first launch
+    if r and r[0] == "Kernel Name":
+        data = data[:k]
+        break
 ia = hdr.index("Address")
 a0 = int(data[0][ia], 16)
 cols = ["# Samples", "Instructions Executed", "Thread Instructions Executed", "stall_long_sb", "stall_no_inst", "stall_wait", "stall_branch_resolving",

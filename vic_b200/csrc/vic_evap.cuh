@@ -109,6 +109,7 @@ VIC_HDI void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doub
     double rc = calc_rc_m(memo, 0, veg.rmin, net_short, veg.RGL, air_temp, vpd, veg.LAI, 1.0);
     double evap = penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t / SEC_PER_DAY * wet_canopy;
     double root_sum = 1.0, spare_evap = 0.0;
+    #pragma unroll 1
     for (int i = 0; i < NL; i++) {
       if (avail_moist[i] >= s.Wcr[i]) layerevap[i] = evap * (double)s.root[i];
       else {
@@ -121,9 +122,11 @@ VIC_HDI void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doub
       }
     }
     if (spare_evap > 0.0)
+      #pragma unroll 1
       for (int i = 0; i < NL; i++)
         if (avail_moist[i] >= s.Wcr[i]) layerevap[i] += (double)s.root[i] * spare_evap / root_sum;
   } else {
+    #pragma unroll 1
     for (int i = 0; i < NL; i++) {
       double gsm_inv;
       if (avail_moist[i] >= s.Wcr[i]) gsm_inv = 1.0;
@@ -135,6 +138,7 @@ VIC_HDI void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doub
       } else layerevap[i] = 0.0;
     }
   }
+  #pragma unroll 1
   for (int i = 0; i < NL; i++) {
     if (ice[i] > 0) {
       if (ice[i] >= s.Wpwp[i]) {
@@ -226,6 +230,7 @@ VIC_HDI double arno_evap(SoilLayer* layer, double rad, double air_temp, double v
       // 30-term series; the running power reproduces the reference's repeated product
       // tmpsum = ratio * ratio * ... (left to right), so the partial products are identical
       double dummy = 1.0, tmpsum = 1.0;
+      #pragma unroll 1
       for (int num_term = 1; num_term <= 30; num_term++) {
         tmpsum = (num_term == 1) ? ratio : tmpsum * ratio;
         dummy += b_infilt * tmpsum / (b_infilt + num_term);
@@ -256,6 +261,8 @@ VIC_HDI void compute_pot_evap(const VegLib& vl, int NVegLibTypes, int veg_class,
                               double net_longwave, double tair, double vpd, double elevation, const RaUsed* aero, double* pot_evap) {
   double net_short = 0.0;
   const bool cur_over = vl.row(veg_class).overstory();
+  const PenmanPre pm = penman_pre(tair, elevation);  // the same air temperature and elevation for all six land covers
+  #pragma unroll 1
   for (int i = 0; i < N_PET_TYPES; i++) {
     const int cls = (i < N_PET_TYPES_NON_NAT) ? NVegLibTypes + i : veg_class;
     VegRow r = vl.row(cls);
@@ -270,7 +277,7 @@ VIC_HDI void compute_pot_evap(const VegLib& vl, int NVegLibTypes, int veg_class,
     double ra = (i < N_PET_TYPES_NON_NAT || !cur_over) ? aero[i].surface : aero[i].overstory;
     net_short = (1.0 - albedo) * shortwave;
     double net_rad = net_short + net_longwave;
-    pot_evap[i] = penman(tair, elevation, net_rad, vpd, ra, rc, rarc) * dt / 24.0;
+    pot_evap[i] = penman_eval(pm, net_rad, vpd, ra, rc, rarc) * dt / 24.0;
   }
 }
 

@@ -74,7 +74,12 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
   const double soil_rough = cp(CP_rough);
   const double wind_NR = cx.f(FV_wind, o.NR);
   double in_prev[8] = {-1, 0, 0, 0, 0, 0, 0, 0};
+  // terms of the loop below that do not depend on the land cover: the leaf-area factor of calc_veg_height()
+  // (calc_veg_params.c:26-37) and the log-profile denominator of the wind correction
+  const double height_den = 1.1 * vlog(1 + vpow(0.2 * veg.LAI, 0.25));
+  const double wind_den = vlog((o.wind_h - 0.) / soil_rough);
   Surf4 snap_displacement = as.displacement, snap_ref_height = as.ref_height, snap_roughness = as.roughness, snap_wind_speed = as.displacement;
+  #pragma unroll 1
   for (int p = 0; p < N_PET_TYPES + 1; p++) {
     const int pet_class = (p < N_PET_TYPES_NON_NAT) ? o.NVegLibTypes + p : veg_class;
     VegRow r = cx.vl.row(pet_class);
@@ -83,11 +88,11 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
     as.displacement[SNOW_FREE] = r.m(VM_displacement, month0);
     overstory = r.overstory();
     if (p >= N_PET_TYPES_NON_NAT && as.roughness[SNOW_FREE] == 0) as.roughness[SNOW_FREE] = soil_rough;
-    height = calc_veg_height(as.displacement[SNOW_FREE], veg.LAI);
+    height = as.displacement[SNOW_FREE] / height_den;
     if (as.displacement[SNOW_FREE] < wind_h) as.ref_height[SNOW_FREE] = wind_h;
     else as.ref_height[SNOW_FREE] = as.displacement[SNOW_FREE] + wind_h + as.roughness[SNOW_FREE];
     // bring the forcing wind from its nominal height to the reference height (log profile over open ground)
-    const double wind_corr = vlog((as.ref_height[SNOW_FREE] - 0.) / soil_rough) / vlog((o.wind_h - 0.) / soil_rough);
+    const double wind_corr = vlog((as.ref_height[SNOW_FREE] - 0.) / soil_rough) / wind_den;
     as.wind_speed[SNOW_FREE] = wind_NR * wind_corr;
     as.wind_speed[CANOPY_OVER] = vnan();
     as.wind_speed[SNOW_COVERED] = vnan();

@@ -149,6 +149,7 @@ struct Hru {
 
 // columns col0 .. col0+count-1 of my record row  ->  dst[0 .. count)
 VIC_HD void cols_to_local(const double* __restrict__ rec, size_t n, int col0, int count, double* __restrict__ dst) {
+  #pragma unroll 1
   for (int k = 0; k < count; k += VIC_XFER_CHUNK) {
     double r[VIC_XFER_CHUNK];
 #pragma unroll
@@ -167,6 +168,7 @@ VIC_HD void cols_to_local(const double* __restrict__ rec, size_t n, int col0, in
   }
 }
 VIC_HD void local_to_cols(const double* __restrict__ src, double* __restrict__ rec, size_t n, int col0, int count) {
+  #pragma unroll 1
   for (int k = 0; k < count; k += VIC_XFER_CHUNK) {
     double r[VIC_XFER_CHUNK];
 #pragma unroll
