@@ -75,9 +75,12 @@ int main(int argc, char** argv) {
       if (status[c] != 0) fail_rec[c] = -1;
     }
 
+  // constants derived from the cell parameters, as the library computes them in vicgpu_set_cells
+  std::vector<double> cellder((size_t)VIC_NCELLDER * ncell);
+  for (int c = 0; c < ncell; c++) derive_cell_constants(CellPar{Col{cellpar.data() + c, (size_t)ncell}, &o.L}, cellder.data() + c, (size_t)ncell);
   Tables t;
   t.ncell = ncell; t.nhru = nhru; t.nclass = (int)cs["veglib"].dims[0];
-  t.veglib = cs["veglib"].f64.data(); t.cellpar = cellpar.data(); t.hrupar = hrupar.data(); t.hrurec = hrurec.data(); t.hrurec_out = hrurec.data(); t.hdiag_out = hdiag.data();
+  t.veglib = cs["veglib"].f64.data(); t.cellpar = cellpar.data(); t.cellder = cellder.data(); t.hrupar = hrupar.data(); t.hrurec = hrurec.data(); t.hrurec_out = hrurec.data(); t.hdiag_out = hdiag.data();
   t.cell_h0 = cell_h0.data(); t.status = status.data(); t.fail_rec = fail_rec.data(); t.carry = carry.data(); t.out = out.data(); t.agg = agg.data();
   t.aggtype = cs["aggtype"].i32.data();
   t.slot_of_hru = slot;

@@ -21,6 +21,7 @@ struct Tables {
   int ncell, nhru, nclass;
   const double* veglib;   // [nclass][vl_stride]
   const double* cellpar;  // [cp_stride][ncell]
+  const double* cellder;  // [VIC_NCELLDER][ncell] constants derived from cellpar (derive_cell_constants), or null
   const double* hrupar;   // [HP_N][nhru]
   const double* hrurec;   // [hr_stride][nhru]  state at the start of the record (read by hru_work)
   double* hrurec_out;     // [hr_stride][nhru]  state at the end of the record (written by hru_work, read by cell_output);
@@ -64,7 +65,7 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   }
   Ctx cx;
   cx.o = o;
-  cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L};
+  cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L, Col{t.cellder ? t.cellder + cell : nullptr, (size_t)t.ncell}};
   cx.vl = VegLib{t.veglib, &o->L};
   cx.hp = hpc;
   cx.f = Forcing{Col{forcing_rec + cell, (size_t)t.ncell}, o->L.f_nslot};
@@ -122,7 +123,7 @@ VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcin
   const int cell = (int)hpc(HP_cell);
   Ctx cx;
   cx.o = o;
-  cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L};
+  cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L, Col{t.cellder ? t.cellder + cell : nullptr, (size_t)t.ncell}};
   cx.vl = VegLib{t.veglib, &o->L};
   cx.hp = hpc;
   const HruPar hp = load_hrupar(hpc);

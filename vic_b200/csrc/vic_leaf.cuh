@@ -255,31 +255,48 @@ VIC_HD void latent_heat_from_snow(double AirDens, double EactAir, double Lv, dou
   }
 }
 
-// Johansen thermal conductivity, soil_conduction.c:7-105
-VIC_HD double soil_conductivity(double moist, double Wu, double soil_dens_min, double bulk_dens_min, double quartz,
-                                double soil_density, double bulk_density, double organic) {
-  const double Ki = 2.2, Kw = 0.57, Kdry_org = 0.05, Ks_org = 0.25;
-  double Ke, Ksat, K;
+// Johansen thermal conductivity, soil_conduction.c:7-105.  Everything that depends on the layer's soil constants only -- the dry and
+// solid conductivities and the two powers of the unfrozen saturated conductivity -- is split off (SoilKPre): the library evaluates it
+// once per (cell, layer) when the cells are set (derive_cell_constants, vic_engine.cuh) instead of at every node and layer of every
+// step; the same operations in the same order, hence the same bits.
+struct SoilKPre {
+  double Kdry, porosity, Ks_pow, Ksat_unfrozen;  // Ks_pow = Ks^(1 - porosity); Ksat_unfrozen = Ks_pow * Kw^porosity
+};
+#define VIC_NKPRE 4
+VIC_HD SoilKPre soil_k_pre(double soil_dens_min, double bulk_dens_min, double quartz, double soil_density, double bulk_density, double organic) {
+  const double Kw = 0.57, Kdry_org = 0.05, Ks_org = 0.25;
+  SoilKPre p;
   double Kdry_min = (0.135 * bulk_dens_min + 64.7) / (soil_dens_min - 0.947 * bulk_dens_min);
-  double Kdry = (1 - organic) * Kdry_min + organic * Kdry_org;
+  p.Kdry = (1 - organic) * Kdry_min + organic * Kdry_org;
+  p.porosity = 1.0 - bulk_density / soil_density;
+  double Ks_min;
+  if (quartz < .2) Ks_min = vpow(7.7, quartz) * vpow(3.0, 1.0 - quartz);
+  else Ks_min = vpow(7.7, quartz) * vpow(2.2, 1.0 - quartz);
+  double Ks = (1 - organic) * Ks_min + organic * Ks_org;
+  p.Ks_pow = vpow(Ks, 1.0 - p.porosity);
+  p.Ksat_unfrozen = p.Ks_pow * vpow(Kw, p.porosity);
+  return p;
+}
+VIC_HD double soil_conductivity_pre(double moist, double Wu, const SoilKPre& p) {
+  const double Ki = 2.2, Kw = 0.57;
+  double Ke, Ksat, K;
   if (moist > 0.) {
-    double porosity = 1.0 - bulk_density / soil_density;
-    double Sr = moist / porosity;
-    double Ks_min;
-    if (quartz < .2) Ks_min = vpow(7.7, quartz) * vpow(3.0, 1.0 - quartz);
-    else Ks_min = vpow(7.7, quartz) * vpow(2.2, 1.0 - quartz);
-    double Ks = (1 - organic) * Ks_min + organic * Ks_org;
+    double Sr = moist / p.porosity;
     if (Wu == moist) {
-      Ksat = vpow(Ks, 1.0 - porosity) * vpow(Kw, porosity);
+      Ksat = p.Ksat_unfrozen;
       Ke = 0.7 * vlog10(Sr) + 1.0;
     } else {
-      Ksat = vpow(Ks, 1.0 - porosity) * vpow(Ki, porosity - Wu) * vpow(Kw, Wu);
+      Ksat = p.Ks_pow * vpow(Ki, p.porosity - Wu) * vpow(Kw, Wu);
       Ke = Sr;
     }
-    K = (Ksat - Kdry) * Ke + Kdry;
-    if (K < Kdry) K = Kdry;
-  } else K = Kdry;
+    K = (Ksat - p.Kdry) * Ke + p.Kdry;
+    if (K < p.Kdry) K = p.Kdry;
+  } else K = p.Kdry;
   return K;
+}
+VIC_HD double soil_conductivity(double moist, double Wu, double soil_dens_min, double bulk_dens_min, double quartz,
+                                double soil_density, double bulk_density, double organic) {
+  return soil_conductivity_pre(moist, Wu, soil_k_pre(soil_dens_min, bulk_dens_min, quartz, soil_density, bulk_density, organic));
 }
 
 // volumetric heat capacity, soil_conduction.c:108-139

@@ -10,6 +10,26 @@
 
 namespace vic {
 
+// derived per-(cell, layer) constants: [layer][VIC_NKPRE] of SoilKPre
+#define VIC_NCELLDER (VICGPU_NLAYER * VIC_NKPRE)
+VIC_HD SoilKPre cell_kpre(const CellPar& cp, int l) {
+  if (cp.d.p) return SoilKPre{cp.d(l * VIC_NKPRE + 0), cp.d(l * VIC_NKPRE + 1), cp.d(l * VIC_NKPRE + 2), cp.d(l * VIC_NKPRE + 3)};
+  return soil_k_pre(cp.layer(CL_soil_dens_min, l), cp.layer(CL_bulk_dens_min, l), cp.layer(CL_quartz, l), cp.layer(CL_soil_density, l),
+                    cp.layer(CL_bulk_density, l), cp.layer(CL_organic, l));
+}
+// fills out[k * stride], k < VIC_NCELLDER, for the cell cp views (device: one thread per cell at vicgpu_set_cells; host port: a loop)
+VIC_HD void derive_cell_constants(const CellPar& cp, double* out, size_t stride) {
+  for (int l = 0; l < VICGPU_NLAYER; l++) {
+    CellPar raw = cp;
+    raw.d = Col{nullptr, 0};
+    const SoilKPre p = cell_kpre(raw, l);
+    out[(size_t)(l * VIC_NKPRE + 0) * stride] = p.Kdry;
+    out[(size_t)(l * VIC_NKPRE + 1) * stride] = p.porosity;
+    out[(size_t)(l * VIC_NKPRE + 2) * stride] = p.Ks_pow;
+    out[(size_t)(l * VIC_NKPRE + 3) * stride] = p.Ksat_unfrozen;
+  }
+}
+
 // runoff.c:773-813
 VIC_HDI void compute_runoff_and_asat(const CellPar& cp, const double* moist, double inflow, double* A, double* runoff) {
   double top_moist = 0., top_max_moist = 0.;
@@ -80,15 +100,15 @@ VIC_HDI void distribute_node_moisture_properties(EnergyBal<NN>& energy, const Ce
       energy.moist[n] = moist[lidx] / d / 1000;
     const double mmn = cp.node(CN_max_moist_node, n);
     if (energy.moist[n] - mmn > 0) energy.moist[n] = mmn;
-    const double sdm = cp.layer(CL_soil_dens_min, lidx), bdm = cp.layer(CL_bulk_dens_min, lidx), q = cp.layer(CL_quartz, lidx);
     const double sd = cp.layer(CL_soil_density, lidx), bd = cp.layer(CL_bulk_density, lidx), org = cp.layer(CL_organic, lidx);
+    const SoilKPre kp = cell_kpre(cp, lidx);
     if (energy.T[n] < 0 && fs) {
       energy.ice[n] = energy.moist[n] - maximum_unfrozen_water(energy.T[n], mmn, cp.node(CN_bubble_node, n), cp.node(CN_expt_node, n));
       if (energy.ice[n] < 0) energy.ice[n] = 0;
-      energy.kappa_node[n] = soil_conductivity(energy.moist[n], energy.moist[n] - energy.ice[n], sdm, bdm, q, sd, bd, org);
+      energy.kappa_node[n] = soil_conductivity_pre(energy.moist[n], energy.moist[n] - energy.ice[n], kp);
     } else {
       energy.ice[n] = 0;
-      energy.kappa_node[n] = soil_conductivity(energy.moist[n], energy.moist[n], sdm, bdm, q, sd, bd, org);
+      energy.kappa_node[n] = soil_conductivity_pre(energy.moist[n], energy.moist[n], kp);
     }
     energy.Cs_node[n] = volumetric_heat_capacity(bd / sd, energy.moist[n] - energy.ice[n], energy.ice[n], org);
     if (zs > Lsum + d && !PAST_BOTTOM) {
@@ -346,8 +366,7 @@ VIC_HDI void prepare_full_energy(Hru<NN>& h, const CellPar& cp, double AreaFract
       const double dl = cp.layer(CL_depth, l);
       const double moist = h.cell.layer[l].moist / dl / 1000;
       const double ice = h.cell.layer[l].soil_ice / dl / 1000;
-      const double kappa = soil_conductivity(moist, moist - ice, cp.layer(CL_soil_dens_min, l), cp.layer(CL_bulk_dens_min, l),
-                                             cp.layer(CL_quartz, l), cp.layer(CL_soil_density, l), cp.layer(CL_bulk_density, l), cp.layer(CL_organic, l));
+      const double kappa = soil_conductivity_pre(moist, moist - ice, cell_kpre(cp, l));
       const double Cs = volumetric_heat_capacity(cp.layer(CL_bulk_density, l) / cp.layer(CL_soil_density, l), moist - ice, ice, cp.layer(CL_organic, l));
       if (l == 0) { h.energy.kappa0 = kappa; h.energy.Cs0 = Cs; }
       else { h.energy.kappa1 = kappa; h.energy.Cs1 = Cs; }

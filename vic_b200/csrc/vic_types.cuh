@@ -64,6 +64,7 @@ struct VegLib {
 struct CellPar {
   Col c;
   const vicgpu_layout* L;
+  Col d;  // constants derived from the cell parameters once per domain (derive_cell_constants); d.p == nullptr: not available
   VIC_HD double operator()(int k) const { return c(k); }
   VIC_HD double layer(int f, int i) const { return c(VICGPU_CP_LAYER(L, f, i)); }
   VIC_HD double node(int f, int i) const { return c(VICGPU_CP_NODE(L, f, i)); }

@@ -105,6 +105,13 @@ __global__ void k_freeze_failed(Tables t, int rec0, int n, double* snap, size_t 
   }
 }
 
+// constants derived from the cell parameters, once per vicgpu_set_cells (vic_soil.cuh derive_cell_constants)
+__global__ void k_derive_cells(const Opts* __restrict__ o, const double* __restrict__ cellpar, double* __restrict__ cellder, int ncell) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  derive_cell_constants(CellPar{Col{cellpar + c, (size_t)ncell}, &o->L}, cellder + c, (size_t)ncell);
+}
+
 __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
                                                      int step_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,7 +293,7 @@ int vicgpu_destroy(vicgpu_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->overlap && h->stream_out) cudaStreamSynchronize(h->stream_out);
-  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar);
+  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_cellder);
   for (int b = 0; b < 2; b++) {
     free_half(h->half[b]);
     free_order(h->order[b]);
@@ -351,7 +358,8 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   const char* deal = getenv("VICGPU_DEAL");
   const bool dealing = deal && atoi(deal) != 0;
   if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru, dealing ? (nhru + h->hru_block - 1) / h->hru_block : 0);
-  cudaFree(h->d_cellpar); cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
+  cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
+  h->d_cellder = nullptr;
   cudaFree(h->d_fail_rec); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]); cudaFree(h->d_warp_ns);
   h->d_cellpar = h->d_carry = h->d_out = h->d_agg = nullptr;
   h->d_cell_h0 = h->d_status = h->d_fail_rec = nullptr;
@@ -370,6 +378,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   while (rbn > 1 && 2 * (size_t)rbn * state_bytes > free_b / 3) rbn--;
   h->rb = rbn;
   CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
+  CK(cudaMalloc(&h->d_cellder, (size_t)ncell * VIC_NCELLDER * sizeof(double)));
   for (int b = 0; b < 2; b++) {
     StateHalf& s = h->half[b];
     CK(cudaMalloc(&s.in, state_bytes));
@@ -413,10 +422,13 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   CK(cudaMemcpy(h->d_cell_h0, h0.data(), (size_t)(ncell + 1) * sizeof(int), cudaMemcpyHostToDevice));
   int rc = upload_transposed(h, cellpar, h->d_cellpar, ncell, L.cp_stride);
   if (rc) return rc;
+  k_derive_cells<<<(ncell + 127) / 128, 128, 0, h->stream>>>(h->d_o, h->d_cellpar, h->d_cellder, ncell);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
   rc = upload_transposed(h, hrupar, h->order[0].hrupar, nhru, HP_N, h->order[0].hru_of_slot);
   if (rc) return rc;
   h->t.ncell = ncell; h->t.nhru = nhru;
-  h->t.cellpar = h->d_cellpar; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
+  h->t.cellpar = h->d_cellpar; h->t.cellder = h->d_cellder; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
   h->t.status = h->d_status; h->t.carry = h->d_carry; h->t.out = h->d_out; h->t.agg = h->d_agg; h->t.aggtype = h->d_aggtype;
   h->cur_half = 0;
   h->d_state_cur = h->half[0].in;

@@ -48,7 +48,7 @@ struct vicgpu_handle {
   int* d_fail_rec = nullptr;
   cudaStream_t stream = nullptr, stream_out = nullptr;  // HRU step / cell output
   cudaEvent_t ev_step = nullptr, ev0 = nullptr, ev1 = nullptr;
-  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_carry = nullptr, *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr,
+  double *d_veglib = nullptr, *d_cellpar = nullptr, *d_cellder = nullptr, *d_carry = nullptr, *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr,
          *d_forcing = nullptr, *d_fstage = nullptr;
   size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
   int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
