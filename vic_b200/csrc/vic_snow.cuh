@@ -19,9 +19,12 @@ struct SnowPackEB {
   double Dt, Ra, Z, Z0_snow, AirDens, EactAir, LongSnowIn, Lv, Press, Rain, NetShortUnder, Vpd, Wind, OldTSurf;
   double SnowDepth, SnowDensity, SurfaceLiquidWater, SweSurfaceLayer, Tair, TGrnd;
   // outputs
+  // (values, not pointers to the caller's variables: an evaluation then reads and writes the functor only; snow_melt binds
+  // references to these members)
   RaUsed* Ra_used;
-  double *AdvectedEnergy, *AdvectedSensibleHeat, *DeltaColdContent, *GroundFlux, *LatentHeat, *LatentHeatSub, *NetLongUnder,
-      *RefreezeEnergy, *SensibleHeat, *vapor_flux, *blowing_flux, *surface_flux;
+  SnowPack* sn;  // vapor_flux, blowing_flux, surface_flux
+  double* NetLongUnder;
+  double AdvectedEnergy, AdvectedSensibleHeat, DeltaColdContent, GroundFlux, LatentHeat, LatentHeatSub, RefreezeEnergy, SensibleHeat;
   StabLog stab;
 
   VIC_HDI double operator()(double TSurf) {
@@ -32,27 +35,27 @@ struct SnowPackEB {
     const double Tmp = TMean + KELVIN;
     *NetLongUnder = LongSnowIn - STEFAN_B * Tmp * Tmp * Tmp * Tmp;
     const double NetRad = NetShortUnder + (*NetLongUnder);
-    *SensibleHeat = AirDens * Cp * (Tair - TMean) / Ra_used->surface;
-    *AdvectedSensibleHeat = 0;
-    double VaporMassFlux = div_pos(*vapor_flux * Density, Dt);
-    double BlowingMassFlux = div_pos(*blowing_flux * Density, Dt);
-    double SurfaceMassFlux = div_pos(*surface_flux * Density, Dt);
-    latent_heat_from_snow(AirDens, EactAir, Lv, Press, Ra_used->surface, TMean, Vpd, LatentHeat, LatentHeatSub, &VaporMassFlux,
+    SensibleHeat = AirDens * Cp * (Tair - TMean) / Ra_used->surface;
+    AdvectedSensibleHeat = 0;
+    double VaporMassFlux = div_pos(sn->vapor_flux * Density, Dt);
+    double BlowingMassFlux = div_pos(sn->blowing_flux * Density, Dt);
+    double SurfaceMassFlux = div_pos(sn->surface_flux * Density, Dt);
+    latent_heat_from_snow(AirDens, EactAir, Lv, Press, Ra_used->surface, TMean, Vpd, &LatentHeat, &LatentHeatSub, &VaporMassFlux,
                           &BlowingMassFlux, &SurfaceMassFlux);
-    *vapor_flux = div_pos(VaporMassFlux * Dt, Density);
-    *blowing_flux = div_pos(BlowingMassFlux * Dt, Density);
-    *surface_flux = div_pos(SurfaceMassFlux * Dt, Density);
-    if (TMean == 0) *AdvectedEnergy = div_pos((CH_WATER * (Tair)*Rain), (Dt));
-    else *AdvectedEnergy = 0.;
-    *DeltaColdContent = div_pos(CH_ICE * SweSurfaceLayer * (TSurf - OldTSurf), (Dt));
-    if (SnowDepth > 0.) *GroundFlux = K_SNOW * SnowDensity * SnowDensity * (TGrnd - TMean) / SnowDepth / (Dt);
-    else *GroundFlux = 0;
-    double RestTerm = NetRad + *SensibleHeat + *LatentHeat + *LatentHeatSub + *AdvectedEnergy + *AdvectedSensibleHeat - *DeltaColdContent + *GroundFlux;
-    *RefreezeEnergy = div_pos((SurfaceLiquidWater * Lf * Density), (Dt));
-    if (TSurf == 0.0 && RestTerm > -(*RefreezeEnergy)) {
-      *RefreezeEnergy = -RestTerm;
+    sn->vapor_flux = div_pos(VaporMassFlux * Dt, Density);
+    sn->blowing_flux = div_pos(BlowingMassFlux * Dt, Density);
+    sn->surface_flux = div_pos(SurfaceMassFlux * Dt, Density);
+    if (TMean == 0) AdvectedEnergy = div_pos((CH_WATER * (Tair)*Rain), (Dt));
+    else AdvectedEnergy = 0.;
+    DeltaColdContent = div_pos(CH_ICE * SweSurfaceLayer * (TSurf - OldTSurf), (Dt));
+    if (SnowDepth > 0.) GroundFlux = K_SNOW * SnowDensity * SnowDensity * (TGrnd - TMean) / SnowDepth / (Dt);
+    else GroundFlux = 0;
+    double RestTerm = NetRad + SensibleHeat + LatentHeat + LatentHeatSub + AdvectedEnergy + AdvectedSensibleHeat - DeltaColdContent + GroundFlux;
+    RefreezeEnergy = div_pos((SurfaceLiquidWater * Lf * Density), (Dt));
+    if (TSurf == 0.0 && RestTerm > -RefreezeEnergy) {
+      RefreezeEnergy = -RestTerm;
       RestTerm = 0.0;
-    } else RestTerm += *RefreezeEnergy;
+    } else RestTerm += RefreezeEnergy;
     return RestTerm;
   }
 };
@@ -63,11 +66,16 @@ struct SnowMeltOut {
 
 // snow_melt.c:119-564.  Returns 0, or ERROR_I when the surface solve fails and TFALLBACK is off.
 VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy, double Tgrnd, double Z0_snow, double aero_resist,
-                      RaUsed& aero_resist_used, double air_temp, double delta_t, double density, double grnd_flux, double LongSnowIn,
+                      RaUsed& aero_resist_used, double air_temp, double delta_t, double density, double grnd_flux_in, double LongSnowIn,
                       double pressure, double rainfall, double snowfall, double vp, double vpd, double wind, double z2, bool UNSTABLE_SNOW,
                       SnowPack& snow, const Opts& o, SnowMeltOut& out, bool GLAC = false, double* firn_to_ice = nullptr) {
   double DeltaPackCC, DeltaPackSwq, SnowMelt = 0, RefrozenWater;
-  double advection = 0, deltaCC = 0, latent_heat = 0, latent_heat_sub = 0, sensible_heat = 0, advected_sensible_heat = 0, RefreezeEnergy = 0;
+  SnowPackEB eb;
+  double &advection = eb.AdvectedEnergy, &deltaCC = eb.DeltaColdContent, &latent_heat = eb.LatentHeat, &latent_heat_sub = eb.LatentHeatSub,
+         &sensible_heat = eb.SensibleHeat, &advected_sensible_heat = eb.AdvectedSensibleHeat, &RefreezeEnergy = eb.RefreezeEnergy,
+         &grnd_flux = eb.GroundFlux;
+  advection = 0; deltaCC = 0; latent_heat = 0; latent_heat_sub = 0; sensible_heat = 0; advected_sensible_heat = 0; RefreezeEnergy = 0;
+  grnd_flux = grnd_flux_in;
   double melt_energy = 0.;
   const double SnowFall = snowfall / 1000.;
   const double RainFall = rainfall / 1000.;
@@ -120,17 +128,14 @@ VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy
   Ice += SnowFall;
   snow.surf_water += RainFall;
 
-  SnowPackEB eb;
   eb.stab.reset();
   eb.Dt = delta_t; eb.Ra = aero_resist; eb.Z = z2; eb.Z0_snow = Z0_snow; eb.AirDens = density; eb.EactAir = vp;
   eb.LongSnowIn = LongSnowIn; eb.Lv = latent_heat_Le; eb.Press = pressure; eb.Rain = RainFall; eb.NetShortUnder = NetShortSnow;
   eb.Vpd = vpd; eb.Wind = wind; eb.OldTSurf = out.OldTSurf; eb.SnowDepth = snow.depth; eb.SnowDensity = snow.density;
   eb.SurfaceLiquidWater = snow.surf_water; eb.SweSurfaceLayer = SurfaceSwq; eb.Tair = Tcanopy; eb.TGrnd = Tgrnd;
   eb.Ra_used = &aero_resist_used;
-  eb.AdvectedEnergy = &advection; eb.AdvectedSensibleHeat = &advected_sensible_heat; eb.DeltaColdContent = &deltaCC;
-  eb.GroundFlux = &grnd_flux; eb.LatentHeat = &latent_heat; eb.LatentHeatSub = &latent_heat_sub; eb.NetLongUnder = &out.NetLongSnow;
-  eb.RefreezeEnergy = &RefreezeEnergy; eb.SensibleHeat = &sensible_heat; eb.vapor_flux = &snow.vapor_flux;
-  eb.blowing_flux = &snow.blowing_flux; eb.surface_flux = &snow.surface_flux;
+  eb.NetLongUnder = &out.NetLongSnow;
+  eb.sn = &snow;
 
   double Qnet = eb(0.0);
   if (!UNSTABLE_SNOW) {
@@ -303,7 +308,7 @@ struct CanopyEB {
   // inputs
   double delta_t, elevation, AirDens, EactAir, Press, latent_heat_Le, Tcanopy, Vpd, IntRain, IntSnow, LongOverIn, LongUnderOut, NetShortOver;
   int AERO_RESIST_CANSNOW;
-  const Surf4 *Ra, *wind_speed, *displacement, *ref_height, *roughness;
+  double ra_free, ra_over, ws_over, zref_over, disp_over, rough_over;  // the entries of the aerodynamic tables the residual reads
   const VegNow* veg;
   const SoilET* soil;
   // in/out
@@ -323,14 +328,14 @@ struct CanopyEB {
     *NetLongOver = LongOverIn - (*LongOverOut);
     const int ar = AERO_RESIST_CANSNOW;
     if (IntSnow > 0) {
-      Ra_used->surface = (*Ra)[SNOW_FREE];
-      Ra_used->overstory = (*Ra)[CANOPY_OVER];
+      Ra_used->surface = ra_free;
+      Ra_used->overstory = ra_over;
       if (ar == AR_COMBO || ar == AR_406 || ar == AR_406_LS || ar == AR_406_FULL) Ra_used->overstory *= 10.;
       const double EsSnow = svp(Tfoliage);
       if (ar == AR_COMBO || ar == AR_410) {
-        if ((*wind_speed)[CANOPY_OVER] > 0.0)
-          Ra_used->overstory /= stab.correction((*ref_height)[CANOPY_OVER], (*displacement)[CANOPY_OVER], Tfoliage, Tcanopy,
-                                                     (*wind_speed)[CANOPY_OVER], (*roughness)[CANOPY_OVER]);
+        if (ws_over > 0.0)
+          Ra_used->overstory /= stab.correction(zref_over, disp_over, Tfoliage, Tcanopy,
+                                                     ws_over, rough_over);
         else Ra_used->overstory = HUGE_RESIST;
       }
       *VaporMassFlux = AirDens * (EPS / Press) * (EactAir - EsSnow) / Ra_used->overstory / RHO_W;
@@ -343,11 +348,11 @@ struct CanopyEB {
       if (ar == AR_406) Ra_used->overstory /= 10;
     } else {
       if (ar == AR_406_FULL || ar == AR_410 || ar == AR_COMBO) {
-        Ra_used->surface = (*Ra)[SNOW_FREE];
-        Ra_used->overstory = (*Ra)[CANOPY_OVER];
+        Ra_used->surface = ra_free;
+        Ra_used->overstory = ra_over;
       } else {
-        Ra_used->surface = (*Ra)[SNOW_FREE];
-        Ra_used->overstory = (*Ra)[SNOW_FREE];
+        Ra_used->surface = ra_free;
+        Ra_used->overstory = ra_free;
       }
       *Wdew = IntRain * 1000.;
       const double prec = *Rainfall * 1000;
@@ -492,7 +497,8 @@ VIC_HDI int snow_intercept(double Dt, double LAI, double latent_heat_Le, double 
   eb.delta_t = Dt; eb.elevation = cp(CP_elevation); eb.AirDens = AirDens; eb.EactAir = EactAir; eb.Press = Press;
   eb.latent_heat_Le = latent_heat_Le; eb.Tcanopy = Tcanopy; eb.Vpd = Vpd; eb.IntRain = IntRainOrg; eb.LongOverIn = LongOverIn;
   eb.LongUnderOut = LongUnderOut; eb.AERO_RESIST_CANSNOW = o.AERO_RESIST_CANSNOW;
-  eb.Ra = &Ra; eb.wind_speed = &wind_speed; eb.displacement = &displacement; eb.ref_height = &ref_height; eb.roughness = &roughness;
+  eb.ra_free = Ra[SNOW_FREE]; eb.ra_over = Ra[CANOPY_OVER]; eb.ws_over = wind_speed[CANOPY_OVER]; eb.zref_over = ref_height[CANOPY_OVER];
+  eb.disp_over = displacement[CANOPY_OVER]; eb.rough_over = roughness[CANOPY_OVER];
   eb.veg = &veg; eb.soil = &soil; eb.Ra_used = &Ra_used; eb.Rainfall = RainFall; eb.Wdew = IntRain; eb.layer = layer; eb.vv = &vv;
   eb.Evap = &Evap; eb.AdvectedEnergy = &energy.canopy_advection; eb.LatentHeat = &energy.canopy_latent;
   eb.LatentHeatSub = &energy.canopy_latent_sub; eb.LongOverOut = LongOverOut; eb.NetLongOver = &energy.NetLongOver;

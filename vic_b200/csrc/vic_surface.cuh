@@ -24,6 +24,10 @@ struct SurfEB {
   const CellPar* cp;
   const VegNow* veg;
   const SoilET* soil;
+  // what the residual reads of *o, *cp, *veg and the aerodynamic tables, copied once per solve (prepare) so that an evaluation
+  // does not chase pointers: each of these was two or three dependent thread-local / global loads per evaluation
+  int QUICK_FLUX, GRND_FLUX_TYPE, FS_FROZEN;
+  double elevation, b_infilt, depth0, resid_moist0, veg_LAI, ws_under, ra_under, zref_under, disp_under, rough_under;
   // scalars captured by value
   int VEG, UnderStory, overstory, INCLUDE_SNOW, NOFLUX, EXP_TRANS, SNOWING, Nnodes;
   double delta_t, Cs1, Cs2, D1, D2, T1_old, T2, Ts_old, bubble, dp, expt, ice0, kappa1, kappa2, max_moist, moist;
@@ -33,12 +37,13 @@ struct SurfEB {
   const Surf4 *displacement, *aero_resist, *ref_height, *roughness, *wind_speed;
   // in/out
   RaUsed* aero_resist_used;
-  double *deltaCC, *refreeze_energy, *vapor_flux, *blowing_flux, *surface_flux;
+  EnergyBal<NN>* en;  // deltaCC, refreeze_energy, deltaH, fusion, grnd_flux, latent, latent_sub, sensible, snow_flux, error
+  SnowPack* sn;       // vapor_flux, blowing_flux, surface_flux
   double *Cs_node, *T_node, *Tnew_node, *Tnew_fbflag, *Tnew_fbcount, *ice_node, *kappa_node, *moist_node;
   SoilLayer* layer;
   VegVar* vv;
   int* FIRST_SOLN;
-  double *NetLongBare, *NetLongSnow, *T1, *deltaH, *fusion, *grnd_flux, *latent_heat, *latent_heat_sub, *sensible_heat, *snow_flux, *store_error;
+  double NetLongBare, NetLongSnow, T1;  // results the caller reads back after the solve
   // sub-expressions of the residual that do not depend on the trial temperature, evaluated once per solve (same operations,
   // same order as func_surf_energy_bal.c / estimate_T1.c evaluate them at every trial)
   double t1_k1, t1_b, t1_c, t1_den, gf_k1, gf_k2e, sc_lg;
@@ -50,6 +55,19 @@ struct SurfEB {
     sc_lg_ok = 0;
     sc_lg = 0;
     t1_k1 = t1_b = t1_c = t1_den = gf_k1 = gf_k2e = 0;
+    QUICK_FLUX = o->QUICK_FLUX;
+    GRND_FLUX_TYPE = o->GRND_FLUX_TYPE;
+    FS_FROZEN = (((*cp)(CP_FS_ACTIVE) != 0.0) && o->FROZEN_SOIL) ? 1 : 0;
+    elevation = (*cp)(CP_elevation);
+    b_infilt = (*cp)(CP_b_infilt);
+    depth0 = cp->layer(CL_depth, 0);
+    resid_moist0 = cp->layer(CL_resid_moist, 0);
+    veg_LAI = veg->LAI;
+    ws_under = (*wind_speed)[UnderStory];
+    ra_under = (*aero_resist)[UnderStory];
+    zref_under = (*ref_height)[UnderStory];
+    disp_under = (*displacement)[UnderStory];
+    rough_under = (*roughness)[UnderStory];
     if (o->QUICK_FLUX) {
       // estimate_T1.c:8-47 with Ts factored out
       const double e_mD1 = vexp(-D1 / dp);
@@ -68,93 +86,93 @@ struct SurfEB {
   VIC_HDI double operator()(double Ts) {
     const double TMean = Ts;
     const double Tmp = TMean + KELVIN;
-    if (snow_coverage > 0 && !INCLUDE_SNOW) *snow_flux = (kappa_snow * (Tsnow_surf - TMean));
+    if (snow_coverage > 0 && !INCLUDE_SNOW) en->snow_flux = (kappa_snow * (Tsnow_surf - TMean));
     else if (INCLUDE_SNOW) {
-      *snow_flux = 0;
+      en->snow_flux = 0;
       Tsnow_surf = TMean;
-    } else *snow_flux = 0;
+    } else en->snow_flux = 0;
     const double cover = (snow_coverage + (1. - snow_coverage) * surf_atten);
-    if (o->QUICK_FLUX) {
-      *T1 = (t1_k1 * (TMean) + t1_b + t1_c) / t1_den;
-      if (o->GRND_FLUX_TYPE == GF_406) *grnd_flux = cover * (gf_k1 * ((*T1) - TMean));
-      else *grnd_flux = cover * (gf_k1 * ((*T1) - TMean) + (gf_k2e * (T2 - (*T1)))) / 2.;
+    if (QUICK_FLUX) {
+      T1 = (t1_k1 * (TMean) + t1_b + t1_c) / t1_den;
+      if (GRND_FLUX_TYPE == GF_406) en->grnd_flux = cover * (gf_k1 * (T1 - TMean));
+      else en->grnd_flux = cover * (gf_k1 * (T1 - TMean) + (gf_k2e * (T2 - T1))) / 2.;
     } else {
       T_node[0] = TMean;
       int Error = solve_T_profile<NN>(Tnew_node, T_node, Tnew_fbflag, Tnew_fbcount, kappa_node, Cs_node, moist_node, delta_t, ice_node, dp,
                                       Nnodes, FIRST_SOLN, NOFLUX, EXP_TRANS, *cp, *o);
       if (Error == ERROR_I) return ERROR_D;
-      *T1 = Tnew_node[1];
-      if (o->GRND_FLUX_TYPE == GF_406) *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean));
-      else *grnd_flux = cover * (kappa1 / D1 * ((*T1) - TMean) + (kappa2 / D2 * (Tnew_node[2] - (*T1)))) / 2.;
+      T1 = Tnew_node[1];
+      if (GRND_FLUX_TYPE == GF_406) en->grnd_flux = cover * (kappa1 / D1 * (T1 - TMean));
+      else en->grnd_flux = cover * (kappa1 / D1 * (T1 - TMean) + (kappa2 / D2 * (Tnew_node[2] - T1))) / 2.;
     }
-    if (o->GRND_FLUX_TYPE == GF_FULL) *deltaH = cover * (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + *T1)) * D1, delta_t) / 2.);
-    else *deltaH = (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + *T1)) * D1, delta_t) / 2.);
-    if (((*cp)(CP_FS_ACTIVE) != 0.0) && o->FROZEN_SOIL) {
+    if (GRND_FLUX_TYPE == GF_FULL) en->deltaH = cover * (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1, delta_t) / 2.);
+    else en->deltaH = (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1, delta_t) / 2.);
+    if (FS_FROZEN) {
       double ice;
-      if ((TMean + *T1) / 2. < 0.) {
-        ice = moist - maximum_unfrozen_water((TMean + *T1) / 2., max_moist, bubble, expt);
+      if ((TMean + T1) / 2. < 0.) {
+        ice = moist - maximum_unfrozen_water((TMean + T1) / 2., max_moist, bubble, expt);
         if (ice < 0.) ice = 0.;
       } else ice = 0.;
-      if (o->GRND_FLUX_TYPE == GF_FULL) *fusion = cover * (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
-      else *fusion = (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
+      if (GRND_FLUX_TYPE == GF_FULL) en->fusion = cover * (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
+      else en->fusion = (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
     }
     if (INCLUDE_SNOW) {
-      if (TMean > 0) *deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (0 - OldTSurf), delta_t);
-      else *deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (TMean - OldTSurf), delta_t);
-      *refreeze_energy = div_pos((snow_water * Lf * snow_density), delta_t);
-      *deltaCC *= snow_coverage;
-      *refreeze_energy *= snow_coverage;
+      if (TMean > 0) en->deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (0 - OldTSurf), delta_t);
+      else en->deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (TMean - OldTSurf), delta_t);
+      en->refreeze_energy = div_pos((snow_water * Lf * snow_density), delta_t);
+      en->deltaCC *= snow_coverage;
+      en->refreeze_energy *= snow_coverage;
     }
     const double LongBareOut = STEFAN_B * Tmp * Tmp * Tmp * Tmp;
-    if (INCLUDE_SNOW) (*NetLongSnow) = (LongSnowIn - snow_coverage * LongBareOut);
-    (*NetLongBare) = (LongBareIn - (1. - snow_coverage) * LongBareOut);
-    const double NetBareRad = (NetShortBare + (*NetLongBare) + *grnd_flux + *deltaH + *fusion);
-    const double ws = (*wind_speed)[UnderStory];
+    if (INCLUDE_SNOW) NetLongSnow = (LongSnowIn - snow_coverage * LongBareOut);
+    NetLongBare = (LongBareIn - (1. - snow_coverage) * LongBareOut);
+    const double NetBareRad = (NetShortBare + NetLongBare + en->grnd_flux + en->deltaH + en->fusion);
+    const double ws = ws_under;
     if (ws > 0.0) {
       // the displacement height is dropped under a snowing overstory (func_surf_energy_bal.c:280-296); which case applies is fixed for the solve
-      const double Zr = (*ref_height)[UnderStory], dr = (overstory && SNOWING) ? 0. : (*displacement)[UnderStory];
+      const double Zr = zref_under, dr = (overstory && SNOWING) ? 0. : disp_under;
       if (!sc_lg_ok && TMean != Tair) {
-        sc_lg = vlog((Zr - dr) / (*roughness)[UnderStory]);
+        sc_lg = vlog((Zr - dr) / rough_under);
         sc_lg_ok = 1;
       }
-      aero_resist_used->surface = (*aero_resist)[UnderStory] / stability_correction_lg(Zr, dr, TMean, Tair, ws, sc_lg);
+      aero_resist_used->surface = ra_under / stability_correction_lg(Zr, dr, TMean, Tair, ws, sc_lg);
     } else aero_resist_used->surface = HUGE_RESIST;
     double Evap;
-    if (VEG && !SNOWING && veg->LAI > 0) {
+    if (VEG && !SNOWING && veg_LAI > 0) {
       Evap = canopy_evap(layer, *vv, true, *veg, Wdew, delta_t, NetBareRad, vpd, NetShortBare, Tair, aero_resist_used->overstory,
-                         (*cp)(CP_elevation), rainfall, *soil, &memo);
+                         elevation, rainfall, *soil, &memo);
     } else if (!SNOWING) {
-      Evap = arno_evap(layer, NetBareRad, Tair, vpd, cp->layer(CL_depth, 0), max_moist * cp->layer(CL_depth, 0) * 1000., (*cp)(CP_elevation),
-                       (*cp)(CP_b_infilt), aero_resist_used->surface, delta_t, cp->layer(CL_resid_moist, 0), &memo);
+      Evap = arno_evap(layer, NetBareRad, Tair, vpd, depth0, max_moist * depth0 * 1000., elevation,
+                       b_infilt, aero_resist_used->surface, delta_t, resid_moist0, &memo);
     } else Evap = 0.;
-    *latent_heat = -RHO_W * latent_heat_Le * Evap;
-    *latent_heat_sub = 0.;
+    en->latent = -RHO_W * latent_heat_Le * Evap;
+    en->latent_sub = 0.;
     if (INCLUDE_SNOW) {
-      double VaporMassFlux = div_pos(*vapor_flux * ice_density, delta_t);
-      double BlowingMassFlux = div_pos(*blowing_flux * ice_density, delta_t);
-      double SurfaceMassFlux = div_pos(*surface_flux * ice_density, delta_t);
+      double VaporMassFlux = div_pos(sn->vapor_flux * ice_density, delta_t);
+      double BlowingMassFlux = div_pos(sn->blowing_flux * ice_density, delta_t);
+      double SurfaceMassFlux = div_pos(sn->surface_flux * ice_density, delta_t);
       double tl, tls;
       latent_heat_from_snow(atmos_density, vp, latent_heat_Le, atmos_pressure, aero_resist_used->surface, TMean, vpd, &tl, &tls, &VaporMassFlux,
                             &BlowingMassFlux, &SurfaceMassFlux);
-      *latent_heat += tl * snow_coverage;
-      *latent_heat_sub = tls * snow_coverage;
-      *vapor_flux = div_pos(VaporMassFlux * delta_t, ice_density);
-      *blowing_flux = div_pos(BlowingMassFlux * delta_t, ice_density);
-      *surface_flux = div_pos(SurfaceMassFlux * delta_t, ice_density);
-    } else *latent_heat *= (1. - snow_coverage);
+      en->latent += tl * snow_coverage;
+      en->latent_sub = tls * snow_coverage;
+      sn->vapor_flux = div_pos(VaporMassFlux * delta_t, ice_density);
+      sn->blowing_flux = div_pos(BlowingMassFlux * delta_t, ice_density);
+      sn->surface_flux = div_pos(SurfaceMassFlux * delta_t, ice_density);
+    } else en->latent *= (1. - snow_coverage);
     if (snow_coverage < 1 || INCLUDE_SNOW) {
-      *sensible_heat = atmos_density * Cp * (Tair - (TMean)) / aero_resist_used->surface;
-      if (!INCLUDE_SNOW) (*sensible_heat) *= (1. - snow_coverage);
-    } else *sensible_heat = 0.;
-    double error = (NetBareRad + NetShortGrnd + NetShortSnow + emissivity * (*NetLongSnow)) + *sensible_heat + (*latent_heat + *latent_heat_sub) +
-                   *snow_flux * snow_coverage + melt_energy + Advection - *deltaCC;
+      en->sensible = atmos_density * Cp * (Tair - (TMean)) / aero_resist_used->surface;
+      if (!INCLUDE_SNOW) en->sensible *= (1. - snow_coverage);
+    } else en->sensible = 0.;
+    double error = (NetBareRad + NetShortGrnd + NetShortSnow + emissivity * NetLongSnow) + en->sensible + (en->latent + en->latent_sub) +
+                   en->snow_flux * snow_coverage + melt_energy + Advection - en->deltaCC;
     if (INCLUDE_SNOW) {
-      if (Tsnow_surf == 0.0 && error > -(*refreeze_energy)) {
-        *refreeze_energy = -error;
+      if (Tsnow_surf == 0.0 && error > -(en->refreeze_energy)) {
+        en->refreeze_energy = -error;
         error = 0.0;
-      } else error += *refreeze_energy;
+      } else error += en->refreeze_energy;
     }
-    *store_error = error;
+    en->error = error;
     return error;
   }
 };
@@ -199,7 +217,7 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
     TmpNetLongSnow = 0.;
     LongSnowIn = 0.;
   }
-  double NetLongBare = 0, T1 = 0, Tsurf;
+  double Tsurf;
 
   SurfEB<NN> eb;
   eb.o = &o; eb.cp = &cp; eb.veg = &veg; eb.soil = &soil;
@@ -216,14 +234,11 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   eb.snow_water = snow.surf_water;
   eb.displacement = &displacement; eb.aero_resist = &aero_resist; eb.ref_height = &ref_height; eb.roughness = &roughness; eb.wind_speed = &wind_speed;
   eb.aero_resist_used = &aero_resist_used;
-  eb.deltaCC = &energy.deltaCC; eb.refreeze_energy = &energy.refreeze_energy; eb.vapor_flux = &snow.vapor_flux; eb.blowing_flux = &snow.blowing_flux;
-  eb.surface_flux = &snow.surface_flux;
+  eb.en = &energy; eb.sn = &snow;
   eb.Cs_node = energy.Cs_node; eb.T_node = energy.T; eb.Tnew_node = Tnew_node; eb.Tnew_fbflag = Tnew_fbflag; eb.Tnew_fbcount = Tnew_fbcount;
   eb.ice_node = energy.ice; eb.kappa_node = energy.kappa_node; eb.moist_node = energy.moist;
   eb.layer = layer; eb.vv = &vv; eb.FIRST_SOLN = FIRST_SOLN;
-  eb.NetLongBare = &NetLongBare; eb.NetLongSnow = &TmpNetLongSnow; eb.T1 = &T1; eb.deltaH = &energy.deltaH; eb.fusion = &energy.fusion;
-  eb.grnd_flux = &energy.grnd_flux; eb.latent_heat = &energy.latent; eb.latent_heat_sub = &energy.latent_sub; eb.sensible_heat = &energy.sensible;
-  eb.snow_flux = &energy.snow_flux; eb.store_error = &energy.error;
+  eb.NetLongBare = 0; eb.NetLongSnow = TmpNetLongSnow; eb.T1 = 0;
   eb.prepare();
 
   if (o.FULL_ENERGY) {
@@ -254,7 +269,7 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   energy.error = error;
   if (o.QUICK_FLUX || !(o.FULL_ENERGY || (o.FROZEN_SOIL && (cp(CP_FS_ACTIVE) != 0.0)))) {
     Tnew_node[0] = Tsurf;
-    Tnew_node[1] = T1;
+    Tnew_node[1] = eb.T1;
     Tnew_node[2] = T2;
   }
   if (calc_layer_average_thermal_props<NN>(energy, layer, cp, Nnodes, Tnew_node, o) == ERROR_I) return ERROR_D;
@@ -268,10 +283,10 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   }
   energy.NetShortGrnd = NetShortGrnd;
   if (INCLUDE_SNOW) {
-    energy.NetLongUnder = NetLongBare + TmpNetLongSnow;
+    energy.NetLongUnder = eb.NetLongBare + eb.NetLongSnow;
     energy.NetShortUnder = NetShortBare + TmpNetShortSnow + NetShortGrnd;
   } else {
-    energy.NetLongUnder = NetLongBare + NetLongSnow;
+    energy.NetLongUnder = eb.NetLongBare + NetLongSnow;
     energy.NetShortUnder = NetShortBare + NetShortSnow + NetShortGrnd;
     energy.latent = (SnowLatent + energy.latent);
     energy.latent_sub = (SnowLatentSub + energy.latent_sub);
