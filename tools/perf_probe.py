@@ -50,6 +50,9 @@ if os.environ.get("VICGPU_WARPTIME"):
     blk = np.array([t1[b * B:(b + 1) * B].max() - t0[b * B:(b + 1) * B].min() for b in range(nb)]) / 1e3
     print(f"WARPS n={len(dur)} dur us: min {dur.min():.0f} mean {dur.mean():.0f} p50 {np.median(dur):.0f} p90 {np.percentile(dur, 90):.0f} max {dur.max():.0f}; "
           f"kernel span {(t1.max() - t0.min()) / 1e3:.0f}; blocks n={nb} mean {blk.mean():.0f} max {blk.max():.0f} min {blk.min():.0f}")
+    print(f"  warp starts us: p50 {np.median(t0)/1e3:.0f} p90 {np.percentile(t0,90)/1e3:.0f} p99 {np.percentile(t0,99)/1e3:.0f} max {t0.max()/1e3:.0f}; ends: p50 {np.median(t1)/1e3:.0f} p90 {np.percentile(t1,90)/1e3:.0f} max {t1.max()/1e3:.0f}")
+    bs = np.array([t0[b * B:(b + 1) * B].min() for b in range(nb)]) / 1e3
+    print("  block starts us (sorted, every 10th):", np.round(np.sort(bs)[::10]).astype(int).tolist())
     for kd in np.unique(kind):
         m = kind == kd
         print(f"  kind {int(kd):8d}: warps {m.sum():4d} mean {dur[m].mean():6.0f} max {dur[m].max():6.0f} us")

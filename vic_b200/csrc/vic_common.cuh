@@ -115,9 +115,14 @@ VIC_HD double vacos(double a) { return dl::acos(a); }
 #endif
 
 // a / b where b is known to be positive and finite (a time step, a density, a count of sub-steps, a resistance).  The device's
-// IEEE double division branches to a ~70-instruction subroutine when the numerator is zero or tiny; 0 / b is the numerator itself
-// (sign included), so that case is returned directly -- the same value the division gives.
-VIC_HD double div_pos(double a, double b) { return (a == 0.0) ? a : a / b; }
+// IEEE double division branches to a ~70-instruction subroutine when the numerator is zero or tiny (|a| < 2^-967); 0 / b is the
+// numerator itself (sign included), so that case never reaches the divider: it is handed 1.0 instead and the quotient discarded
+// (a plain `a == 0 ? a : a / b` does not help -- the compiler evaluates the division speculatively and selects afterwards).
+VIC_HD double div_pos(double a, double b) {
+  const bool z = (a == 0.0);
+  const double q = (z ? 1.0 : a) / b;
+  return z ? a : q;
+}
 
 VIC_HD double vnan() {
 #if defined(__CUDA_ARCH__)

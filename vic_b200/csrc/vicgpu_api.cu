@@ -262,6 +262,8 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   h->warp_timing = wt && atoi(wt) != 0;
   const char* noov = getenv("VICGPU_NOOVERLAP");  // run the cell output in the step's stream
   h->overlap = !(noov && atoi(noov) != 0);
+  const char* pdl = getenv("VICGPU_PDL");  // 0: cell output on a second stream instead of a programmatic dependent launch
+  h->pdl = !(pdl && atoi(pdl) == 0) && h->overlap;
   const char* rbk = getenv("VICGPU_RECBLOCK");  // records advanced per launch of the step kernel (1 .. VICGPU_RECBLOCK_MAX)
   h->recblock = rbk ? std::max(1, std::min(VICGPU_RECBLOCK_MAX, atoi(rbk))) : VICGPU_RECBLOCK_MAX;
   const char* nobin = getenv("VICGPU_NOBIN");  // keep the caller's row order (no binning at all)
@@ -282,6 +284,12 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   CK(cudaMemcpy(h->d_aggtype, agg, sizeof(agg), cudaMemcpyHostToDevice));
   // the step kernel keeps one HRU (about 2 KB) plus its working copies in thread-local memory
   CK(cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024));
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const char* ev = getenv("VICGPU_EVEN");  // 1: round the step grid up to whole blocks per SM (measured: no gain)
+    h->nsm = (ev && atoi(ev) != 0) ? prop.multiProcessorCount : 0;
+  }
   const char* blk = getenv("VICGPU_BLOCK");  // threads per block of the per-HRU step kernel (multiple of 32, <= VICGPU_HRU_BLOCK_MAX)
   if (blk && atoi(blk) >= 32 && atoi(blk) <= VICGPU_HRU_BLOCK_MAX && atoi(blk) % 32 == 0) h->hru_block = atoi(blk);
   *out = h;
@@ -522,7 +530,9 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
   const size_t per = (size_t)h->t.ncell * L.f_stride;
   const size_t rowsz = (size_t)h->t.ncell * h->nout;
   const size_t snap_stride = (size_t)nhru * L.hr_stride;
-  const int B = 128;
+  // one warp per block: such a block fits beside a resident step block on every SM (vicgpu_step.inc)
+  const char* cb = getenv("VICGPU_OUTBLOCK");
+  const int B = (cb && atoi(cb) >= 32 && atoi(cb) <= 128) ? atoi(cb) : 32;
   const int cgrid = (h->t.ncell + B - 1) / B;
   h->last_launches = 0;
   int nagg = 0;
@@ -540,6 +550,133 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
   }
   cudaStream_t so = h->stream_out;
   CK(cudaEventRecord(h->ev0, h->stream));
+  // ---- one record per launch, cell output as a programmatic dependent launch -----------------------------------------------------
+  // Everything runs in ONE stream: step(r), then output(r-1) launched with programmatic stream serialization.  The output kernel does
+  // not wait for step(r) to finish (it reads the state step(r-1) wrote), only for every block of step(r) to be resident
+  // (griddepcontrol.launch_dependents at the top of the step kernel); its one-warp blocks then fit beside the step blocks (160
+  // registers x 384 threads + 128 x 32 = the register file).  Launched from a second stream instead, the output blocks reach the
+  // SMs first and the step blocks, which need a whole SM, wait for them: measured 0.3-0.4 ms per record.  step(r+1), an ordinary
+  // launch, starts when both have finished, which also protects the state buffer output(r-1) reads.
+  if (h->pdl && h->rb == 1) {
+    struct Pending { bool valid; Tables t; const double* frec; int rec, step_count, idx; } pend = {false, h->t, nullptr, 0, 0, 0};
+    auto launch_output = [&](const Pending& p, bool dependent) -> int {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cgrid);
+      cfg.blockDim = dim3(B);
+      cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = dependent ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, k_cell_output, (const Opts*)h->d_o, p.t, p.frec, p.rec, p.step_count));
+      h->last_launches++;
+      if (out_data) {
+        int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1, h->stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out_data + (size_t)p.idx * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      }
+      if (p.step_count == h->o.out_step_ratio) {
+        if (out_agg) {
+          int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1, h->stream);
+          if (rc) return rc;
+          CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        nagg++;
+        CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), h->stream));
+      }
+      return VICGPU_OK;
+    };
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < nrec; i++) {
+      const int rec = rec0 + i;
+      StateHalf& S = h->half[h->cur_half];
+      StateHalf& D = h->half[h->cur_half ^ 1];
+      const double* input = h->d_state_cur;
+      if (h->rebin && h->recs_since_rebin >= h->rebin_every) {
+        // the pending output still needs the old row order and the state it was launched for: run it now, undeferred
+        if (pend.valid) {
+          int rc = launch_output(pend, false);
+          if (rc) return rc;
+          pend.valid = false;
+        }
+        int rc = rebin_rows(h, h->order[S.ord], h->order[S.ord ^ 1], h->d_state_cur, D.in);
+        if (rc) return rc;
+        D.ord = S.ord ^ 1;
+        input = D.in;
+        h->recs_since_rebin = 0;
+      } else {
+        D.ord = S.ord;
+      }
+      h->recs_since_rebin++;
+      const RowOrder& R = h->order[D.ord];
+      Tables t = h->t;
+      t.hrupar = R.hrupar;
+      t.slot_of_hru = R.slot_of_hru;
+      t.hrurec = input;
+      t.hrurec_out = D.snap;
+      t.hdiag_out = D.hdiag;
+      const int* d = &dmy[i * 5];
+      const Dmy dm = {d[0], d[1], d[2], d[3], d[4]};
+      const GlacAccum ga = glacier_accum_flags(h->o, d, d + 5, rec, &h->glac_started);
+      if (rec == 0) {
+        // storage terms of the initial state: put_data(rec = -nrecs), vicNl.c:524-541
+        Tables t0 = t;
+        t0.hrurec_out = const_cast<double*>(input);
+        k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, t0, nullptr, -1, h->step_count + 1);
+        h->last_launches++;
+      }
+      const double* frec = h->d_forcing + (size_t)(rec - h->frec0) * per;
+      unsigned long long* wns = nullptr;
+      if (h->profiling && h->warp_timing) {
+        const size_t nw = ((size_t)nhru + 31) / 32;
+        if (!h->d_warp_ns) CK(cudaMalloc(&h->d_warp_ns, 2 * nw * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(h->d_warp_ns, 0, 2 * nw * sizeof(unsigned long long), h->stream));
+        wns = h->d_warp_ns;
+      }
+      if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
+      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm);
+      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm);
+      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm);
+      h->last_launches++;
+      // the previous record's output rides on this step
+      if (pend.valid) {
+        int rc = launch_output(pend, true);
+        if (rc) return rc;
+      }
+      if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));  // step(r) and the output riding on it
+      h->step_count++;
+      pend.valid = true;
+      pend.t = t;
+      pend.frec = frec;
+      pend.rec = rec;
+      pend.step_count = h->step_count;
+      pend.idx = i;
+      if (h->step_count == h->o.out_step_ratio) h->step_count = 0;
+      h->d_state_cur = D.snap;
+      h->cur_half ^= 1;
+    }
+    if (pend.valid) {
+      int rc = launch_output(pend, false);
+      if (rc) return rc;
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    float msp = 0;
+    CK(cudaEventElapsedTime(&msp, h->ev0, h->ev1));
+    h->last_ms = msp;
+    if (h->profiling) {
+      for (int i = 0; i < nrec; i++) {
+        float k = 0;
+        CK(cudaEventElapsedTime(&k, h->pev[2 * i], h->pev[2 * i + 1]));
+        h->prof_hru_ms += k;
+        h->prof_hru_launches++;
+      }
+    }
+    return VICGPU_OK;
+  }
+
   for (int blk = 0; blk < nblocks; blk++) {
     const int i0 = blk * h->rb;
     const int n = std::min(h->rb, nrec - i0);
@@ -599,9 +736,9 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
       t.hrurec_out = D.snap;
       t.hdiag_out = D.hdiag;
       const GlacAccum ga = {rb.ga[0] & 1, (rb.ga[0] >> 1) & 1, (rb.ga[0] >> 2) & 1, (rb.ga[0] >> 3) & 1};
-      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns);
-      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns);
-      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns);
+      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm);
+      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm);
+      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm);
       h->last_launches++;
     } else {
       if (h->o.Nnode <= 3) vicgpu_launch_hru_steps_nn3(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);

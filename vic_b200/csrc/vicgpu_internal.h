@@ -44,7 +44,7 @@ struct vicgpu_handle {
   int cur_half = 0;               // the half whose row order d_state_cur is in
   double* d_state_cur = nullptr;  // current state: half.in after set_state, else the last snapshot of the last block
   int recblock = VICGPU_RECBLOCK_MAX, rb = 1;  // records per launch: requested, and what fits in memory
-  bool binned = true, rebin = true, overlap = true;
+  bool binned = true, rebin = true, overlap = true, pdl = true;
   int* d_fail_rec = nullptr;
   cudaStream_t stream = nullptr, stream_out = nullptr;  // HRU step / cell output
   cudaEvent_t ev_step = nullptr, ev0 = nullptr, ev1 = nullptr;
@@ -53,6 +53,7 @@ struct vicgpu_handle {
   size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
   int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
   int hru_block = VICGPU_HRU_BLOCK;
+  int nsm = 0;  // SM count when the step grid is rounded up to whole blocks per SM (0: not)
   // re-binning scratch (vicgpu_api.cu rebin_rows)
   unsigned long long* d_keys[2] = {nullptr, nullptr};
   int* d_oldslot[2] = {nullptr, nullptr};
