@@ -494,6 +494,11 @@ typedef struct vicgpu_disagg_options {
  * annual precipitation, band temperature factors, rain/snow thresholds are cell parameters). */
 int vicgpu_disagg(vicgpu_handle *h, const vicgpu_disagg_options *dopt, const double *daily, double *forcing_out);
 
+/* accumulateGlacierMassBalance()'s per-cell result (vicNl.c:563, cell_info_struct::gmbEquation, written to the state file by
+ * write_model_state.c:153-156): gmb[ncell][4] = b0, b1, b2, fitError of the quadratic fitted to (band elevation, cumulative mass
+ * balance of the cell's glacier HRUs) at the end of the last completed accumulation interval; 0, 0, 0, -1 before the first. */
+int vicgpu_get_glacier_fit(vicgpu_handle *h, double *gmb);
+
 /* measurement aid: with profiling on, every launch of the per-HRU step kernel inside vicgpu_step is bracketed
  * by CUDA events on the library's stream; get_kernel_profile returns the summed duration and the launch count
  * since profiling was switched on. */

@@ -295,6 +295,16 @@ int main(int argc, char **argv) {
     cw->f64("balance_ref", be.data(), 2, d7);
     int64_t d8[1] = {ncell};
     cw->i32("status_ref", st.data(), 1, d8);
+    // the cell's glacier mass-balance curve as left by accumulateGlacierMassBalance() (what write_model_state.c:153-156 stores)
+    std::vector<double> gm((size_t)ncell * 4);
+    for (int c = 0; c < ncell; c++) {
+      gm[c * 4 + 0] = cells[c].gmbEquation.b0;
+      gm[c * 4 + 1] = cells[c].gmbEquation.b1;
+      gm[c * 4 + 2] = cells[c].gmbEquation.b2;
+      gm[c * 4 + 3] = cells[c].gmbEquation.fitError;
+    }
+    int64_t d9[2] = {ncell, 4};
+    cw->f64("gmb_ref", gm.data(), 2, d9);
     delete cw;
   }
   return 0;

@@ -78,10 +78,12 @@ int main(int argc, char** argv) {
   // constants derived from the cell parameters, as the library computes them in vicgpu_set_cells
   std::vector<double> cellder((size_t)VIC_NCELLDER * ncell);
   for (int c = 0; c < ncell; c++) derive_cell_constants(CellPar{Col{cellpar.data() + c, (size_t)ncell}, &o.L}, cellder.data() + c, (size_t)ncell);
+  std::vector<double> gmb_cum((size_t)nhru, 0.0), gmb((size_t)4 * ncell, 0.0);
+  for (int c = 0; c < ncell; c++) gmb[(size_t)3 * ncell + c] = -1;  // GraphingEquation(): fitError -1
   Tables t;
   t.ncell = ncell; t.nhru = nhru; t.nclass = (int)cs["veglib"].dims[0];
   t.veglib = cs["veglib"].f64.data(); t.cellpar = cellpar.data(); t.cellder = cellder.data(); t.hrupar = hrupar.data(); t.hrurec = hrurec.data(); t.hrurec_out = hrurec.data(); t.hdiag_out = hdiag.data();
-  t.cell_h0 = cell_h0.data(); t.status = status.data(); t.fail_rec = fail_rec.data(); t.carry = carry.data(); t.out = out.data(); t.agg = agg.data();
+  t.cell_h0 = cell_h0.data(); t.status = status.data(); t.gmb_cum = gmb_cum.data(); t.gmb = gmb.data(); t.fail_rec = fail_rec.data(); t.carry = carry.data(); t.out = out.data(); t.agg = agg.data();
   t.aggtype = cs["aggtype"].i32.data();
   t.slot_of_hru = slot;
 
@@ -106,6 +108,8 @@ int main(int argc, char** argv) {
     if (o.Nnode <= 3) run_record<3>(&o, t, frec.data(), d, rec, ga);
     else if (o.Nnode <= 10) run_record<10>(&o, t, frec.data(), d, rec, ga);
     else run_record<VICGPU_MAX_NODES>(&o, t, frec.data(), d, rec, ga);
+    if (ga.enabled && ga.reset_after)
+      for (int c = 0; c < ncell; c++) cell_gmb(&o, t, c);
     for (int c = 0; c < ncell; c++) cell_output(&o, t, frec.data(), c, rec, step_count);
     to_rowmajor(out.data(), ncell, nout, &out_all[(size_t)rec * ncell * nout]);
     while (nd < dump_recs.size() && dump_recs[nd] < rec) nd++;
@@ -140,5 +144,12 @@ int main(int argc, char** argv) {
   int64_t d7[1] = {ncell};
   std::vector<int32_t> st(status.begin(), status.end());
   cw.i32("status", st.data(), 1, d7);
+  {
+    std::vector<double> g((size_t)ncell * 4);
+    for (int c = 0; c < ncell; c++)
+      for (int k = 0; k < 4; k++) g[(size_t)c * 4 + k] = gmb[(size_t)k * ncell + c];
+    int64_t d8[2] = {ncell, 4};
+    cw.f64("gmb", g.data(), 2, d8);
+  }
   return 0;
 }

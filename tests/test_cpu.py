@@ -144,6 +144,23 @@ def test_year_long_sensitivity_to_math_library(cfgname, nlat, nlon, seed, ref_ha
     assert np.array_equal(res["status"], c["status_ref"])
 
 
+def test_glacier_mass_balance_fit_matches_reference(ref_harness_dl, vicport, tmp_path):
+    """accumulateGlacierMassBalance's quadratic fit (GraphingEquation.c:35-126) at the end of the first accumulation interval: four
+    glacier HRUs in four bands per cell, 367 days (the interval of the synthetic set-up ends with the last hour of 1 Jan of the
+    second year); coefficients and fit error bit-identical"""
+    import dataclasses
+    from vic_b200 import synth
+    cfg = dataclasses.replace(synth.CONFIGS["glacier_multi"], ndays=367)
+    r = synth.generate(str(tmp_path / "in"), cfg, 2, 2, 303)
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "res.bin")
+    subprocess.run([ref_harness_dl, "-g", r["global_file"], "-o", case, "--dump-every", "2400"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([vicport, case, out], check=True)
+    c, res = read_case(case), read_case(out)
+    assert np.all(c["gmb_ref"][:, 2] != 0) and np.all(c["gmb_ref"][:, 3] > 0)  # a genuine quadratic with a residual
+    assert np.array_equal(res["gmb"], c["gmb_ref"])
+    assert np.array_equal(res["hrurec"], c["hrurec_ref"], equal_nan=True)
+
+
 def test_portable_math_accuracy(root):
     """vic_math.cuh against glibc on the argument ranges of the hot path: error bounds stated in its header"""
     exe = os.path.join(root, "oracle", "_ref", "mathcheck")

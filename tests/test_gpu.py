@@ -103,6 +103,16 @@ def test_bit_exact_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref
     assert np.array_equal(res["balance"], c["balance_ref"], equal_nan=True)
 
 
+def test_glacier_mass_balance_fit(ref_harness_dl, tmp_path):
+    """the per-cell quadratic mass-balance curve at the end of an accumulation interval (accumulateGlacierMassBalance,
+    GraphingEquation.c:35-126): four glacier HRUs in four bands per cell, 367 days; bit-identical to the reference"""
+    c = _reference_case(ref_harness_dl, "glacier_multi", 2, 2, 367, 303, tmp_path)
+    res = api.run_case(c, device=0, want_out=False)
+    assert np.all(c["gmb_ref"][:, 2] != 0)
+    assert np.array_equal(res["gmb"], c["gmb_ref"])
+    assert np.array_equal(res["hrurec"], c["hrurec_ref"], equal_nan=True)
+
+
 @pytest.mark.parametrize("name", GOLDEN)
 def test_disagg_golden(name):
     """vicgpu_disagg against the reference's initialize_atmos() output for the same daily inputs; then the model is

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times",
+    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit",
 ]
 
 
@@ -69,6 +69,7 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_set_profiling.argtypes = [vp, C.c_int]
     lib.vicgpu_get_kernel_profile.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.vicgpu_get_warp_times.argtypes = [vp, dp, dp, C.c_int]
+    lib.vicgpu_get_glacier_fit.argtypes = [vp, dp]
     for s in SYMBOLS:
         getattr(lib, s)
     _lib = lib
@@ -197,6 +198,12 @@ class VicGpu:
         self._chk(self.lib.vicgpu_get_balance_errors(self.h, _dptr(e)))
         return e
 
+    def glacier_fit(self):
+        """[ncell][4]: b0, b1, b2, fitError of the glacier mass-balance curve of the last completed accumulation interval"""
+        g = np.empty((self.ncell, 4), dtype=np.float64)
+        self._chk(self.lib.vicgpu_get_glacier_fit(self.h, _dptr(g)))
+        return g
+
     def set_profiling(self, on=True):
         self._chk(self.lib.vicgpu_set_profiling(self.h, 1 if on else 0))
 
@@ -257,7 +264,7 @@ def run_case(case, device=0, nrec=None, want_out=True, block=None):
             if (c - 1) in dump_recs:
                 hru.append(g.get_state())
             r0 = c
-        res = {"agg": agg, "hrurec": np.array(hru), "balance": g.balance_errors(), "status": g.cell_status()}
+        res = {"agg": agg, "hrurec": np.array(hru), "balance": g.balance_errors(), "status": g.cell_status(), "gmb": g.glacier_fit()}
         if want_out:
             res["out"] = out
         return res

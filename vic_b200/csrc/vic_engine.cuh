@@ -13,6 +13,7 @@
 #include <vector>
 #include "vic_step.cuh"
 #include "vic_output.cuh"
+#include "vic_gmb.cuh"
 
 namespace vic {
 
@@ -36,6 +37,8 @@ struct Tables {
   double* out;            // [nout][ncell]  OutputData::data of the current record
   double* agg;            // [nout][ncell]  OutputData::aggdata
   const int* aggtype;     // [N_OUTVARS]
+  double* gmb_cum;        // [nhru] glacier.cum_mass_balance of an HRU at the end of the last accumulation interval, before its reset
+  double* gmb;            // [4][ncell] b0, b1, b2, fitError of the cell's mass-balance curve (GraphingEquation), or null
 };
 
 // what accumulateGlacierMassBalance does at this record (decided on the host from the calendar,
@@ -90,7 +93,10 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   if (ga.enabled && hp.isGlacier) {
     if (ga.reset_first) hru.glac.cum_mass_balance = 0;
     if (ga.accumulate && is_valid(hru.glac.mass_balance)) hru.glac.cum_mass_balance += hru.glac.mass_balance;
-    if (ga.reset_after) hru.glac.cum_mass_balance = 0;
+    if (ga.reset_after) {
+      if (t.gmb_cum) t.gmb_cum[h] = hru.glac.cum_mass_balance;  // what GlacierMassBalanceResult reads (accumulateGlacierMassBalance.c:59-64)
+      hru.glac.cum_mass_balance = 0;
+    }
   }
   store_hru<NN>(hru, t.hrurec_out + h, nh, &o->L);
   dg[0] = d.out_prec * hp.Cv;
@@ -162,7 +168,10 @@ VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcin
     if ((ga & 1) && hp.isGlacier) {
       if (ga & 2) hru.glac.cum_mass_balance = 0;
       if ((ga & 4) && is_valid(hru.glac.mass_balance)) hru.glac.cum_mass_balance += hru.glac.mass_balance;
-      if (ga & 8) hru.glac.cum_mass_balance = 0;
+      if (ga & 8) {
+        if (t.gmb_cum) t.gmb_cum[h] = hru.glac.cum_mass_balance;
+        hru.glac.cum_mass_balance = 0;
+      }
     }
     store_hru<NN>(hru, out + h, nh, &o->L);
     dg[0] = d.out_prec * hp.Cv;
@@ -183,6 +192,45 @@ VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_r
   Forcing f{Col{forcing_rec ? forcing_rec + cell : nullptr, nc}, o->L.f_nslot};
   put_data_cell(*o, cp, vl, &f, t.hrurec_out, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count, t.aggtype,
                 RowRW{t.carry + cell, nc}, RowRW{t.out + cell, nc}, RowRW{t.agg + cell, nc});
+}
+
+// the cell's mass-balance curve at the end of an accumulation interval (GlacierMassBalanceResult.c:35-72): one point per band
+// elevation that holds glacier HRUs, cumulative balances of HRUs at the same elevation added up, in hruList order
+VIC_HDI void cell_gmb(const Opts* o, const Tables& t, int cell) {
+  if (t.status[cell] != 0) return;  // the reference leaves an invalid cell alone (vicNl.c:521)
+  const size_t nc = (size_t)t.ncell, nh = (size_t)t.nhru;
+  CellPar cp{Col{t.cellpar + cell, nc}, &o->L};
+  double x[VICGPU_MAX_BANDS], y[VICGPU_MAX_BANDS];
+  int n = 0;
+  for (int hh = t.cell_h0[cell]; hh < t.cell_h0[cell + 1]; hh++) {
+    const int h = t.slot_of_hru ? t.slot_of_hru[hh] : hh;
+    if (t.hrupar[(size_t)HP_isGlacier * nh + h] == 0.0) continue;
+    const double cum = t.gmb_cum[h];
+    if (!is_valid(cum)) continue;
+    const double elev = cp.band(CB_BandElev, (int)t.hrupar[(size_t)HP_band * nh + h]);
+    bool found = false;
+    for (int k = 0; k < n; k++)
+      if (x[k] == elev) {
+        y[k] += cum;
+        found = true;
+      }
+    if (!found && n < VICGPU_MAX_BANDS) {
+      x[n] = elev;
+      y[n] = cum;
+      n++;
+    }
+  }
+  // points at elevation 0 carry no data (GlacierMassBalanceResult.c:57-65: lastElevation stays 0)
+  int m = 0;
+  for (int k = 0; k < n; k++)
+    if (!(x[k] == 0 && x[k] <= 0)) {
+      x[m] = x[k];
+      y[m] = y[k];
+      m++;
+    }
+  double eq[4] = {0, 0, 0, -1};  // a GraphingEquation as constructed: no fit yet
+  if (m > 0) gmb_fit(m, x, y, eq);
+  for (int k = 0; k < 4; k++) t.gmb[(size_t)k * nc + cell] = eq[k];
 }
 
 // options as the kernels want them

@@ -112,6 +112,13 @@ __global__ void k_derive_cells(const Opts* __restrict__ o, const double* __restr
   derive_cell_constants(CellPar{Col{cellpar + c, (size_t)ncell}, &o->L}, cellder + c, (size_t)ncell);
 }
 
+// the cells' glacier mass-balance curves at the end of an accumulation interval (vic_engine.cuh cell_gmb)
+__global__ void k_cell_gmb(const Opts* __restrict__ o, Tables t) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= t.ncell) return;
+  cell_gmb(o, t, c);
+}
+
 __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
                                                      int step_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,7 +308,7 @@ int vicgpu_destroy(vicgpu_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->overlap && h->stream_out) cudaStreamSynchronize(h->stream_out);
-  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_cellder);
+  cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_gmb_cum); cudaFree(h->d_gmb);
   for (int b = 0; b < 2; b++) {
     free_half(h->half[b]);
     free_order(h->order[b]);
@@ -366,6 +373,8 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   const char* deal = getenv("VICGPU_DEAL");
   const bool dealing = deal && atoi(deal) != 0;
   if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru, dealing ? (nhru + h->hru_block - 1) / h->hru_block : 0);
+  cudaFree(h->d_gmb_cum); cudaFree(h->d_gmb);
+  h->d_gmb_cum = h->d_gmb = nullptr;
   cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
   h->d_cellder = nullptr;
   cudaFree(h->d_fail_rec); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]); cudaFree(h->d_warp_ns);
@@ -387,6 +396,14 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   h->rb = rbn;
   CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
   CK(cudaMalloc(&h->d_cellder, (size_t)ncell * VIC_NCELLDER * sizeof(double)));
+  CK(cudaMalloc(&h->d_gmb_cum, (size_t)nhru * sizeof(double)));
+  CK(cudaMemset(h->d_gmb_cum, 0, (size_t)nhru * sizeof(double)));
+  CK(cudaMalloc(&h->d_gmb, (size_t)ncell * 4 * sizeof(double)));
+  {
+    std::vector<double> g0((size_t)ncell * 4, 0.0);
+    for (int c = 0; c < ncell; c++) g0[(size_t)3 * ncell + c] = -1;  // GraphingEquation(): fitError -1
+    CK(cudaMemcpy(h->d_gmb, g0.data(), g0.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   for (int b = 0; b < 2; b++) {
     StateHalf& s = h->half[b];
     CK(cudaMalloc(&s.in, state_bytes));
@@ -436,6 +453,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   rc = upload_transposed(h, hrupar, h->order[0].hrupar, nhru, HP_N, h->order[0].hru_of_slot);
   if (rc) return rc;
   h->t.ncell = ncell; h->t.nhru = nhru;
+  h->t.gmb_cum = h->d_gmb_cum; h->t.gmb = h->d_gmb;
   h->t.cellpar = h->d_cellpar; h->t.cellder = h->d_cellder; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
   h->t.status = h->d_status; h->t.carry = h->d_carry; h->t.out = h->d_out; h->t.agg = h->d_agg; h->t.aggtype = h->d_aggtype;
   h->cur_half = 0;
@@ -644,6 +662,10 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
         int rc = launch_output(pend, true);
         if (rc) return rc;
       }
+      if (ga.enabled && ga.reset_after) {  // end of a glacier accumulation interval: the cells' mass-balance curves
+        k_cell_gmb<<<(h->t.ncell + 127) / 128, 128, 0, h->stream>>>(h->d_o, t);
+        h->last_launches++;
+      }
       if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));  // step(r) and the output riding on it
       h->step_count++;
       pend.valid = true;
@@ -748,6 +770,12 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
       h->last_launches += 2;
     }
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * blk + 1], h->stream));
+    bool interval_end = false;  // a glacier accumulation interval ended inside the block: the step kernel left the balances in gmb_cum
+    for (int i = 0; i < n; i++) interval_end = interval_end || (rb.ga[i] & 8);
+    if (interval_end) {
+      k_cell_gmb<<<(h->t.ncell + 127) / 128, 128, 0, h->stream>>>(h->d_o, t);
+      h->last_launches++;
+    }
     if (h->overlap) {
       CK(cudaEventRecord(h->ev_step, h->stream));
       CK(cudaStreamWaitEvent(so, h->ev_step, 0));
@@ -851,6 +879,16 @@ int vicgpu_get_warp_times(vicgpu_handle* h, double* times, double* kind, int max
     }
   }
   return nw;
+}
+
+int vicgpu_get_glacier_fit(vicgpu_handle* h, double* gmb) {
+  if (!h || !gmb || !h->have_cells) return fail(VICGPU_ESTATE, "set_cells first");
+  CK(cudaSetDevice(h->device));
+  std::vector<double> g((size_t)4 * h->t.ncell);
+  CK(cudaMemcpy(g.data(), h->d_gmb, g.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < h->t.ncell; c++)
+    for (int k = 0; k < 4; k++) gmb[(size_t)c * 4 + k] = g[(size_t)k * h->t.ncell + c];
+  return VICGPU_OK;
 }
 
 int vicgpu_get_last_step_timing(vicgpu_handle* h, double* kernel_ms, long long* launches) {

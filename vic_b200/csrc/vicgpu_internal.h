@@ -48,6 +48,7 @@ struct vicgpu_handle {
   int* d_fail_rec = nullptr;
   cudaStream_t stream = nullptr, stream_out = nullptr;  // HRU step / cell output
   cudaEvent_t ev_step = nullptr, ev0 = nullptr, ev1 = nullptr;
+  double *d_gmb_cum = nullptr, *d_gmb = nullptr;  // glacier mass-balance fit (vic_engine.cuh cell_gmb)
   double *d_veglib = nullptr, *d_cellpar = nullptr, *d_cellder = nullptr, *d_carry = nullptr, *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr,
          *d_forcing = nullptr, *d_fstage = nullptr;
   size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;

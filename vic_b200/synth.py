@@ -36,6 +36,7 @@ class Config:
     snow_step: int = 1
     nbands: int = 1
     glacier: bool = False
+    glacier_tiles: int = 1  # glacier HRUs per cell, each in its own band (>= 3: the quadratic mass-balance fit has something to fit)
     output_force: bool = False
     ntiles: int = 5
     startyear: int = 2001  # leap-free year
@@ -57,6 +58,8 @@ CONFIGS = {
     "frozen_bands": Config("frozen_bands", frozen_soil=True, quick_flux=False, nodes=10, nbands=5),
     # configs[3]: PCIC glacier mass-balance mode
     "glacier": Config("glacier", glacier=True, nbands=5),
+    # the same with glacier HRUs in four bands of every cell: exercises accumulateGlacierMassBalance's quadratic fit
+    "glacier_multi": Config("glacier_multi", glacier=True, nbands=5, glacier_tiles=4),
     # configs[4] (first half): OUTPUT_FORCE disaggregation only
     "disagg": Config("disagg", output_force=True),
 }
@@ -199,16 +202,20 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
             classes = list(over_cls) + list(short_cls)
             tiles = []
             if cfg.glacier:
-                classes = classes[:-1] + [GLACIER_ID]
+                classes = classes[:-1] + [GLACIER_ID] * cfg.glacier_tiles
             w = rng.dirichlet(np.full(len(classes), 3.0))
             # leave bare soil in ~1/4 of the cells so the artificial bare-soil HRU path is exercised
             tot = 1.0 if rng.uniform() > 0.25 else rng.uniform(0.7, 0.95)
             cv = np.round(w * tot, 4)
             if tot == 1.0:
                 cv[0] = round(1.0 - cv[1:].sum(), 4)
+            nglac = 0
             for k, cl in enumerate(classes):
                 if cfg.nbands > 1:
-                    if cl == GLACIER_ID:
+                    if cl == GLACIER_ID and cfg.glacier_tiles > 1:
+                        band = cfg.nbands - 1 - nglac  # one glacier HRU per band, from the top down
+                        nglac += 1
+                    elif cl == GLACIER_ID:
                         band = cfg.nbands - 1 - int(rng.integers(0, 2))
                     else:
                         band = int(rng.integers(0, cfg.nbands))
