@@ -162,3 +162,40 @@ def test_call_order_errors():
     with pytest.raises(api.VicGpuError):
         gp.step(0, 4, g["dmy"][:5])  # no forcing resident
     gp.close()
+
+
+@pytest.mark.parametrize("ncell,nrec", [(10000, 48), (100000, 24)])
+def test_full_size_domain_properties(ncell, nrec):
+    """BASELINE-size domains (configs[1]: 10,000 cells; configs[2]-size: 100,000), through properties that do not need the reference
+    to run at that size: (1) cells are independent, so the first 256 cells of the big domain -- the unperturbed base domain the
+    reference itself is timed on -- must give bit-identical outputs and state whether they are advanced alone or inside the big domain
+    (different row binning, different block placement, different re-sort decisions); (2) the reference's own closure check holds in every
+    cell: |water balance error| of a step < 1e-5 mm (calc_water_energy_balance_errors.c:33-43); (3) no cell is flagged invalid."""
+    import bench
+    dom = bench.build_domain(ncell, 1)
+    nb = 256
+    h_nb = int(np.searchsorted(dom["hrupar"][:, TABLES["hpar"].index("HP_cell")], nb))
+
+    def run(nc, nh):
+        g = api.VicGpu(dom["options_raw"])
+        g.set_veglib(dom["veglib"]); g.set_output_spec(dom["aggtype"])
+        g.set_cells(dom["cellpar"][:nc], dom["hrupar"][:nh]); g.set_state(dom["hrurec0"][:nh])
+        g.set_forcing(0, np.ascontiguousarray(fbig[:, :nc]))
+        out = np.zeros((nrec, nc, g.L.nout))
+        g.step(0, nrec, bench.make_dmy(nrec), out, None)
+        st, status, bal = g.get_state(), g.cell_status(), g.balance_errors()
+        g.close()
+        return out, st, status, bal
+
+    L = layout_from_options(parse_options(dom["options_raw"]))
+    fbig = np.empty((nrec, ncell, L.f_stride))
+    for d in range(nrec // 24):
+        bench.forcing_day(dom, d, 1, fbig[d * 24:(d + 1) * 24])
+    out_big, st_big, status_big, bal_big = run(ncell, dom["hrupar"].shape[0])
+    out_small, st_small, status_small, _ = run(nb, h_nb)
+    assert np.array_equal(out_big[:, :nb], out_small, equal_nan=True)
+    assert np.array_equal(st_big[:h_nb], st_small, equal_nan=True)
+    assert not status_big.any() and not status_small.any()
+    werr = out_big[:, :, L.out_names.index("WATER_ERROR")]
+    assert np.nanmax(np.abs(werr)) < 1e-5, np.nanmax(np.abs(werr))
+    assert np.all(np.abs(bal_big[:, 2]) < 1e-5 + 1e-12)  # CellBalanceErrors::water_max_error
