@@ -315,11 +315,25 @@ def main():
         per_launch_bytes = ALGO_BYTES_PER_CELL_STEP * a.cells * recs_per_launch
         hru_avg_s = hru_ms / 1e3 / max(hru_n, 1)
         achieved = per_launch_bytes / hru_avg_s / 1e9
-        traffic = None
-        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_hru_step_nn3"]["dram_bytes_per_launch"]
+        traffic, fp64_flop = None, None
+        try:  # DRAM bytes and FP64 flops per launch of the same kernel from the committed ncu --set full capture (profiles/)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_hru_step_nn3"]
+            traffic = prof["dram_bytes_per_launch"]
+            fp64_flop = prof.get("fp64_flop_per_launch")
         except Exception:
             pass
+        fp64 = None
+        if fp64_flop:
+            # SURVEY 8(d) asks for the FP64 fraction beside the HBM one: executed DFMA x 2 + DADD + DMUL per launch (ncu, per 10,000 cells)
+            # over the live launch time, against the DFMA throughput measured on this device just now
+            try:
+                peak_tf = api.measure_fp64_peak(local_rank)
+                ach_tf = fp64_flop * (a.cells / 10000.0) * recs_per_launch / hru_avg_s / 1e12
+                fp64 = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                        "flop_per_launch": fp64_flop * (a.cells / 10000.0) * recs_per_launch,
+                        "peak_source": "vicgpu_measure_fp64_peak (register-resident DFMA loop, best of 5, this run)"}
+            except Exception as e:
+                fp64 = {"bound": "fp64", "unavailable": str(e)}
         line = {"metric": "cell-timesteps/s", "value": units / dev_s, "unit": "cell-timesteps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "cells_per_gpu": a.cells, "hrus_per_gpu": int(g.nhru), "records_per_step": RECS_PER_STEP,
@@ -333,6 +347,7 @@ def main():
                              "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6544.7",
                              "kernel_share_of_step": (hru_ms / 1e3) / dev_s if dev_s > 0 else None,
                              "note": "latency / instruction-cache bound, not bandwidth bound: see profiles/ and DESIGN.md section 6"},
+                "roofline_fp64": fp64,
                 "clocks": cs.summary()}
         if not a.no_e2e:
             line["e2e"] = {"value": units / e2e_s, "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(24 * a.cells * L.f_stride * 8),

@@ -499,6 +499,10 @@ int vicgpu_disagg(vicgpu_handle *h, const vicgpu_disagg_options *dopt, const dou
  * balance of the cell's glacier HRUs) at the end of the last completed accumulation interval; 0, 0, 0, -1 before the first. */
 int vicgpu_get_glacier_fit(vicgpu_handle *h, double *gmb);
 
+/* measurement aid: the device's FP64 fused-multiply-add throughput [TFLOP/s, 2 flops per FMA] from a register-resident DFMA loop
+ * timed with CUDA events (best of 5) -- the denominator of the FP64 roofline fraction bench.py reports. */
+int vicgpu_measure_fp64_peak(int device, double *tflops);
+
 /* measurement aid: with profiling on, every launch of the per-HRU step kernel inside vicgpu_step is bracketed
  * by CUDA events on the library's stream; get_kernel_profile returns the summed duration and the launch count
  * since profiling was switched on. */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit",
+    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
 ]
 
 
@@ -70,6 +70,7 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_get_kernel_profile.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.vicgpu_get_warp_times.argtypes = [vp, dp, dp, C.c_int]
     lib.vicgpu_get_glacier_fit.argtypes = [vp, dp]
+    lib.vicgpu_measure_fp64_peak.argtypes = [C.c_int, dp]
     for s in SYMBOLS:
         getattr(lib, s)
     _lib = lib
@@ -228,6 +229,16 @@ class VicGpu:
         n = C.c_longlong()
         self._chk(self.lib.vicgpu_get_last_step_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+def measure_fp64_peak(device=0):
+    """FP64 FMA throughput of the device in TFLOP/s (vicgpu_measure_fp64_peak)"""
+    lib = load_library()
+    v = C.c_double()
+    rc = lib.vicgpu_measure_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise VicGpuError(rc, (lib.vicgpu_last_error() or b"").decode())
+    return v.value
 
 
 def run_case(case, device=0, nrec=None, want_out=True, block=None):

@@ -105,6 +105,17 @@ __global__ void k_freeze_failed(Tables t, int rec0, int n, double* snap, size_t 
   }
 }
 
+// FP64 FMA throughput probe: 8 independent chains per thread, nothing but DFMA in the loop
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;  // keeps the chains alive
+}
+
 // constants derived from the cell parameters, once per vicgpu_set_cells (vic_soil.cuh derive_cell_constants)
 __global__ void k_derive_cells(const Opts* __restrict__ o, const double* __restrict__ cellpar, double* __restrict__ cellder, int ncell) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -888,6 +899,37 @@ int vicgpu_get_glacier_fit(vicgpu_handle* h, double* gmb) {
   CK(cudaMemcpy(g.data(), h->d_gmb, g.size() * sizeof(double), cudaMemcpyDeviceToHost));
   for (int c = 0; c < h->t.ncell; c++)
     for (int k = 0; k < 4; k++) gmb[(size_t)c * 4 + k] = g[(size_t)k * h->t.ncell + c];
+  return VICGPU_OK;
+}
+
+int vicgpu_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(VICGPU_EINVAL, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(VICGPU_ENODEV, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int iters = 1 << 16, threads = 256, blocks = prop.multiProcessorCount * 8;
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++) {
+    CK(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(d, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * (double)iters * threads * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;  // the first launch warms up
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
   return VICGPU_OK;
 }
 
