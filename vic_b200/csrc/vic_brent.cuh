@@ -116,5 +116,203 @@ VIC_HDI double root_brent(double LowerBound, double UpperBound, F& f) {
   return ERROR_D;
 }
 
+// The same solver with ONE call site of the residual: the control flow above turned into a state machine around a single
+// `fx = f(x)`.  It evaluates the residual at exactly the same points in exactly the same order and returns the same value
+// (oracle/brentcheck.cpp drives both with random residuals, including ERROR regions, and compares the evaluation sequences).  With a
+// single call site the residual can be inlined into its caller, which lets the compiler keep the solve's constants in registers
+// instead of re-reading a functor object from thread-local memory at every evaluation.
+// What a caller that needs the residual once more at the accepted root passes along (calc_surf_energy_bal.c:346-400 evaluates the
+// energy balance a last time at Tsurf, or at the old temperature when the solve failed and TFALLBACK is on, or at the air
+// temperature when the energy balance is not solved at all): that evaluation goes through the same single call site.
+struct BrentFinal {
+  bool do_solve, allow_fallback;
+  double fallback_x, nosolve_x;
+  double f_final;  // out: the residual at the returned point
+  int fell_back;   // out: 1 when the solve failed and fallback_x was used
+};
+
+template <bool FINAL, class F>
+VIC_HD double root_brent_ss_impl(double LowerBound, double UpperBound, F& f, BrentFinal* fin) {
+  const int MAXTRIES = 5, MAXITER = 1000;
+  const double MACHEPS = 3e-8, TSTEP = 10, T = 1e-7;
+  double a = LowerBound, b = UpperBound, c = 0, d = 0, e = 0, fa = 0, fb = 0, fc = 0, m, p, q, r, s, tol;
+  double last_bad = 0, last_good = 0;
+  int which_err = 0, i = 0, j = 0, st = 0;
+  double x = a, res = 0;
+  if constexpr (FINAL) {
+    if (!fin->do_solve) {
+      res = fin->nosolve_x;
+      f.before_final();
+      x = res;
+      st = 99;
+    }
+  }
+  for (;;) {
+    const double fx = f(x);
+    switch (st) {
+      case 0:
+        fa = fx;
+        x = b;
+        st = 1;
+        continue;
+      case 1:
+        fb = fx;
+        if (fa == ERROR_D && fb == ERROR_D) { res = (ERROR_D); goto done; }
+        if (fa == ERROR_D || fb == ERROR_D) {
+          if (fa == ERROR_D) { which_err = -1; last_bad = a; last_good = b; }
+          else { which_err = 1; last_good = a; last_bad = b; }
+          c = 0.5 * (last_bad + last_good);
+          x = c;
+          j = 0;
+          st = 2;
+          continue;
+        }
+        j = 0;
+        goto expand_check;
+      case 2:  // bisection towards the good bound while the residual is undefined
+        fc = fx;
+        if (fc == ERROR_D && j < MAXITER) {
+          last_bad = c;
+          c = 0.5 * (last_bad + last_good);
+          x = c;
+          j++;
+          continue;
+        }
+        if (fc == ERROR_D) { res = (ERROR_D); goto done; }
+        if (which_err == -1) { a = c; fa = fc; } else { b = c; fb = fc; }
+        j = 0;
+        goto expand_check;
+      case 4:
+        fa = fx;
+        x = b;
+        st = 5;
+        continue;
+      case 5:
+        fb = fx;
+        j++;
+        goto expand_check;
+      case 6:
+        fb = fx;
+        if (fb == ERROR_D) { res = (ERROR_D); goto done; }
+        last_good = a;
+        c = 0.5 * (last_good + last_bad);
+        x = c;
+        i = 0;
+        st = 8;
+        continue;
+      case 7:
+        fa = fx;
+        if (fa == ERROR_D) { res = (ERROR_D); goto done; }
+        last_good = b;
+        c = 0.5 * (last_good + last_bad);
+        x = c;
+        i = 0;
+        st = 8;
+        continue;
+      case 8:
+        fc = fx;
+        if (fc == ERROR_D && i < MAXITER) {
+          last_bad = c;
+          c = 0.5 * (last_bad + last_good);
+          x = c;
+          i++;
+          continue;
+        }
+        if (fc == ERROR_D) { res = (ERROR_D); goto done; }
+        if (which_err == -1) { a = c; fa = fc; } else { b = c; fb = fc; }
+        j++;
+        goto expand_check;
+      case 99:  // the extra evaluation at the accepted point (FINAL only)
+        if constexpr (FINAL) fin->f_final = fx;
+        return res;
+      default:  // 10: an iteration of the main loop has evaluated f(b)
+        fb = fx;
+        if (fb == ERROR_D) { res = (ERROR_D); goto done; }
+        i++;
+        goto main_top;
+    }
+  expand_check:
+    if ((fa * fb) >= 0 && j < MAXTRIES) {
+      if (which_err == 0) {
+        a -= TSTEP;
+        b += TSTEP;
+        x = a;
+        st = 4;
+      } else if (which_err == -1) {
+        b += TSTEP;
+        x = b;
+        st = 6;
+      } else {
+        a -= TSTEP;
+        x = a;
+        st = 7;
+      }
+      continue;
+    }
+    if ((fa * fb) >= 0) { res = (ERROR_D); goto done; }
+    fc = fb;
+    i = 0;
+  main_top:
+    if (i >= MAXITER) { res = (ERROR_D); goto done; }
+    if (fb * fc > 0) {
+      c = a;
+      fc = fa;
+      d = b - a;
+      e = d;
+    }
+    if (fabs(fc) < fabs(fb)) {
+      a = b; b = c; c = a;
+      fa = fb; fb = fc; fc = fa;
+    }
+    tol = 2 * MACHEPS * fabs(b) + T;
+    m = 0.5 * (c - b);
+    if (fabs(m) <= tol || fb == 0) { res = (b); goto done; }
+    if (fabs(e) < tol || fabs(fa) <= fabs(fb)) {
+      d = m;
+      e = d;
+    } else {
+      s = fb / fa;
+      if (a == c) {
+        p = 2 * m * s;
+        q = 1 - s;
+      } else {
+        q = fa / fc;
+        r = fb / fc;
+        p = s * (2 * m * q * (q - r) - (b - a) * (r - 1));
+        q = (q - 1) * (r - 1) * (s - 1);
+      }
+      if (p > 0) q = -q; else p = -p;
+      s = e;
+      e = d;
+      if ((2 * p) < (3 * m * q - fabs(tol * q)) && p < fabs(0.5 * s * q)) d = p / q;
+      else { d = m; e = d; }
+    }
+    a = b;
+    fa = fb;
+    b += (fabs(d) > tol) ? d : ((m > 0) ? tol : -tol);
+    x = b;
+    st = 10;
+    continue;
+  done:
+    if constexpr (!FINAL) {
+      return res;
+    } else {
+      if (result_is_error(res)) {
+        if (!fin->allow_fallback) return res;
+        res = fin->fallback_x;
+        fin->fell_back = 1;
+      }
+      f.before_final();
+      x = res;
+      st = 99;
+    }
+  }
+}
+
+template <class F>
+VIC_HD double root_brent_ss(double LowerBound, double UpperBound, F& f) {
+  return root_brent_ss_impl<false>(LowerBound, UpperBound, f, (BrentFinal*)nullptr);
+}
+
 }  // namespace vic
 #endif

@@ -48,10 +48,12 @@ struct SurfEB {
   // same order as func_surf_energy_bal.c / estimate_T1.c evaluate them at every trial)
   double t1_k1, t1_b, t1_c, t1_den, gf_k1, gf_k2e, sc_lg;
   int sc_lg_ok;
-  EvapMemo memo;
+  EvapMemo* memo;  // the caller's (the functor itself must not have its address taken, or its members stay in memory)
+  double Tsnow_surf_final;  // what Tsnow_surf restarts from at the evaluation after the solve
+  VIC_HD void before_final() { Tsnow_surf = Tsnow_surf_final; }
 
   VIC_HD void prepare() {
-    memo.reset();
+    memo->reset();
     sc_lg_ok = 0;
     sc_lg = 0;
     t1_k1 = t1_b = t1_c = t1_den = gf_k1 = gf_k2e = 0;
@@ -83,7 +85,9 @@ struct SurfEB {
     }
   }
 
-  VIC_HDI double operator()(double Ts) {
+  VIC_HDI double operator()(double Ts) { return eval(Ts); }
+  // the residual proper, inlined into the single call site of root_brent_ss_impl (calc_surf_energy_bal)
+  VIC_HD double eval(double Ts) {
     const double TMean = Ts;
     const double Tmp = TMean + KELVIN;
     if (snow_coverage > 0 && !INCLUDE_SNOW) en->snow_flux = (kappa_snow * (Tsnow_surf - TMean));
@@ -140,10 +144,10 @@ struct SurfEB {
     double Evap;
     if (VEG && !SNOWING && veg_LAI > 0) {
       Evap = canopy_evap(layer, *vv, true, *veg, Wdew, delta_t, NetBareRad, vpd, NetShortBare, Tair, aero_resist_used->overstory,
-                         elevation, rainfall, *soil, &memo);
+                         elevation, rainfall, *soil, memo);
     } else if (!SNOWING) {
       Evap = arno_evap(layer, NetBareRad, Tair, vpd, depth0, max_moist * depth0 * 1000., elevation,
-                       b_infilt, aero_resist_used->surface, delta_t, resid_moist0, &memo);
+                       b_infilt, aero_resist_used->surface, delta_t, resid_moist0, memo);
     } else Evap = 0.;
     en->latent = -RHO_W * latent_heat_Le * Evap;
     en->latent_sub = 0.;
@@ -239,32 +243,36 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   eb.ice_node = energy.ice; eb.kappa_node = energy.kappa_node; eb.moist_node = energy.moist;
   eb.layer = layer; eb.vv = &vv; eb.FIRST_SOLN = FIRST_SOLN;
   eb.NetLongBare = 0; eb.NetLongSnow = TmpNetLongSnow; eb.T1 = 0;
+  EvapMemo memo;
+  eb.memo = &memo;
+  eb.Tsnow_surf_final = snow.surf_temp;
   eb.prepare();
 
-  if (o.FULL_ENERGY) {
-    double T_lower, T_upper;
-    if (INCLUDE_SNOW) {
-      T_lower = energy.T[0] - SURF_DT;
-      T_upper = 0.;
-    } else {
-      T_lower = 0.5 * (energy.T[0] + Tair) - SURF_DT;
-      T_upper = 0.5 * (energy.T[0] + Tair) + SURF_DT;
-    }
-    // QUICK_SOLVE (reduced-node first pass, calc_surf_energy_bal.c:289-314, 400-475) is rejected at create time
-    Tsurf = root_brent(T_lower, T_upper, eb);
-    if (result_is_error(Tsurf)) {
-      if (o.TFALLBACK) {
-        Tsurf = Ts_old;
-        Tsurf_fbflag = 1;
-        Tsurf_fbcount += 1;
-      } else return ERROR_D;
-    }
+  // The solve (FULL_ENERGY) and the evaluation at the accepted temperature -- in the reference a fresh functor, i.e. Tsnow_surf restarts
+  // from snow.surf_temp -- go through the one residual call site of root_brent_ss_impl, so the residual is inlined here and the
+  // solve's constants live in registers.  QUICK_SOLVE (reduced-node first pass, calc_surf_energy_bal.c:289-314, 400-475) is rejected
+  // at create time.
+  double T_lower, T_upper;
+  if (INCLUDE_SNOW) {
+    T_lower = energy.T[0] - SURF_DT;
+    T_upper = 0.;
   } else {
-    Tsurf = Tair;
+    T_lower = 0.5 * (energy.T[0] + Tair) - SURF_DT;
+    T_upper = 0.5 * (energy.T[0] + Tair) + SURF_DT;
   }
-  // final evaluation at the accepted temperature: a fresh functor in the reference, i.e. Tsnow_surf restarts from snow.surf_temp
-  eb.Tsnow_surf = snow.surf_temp;
-  double error = eb(Tsurf);
+  struct Inlined {
+    SurfEB<NN>& f;
+    VIC_HD double operator()(double x) { return f.eval(x); }
+    VIC_HD void before_final() { f.before_final(); }
+  } call{eb};
+  BrentFinal fin{o.FULL_ENERGY != 0, o.TFALLBACK != 0, Ts_old, Tair, 0., 0};
+  Tsurf = root_brent_ss_impl<true>(T_lower, T_upper, call, &fin);
+  if (o.FULL_ENERGY && !fin.fell_back && result_is_error(Tsurf)) return ERROR_D;  // the solve failed and TFALLBACK is off
+  if (fin.fell_back) {
+    Tsurf_fbflag = 1;
+    Tsurf_fbcount += 1;
+  }
+  const double error = fin.f_final;
   if (error == ERROR_D) return ERROR_D;
   energy.error = error;
   if (o.QUICK_FLUX || !(o.FULL_ENERGY || (o.FROZEN_SOIL && (cp(CP_FS_ACTIVE) != 0.0)))) {
@@ -665,6 +673,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     step_snow.surface_flux = 0;
     const double LongUnderOut = soil_energy.LongUnderOut;
 
+    cx.rendezvous(0);
     SolveSnowOut ss;
     ss.coverage = coverage;
     ss.delta_coverage = delta_coverage;
@@ -686,6 +695,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
       step_melt_energy = 0;
     } else INCLUDE_SNOW = 0;
 
+    cx.rendezvous(1);
     double Tsurf = calc_surf_energy_bal<NN>(latent_heat_Le, ss.LongUnderIn, ss.NetLongSnow, ss.NetShortGrnd, ss.NetShortSnow, ss.Torg_snow,
                                             ss.ShortUnderIn, step_snow.albedo, snow_energy.latent, snow_energy.latent_sub, snow_energy.sensible,
                                             Tcanopy, VPDcanopy, VPcanopy, prev_coldcontent, delta_coverage, dp, ice0, step_melt_energy, moist0,
@@ -705,6 +715,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     soil_energy.Tcanopy = Tcanopy;
     snow_energy.Tcanopy = Tcanopy;
 
+    cx.rendezvous(2);
     // potential evaporation with the stability-corrected resistances
     double stability_factor[2];
     if (aero_used.surface == HUGE_RESIST) stability_factor[0] = HUGE_RESIST;

@@ -249,6 +249,17 @@ VIC_HDI void store_hru(const Hru<NN>& h, double* __restrict__ rec, size_t n, con
 }
 
 // everything a physics routine needs to know about "where am I"
+// Rendezvous of the warps of a thread block at a phase boundary of the step (device only; a hint, never a requirement).  The kernel is
+// bound by instruction fetch as soon as the warps of an SM spread over different phases of its 0.6 MB of code:
+// at a phase boundary a warp waits -- for a bounded time, so that warps on other paths or already retired cannot block it -- until
+// the block's other warps have arrived, and the block then runs the next phase's code together.
+struct PhaseSync {
+  unsigned* count;  // [VIC_NPHASE] in shared memory, zeroed at kernel start; null: no rendezvous
+  int nwarps;       // warps of the block that run the step
+  long long limit;  // clock cycles a warp is prepared to wait
+};
+#define VIC_NPHASE 4
+
 struct Ctx {
   const Opts* o;
   CellPar cp;
@@ -257,6 +268,21 @@ struct Ctx {
   Forcing f;     // my cell's forcing record of the current model step
   Dmy dmy;
   int rec;
+  PhaseSync ps;
+  VIC_HD void rendezvous(int phase) const {
+#if defined(__CUDA_ARCH__)
+    if (!ps.count) return;
+    const unsigned m = __activemask();
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+      atomicAdd(&ps.count[phase], 1u);
+      const long long t0 = clock64();
+      while (*(volatile unsigned*)&ps.count[phase] < (unsigned)ps.nwarps && clock64() - t0 < ps.limit) __nanosleep(100);
+    }
+    __syncwarp(m);
+#else
+    (void)phase;
+#endif
+  }
 };
 
 }  // namespace vic

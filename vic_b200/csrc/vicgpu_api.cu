@@ -282,6 +282,8 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   h->overlap = !(noov && atoi(noov) != 0);
   const char* pdl = getenv("VICGPU_PDL");  // 0: cell output on a second stream instead of a programmatic dependent launch
   h->pdl = !(pdl && atoi(pdl) == 0) && h->overlap;
+  const char* sl = getenv("VICGPU_SYNC");  // clock cycles a warp waits for its block at a phase boundary of the step (0: no rendezvous)
+  h->sync_limit = sl ? atoll(sl) : 0;
   const char* rbk = getenv("VICGPU_RECBLOCK");  // records advanced per launch of the step kernel (1 .. VICGPU_RECBLOCK_MAX)
   h->recblock = rbk ? std::max(1, std::min(VICGPU_RECBLOCK_MAX, atoi(rbk))) : VICGPU_RECBLOCK_MAX;
   const char* nobin = getenv("VICGPU_NOBIN");  // keep the caller's row order (no binning at all)
@@ -664,9 +666,9 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
         wns = h->d_warp_ns;
       }
       if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm);
-      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm);
-      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm);
+      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
+      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
+      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
       h->last_launches++;
       // the previous record's output rides on this step
       if (pend.valid) {
@@ -769,9 +771,9 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
       t.hrurec_out = D.snap;
       t.hdiag_out = D.hdiag;
       const GlacAccum ga = {rb.ga[0] & 1, (rb.ga[0] >> 1) & 1, (rb.ga[0] >> 2) & 1, (rb.ga[0] >> 3) & 1};
-      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm);
-      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm);
-      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm);
+      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
+      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
+      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
       h->last_launches++;
     } else {
       if (h->o.Nnode <= 3) vicgpu_launch_hru_steps_nn3(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);

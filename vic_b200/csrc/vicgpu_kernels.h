@@ -10,9 +10,9 @@
 #define VICGPU_HRU_BLOCK 384
 #define VICGPU_HRU_BLOCK_MAX 384
 
-void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0);
-void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0);
-void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0);
+void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0, long long sync_limit = 0);
+void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0, long long sync_limit = 0);
+void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0, long long sync_limit = 0);
 
 void vicgpu_launch_hru_steps_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* forcing, size_t per, const vic::RecBlock& rb, double* snap,
                                  size_t snap_stride, double* hdiag, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr);
