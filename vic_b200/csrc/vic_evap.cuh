@@ -85,7 +85,7 @@ VIC_HD double pow23_m(EvapMemo* m, int site, double x) {
 }
 
 // canopy_evap.c:218-442
-VIC_HDI void transpiration(SoilLayer* layer, const VegNow& veg, double rad, double vpd, double net_short, double air_temp,
+VIC_HD void transpiration(SoilLayer* layer, const VegNow& veg, double rad, double vpd, double net_short, double air_temp,
                            double ra, double f, double delta_t, double Wdew, double elevation, const SoilET& s,
                            double* layerevap, EvapMemo* memo = nullptr) {
   const int NL = VICGPU_NLAYER;
@@ -156,7 +156,7 @@ VIC_HDI void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doub
 // canopy_evap.c:46-212.  Wdew_in: interception store at the start of the sub-step [mm];
 // ppt: rain reaching the canopy [mm]; returns total evaporation [m/s] and leaves
 // canopyevap / throughfall / Wdew in veg and layer[].evap.
-VIC_HDI double canopy_evap(SoilLayer* layer, VegVar& vv, bool CALC_EVAP, const VegNow& veg, double Wdew_in, double delta_t,
+VIC_HD double canopy_evap(SoilLayer* layer, VegVar& vv, bool CALC_EVAP, const VegNow& veg, double Wdew_in, double delta_t,
                            double rad, double vpd, double net_short, double air_temp, double ra, double elevation, double ppt,
                            const SoilET& s, EvapMemo* memo = nullptr) {
   double layerevap[VICGPU_NLAYER];
@@ -196,7 +196,7 @@ VIC_HDI double canopy_evap(SoilLayer* layer, VegVar& vv, bool CALC_EVAP, const V
 
 // arno_evap.c:61-228; returns evaporation [m/s] or ERROR_D.  Only Epot depends on the net radiation and the resistance: the
 // infiltration-curve factor (three pow and a 30-term series) goes through the memo.
-VIC_HDI double arno_evap(SoilLayer* layer, double rad, double air_temp, double vpd, double depth1, double max_moist, double elevation,
+VIC_HD double arno_evap(SoilLayer* layer, double rad, double air_temp, double vpd, double depth1, double max_moist, double elevation,
                          double b_infilt, double ra, double delta_t, double moist_resid, EvapMemo* memo = nullptr) {
   double tmp, ratio, as, evap;
   double moist = layer[0].moist - layer[0].soil_ice;
