@@ -64,7 +64,10 @@ int main(int argc, char** argv) {
   if (binned) bin_hrus(cs["hrupar"].f64.data(), nhru, hru_of_slot, slot_of_hru);
   const int* slot = binned ? slot_of_hru.data() : nullptr;
   to_colmajor(cs["hrupar"].f64, nhru, HP_N, hrupar, slot);
-  to_colmajor(cs["hrurec0"].f64, nhru, L.hr_stride, hrurec, slot);
+  // the HRU state is tile-major (vic_types.cuh hr_off), like on the device
+  hrurec.assign(hr_rows(nhru) * L.hr_stride, 0.0);
+  for (int r = 0; r < nhru; r++)
+    for (int c = 0; c < L.hr_stride; c++) hrurec[hr_off(slot ? slot[r] : r, L.hr_stride) + (size_t)c * VIC_HR_TILE] = cs["hrurec0"].f64[(size_t)r * L.hr_stride + c];
   std::vector<double> hdiag((size_t)3 * nhru, 0.0), carry((size_t)CC_N * ncell, 0.0), out((size_t)nout * ncell, 0.0), agg((size_t)nout * ncell, 0.0);
   std::vector<int> cell_h0(ncell + 1, 0), status(ncell, 0), fail_rec(ncell, INT_MAX);
   for (int h = 0; h < nhru; h++) cell_h0[(int)cs["hrupar"].f64[(size_t)h * HP_N + HP_cell] + 1]++;
@@ -116,7 +119,8 @@ int main(int argc, char** argv) {
     if (nd < dump_recs.size() && dump_recs[nd] == rec) {
       size_t base = hru_all.size();
       hru_all.resize(base + (size_t)nhru * L.hr_stride);
-      to_rowmajor(hrurec.data(), nhru, L.hr_stride, &hru_all[base], slot);
+      for (int r = 0; r < nhru; r++)
+        for (int c = 0; c < L.hr_stride; c++) hru_all[base + (size_t)r * L.hr_stride + c] = hrurec[hr_off(slot ? slot[r] : r, L.hr_stride) + (size_t)c * VIC_HR_TILE];
       nd++;
     }
     if (step_count == o.out_step_ratio) {

@@ -24,7 +24,7 @@ struct Tables {
   const double* cellpar;  // [cp_stride][ncell]
   const double* cellder;  // [VIC_NCELLDER][ncell] constants derived from cellpar (derive_cell_constants), or null
   const double* hrupar;   // [HP_N][nhru]
-  const double* hrurec;   // [hr_stride][nhru]  state at the start of the record (read by hru_work)
+  const double* hrurec;   // tiles [hr_stride][32] (vic_types.cuh hr_off): state at the start of the record (read by hru_work)
   double* hrurec_out;     // [hr_stride][nhru]  state at the end of the record (written by hru_work, read by cell_output);
                           //                    the CUDA library ping-pongs two buffers so that cell_output of record r runs
                           //                    beside hru_work of record r+1; the host port passes hrurec_out == hrurec
@@ -50,8 +50,8 @@ struct GlacAccum {
 // an HRU that is not stepped (its cell is invalid) keeps its state: copy the record to the output buffer when there are two
 VIC_HDI void carry_hru_record(const Tables& t, int h, int hr_stride) {
   if (t.hrurec_out == t.hrurec) return;
-  const size_t nh = (size_t)t.nhru;
-  for (int k = 0; k < hr_stride; k++) t.hrurec_out[(size_t)k * nh + h] = t.hrurec[(size_t)k * nh + h];
+  const size_t off = hr_off(h, hr_stride);
+  for (int k = 0; k < hr_stride; k++) t.hrurec_out[off + (size_t)k * VIC_HR_TILE] = t.hrurec[off + (size_t)k * VIC_HR_TILE];
 }
 
 // h: row of the HRU tables
@@ -78,7 +78,7 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   cx.ps = ps;
   const HruPar hp = load_hrupar(hpc);
   Hru<NN> hru;
-  load_hru<NN>(hru, t.hrurec + h, nh, &o->L);
+  load_hru<NN>(hru, t.hrurec + hr_off(h, o->L.hr_stride), VIC_HR_TILE, &o->L);
   HruStepDiag d;
   int e = hru_step<NN>(hru, hp, cx, d);
   if (e == ERROR_I) {
@@ -100,7 +100,7 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
       hru.glac.cum_mass_balance = 0;
     }
   }
-  store_hru<NN>(hru, t.hrurec_out + h, nh, &o->L);
+  store_hru<NN>(hru, t.hrurec_out + hr_off(h, o->L.hr_stride), VIC_HR_TILE, &o->L);
   dg[0] = d.out_prec * hp.Cv;
   dg[nh] = d.out_rain * hp.Cv;
   dg[2 * nh] = d.out_snow * hp.Cv;
@@ -138,14 +138,15 @@ VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcin
   const HruPar hp = load_hrupar(hpc);
   Hru<NN> hru;
   const double* prev = t.hrurec;
-  load_hru<NN>(hru, prev + h, nh, &o->L);
+  const size_t hoff = hr_off(h, o->L.hr_stride);
+  load_hru<NN>(hru, prev + hoff, VIC_HR_TILE, &o->L);
   for (int i = 0; i < rb.n; i++) {
     const int rec = rb.rec0 + i;
     double* out = snap + (size_t)i * snap_stride;
     double* dg = hdiag + (size_t)i * 3 * nh + h;
     if (t.fail_rec[cell] <= rec) {
       dg[0] = dg[nh] = dg[2 * nh] = 0;
-      store_hru<NN>(hru, out + h, nh, &o->L);
+      store_hru<NN>(hru, out + hoff, VIC_HR_TILE, &o->L);
       prev = out;
       continue;
     }
@@ -162,8 +163,8 @@ VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcin
       if (rec < t.fail_rec[cell]) t.fail_rec[cell] = rec;
 #endif
       dg[0] = dg[nh] = dg[2 * nh] = 0;
-      load_hru<NN>(hru, prev + h, nh, &o->L);  // the failed step left the working set half updated: back to the last good record
-      store_hru<NN>(hru, out + h, nh, &o->L);
+      load_hru<NN>(hru, prev + hoff, VIC_HR_TILE, &o->L);  // the failed step left the working set half updated: back to the last good record
+      store_hru<NN>(hru, out + hoff, VIC_HR_TILE, &o->L);
       prev = out;
       continue;
     }
@@ -176,7 +177,7 @@ VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcin
         hru.glac.cum_mass_balance = 0;
       }
     }
-    store_hru<NN>(hru, out + h, nh, &o->L);
+    store_hru<NN>(hru, out + hoff, VIC_HR_TILE, &o->L);
     dg[0] = d.out_prec * hp.Cv;
     dg[nh] = d.out_rain * hp.Cv;
     dg[2 * nh] = d.out_snow * hp.Cv;

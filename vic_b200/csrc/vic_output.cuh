@@ -35,7 +35,7 @@ VIC_HDI void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, c
   const int nout = L.out_off[VICGPU_N_OUTVARS];
   const int Nbands = o.Nbands;
 #define OUT(v, e) out[L.out_off[VOUT_##v] + (e)]
-#define HR(k) hrec[(size_t)(k) * nhru + h]
+#define HR(k) hrec[hr_off(h, L.hr_stride) + (size_t)(k) * VIC_HR_TILE]
 #define HP(k) hpar[(size_t)(k) * nhru + h]
   double bandCv[VICGPU_MAX_BANDS], TreeAdjustFactor[VICGPU_MAX_BANDS];
   for (int b = 0; b < VICGPU_MAX_BANDS; b++) bandCv[b] = 0;

@@ -139,6 +139,15 @@ struct Hru {
 };
 
 // HRU record (column-major in memory, stride n) -> working set
+// ---- layout of the HRU state tables ---------------------------------------------------------------------------------------------
+// Tile-major: the records of 32 consecutive rows (one warp) form one contiguous tile [hr_stride][32], tiles follow each other.
+// Column k of row h lives at base[hr_off(h, hr_stride) + k * VIC_HR_TILE]: the 32 lanes of a warp still read 256 contiguous bytes
+// per column, and a warp's whole record (181 columns = 46 KB) is ONE contiguous block of memory instead of 181 pieces 0.4 MB apart
+// (DRAM pages, TLB reach, prefetch).  Tables hold round32(nhru) rows.
+#define VIC_HR_TILE 32
+VIC_HD size_t hr_off(int h, int ncol) { return (size_t)(h >> 5) * (size_t)ncol * VIC_HR_TILE + (size_t)(h & 31); }
+VIC_HD size_t hr_rows(int nhru) { return ((size_t)nhru + 31) / 32 * 32; }
+
 // ---- record <-> working set ------------------------------------------------------------------------------------------
 // The scalar columns of the HRU record (include/vicgpu_fields.h) and the members of EnergyBal / SnowPack / SoilCol / VegVar /
 // Glacier are generated from the same X-macro tables in the same order, and every member is a double: a group of columns is

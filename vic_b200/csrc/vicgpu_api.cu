@@ -57,11 +57,34 @@ __global__ void k_gather_rows(const double* __restrict__ in /* [cols][rows] */, 
   out[i] = in[(size_t)c * rows + row_of_rec[r]];
 }
 
+// the same two conversions for the tile-major HRU state (vic_types.cuh hr_off)
+__global__ void k_scatter_state(const double* __restrict__ in /* [rows][cols] */, double* __restrict__ out /* tiles */, int rows, int cols,
+                                const int* __restrict__ rec_of_row /* may be null */) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int c = (int)(i / rows), r = (int)(i % rows);
+  out[hr_off(r, cols) + (size_t)c * VIC_HR_TILE] = in[(size_t)(rec_of_row ? rec_of_row[r] : r) * cols + c];
+}
+__global__ void k_gather_state(const double* __restrict__ in /* tiles */, double* __restrict__ out /* [rows][cols] */, int rows, int cols,
+                               const int* __restrict__ row_of_rec /* may be null */) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  out[i] = in[hr_off(row_of_rec ? row_of_rec[r] : r, cols) + (size_t)c * VIC_HR_TILE];
+}
+// tile-major state: out row s = in row src[s]
+__global__ void k_permute_state(const double* __restrict__ in, double* __restrict__ out, int rows, int cols, const int* __restrict__ src) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int c = (int)(i / rows), r = (int)(i % rows);
+  out[hr_off(r, cols) + (size_t)c * VIC_HR_TILE] = in[hr_off(src[r], cols) + (size_t)c * VIC_HR_TILE];
+}
+
 // ---- dynamic binning: rows of the HRU tables re-ordered by (kind, snow on the ground or in the canopy, cell) ----------------
 // The step's control flow differs most between glacier / bare / vegetated HRUs (static: bin_hrus) and between HRUs with and
 // without snow (dynamic: solve_snow's pack and canopy balances, sub-stepping, evaporation switched off under snow).  Every
 // `rebin_interval` records the rows are re-sorted on the device so that the 32 HRUs of a warp share both.
-__global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __restrict__ hrurec, int nhru, const int* __restrict__ hru_of_slot,
+__global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __restrict__ hrurec, int nhru, int hr_stride, const int* __restrict__ hru_of_slot,
                            unsigned long long* __restrict__ keys, int* __restrict__ old_slot) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nhru) return;
@@ -69,7 +92,8 @@ __global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __re
   unsigned long long kind = (unsigned long long)(long long)hrupar[(size_t)HP_vegIndex * n + s] & 0xfffffull;
   if (hrupar[(size_t)HP_isArtBare * n + s] != 0.0) kind |= 1ull << 20;
   if (hrupar[(size_t)HP_isGlacier * n + s] != 0.0) kind |= 1ull << 21;
-  const bool snowy = hrurec[(size_t)HR_S_swq * n + s] > 0.0 || hrurec[(size_t)HR_S_snow_canopy * n + s] > 0.0;
+  const size_t so = hr_off(s, hr_stride);
+  const bool snowy = hrurec[so + (size_t)HR_S_swq * VIC_HR_TILE] > 0.0 || hrurec[so + (size_t)HR_S_snow_canopy * VIC_HR_TILE] > 0.0;
   // low 32 bits: the HRU's own index, i.e. cell order within a bin (and a total order: the sort is deterministic)
   keys[s] = (kind << 33) | ((unsigned long long)(snowy ? 1 : 0) << 32) | (unsigned long long)(unsigned)hru_of_slot[s];
   old_slot[s] = s;
@@ -98,10 +122,10 @@ __global__ void k_freeze_failed(Tables t, int rec0, int n, double* snap, size_t 
   const int cell = (int)t.hrupar[(size_t)HP_cell * nh + h];
   const int fr = t.fail_rec[cell];
   if (fr < rec0 || fr >= rec0 + n - 1) return;
-  const double* good = snap + (size_t)(fr - rec0) * snap_stride;
+  const double* good = snap + (size_t)(fr - rec0) * snap_stride + hr_off(h, hr_stride);
   for (int i = fr - rec0 + 1; i < n; i++) {
-    double* out = snap + (size_t)i * snap_stride;
-    for (int k = 0; k < hr_stride; k++) out[(size_t)k * nh + h] = good[(size_t)k * nh + h];
+    double* out = snap + (size_t)i * snap_stride + hr_off(h, hr_stride);
+    for (int k = 0; k < hr_stride; k++) out[(size_t)k * VIC_HR_TILE] = good[(size_t)k * VIC_HR_TILE];
   }
 }
 
@@ -225,7 +249,7 @@ static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const do
   const int nhru = h->t.nhru;
   const vicgpu_layout& L = h->o.L;
   const int T = 256, G = (nhru + T - 1) / T;
-  k_bin_keys<<<G, T, 0, h->stream>>>(S.hrupar, src_state, nhru, S.hru_of_slot, h->d_keys[0], h->d_oldslot[0]);
+  k_bin_keys<<<G, T, 0, h->stream>>>(S.hrupar, src_state, nhru, L.hr_stride, S.hru_of_slot, h->d_keys[0], h->d_oldslot[0]);
   size_t need = 0;
   CK(cub::DeviceRadixSort::SortPairs(nullptr, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
   if (need > h->sort_tmp_bytes) {
@@ -238,7 +262,7 @@ static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const do
   }
   CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
   const size_t ns = (size_t)nhru * L.hr_stride, np = (size_t)nhru * HP_N;
-  k_permute_rows<<<(unsigned)((ns + T - 1) / T), T, 0, h->stream>>>(src_state, dst_state, nhru, L.hr_stride, h->d_oldslot[1]);
+  k_permute_state<<<(unsigned)((ns + T - 1) / T), T, 0, h->stream>>>(src_state, dst_state, nhru, L.hr_stride, h->d_oldslot[1]);
   k_permute_rows<<<(unsigned)((np + T - 1) / T), T, 0, h->stream>>>(S.hrupar, D.hrupar, nhru, HP_N, h->d_oldslot[1]);
   k_slot_maps<<<G, T, 0, h->stream>>>(h->d_keys[1], nhru, D.hru_of_slot, D.slot_of_hru);
   h->last_launches += 5 + 2;  // + the radix sort's own passes (counted as two)
@@ -401,7 +425,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     free_order(h->order[b]);
   }
   // records per launch: as many as fit in a third of the free memory (two halves of snapshots), at most `recblock`
-  const size_t state_bytes = (size_t)nhru * L.hr_stride * sizeof(double);
+  const size_t state_bytes = hr_rows(nhru) * L.hr_stride * sizeof(double);  // whole 32-row tiles
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   int rbn = h->recblock;
@@ -421,6 +445,8 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     StateHalf& s = h->half[b];
     CK(cudaMalloc(&s.in, state_bytes));
     CK(cudaMalloc(&s.snap, (size_t)h->rb * state_bytes));
+    CK(cudaMemset(s.in, 0, state_bytes));
+    CK(cudaMemset(s.snap, 0, (size_t)h->rb * state_bytes));
     CK(cudaMalloc(&s.hdiag, (size_t)h->rb * nhru * 3 * sizeof(double)));
     CK(cudaMemset(s.hdiag, 0, (size_t)h->rb * nhru * 3 * sizeof(double)));
     RowOrder& r = h->order[b];
@@ -506,8 +532,16 @@ int vicgpu_set_state(vicgpu_handle* h, const double* hrurec) {
   if (!h->have_cells) return fail(VICGPU_ESTATE, "set_cells before set_state");
   CK(cudaSetDevice(h->device));
   StateHalf& s = h->half[h->cur_half];
-  int rc = upload_transposed(h, hrurec, s.in, h->t.nhru, h->o.L.hr_stride, h->order[s.ord].hru_of_slot);
-  if (rc) return rc;
+  {
+    const int rows = h->t.nhru, cols = h->o.L.hr_stride;
+    const size_t n = (size_t)rows * cols;
+    int rc = ensure_stage(h, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_stage, hrurec, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_scatter_state<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_stage, s.in, rows, cols, h->order[s.ord].hru_of_slot);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
   h->d_state_cur = s.in;
   h->have_state = true;
   h->recs_since_rebin = 1 << 30;
@@ -518,7 +552,15 @@ int vicgpu_get_state(vicgpu_handle* h, double* hrurec) {
   if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
   if (!h->have_state) return fail(VICGPU_ESTATE, "no state set");
   CK(cudaSetDevice(h->device));
-  return download_transposed(h, h->d_state_cur, hrurec, h->t.nhru, h->o.L.hr_stride, true, h->order[h->half[h->cur_half].ord].slot_of_hru);
+  const int rows = h->t.nhru, cols = h->o.L.hr_stride;
+  const size_t n = (size_t)rows * cols;
+  int rc = ensure_stage(h, n);
+  if (rc) return rc;
+  k_gather_state<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_state_cur, h->d_stage, rows, cols, h->order[h->half[h->cur_half].ord].slot_of_hru);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hrurec, h->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return VICGPU_OK;
 }
 
 int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forcing) {
@@ -560,7 +602,7 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
   const int nhru = h->t.nhru;
   const size_t per = (size_t)h->t.ncell * L.f_stride;
   const size_t rowsz = (size_t)h->t.ncell * h->nout;
-  const size_t snap_stride = (size_t)nhru * L.hr_stride;
+  const size_t snap_stride = hr_rows(nhru) * L.hr_stride;
   // one warp per block: such a block fits beside a resident step block on every SM (vicgpu_step.inc)
   const char* cb = getenv("VICGPU_OUTBLOCK");
   const int B = (cb && atoi(cb) >= 32 && atoi(cb) <= 128) ? atoi(cb) : 32;
