@@ -346,7 +346,7 @@ def main():
                              "kernel": "k_hru_step_nn3", "avg_launch_us": hru_avg_s * 1e6, "launches_timed": int(hru_n),
                              "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6544.7",
                              "kernel_share_of_step": (hru_ms / 1e3) / dev_s if dev_s > 0 else None,
-                             "note": "latency / instruction-cache bound, not bandwidth bound: see profiles/ and DESIGN.md section 6"},
+                             "note": "latency bound (thread-local memory, dependent FP64 chains), not bandwidth bound: see profiles/r01c_summary.md and DESIGN.md section 6"},
                 "roofline_fp64": fp64,
                 "clocks": cs.summary()}
         if not a.no_e2e:

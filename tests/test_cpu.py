@@ -161,6 +161,19 @@ def test_glacier_mass_balance_fit_matches_reference(ref_harness_dl, vicport, tmp
     assert np.array_equal(res["hrurec"], c["hrurec_ref"], equal_nan=True)
 
 
+def test_single_call_site_brent_is_the_same_solver(root):
+    """root_brent_ss_impl (the state machine the ground-surface solve runs through) against root_brent (the restatement of
+    root_brent.c:97-335): 400,000 random residuals with undefined regions, bracket expansion and failing solves must give identical
+    sequences of evaluation points and identical results"""
+    exe = os.path.join(root, "oracle", "_ref", "brentcheck")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/brentcheck not built")
+    out = subprocess.run([exe], check=True, stdout=subprocess.PIPE, text=True).stdout.split()
+    stats = dict(zip(out[0::2], (int(x) for x in out[1::2])))
+    assert stats["mismatches"] == 0 and stats["cases"] == 400000, stats
+    assert stats["failed_solves"] > 10000 and stats["one_bound_undefined"] > 10000 and stats["both_undefined"] > 1000, stats  # the rare paths were exercised
+
+
 def test_portable_math_accuracy(root):
     """vic_math.cuh against glibc on the argument ranges of the hot path: error bounds stated in its header"""
     exe = os.path.join(root, "oracle", "_ref", "mathcheck")
