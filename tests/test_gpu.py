@@ -199,3 +199,21 @@ def test_full_size_domain_properties(ncell, nrec):
     werr = out_big[:, :, L.out_names.index("WATER_ERROR")]
     assert np.nanmax(np.abs(werr)) < 1e-5, np.nanmax(np.abs(werr))
     assert np.all(np.abs(bal_big[:, 2]) < 1e-5 + 1e-12)  # CellBalanceErrors::water_max_error
+
+
+@pytest.mark.parametrize("env", [{"VICGPU_PDL": "0"}, {"VICGPU_NOOVERLAP": "1"}, {"VICGPU_RECBLOCK": "24"}, {"VICGPU_RECBLOCK": "5"}, {"VICGPU_NOBIN": "1"},
+                                 {"VICGPU_REBIN": "0"}, {"VICGPU_REBIN": "1"}, {"VICGPU_SYNC": "50000"}, {"VICGPU_EVEN": "1"}, {"VICGPU_DEAL": "1"},
+                                 {"VICGPU_BLOCK": "128"}, {"VICGPU_OUTBLOCK": "128"}], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_every_launch_mode_gives_the_same_bits(env, monkeypatch):
+    """the tuning / A-B knobs of libvicgpu.so (read from the environment at vicgpu_create) change how the work is laid out and launched --
+    row order, records per launch, streams, block sizes -- never the arithmetic: every mode must reproduce the reference bit for bit"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name in ("fe_hourly_winter_dl", "glacier_dl"):
+        g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+        res = api.run_case(g, device=0, nrec=96)
+        n = res["hrurec"].shape[0]
+        assert n >= 1
+        assert np.array_equal(res["hrurec"], g["hrurec_ref"][:n], equal_nan=True)
+        assert np.array_equal(res["out"][:24], g["out_ref_head"], equal_nan=True)
+        assert np.array_equal(res["agg"][1:], g["agg_ref"][1:res["agg"].shape[0]], equal_nan=True)

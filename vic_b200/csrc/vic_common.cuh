@@ -120,7 +120,12 @@ VIC_HD double vacos(double a) { return dl::acos(a); }
 // (a plain `a == 0 ? a : a / b` does not help -- the compiler evaluates the division speculatively and selects afterwards).
 VIC_HD double div_pos(double a, double b) {
   const bool z = (a == 0.0);
-  const double q = (z ? 1.0 : a) / b;
+  double n = z ? 1.0 : a;
+#if defined(__CUDA_ARCH__)
+  // opaque to the optimiser: otherwise it proves that n == a on the path that uses the quotient and divides a itself again
+  asm volatile("" : "+d"(n));
+#endif
+  const double q = n / b;
   return z ? a : q;
 }
 
