@@ -45,9 +45,9 @@ def col(table, name):
 
 
 # ---------------------------------------------------------------------------------------------- domain
-def build_domain(ncell, seed):
+def build_domain(ncell, seed, base="fe_hourly"):
     """tile the 256-cell base domain to ncell cells; tile 0 is the base domain itself"""
-    b = dict(np.load(os.path.join(ROOT, "bench_data", "base_fe_hourly.npz")))
+    b = dict(np.load(os.path.join(ROOT, "bench_data", f"base_{base}.npz")))
     nb = b["cellpar"].shape[0]
     cell_of_hru = b["hrupar"][:, col("hpar", "HP_cell")].astype(np.int64)
     h0 = np.searchsorted(cell_of_hru, np.arange(nb + 1))

@@ -47,9 +47,7 @@ def _tol(name):
 def test_golden_case(name):
     g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
     L = layout_from_options(parse_options(g["options_raw"]))
-    # QUICK_FLUX=FALSE: a soil profile that fails to converge costs 1000 Gauss-Seidel sweeps x per-node Brent solves
-    # (frozen_soil.c:380-468); one such HRU stalls its whole warp, so the GPU case is kept to the first two days
-    nrec = 48 if name == "frozen_bands" else None
+    nrec = None
     res = api.run_case(g, device=0, nrec=nrec)
     tol = _tol(name)
     _check(res, g, (("hrurec", "hrurec_ref", L.hru_names),), L, tol)
@@ -78,7 +76,7 @@ def _reference_case(harness, cfgname, nlat, nlon, ndays, seed, tmp_path):
     return read_case(case)
 
 
-@pytest.mark.parametrize("cfgname,nlat,nlon,ndays,seed", [("fe_hourly", 6, 6, 60, 101), ("wb_daily", 5, 5, 80, 102), ("glacier", 4, 4, 120, 103), ("frozen_bands", 2, 3, 2, 104)])
+@pytest.mark.parametrize("cfgname,nlat,nlon,ndays,seed", [("fe_hourly", 6, 6, 60, 101), ("wb_daily", 5, 5, 80, 102), ("glacier", 4, 4, 120, 103), ("frozen_bands", 2, 3, 6, 104)])
 def test_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref_harness, tmp_path):
     """glibc-linked reference: north_star tolerance.  Run lengths stay below the first last-bit tie of these seeds (see
     tests/test_cpu.py::test_year_long_sensitivity_to_math_library for what happens after one)"""
@@ -90,7 +88,7 @@ def test_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref_harness, 
     assert np.array_equal(res["status"], c["status_ref"])
 
 
-@pytest.mark.parametrize("cfgname,nlat,nlon,ndays,seed", [("fe_hourly", 6, 6, 365, 201), ("wb_daily", 5, 5, 365, 202), ("glacier", 4, 4, 365, 203), ("frozen_bands", 2, 3, 2, 204)])
+@pytest.mark.parametrize("cfgname,nlat,nlon,ndays,seed", [("fe_hourly", 6, 6, 365, 201), ("wb_daily", 5, 5, 365, 202), ("glacier", 4, 4, 365, 203), ("frozen_bands", 2, 3, 8, 204)])
 def test_bit_exact_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref_harness_dl, tmp_path):
     """reference linked against the portable elementary functions: every record's 184 outputs, the state at every
     240th record, balance errors and status are bit-identical -- over a full year, so annual runoff / baseflow / SWE /
@@ -130,7 +128,7 @@ def test_disagg_golden(name):
         # sunrise ties: see tests/test_cpu.py::_check_forcing_against_glibc_reference
         bad = row_errors(f, g["forcing"], names) > TOL_STEP
         assert np.sum(bad.any(axis=0)) <= bad.shape[1] // 2 and bad.mean() < 0.12, bad.sum(axis=0)
-    nrec = 24 if name == "frozen_bands" else min(int(g["dump_recs"][1]) + 1, f.shape[0])
+    nrec = min(int(g["dump_recs"][1]) + 1, f.shape[0])
     gp.step(0, nrec, g["dmy"][:nrec + 1])
     k = 1 if nrec == int(g["dump_recs"][1]) + 1 else None
     if k is not None:

@@ -21,8 +21,9 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--start-day", type=int, default=0)
 ap.add_argument("--tag", default="")
+ap.add_argument("--config", default="fe_hourly", help="fe_hourly | frozen_bands | glacier (bench_data/base_<config>.npz)")
 a = ap.parse_args()
-dom = bench.build_domain(a.cells, 1)
+dom = bench.build_domain(a.cells, 1, a.config)
 g = api.VicGpu(dom["options_raw"], device=0)
 g.set_veglib(dom["veglib"]); g.set_output_spec(dom["aggtype"]); g.set_cells(dom["cellpar"], dom["hrupar"]); g.set_state(dom["hrurec0"])
 nd = a.warmup + a.steps
@@ -40,7 +41,7 @@ for s in range(a.warmup, nd):
     ms += g.last_step_timing()[0]
 kms, kn = g.kernel_profile()
 env = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("VICGPU_"))
-print(f"PROBE {a.tag} [{env}] cells={a.cells} hrus={g.nhru} ms_per_step={ms / a.steps:.3f} hru_kernel_us={kms / max(kn, 1) * 1e3:.1f} "
+print(f"PROBE {a.tag} {a.config} [{env}] cells={a.cells} hrus={g.nhru} ms_per_step={ms / a.steps:.3f} hru_kernel_us={kms / max(kn, 1) * 1e3:.1f} "
       f"cell_steps_per_s={a.cells * 24 * a.steps / (ms / 1e3):.4g} state_sum={np.nansum(g.get_state()):.17g}", flush=True)
 if os.environ.get("VICGPU_WARPTIME"):
     t0, t1, kind = g.warp_times()

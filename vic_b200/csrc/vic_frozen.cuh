@@ -97,8 +97,18 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
     Tfbflag[j] = 0;
     Tfbcount[j] = 0;
   }
+  // A profile that does not converge does not wander: the Gauss-Seidel sweep is a deterministic map of the node temperatures, and
+  // within a dozen sweeps the iterates repeat EXACTLY with period 2 or 3.  From an exact repeat on, every later sweep is known --
+  // it can neither converge (the periodic sweeps did not) nor differ -- so the remaining sweeps up to MAXIT are not executed: the
+  // temperatures after sweep MAXIT are read off the cycle and the per-node fallback counts of the skipped sweeps are added from the
+  // cycle's own counts.  Bit-identical to running all 1000 sweeps (which cost ~0.25 s of a warp per residual evaluation and,
+  // because a whole grid waits for its slowest warp, were the entire run time of the frozen-soil configuration).
+  const int HIST = 8;
+  double Th[HIST][NN];     // temperatures after the last HIST sweeps
+  unsigned fbh[HIST];      // nodes whose Brent solve fell back, per sweep
   while (!Done && ItCount < MAXIT) {
     ItCount++;
+    unsigned fbmask = 0;
     double maxdiff = threshold;
     const int jend = NOFLUX ? Nnodes : Nnodes - 1;
     for (int j = 1; j < jend; j++) {
@@ -121,6 +131,7 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
             T[j] = T0[j];
             Tfbflag[j] = 1;
             Tfbcount[j] += 1;
+            fbmask |= 1u << j;
           } else return ERROR_I;
         }
       }
@@ -128,6 +139,38 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
       if (diff > maxdiff) maxdiff = diff;
     }
     if (maxdiff <= threshold) Done = true;
+    if (!Done && ItCount >= 6 && ItCount < MAXIT) {
+      // exact repeat of an earlier iterate?  (period p: the state after this sweep equals the state p sweeps ago)
+      int period = 0;
+      for (int p = 1; p < HIST && p < ItCount && period == 0; p++) {
+        bool same = true;
+        for (int j = 0; j < Nnodes && same; j++) same = (T[j] == Th[(ItCount - p) % HIST][j]) && !(T[j] != T[j]);
+        if (same) period = p;
+      }
+      if (period > 0) {
+        Th[ItCount % HIST][0] = T[0];
+        for (int j = 0; j < Nnodes; j++) Th[ItCount % HIST][j] = T[j];
+        fbh[ItCount % HIST] = fbmask;
+        // sweeps ItCount+1 .. MAXIT repeat sweeps ItCount-period+1 .. ItCount
+        for (int sweep = ItCount + 1; sweep <= MAXIT; sweep++) {
+          const int src = ItCount - period + 1 + (sweep - ItCount - 1) % period;
+          const unsigned m = fbh[src % HIST];
+          if (m) {
+            for (int j = 0; j < Nnodes; j++)
+              if (m & (1u << j)) {
+                Tfbflag[j] = 1;
+                Tfbcount[j] += 1;
+              }
+          }
+        }
+        const int last = ItCount - period + 1 + (MAXIT - ItCount - 1) % period;
+        for (int j = 0; j < Nnodes; j++) T[j] = Th[last % HIST][j];
+        ItCount = MAXIT;
+        break;
+      }
+    }
+    for (int j = 0; j < Nnodes; j++) Th[ItCount % HIST][j] = T[j];
+    fbh[ItCount % HIST] = fbmask;
   }
   if (o.TFALLBACK) {
     // "cold nose" repair (frozen_soil.c:470-484)
