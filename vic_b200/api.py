@@ -14,7 +14,7 @@ import numpy as np
 from .layout import OPTION_INT_FIELDS, layout_from_options, parse_options
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvicgpu.so")
+LIB_PATH = os.environ.get("VICGPU_LIB") or os.path.join(_HERE, "lib", "libvicgpu.so")  # VICGPU_LIB: an alternative build, for A/B measurements
 
 N_OUTVARS = 184
 

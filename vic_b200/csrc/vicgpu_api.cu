@@ -335,7 +335,15 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
     h->nsm = (ev && atoi(ev) != 0) ? prop.multiProcessorCount : 0;
   }
   const char* blk = getenv("VICGPU_BLOCK");  // threads per block of the per-HRU step kernel (multiple of 32, <= VICGPU_HRU_BLOCK_MAX)
-  if (blk && atoi(blk) >= 32 && atoi(blk) <= VICGPU_HRU_BLOCK_MAX && atoi(blk) % 32 == 0) h->hru_block = atoi(blk);
+  if (blk && atoi(blk) >= 32 && atoi(blk) <= VICGPU_HRU_BLOCK_MAX && atoi(blk) % 32 == 0) {
+    h->hru_block = atoi(blk);
+    h->hru_block_fixed = true;
+  }
+  {
+    cudaDeviceProp prop2;
+    CK(cudaGetDeviceProperties(&prop2, device));
+    h->sm_count = prop2.multiProcessorCount;
+  }
   *out = h;
   return VICGPU_OK;
 }
@@ -491,6 +499,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   CK(cudaStreamSynchronize(h->stream));
   rc = upload_transposed(h, hrupar, h->order[0].hrupar, nhru, HP_N, h->order[0].hru_of_slot);
   if (rc) return rc;
+  if (!h->hru_block_fixed) h->hru_block = ((long long)nhru <= (long long)h->sm_count * VICGPU_HRU_BLOCK) ? VICGPU_HRU_BLOCK : VICGPU_HRU_BLOCK_MAX;
   h->t.ncell = ncell; h->t.nhru = nhru;
   h->t.gmb_cum = h->d_gmb_cum; h->t.gmb = h->d_gmb;
   h->t.cellpar = h->d_cellpar; h->t.cellder = h->d_cellder; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;

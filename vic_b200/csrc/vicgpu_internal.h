@@ -54,6 +54,8 @@ struct vicgpu_handle {
   size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
   int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
   int hru_block = VICGPU_HRU_BLOCK;
+  bool hru_block_fixed = false;  // set through VICGPU_BLOCK
+  int sm_count = 148;
   long long sync_limit = 0;  // PhaseSync::limit
   int nsm = 0;  // SM count when the step grid is rounded up to whole blocks per SM (0: not)
   // re-binning scratch (vicgpu_api.cu rebin_rows)
