@@ -57,7 +57,7 @@ VIC_HDI void carry_hru_record(const Tables& t, int h, int hr_stride) {
 // h: row of the HRU tables
 template <int NN>
 VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec /* [f_stride][ncell] */, int h, Dmy dmy, int rec, GlacAccum ga,
-                      PhaseSync ps = PhaseSync{nullptr, 0, 0}) {
+                      PhaseSync ps = PhaseSync{nullptr, 0}) {
   const size_t nh = (size_t)t.nhru;
   Col hpc{t.hrupar + h, nh};
   const int cell = (int)hpc(HP_cell);
@@ -134,7 +134,7 @@ VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcin
   cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L, Col{t.cellder ? t.cellder + cell : nullptr, (size_t)t.ncell}};
   cx.vl = VegLib{t.veglib, &o->L};
   cx.hp = hpc;
-  cx.ps = PhaseSync{nullptr, 0, 0};
+  cx.ps = PhaseSync{nullptr, 0};
   const HruPar hp = load_hrupar(hpc);
   Hru<NN> hru;
   const double* prev = t.hrurec;

@@ -299,6 +299,7 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
       step_energy.LongUnderOut = LongUnderIn - NetLongSnow;
       step_glacier.accumulation = 0.;
     }
+    cx.rendezvous(4, 1);
     step_energy.AtmosLatent = step_energy.latent;
     step_energy.AtmosLatentSub = step_energy.latent_sub;
     step_energy.AtmosSensible = step_energy.sensible;
@@ -446,6 +447,7 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
   hru.glac.outflow = hru.glac.outflow_coef * hru.glac.water_storage;
   hru.glac.water_storage -= hru.glac.outflow;
   hru.cell.inflow = ppt;
+  cx.rendezvous(5, 1);
   int e = runoff<NN>(hru.cell, hru.energy, cp, ppt, o);
   hru.cell.runoff += (hru.glac.outflow * 1000.);
   return e;

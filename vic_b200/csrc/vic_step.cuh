@@ -55,6 +55,11 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
     hru.snow.vapor_flux = 0.;
     hru.snow.canopy_vapor_flux = 0.;
   }
+  // the lanes that will run a surface-flux step register for the phase rendezvous of their path (vic_types.cuh PhaseSync)
+  if ((AreaFract > 0) || (hp.isGlacier && o.GLACIER_DYNAMICS && AreaFract >= 0.0)) {
+    if (hp.isGlacier) cx.join(1);
+    else cx.join(0);
+  }
   const int veg_class = hp.vegIndex;
   const VegNow veg = veg_now(cx.vl, veg_class, month0);
   const double wind_h = veg.wind_h;

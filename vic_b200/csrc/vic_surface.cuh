@@ -673,7 +673,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     step_snow.surface_flux = 0;
     const double LongUnderOut = soil_energy.LongUnderOut;
 
-    cx.rendezvous(0);
+    cx.rendezvous(0, 0);
     SolveSnowOut ss;
     ss.coverage = coverage;
     ss.delta_coverage = delta_coverage;
@@ -695,7 +695,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
       step_melt_energy = 0;
     } else INCLUDE_SNOW = 0;
 
-    cx.rendezvous(1);
+    cx.rendezvous(1, 0);
     double Tsurf = calc_surf_energy_bal<NN>(latent_heat_Le, ss.LongUnderIn, ss.NetLongSnow, ss.NetShortGrnd, ss.NetShortSnow, ss.Torg_snow,
                                             ss.ShortUnderIn, step_snow.albedo, snow_energy.latent, snow_energy.latent_sub, snow_energy.sensible,
                                             Tcanopy, VPDcanopy, VPcanopy, prev_coldcontent, delta_coverage, dp, ice0, step_melt_energy, moist0,
@@ -715,7 +715,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     soil_energy.Tcanopy = Tcanopy;
     snow_energy.Tcanopy = Tcanopy;
 
-    cx.rendezvous(2);
+    cx.rendezvous(2, 0);
     // potential evaporation with the stability-corrected resistances
     double stability_factor[2];
     if (aero_used.surface == HUGE_RESIST) stability_factor[0] = HUGE_RESIST;

@@ -258,16 +258,17 @@ VIC_HDI void store_hru(const Hru<NN>& h, double* __restrict__ rec, size_t n, con
 }
 
 // everything a physics routine needs to know about "where am I"
-// Rendezvous of the warps of a thread block at a phase boundary of the step (device only; a hint, never a requirement).  The kernel is
-// bound by instruction fetch as soon as the warps of an SM spread over different phases of its 0.6 MB of code:
-// at a phase boundary a warp waits -- for a bounded time, so that warps on other paths or already retired cannot block it -- until
-// the block's other warps have arrived, and the block then runs the next phase's code together.
+// Rendezvous of the warps of a thread block at the phase boundaries of the step (device only; a hint, never a requirement).  The
+// kernel stalls on instruction fetch as soon as the warps of an SM spread over different phases of its 0.6 MB of code (DESIGN.md
+// section 6): at a phase boundary a warp waits until the block's other warps that take the same path have arrived, and the block
+// then runs the next phase's code together -- measured 821 -> 665 us per launch.  Warps register for a path (group 0: surface_fluxes,
+// group 1: surface_fluxes_glac) when they enter the step; the wait is bounded by `limit` clock cycles so that a warp that leaves its
+// path early (an ERROR return) cannot hold the others for long.
+#define VIC_NPHASE 8
 struct PhaseSync {
-  unsigned* count;  // [VIC_NPHASE] in shared memory, zeroed at kernel start; null: no rendezvous
-  int nwarps;       // warps of the block that run the step
+  unsigned* count;  // [VIC_NPHASE + 2] in shared memory, zeroed at kernel start: arrivals per phase, then the two groups' sizes; null: off
   long long limit;  // clock cycles a warp is prepared to wait
 };
-#define VIC_NPHASE 4
 
 struct Ctx {
   const Opts* o;
@@ -278,18 +279,30 @@ struct Ctx {
   Dmy dmy;
   int rec;
   PhaseSync ps;
-  VIC_HD void rendezvous(int phase) const {
+  // the calling lanes (one path of a possibly divergent warp) join group `group`
+  VIC_HD void join(int group) const {
+#if defined(__CUDA_ARCH__)
+    if (!ps.count) return;
+    const unsigned m = __activemask();
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&ps.count[VIC_NPHASE + group], 1u);
+    __syncwarp(m);
+#else
+    (void)group;
+#endif
+  }
+  VIC_HD void rendezvous(int phase, int group) const {
 #if defined(__CUDA_ARCH__)
     if (!ps.count) return;
     const unsigned m = __activemask();
     if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
       atomicAdd(&ps.count[phase], 1u);
       const long long t0 = clock64();
-      while (*(volatile unsigned*)&ps.count[phase] < (unsigned)ps.nwarps && clock64() - t0 < ps.limit) __nanosleep(100);
+      while (*(volatile unsigned*)&ps.count[phase] < *(volatile unsigned*)&ps.count[VIC_NPHASE + group] && clock64() - t0 < ps.limit) __nanosleep(100);
     }
     __syncwarp(m);
 #else
     (void)phase;
+    (void)group;
 #endif
   }
 };

@@ -306,8 +306,8 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   h->overlap = !(noov && atoi(noov) != 0);
   const char* pdl = getenv("VICGPU_PDL");  // 0: cell output on a second stream instead of a programmatic dependent launch
   h->pdl = !(pdl && atoi(pdl) == 0) && h->overlap;
-  const char* sl = getenv("VICGPU_SYNC");  // clock cycles a warp waits for its block at a phase boundary of the step (0: no rendezvous)
-  h->sync_limit = sl ? atoll(sl) : 0;
+  const char* sl = getenv("VICGPU_SYNC");  // most clock cycles a warp waits for its block at a phase boundary of the step (0: no rendezvous)
+  h->sync_limit = sl ? atoll(sl) : 1000000;  // 0.5 ms: a safety bound, not a tuning parameter (waits end when the group has arrived)
   const char* rbk = getenv("VICGPU_RECBLOCK");  // records advanced per launch of the step kernel (1 .. VICGPU_RECBLOCK_MAX)
   h->recblock = rbk ? std::max(1, std::min(VICGPU_RECBLOCK_MAX, atoi(rbk))) : VICGPU_RECBLOCK_MAX;
   const char* nobin = getenv("VICGPU_NOBIN");  // keep the caller's row order (no binning at all)
