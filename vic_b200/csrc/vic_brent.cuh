@@ -124,32 +124,62 @@ VIC_HDI double root_brent(double LowerBound, double UpperBound, F& f) {
 // What a caller that needs the residual once more at the accepted root passes along (calc_surf_energy_bal.c:346-400 evaluates the
 // energy balance a last time at Tsurf, or at the old temperature when the solve failed and TFALLBACK is on, or at the air
 // temperature when the energy balance is not solved at all): that evaluation goes through the same single call site.
+// A caller whose bracket depends on the residual at a first point (snow_melt.c:284-379 evaluates the pack's balance at 0 C and only
+// solves when that is not zero; snow_intercept.c:391-430 does the same for the canopy) passes PRE: the machine evaluates x_pre, hands
+// the value to `decide`, which fills in do_solve / do_final / lo / hi, and carries on from there -- still one residual call site.
 struct BrentFinal {
   bool do_solve, allow_fallback;
+  bool do_final = true;            // evaluate once more at the accepted point
+  bool final_needs_valid = false;  // ... but only when that point is a number
   double fallback_x, nosolve_x;
+  double lo = 0, hi = 0;  // PRE: the bracket, set by `decide`
   double f_final;  // out: the residual at the returned point
   int fell_back;   // out: 1 when the solve failed and fallback_x was used
 };
 
-template <bool FINAL, class F>
-VIC_HD double root_brent_ss_impl(double LowerBound, double UpperBound, F& f, BrentFinal* fin) {
+struct BrentNoDecide {
+  VIC_HD void operator()(double) const {}
+};
+
+template <bool FINAL, bool PRE = false, class F, class D = BrentNoDecide>
+VIC_HD double root_brent_ss_impl(double LowerBound, double UpperBound, F& f, BrentFinal* fin, bool pre = false, double x_pre = 0,
+                                 D decide = D()) {
   const int MAXTRIES = 5, MAXITER = 1000;
   const double MACHEPS = 3e-8, TSTEP = 10, T = 1e-7;
   double a = LowerBound, b = UpperBound, c = 0, d = 0, e = 0, fa = 0, fb = 0, fc = 0, m, p, q, r, s, tol;
   double last_bad = 0, last_good = 0;
-  int which_err = 0, i = 0, j = 0, st = 0;
+  int which_err = 0, i = 0, j = 0, st = 97;
   double x = a, res = 0;
-  if constexpr (FINAL) {
-    if (!fin->do_solve) {
-      res = fin->nosolve_x;
-      f.before_final();
-      x = res;
-      st = 99;
+  if constexpr (PRE) {
+    if (pre) {
+      x = x_pre;
+      st = 98;
     }
   }
   for (;;) {
+    if (st == 97) {  // start (after the pre-evaluation, if there was one)
+      if constexpr (PRE) {
+        a = fin->lo;
+        b = fin->hi;
+      }
+      x = a;
+      st = 0;
+      if constexpr (FINAL) {
+        if (!fin->do_solve) {
+          res = fin->nosolve_x;
+          if (!fin->do_final) return res;
+          f.before_final();
+          x = res;
+          st = 99;
+        }
+      }
+    }
     const double fx = f(x);
     switch (st) {
+      case 98:
+        if constexpr (PRE) decide(fx);
+        st = 97;
+        continue;
       case 0:
         fa = fx;
         x = b;
@@ -302,6 +332,7 @@ VIC_HD double root_brent_ss_impl(double LowerBound, double UpperBound, F& f, Bre
         res = fin->fallback_x;
         fin->fell_back = 1;
       }
+      if (!fin->do_final || (fin->final_needs_valid && !is_valid(res))) return res;
       f.before_final();
       x = res;
       st = 99;

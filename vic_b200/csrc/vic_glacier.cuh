@@ -20,7 +20,9 @@ struct GlacierEB {
   double *AdvectedEnergy, *DeltaColdContent, *GroundFlux, *LatentHeat, *LatentHeatSub, *NetLongUnder, *SensibleHeat, *vapor_flux;
   StabLog stab;
 
-  VIC_HDI double operator()(double TSurf) {
+  VIC_HDI double operator()(double TSurf) { return eval(TSurf); }
+  // the residual proper, inlined into the one call site of glacier_melt's solve
+  VIC_HD double eval(double TSurf) {
     const double TMean = (TSurf + TGrnd) / 2;
     const double OldTMean = (OldTSurf + TGrnd) / 2;
     const double Density = RHO_W;
@@ -75,7 +77,28 @@ VIC_HDI int glacier_melt(double Le, double NetShort, double Tgrnd, double Z0_sno
   eb.IceDepth = cp(CP_GLAC_SURF_THICK); eb.Tair = air_temp; eb.TGrnd = Tgrnd; eb.Ra_used = &aero_resist_used;
   eb.AdvectedEnergy = &advection; eb.DeltaColdContent = &deltaCC_glac; eb.GroundFlux = &grnd_flux; eb.LatentHeat = &latent_heat;
   eb.LatentHeatSub = &latent_heat_sub; eb.NetLongUnder = NetLong; eb.SensibleHeat = &sensible_heat; eb.vapor_flux = &glacier.vapor_flux;
-  double Qnet = eb(0.0);
+  // the balance at 0 C, the solve when that is not zero and the last evaluation (glacier_melt.c:134-176) through one residual call site
+  struct Inlined {
+    GlacierEB& f;
+    VIC_HD double operator()(double x) { return f.eval(x); }
+    VIC_HD void before_final() {}
+  } call{eb};
+  BrentFinal fin;
+  fin.allow_fallback = o.TFALLBACK;
+  fin.fallback_x = *OldTSurf;
+  fin.nosolve_x = 0;
+  fin.f_final = 0;
+  fin.fell_back = 0;
+  double Qnet = 0;
+  const double T_guess = glacier.surf_temp;
+  auto decide = [&](double f0) {
+    Qnet = f0;
+    fin.do_solve = (f0 != 0.0);
+    fin.do_final = fin.do_solve;
+    fin.lo = T_guess - SNOW_DT;
+    fin.hi = T_guess + SNOW_DT;
+  };
+  const double T_solved = root_brent_ss_impl<true, true>(0., 0., call, &fin, true, 0.0, decide);
   if (Qnet == 0.0) {
     // surplus energy at a melting surface: all of it melts ice
     glacier.surf_temp = 0.;
@@ -83,16 +106,13 @@ VIC_HDI int glacier_melt(double Le, double NetShort, double Tgrnd, double Z0_sno
     GlacMelt = melt_energy / (Lf * RHO_W) * delta_t;
     GlacCC = 0.;
   } else {
-    glacier.surf_temp = root_brent((double)(glacier.surf_temp - SNOW_DT), (double)(glacier.surf_temp + SNOW_DT), eb);
-    if (result_is_error(glacier.surf_temp)) {
-      if (o.TFALLBACK) {
-        glacier.surf_temp = *OldTSurf;
-        glacier.surf_temp_fbflag = 1;
-        glacier.surf_temp_fbcount += 1;
-      } else return ERROR_I;
-    }
-    if (!result_is_error(glacier.surf_temp)) {
-      Qnet = eb(glacier.surf_temp);
+    glacier.surf_temp = T_solved;
+    if (fin.fell_back) {
+      glacier.surf_temp_fbflag = 1;
+      glacier.surf_temp_fbcount += 1;
+    } else if (result_is_error(glacier.surf_temp)) return ERROR_I;
+    {
+      Qnet = fin.f_final;
       GlacMelt = 0.0;
       GlacCC = CH_ICE * glacier.surf_temp * cp(CP_GLAC_SURF_THICK) / 1000.;
     }

@@ -27,7 +27,9 @@ struct SnowPackEB {
   double AdvectedEnergy, AdvectedSensibleHeat, DeltaColdContent, GroundFlux, LatentHeat, LatentHeatSub, RefreezeEnergy, SensibleHeat;
   StabLog stab;
 
-  VIC_HDI double operator()(double TSurf) {
+  VIC_HDI double operator()(double TSurf) { return eval(TSurf); }
+  // the residual proper, inlined into the one call site of snow_melt's solve
+  VIC_HD double eval(double TSurf) {
     const double TMean = TSurf;
     const double Density = RHO_W;
     if (Wind > 0.0) Ra_used->surface = Ra / stab.correction(Z, 0., TMean, Tair, Wind, Z0_snow);
@@ -137,7 +139,35 @@ VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy
   eb.NetLongUnder = &out.NetLongSnow;
   eb.sn = &snow;
 
-  double Qnet = eb(0.0);
+  // The balance at 0 C, the solve it may call for and the last evaluation at the accepted temperature (snow_melt.c:284-379) all go
+  // through the one residual call site of root_brent_ss_impl, so the residual is inlined here.
+  struct Inlined {
+    SnowPackEB& f;
+    VIC_HD double operator()(double x) { return f.eval(x); }
+    VIC_HD void before_final() {}
+  } call{eb};
+  BrentFinal fin;
+  fin.do_solve = false;
+  fin.do_final = false;
+  fin.final_needs_valid = true;
+  fin.allow_fallback = o.TFALLBACK;
+  fin.fallback_x = out.OldTSurf;
+  fin.nosolve_x = 0;
+  fin.f_final = 0;
+  fin.fell_back = 0;
+  double Qnet = 0;
+  const bool thick = GLAC || SurfaceSwq > MIN_SWQ_EB_THRES;
+  const double T_guess = snow.surf_temp;
+  auto decide = [&](double f0) {
+    Qnet = f0;
+    if (!UNSTABLE_SNOW && f0 != 0.0 && thick) {
+      fin.do_solve = true;
+      fin.do_final = true;
+      fin.lo = T_guess - SNOW_DT;
+      fin.hi = T_guess + SNOW_DT;
+    }
+  };
+  const double T_solved = root_brent_ss_impl<true, true>(0., 0., call, &fin, true, 0.0, decide);
   if (!UNSTABLE_SNOW) {
     if (Qnet == 0.0) {
       // pack is melting or isothermal at 0 C
@@ -190,20 +220,17 @@ VIC_HDI int snow_melt(double latent_heat_Le, double NetShortSnow, double Tcanopy
       }
     } else {
       // pack surface below freezing: solve for its temperature
-      if (GLAC || SurfaceSwq > MIN_SWQ_EB_THRES) {
-        snow.surf_temp = root_brent((double)(snow.surf_temp - SNOW_DT), (double)(snow.surf_temp + SNOW_DT), eb);
-        if (result_is_error(snow.surf_temp)) {
-          if (o.TFALLBACK) {
-            snow.surf_temp = out.OldTSurf;
-            snow.surf_temp_fbflag = 1;
-            snow.surf_temp_fbcount += 1;
-          } else return ERROR_I;
-        }
+      if (thick) {
+        snow.surf_temp = T_solved;
+        if (fin.fell_back) {
+          snow.surf_temp_fbflag = 1;
+          snow.surf_temp_fbcount += 1;
+        } else if (result_is_error(snow.surf_temp)) return ERROR_I;
       } else {
         snow.surf_temp = vnan();  // thin pack: solved together with the ground surface
       }
       if (is_valid(snow.surf_temp) && !result_is_error(snow.surf_temp)) {
-        Qnet = eb(snow.surf_temp);
+        Qnet = fin.f_final;
         SnowMelt = 0.0;
         SurfaceSwq += snow.surf_water;
         Ice += snow.surf_water;
@@ -321,7 +348,9 @@ struct CanopyEB {
   StabLog stab;
   EvapMemo memo;
 
-  VIC_HDI double operator()(double Tfoliage) {
+  VIC_HDI double operator()(double Tfoliage) { return eval(Tfoliage); }
+  // the residual proper, inlined into the one call site of snow_intercept's solve
+  VIC_HD double eval(double Tfoliage) {
     const double Tmp = Tfoliage + KELVIN;
     *LongOverOut = STEFAN_B * (Tmp * Tmp * Tmp * Tmp);
     *NetRadiation = NetShortOver + LongOverIn + LongUnderOut - 2 * (*LongOverOut);
@@ -505,37 +534,55 @@ VIC_HDI int snow_intercept(double Dt, double LAI, double latent_heat_Le, double 
   eb.NetRadiation = &NetRadiation; eb.RefreezeEnergy = &RefreezeEnergy; eb.SensibleHeat = &energy.canopy_sensible;
   eb.VaporMassFlux = VaporMassFlux;
 
-  double Tupper = vnan(), Tlower = vnan();
-  if (*IntSnow > 0 || *SnowFall > 0) {
-    energy.AlbedoOver = cp(CP_NEW_SNOW_ALB);
-    energy.NetShortOver = (1. - energy.AlbedoOver) * ShortOverIn;
-    eb.IntSnow = *IntSnow;
-    eb.NetShortOver = energy.NetShortOver;
-    Qnet = eb(0.);
-    if (Qnet != 0) {
-      Tupper = 0;
-      if ((*Tfoliage) <= 0.) Tlower = (*Tfoliage) - SNOW_DT;
-      else Tlower = -SNOW_DT;
-    } else *Tfoliage = 0.;
-  } else {
-    energy.AlbedoOver = bare_albedo;
-    energy.NetShortOver = (1. - energy.AlbedoOver) * ShortOverIn;
-    Qnet = vnan();
-    Tupper = (*Tfoliage) + SNOW_DT;
-    Tlower = (*Tfoliage) - SNOW_DT;
-  }
-  if (is_valid(Tupper) && is_valid(Tlower)) {
-    eb.IntSnow = *IntSnow;
-    eb.NetShortOver = energy.NetShortOver;
-    *Tfoliage = root_brent(Tlower, Tupper, eb);
-    if (result_is_error(*Tfoliage)) {
-      if (o.TFALLBACK) {
-        *Tfoliage = OldTfoliage;
-        energy.Tfoliage_fbflag = 1;
-        energy.Tfoliage_fbcount += 1;
-      } else return ERROR_I;
+  // The balance at 0 C when there is snow in or falling on the canopy, the solve it may call for and the last evaluation at the
+  // accepted temperature (snow_intercept.c:391-430) go through the one residual call site of root_brent_ss_impl.
+  const bool snowy = (*IntSnow > 0 || *SnowFall > 0);
+  energy.AlbedoOver = snowy ? cp(CP_NEW_SNOW_ALB) : bare_albedo;
+  energy.NetShortOver = (1. - energy.AlbedoOver) * ShortOverIn;
+  eb.IntSnow = *IntSnow;
+  eb.NetShortOver = energy.NetShortOver;
+  struct Inlined {
+    CanopyEB& f;
+    VIC_HD double operator()(double x) { return f.eval(x); }
+    VIC_HD void before_final() {}
+  } call{eb};
+  BrentFinal fin;
+  fin.allow_fallback = o.TFALLBACK;
+  fin.fallback_x = OldTfoliage;
+  fin.nosolve_x = 0;
+  fin.f_final = 0;
+  fin.fell_back = 0;
+  const double T_guess = *Tfoliage;
+  bool at_zero = false;
+  Qnet = vnan();
+  auto decide = [&](double f0) {
+    Qnet = f0;
+    if (f0 != 0) {
+      fin.hi = 0;
+      fin.lo = (T_guess <= 0.) ? T_guess - SNOW_DT : -SNOW_DT;
+      fin.do_solve = is_valid(fin.lo);
+    } else {
+      at_zero = true;
+      fin.do_solve = false;
     }
-    Qnet = eb(*Tfoliage);
+    fin.do_final = fin.do_solve;
+  };
+  if (!snowy) {
+    fin.hi = T_guess + SNOW_DT;
+    fin.lo = T_guess - SNOW_DT;
+    fin.do_solve = is_valid(fin.hi) && is_valid(fin.lo);
+    fin.do_final = fin.do_solve;
+  }
+  const double T_solved = root_brent_ss_impl<true, true>(0., 0., call, &fin, snowy, 0.0, decide);
+  if (at_zero) *Tfoliage = 0.;
+  if (fin.do_solve) {
+    if (fin.fell_back) {
+      *Tfoliage = OldTfoliage;
+      energy.Tfoliage_fbflag = 1;
+      energy.Tfoliage_fbcount += 1;
+    } else if (result_is_error(T_solved)) return ERROR_I;
+    else *Tfoliage = T_solved;
+    Qnet = fin.f_final;
   }
   (void)Qnet;
   if (*IntSnow <= 0) RainThroughFall = vv.throughfall / 1000.;

@@ -265,7 +265,13 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
     VIC_HD double operator()(double x) { return f.eval(x); }
     VIC_HD void before_final() { f.before_final(); }
   } call{eb};
-  BrentFinal fin{o.FULL_ENERGY != 0, o.TFALLBACK != 0, Ts_old, Tair, 0., 0};
+  BrentFinal fin;
+  fin.do_solve = o.FULL_ENERGY != 0;
+  fin.allow_fallback = o.TFALLBACK != 0;
+  fin.fallback_x = Ts_old;
+  fin.nosolve_x = Tair;
+  fin.f_final = 0.;
+  fin.fell_back = 0;
   Tsurf = root_brent_ss_impl<true>(T_lower, T_upper, call, &fin);
   if (o.FULL_ENERGY && !fin.fell_back && result_is_error(Tsurf)) return ERROR_D;  // the solve failed and TFALLBACK is off
   if (fin.fell_back) {
