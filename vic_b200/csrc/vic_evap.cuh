@@ -109,7 +109,7 @@ VIC_HD void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doubl
     double rc = calc_rc_m(memo, 0, veg.rmin, net_short, veg.RGL, air_temp, vpd, veg.LAI, 1.0);
     double evap = penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t / SEC_PER_DAY * wet_canopy;
     double root_sum = 1.0, spare_evap = 0.0;
-    #pragma unroll 1
+    #pragma unroll
     for (int i = 0; i < NL; i++) {
       if (avail_moist[i] >= s.Wcr[i]) layerevap[i] = evap * (double)s.root[i];
       else {
@@ -122,11 +122,11 @@ VIC_HD void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doubl
       }
     }
     if (spare_evap > 0.0)
-      #pragma unroll 1
+      #pragma unroll
       for (int i = 0; i < NL; i++)
         if (avail_moist[i] >= s.Wcr[i]) layerevap[i] += (double)s.root[i] * spare_evap / root_sum;
   } else {
-    #pragma unroll 1
+    #pragma unroll
     for (int i = 0; i < NL; i++) {
       double gsm_inv;
       if (avail_moist[i] >= s.Wcr[i]) gsm_inv = 1.0;
@@ -138,7 +138,7 @@ VIC_HD void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doubl
       } else layerevap[i] = 0.0;
     }
   }
-  #pragma unroll 1
+  #pragma unroll
   for (int i = 0; i < NL; i++) {
     if (ice[i] > 0) {
       if (ice[i] >= s.Wpwp[i]) {
