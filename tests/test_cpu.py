@@ -144,6 +144,46 @@ def test_year_long_sensitivity_to_math_library(cfgname, nlat, nlon, seed, ref_ha
     assert np.array_equal(res["status"], c["status_ref"])
 
 
+def _failing_case(harness, tmp_path):
+    """frozen soil without TFALLBACK: every failed solve is an error, and each of the nine cells is invalidated somewhere in the
+    first day (vicNl.c:545-559), at a different record"""
+    import dataclasses
+    from vic_b200 import synth
+    cfg = dataclasses.replace(synth.CONFIGS["frozen_bands"], ndays=1, extra_global=["TFALLBACK FALSE"])
+    r = synth.generate(str(tmp_path / "in"), cfg, 3, 3, 312)
+    case = str(tmp_path / "case.bin")
+    subprocess.run([harness, "-g", r["global_file"], "-o", case, "--dump-every", "24"], check=True, stdout=subprocess.DEVNULL)
+    return case, read_case(case)
+
+
+def check_until_invalid(out, c):
+    """rows of every cell bit-identical up to the record at which the reference invalidates it, and the same cells invalid.  The
+    reference still writes a row AT the failing record, from a half-stepped cell (dist_prec.c:159-171 calls put_data after a failed
+    full_energy: HRUs before the failing one stepped, the rest not); the library keeps the last good row instead."""
+    ref = c["out_ref"]
+    nrec, ncell = ref.shape[:2]
+    fails = []
+    for cell in range(ncell):
+        changed = [r for r in range(1, nrec) if not np.array_equal(ref[r, cell], ref[r - 1, cell], equal_nan=True)]
+        f = changed[-1] if c["status_ref"][cell] != 0 else nrec  # the last row the reference wrote for an invalid cell
+        fails.append(f)
+        assert f > 0
+        assert np.array_equal(out[:f, cell], ref[:f, cell], equal_nan=True), (cell, f)
+        if f < nrec:
+            assert np.array_equal(out[f:, cell], np.broadcast_to(out[f - 1, cell], out[f:, cell].shape), equal_nan=True), cell  # frozen at the last good row
+    return fails
+
+
+def test_cells_invalidated_like_the_reference(ref_harness_dl, vicport, tmp_path):
+    case, c = _failing_case(ref_harness_dl, tmp_path)
+    out = str(tmp_path / "res.bin")
+    subprocess.run([vicport, case, out], check=True)
+    res = read_case(out)
+    assert np.array_equal(res["status"], c["status_ref"]) and (c["status_ref"] != 0).all()
+    fails = check_until_invalid(res["out"], c)
+    assert len(set(fails)) >= 4, fails  # cells drop out at different records, the others carry on
+
+
 def test_glacier_mass_balance_fit_matches_reference(ref_harness_dl, vicport, tmp_path):
     """accumulateGlacierMassBalance's quadratic fit (GraphingEquation.c:35-126) at the end of the first accumulation interval: four
     glacier HRUs in four bands per cell, 367 days (the interval of the synthetic set-up ends with the last hour of 1 Jan of the

@@ -215,3 +215,22 @@ def test_every_launch_mode_gives_the_same_bits(env, monkeypatch):
         assert np.array_equal(res["hrurec"], g["hrurec_ref"][:n], equal_nan=True)
         assert np.array_equal(res["out"][:24], g["out_ref_head"], equal_nan=True)
         assert np.array_equal(res["agg"][1:], g["agg_ref"][1:res["agg"].shape[0]], equal_nan=True)
+
+
+def test_cells_invalidated_like_the_reference(ref_harness_dl, tmp_path):
+    """error behaviour: without TFALLBACK a failed solve invalidates the cell (vicNl.c:545-559).  Nine frozen-soil cells drop out at
+    nine different records of the first day while the others carry on: same cells invalid, every row up to a cell's failing record
+    bit-identical, the row frozen from there on -- in every launch mode that treats records differently"""
+    from test_cpu import _failing_case, check_until_invalid
+    _, c = _failing_case(ref_harness_dl, tmp_path)
+    for env in ({}, {"VICGPU_RECBLOCK": "8"}, {"VICGPU_PDL": "0"}):
+        for k, v in env.items():
+            os.environ[k] = v
+        try:
+            res = api.run_case(c, device=0)
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert np.array_equal(res["status"], c["status_ref"]) and (c["status_ref"] != 0).all(), env
+        fails = check_until_invalid(res["out"], c)
+        assert len(set(fails)) >= 4, fails
