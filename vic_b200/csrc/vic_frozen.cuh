@@ -151,15 +151,18 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
         Th[ItCount % HIST][0] = T[0];
         for (int j = 0; j < Nnodes; j++) Th[ItCount % HIST][j] = T[j];
         fbh[ItCount % HIST] = fbmask;
-        // sweeps ItCount+1 .. MAXIT repeat sweeps ItCount-period+1 .. ItCount
-        for (int sweep = ItCount + 1; sweep <= MAXIT; sweep++) {
-          const int src = ItCount - period + 1 + (sweep - ItCount - 1) % period;
-          const unsigned m = fbh[src % HIST];
+        // sweeps ItCount+1 .. MAXIT repeat sweeps ItCount-period+1 .. ItCount: position q of the cycle comes up once for every
+        // k = q, q + period, ... below the number of skipped sweeps (the counts are small integers held in doubles: adding the
+        // number of visits at once is the same as adding 1 that many times)
+        const int skipped = MAXIT - ItCount;
+        for (int q = 0; q < period && q < skipped; q++) {
+          const unsigned m = fbh[(ItCount - period + 1 + q) % HIST];
           if (m) {
+            const int visits = (skipped - q + period - 1) / period;
             for (int j = 0; j < Nnodes; j++)
               if (m & (1u << j)) {
                 Tfbflag[j] = 1;
-                Tfbcount[j] += 1;
+                Tfbcount[j] += visits;
               }
           }
         }
