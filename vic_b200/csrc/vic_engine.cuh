@@ -185,6 +185,7 @@ VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcin
   }
 }
 
+#define VIC_OUT_LOCAL_MAX 512  // doubles of thread-local row (the three-node layout has 365 columns, ten nodes 400)
 VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count) {
   if (rec >= 0 && t.fail_rec[cell] <= rec) {
     // the reference stops touching an invalid cell (vicNl.c:521); its data row keeps the last values
@@ -194,6 +195,16 @@ VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_r
   CellPar cp{Col{t.cellpar + cell, nc}, &o->L};
   VegLib vl{t.veglib, &o->L};
   Forcing f{Col{forcing_rec ? forcing_rec + cell : nullptr, nc}, o->L.f_nslot};
+#if defined(__CUDA_ARCH__)
+  const int nout = o->L.out_off[VICGPU_N_OUTVARS];
+  double row[VIC_OUT_LOCAL_MAX];
+  if (nout <= VIC_OUT_LOCAL_MAX) {
+    put_data_cell(*o, cp, vl, &f, t.hrurec_out, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count,
+                  t.aggtype, RowRW{t.carry + cell, nc}, RowLocal{row}, RowRW{t.agg + cell, nc});
+    for (int k = 0; k < nout; k++) t.out[(size_t)k * nc + cell] = row[k];
+    return;
+  }
+#endif
   put_data_cell(*o, cp, vl, &f, t.hrurec_out, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count, t.aggtype,
                 RowRW{t.carry + cell, nc}, RowRW{t.out + cell, nc}, RowRW{t.agg + cell, nc});
 }

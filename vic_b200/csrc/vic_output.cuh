@@ -23,19 +23,32 @@ struct RowRW {
   VIC_HD double& operator[](int k) const { return p[(size_t)k * n]; }
 };
 
+// the row of one cell held in the thread's own memory while it is built up (cell_output on the device): the ~180 variables are
+// accumulated HRU by HRU, and read-modify-write chains through global memory serialise on the L2 latency (one warp per scheduler:
+// nothing hides it).  put_data_cell is inlined into cell_output so that the compiler sees a local array, not a generic pointer.
+struct RowLocal {
+  double* p;
+  VIC_HD double& operator[](int k) const { return p[k]; }
+};
+
 // out: the cell's row of OutputData::data; agg: its row of aggdata (may be null when rec < 0).
 // hrec/hpar/hdiag are the column-major HRU tables, [h0, h1) the cell's HRUs in hruList order; slot (may be null = identity)
 // maps an HRU to the table row it currently occupies (the device keeps HRUs binned by kind, not by cell).
 // rec < 0 reproduces the storage initialisation call put_data(rec = -nrecs) (vicNl.c:524-541).
-VIC_HDI void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, const Forcing* f, const double* hrec, const double* hpar,
-                           const double* hdiag, size_t nhru, const int* slot, int h0, int h1, int rec, int step_count, const int* aggtype, RowRW carry,
-                           RowRW out, RowRW agg) {
+template <class OutRow>
+VIC_HD void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, const Forcing* f, const double* __restrict__ hrec, const double* __restrict__ hpar,
+                          const double* __restrict__ hdiag, size_t nhru, const int* __restrict__ slot, int h0, int h1, int rec, int step_count, const int* aggtype, RowRW carry,
+                          OutRow out, RowRW agg) {
   const vicgpu_layout& L = o.L;
   const int NL = VICGPU_NLAYER;
   const int nout = L.out_off[VICGPU_N_OUTVARS];
   const int Nbands = o.Nbands;
 #define OUT(v, e) out[L.out_off[VOUT_##v] + (e)]
+#if defined(__CUDA_ARCH__)
+#define HR(k) __ldg(&hrec[hr_off(h, L.hr_stride) + (size_t)(k) * VIC_HR_TILE])
+#else
 #define HR(k) hrec[hr_off(h, L.hr_stride) + (size_t)(k) * VIC_HR_TILE]
+#endif
 #define HP(k) hpar[(size_t)(k) * nhru + h]
   double bandCv[VICGPU_MAX_BANDS], TreeAdjustFactor[VICGPU_MAX_BANDS];
   for (int b = 0; b < VICGPU_MAX_BANDS; b++) bandCv[b] = 0;

@@ -8,6 +8,7 @@
 // a tiled transpose ON THE DEVICE after a straight host->device copy, never a host loop.
 //
 // There is no CPU path in this file: without a CUDA device vicgpu_create fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -270,6 +271,61 @@ static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const do
   return VICGPU_OK;
 }
 
+// ---- SM partition (VICGPU_GREEN=<SMs for the cell output>) -----------------------------------------------------------------------
+// Two green contexts split the device's SMs between the step kernel and the cell-output kernel, so that the output of record r - 1
+// runs beside step r without its blocks sharing an SM (and an L1) with step blocks.  The driver entry points are looked up at run
+// time: the library has no link-time dependency on libcuda.
+struct GreenPartition {
+  CUgreenCtx ctx[2] = {nullptr, nullptr};
+  int sms[2] = {0, 0};
+};
+template <class F>
+static F driver_fn(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  return reinterpret_cast<F>(fn);
+}
+static bool green_streams(int device, int out_sms, int total_sms, int prio_hi, int prio_lo, GreenPartition* gp, cudaStream_t* s_step, cudaStream_t* s_out) {
+  typedef CUresult (*f_devget)(CUdevice*, int);
+  typedef CUresult (*f_getres)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*f_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*f_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*f_create)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*f_stream)(CUstream*, CUgreenCtx, unsigned int, int);
+  f_devget devget = driver_fn<f_devget>("cuDeviceGet");
+  f_getres getres = driver_fn<f_getres>("cuDeviceGetDevResource");
+  f_split split = driver_fn<f_split>("cuDevSmResourceSplitByCount");
+  f_desc mkdesc = driver_fn<f_desc>("cuDevResourceGenerateDesc");
+  f_create create = driver_fn<f_create>("cuGreenCtxCreate");
+  f_stream mkstream = driver_fn<f_stream>("cuGreenCtxStreamCreate");
+  if (!devget || !getres || !split || !mkdesc || !create || !mkstream) return false;
+  cudaFree(0);  // the primary context exists
+  CUdevice dev;
+  if (devget(&dev, device) != CUDA_SUCCESS) return false;
+  CUdevResource all, part[2];
+  if (getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  unsigned int ngroups = 1;
+  const CUresult sr = split(&part[0], &ngroups, &all, &part[1], 0, (unsigned)(total_sms - out_sms));
+  if (sr != CUDA_SUCCESS || ngroups != 1) {
+    fprintf(stderr, "vicgpu: cuDevSmResourceSplitByCount(%d of %u SMs) -> %d, %u groups\n", total_sms - out_sms, all.sm.smCount, (int)sr, ngroups);
+    return false;
+  }
+  if (part[1].sm.smCount == 0) return false;
+  CUstream st[2];
+  const int prio[2] = {prio_hi, prio_lo};
+  for (int k = 0; k < 2; k++) {
+    CUdevResourceDesc d;
+    if (mkdesc(&d, &part[k], 1) != CUDA_SUCCESS) return false;
+    if (create(&gp->ctx[k], d, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (mkstream(&st[k], gp->ctx[k], CU_STREAM_NON_BLOCKING, prio[k]) != CUDA_SUCCESS) return false;
+    gp->sms[k] = (int)part[k].sm.smCount;
+  }
+  *s_step = (cudaStream_t)st[0];
+  *s_out = (cudaStream_t)st[1];
+  return true;
+}
+
 extern "C" {
 
 int vicgpu_abi_version(void) { return VICGPU_ABI_VERSION; }
@@ -296,7 +352,21 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   // the HRU step owns the machine: its stream has the highest priority, the cell-output stream the lowest
   int prio_lo = 0, prio_hi = 0;
   CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+  const char* green = getenv("VICGPU_GREEN");  // SMs set aside for the cell output (two green contexts); 0 / unset: one context
+  int green_sms = 0;
+  if (green && atoi(green) > 0) {
+    cudaDeviceProp gprop;
+    CK(cudaGetDeviceProperties(&gprop, device));
+    GreenPartition gp;
+    if (atoi(green) < gprop.multiProcessorCount && green_streams(device, atoi(green), gprop.multiProcessorCount, prio_hi, prio_lo, &gp, &h->stream, &h->stream_out)) {
+      green_sms = gp.sms[0];
+      fprintf(stderr, "vicgpu: SM partition %d (step) + %d (cell output)\n", gp.sms[0], gp.sms[1]);
+    } else {
+      delete h;
+      return fail(VICGPU_EUNSUPPORTED, "VICGPU_GREEN: the driver could not split the SMs as asked");
+    }
+  }
+  if (!green_sms) CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   // tuning / A-B knobs (environment, read once per handle)
@@ -305,7 +375,7 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   const char* noov = getenv("VICGPU_NOOVERLAP");  // run the cell output in the step's stream
   h->overlap = !(noov && atoi(noov) != 0);
   const char* pdl = getenv("VICGPU_PDL");  // 0: cell output on a second stream instead of a programmatic dependent launch
-  h->pdl = !(pdl && atoi(pdl) == 0) && h->overlap;
+  h->pdl = !(pdl && atoi(pdl) == 0) && h->overlap && !green_sms;  // a programmatic dependent launch stays in one stream, i.e. one partition
   const char* sl = getenv("VICGPU_SYNC");  // most clock cycles a warp waits for its block at a phase boundary of the step (0: no rendezvous)
   h->sync_limit = sl ? atoll(sl) : 1000000;  // 0.5 ms: a safety bound, not a tuning parameter (waits end when the group has arrived)
   const char* rbk = getenv("VICGPU_RECBLOCK");  // records advanced per launch of the step kernel (1 .. VICGPU_RECBLOCK_MAX)
@@ -316,7 +386,8 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   h->rebin_every = rb ? atoi(rb) : 24;
   h->rebin = h->binned && h->rebin_every > 0;
   h->recblock = rbk ? h->recblock : 1;  // default: one record per launch (warps that drift apart lose the shared instruction cache)
-  if (h->overlap) CK(cudaStreamCreateWithPriority(&h->stream_out, cudaStreamNonBlocking, prio_lo));
+  if (green_sms) h->overlap = true;
+  else if (h->overlap) CK(cudaStreamCreateWithPriority(&h->stream_out, cudaStreamNonBlocking, prio_lo));
   else h->stream_out = h->stream;
   CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
   for (int b = 0; b < 2; b++) CK(cudaEventCreateWithFlags(&h->half[b].ev_out, cudaEventDisableTiming));
@@ -342,7 +413,7 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   {
     cudaDeviceProp prop2;
     CK(cudaGetDeviceProperties(&prop2, device));
-    h->sm_count = prop2.multiProcessorCount;
+    h->sm_count = green_sms ? green_sms : prop2.multiProcessorCount;
   }
   *out = h;
   return VICGPU_OK;
