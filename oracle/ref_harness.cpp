@@ -14,6 +14,7 @@
 //
 // Usage: vic_ref_harness -g global.txt [-o case.bin] [--nrec N] [--dump-every K] [--threads T]
 //                        [--forcing-bin forcing.bin] [--time-only] [--time-from REC] [--no-run] [--verbose]
+//                        [--agg-only]   keep out_ref only at output steps (agg_ref): large domains over long runs
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -64,7 +65,7 @@ static int init_cell(cell_info_struct &cell, filep_struct filep, dmy_struct *dmy
 int main(int argc, char **argv) {
   const char *global_file = NULL, *out_path = NULL, *forcing_path = NULL;
   int nrec_limit = -1, dump_every = 0, threads = 1, time_from = 0;
-  bool time_only = false, no_run = false, verbose = false;
+  bool time_only = false, no_run = false, verbose = false, agg_only = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "-g" && i + 1 < argc) global_file = argv[++i];
@@ -77,6 +78,7 @@ int main(int argc, char **argv) {
     else if (a == "--time-from" && i + 1 < argc) time_from = atoi(argv[++i]);
     else if (a == "--no-run") no_run = true;
     else if (a == "--verbose") verbose = true;
+    else if (a == "--agg-only") agg_only = true;
     else die("bad argument");
   }
   if (!global_file) die("need -g <global file>");
@@ -215,7 +217,7 @@ int main(int argc, char **argv) {
   if (dump_every > 0) for (int r = 0; r < nrec; r++) if ((r + 1) % dump_every == 0 || r == nrec - 1 || r == 0) dump_recs.push_back(r);
   std::vector<double> hru_dump, out_dump, agg_dump;
   std::vector<int32_t> agg_recs;
-  if (cw) out_dump.resize((size_t)nrec * ncell * nout);
+  if (cw && !agg_only) out_dump.resize((size_t)nrec * ncell * nout);
 
   auto t2 = std::chrono::steady_clock::now();
   size_t nd = 0;
@@ -237,7 +239,7 @@ int main(int argc, char **argv) {
         accumulateGlacierMassBalance(&(cells[c].gmbEquation), dmy, rec, &(cells[c].prcp), &(cells[c].soil_con), &state);
     }
     if (cw) {
-      for (int c = 0; c < ncell; c++)
+      for (int c = 0; c < ncell && !agg_only; c++)
         vicgpu_pack_outdata(current_output_data[c], &L, &out_dump[((size_t)rec * ncell + c) * nout], false);
       if (nd < dump_recs.size() && dump_recs[nd] == rec) {
         size_t base = hru_dump.size();
@@ -275,7 +277,7 @@ int main(int argc, char **argv) {
     cw->i32("dump_recs", dr.data(), 1, d1);
     int64_t d3[3] = {(int64_t)dr.size(), nhru, L.hr_stride};
     cw->f64("hrurec_ref", hru_dump.data(), 3, d3);
-    int64_t d4[3] = {nrec, ncell, nout};
+    int64_t d4[3] = {agg_only ? 0 : nrec, ncell, nout};
     cw->f64("out_ref", out_dump.data(), 3, d4);
     int64_t d5[1] = {(int64_t)agg_recs.size()};
     cw->i32("agg_recs", agg_recs.data(), 1, d5);

@@ -27,15 +27,6 @@ def ref_harness():
 
 
 @pytest.fixture(scope="session")
-def ref_harness_dl():
-    """the same reference objects linked against vic_b200/csrc/vic_math.cuh (oracle/dlibm_override.cpp)"""
-    p = os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness_dl")
-    if not os.path.exists(p):
-        pytest.skip("oracle/_ref/vic_ref_harness_dl not built (needs /root/reference; see oracle/Makefile)")
-    return p
-
-
-@pytest.fixture(scope="session")
 def vicport():
     p = os.path.join(ROOT, "oracle", "_ref", "vicport")
     if not os.path.exists(p):

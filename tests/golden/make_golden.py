@@ -3,12 +3,9 @@
 Run in the development container (needs /root/reference, built through oracle/Makefile):
     python tests/golden/make_golden.py
 For every configuration it writes synthetic inputs with vic_b200.synth (fixed seed) and runs the reference's
-unmodified physics twice:
-  <name>.npz     oracle/_ref/vic_ref_harness      linked against the platform's libm (glibc): the CUDA library must agree
-                                                  within the north_star tolerance (1e-9 relative per step)
-  <name>_dl.npz  oracle/_ref/vic_ref_harness_dl   the same objects, exp/log/pow/sin/cos/acos resolved to the portable
-                                                  functions of vic_b200/csrc/vic_math.cuh: the CUDA library must agree
-                                                  BIT FOR BIT (state, outputs, forcing, counters)
+unmodified physics (oracle/_ref/vic_ref_harness: the reference's own sources, linked against the platform's glibc 2.39 libm).
+The CUDA library must agree BIT FOR BIT (state, outputs, disaggregated forcing, counters): its elementary functions are
+the operation-by-operation restatement of that libm (vic_b200/csrc/vic_glibm.cuh).
 Each file keeps, compressed:
   the flat C-ABI inputs (options_raw, veglib, cellpar, hrupar, hrurec0, aggtype, valid0, dmy, forcing; disagg_raw + daily:
   the daily PREC/TMAX/TMIN/WIND the reference read, of which `forcing` is ITS disaggregation = the answer for vicgpu_disagg)
@@ -28,7 +25,7 @@ sys.path.insert(0, ROOT)
 from vic_b200 import synth  # noqa: E402
 from vic_b200.casefile import read_case  # noqa: E402
 
-HARNESS = {"": os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness"), "_dl": os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness_dl")}
+HARNESS = {"": os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness")}
 
 # name -> (config name, overrides, nlat, nlon, seed, dump_every)
 GOLDEN = {

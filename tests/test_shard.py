@@ -11,7 +11,7 @@ import pytest
 from vic_b200.shard import cell_ranges, shard_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = os.path.join(ROOT, "tests", "golden", "fe_hourly_winter_dl.npz")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "fe_hourly_winter.npz")
 KEYS = ("options_raw", "meta", "veglib", "cellpar", "hrupar", "hrurec0", "aggtype", "valid0", "dmy", "forcing", "dump_recs")
 
 

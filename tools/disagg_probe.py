@@ -20,7 +20,7 @@ ap.add_argument("--cells", type=int, default=10000)
 ap.add_argument("--days", type=int, default=365)
 a = ap.parse_args()
 dom = bench.build_domain(a.cells, 1)
-gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "fe_hourly_winter_dl.npz")))
+gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "fe_hourly_winter.npz")))
 raw = gold["disagg_raw"].copy()
 raw[5] = a.days
 opt = api.parse_options(dom["options_raw"])

@@ -13,7 +13,7 @@
 #include <math.h>
 #include <limits.h>
 #include "vicgpu.h"
-#include "vic_math.cuh"
+#include "vic_glibm.cuh"
 
 // VIC_HD : small leaf relations, always inlined.
 // VIC_HDI: the larger routines and the residual functors' operator(): real calls (one copy of
@@ -93,9 +93,10 @@ enum { N_PET_TYPES = 6, N_PET_TYPES_NON_NAT = 4, PET_VEGNOCR = 5 };
 // surface types of the aerodynamic tables (VegConditions.h)
 enum Surf { SNOW_FREE = 0, CANOPY_OVER = 1, SNOW_COVERED = 2, GLACIER_SURF = 3, SURF_UNSET = 4 };
 
-// Elementary functions: the portable implementations of vic_math.cuh, identical on device and host (see there).
-// -DVIC_USE_LIBM swaps in the platform's libm; it exists only so that the host port can ALSO be compared bit for
-// bit with the glibc-linked reference build (oracle/Makefile builds both flavours); libvicgpu.so never uses it.
+// Elementary functions: vic_glibm.cuh, the operation-by-operation restatement of glibc 2.39's exp/log/log10/pow/sin/cos/acos
+// (bit-identical to the libm the reference is linked against, on the device and on the host).
+// -DVIC_USE_LIBM swaps in the platform's libm itself; it exists only so that the host port can be run both ways and the two
+// compared (oracle/Makefile builds both flavours; tests/test_cpu.py); libvicgpu.so never uses it.
 #if defined(VIC_USE_LIBM) && !defined(__CUDACC__)
 inline double vpow(double a, double b) { return pow(a, b); }
 inline double vexp(double a) { return exp(a); }
@@ -105,13 +106,13 @@ inline double vsin(double a) { return sin(a); }
 inline double vcos(double a) { return cos(a); }
 inline double vacos(double a) { return acos(a); }
 #else
-VIC_HD double vpow(double a, double b) { return dl::pow(a, b); }
-VIC_HD double vexp(double a) { return dl::exp(a); }
-VIC_HD double vlog(double a) { return dl::log(a); }
-VIC_HD double vlog10(double a) { return dl::log10(a); }
-VIC_HD double vsin(double a) { return dl::sin(a); }
-VIC_HD double vcos(double a) { return dl::cos(a); }
-VIC_HD double vacos(double a) { return dl::acos(a); }
+VIC_HD double vpow(double a, double b) { return gl::pow(a, b); }
+VIC_HD double vexp(double a) { return gl::exp(a); }
+VIC_HD double vlog(double a) { return gl::log(a); }
+VIC_HD double vlog10(double a) { return gl::log10(a); }
+VIC_HD double vsin(double a) { return gl::sin(a); }
+VIC_HD double vcos(double a) { return gl::cos(a); }
+VIC_HD double vacos(double a) { return gl::acos(a); }
 #endif
 
 // a / b where b is known to be positive and finite (a time step, a density, a count of sub-steps, a resistance).  The device's

@@ -158,8 +158,13 @@ __global__ void k_cell_gmb(const Opts* __restrict__ o, Tables t) {
 __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
                                                      int step_count) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= t.ncell) return;
-  cell_output(o, t, forcing_rec, c, rec, step_count);
+  if (c < t.ncell) cell_output(o, t, forcing_rec, c, rec, step_count);
+  // Launched as a programmatic dependent of step(rec + 1) (vicgpu_step), this grid starts while that step is still running.  It
+  // reads only what step(rec) left behind -- hru_work of step(rec + 1) writes the OTHER state half, and its atomicMin on fail_rec
+  // cannot change the `fail_rec <= rec` test made here -- so the work above needs no ordering with it.  The wait below is what makes
+  // COMPLETION of this grid imply completion of the step grid it rode on: step(rec + 2), the transposes and copies that follow are
+  // ordinary launches ordered after this grid only (PTX ISA griddepcontrol.wait).  A no-op for an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch, cudaStream_t st) {
@@ -326,6 +331,8 @@ static bool green_streams(int device, int out_sms, int total_sms, int prio_hi, i
   return true;
 }
 
+static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const Opts& o, int device);
+
 extern "C" {
 
 int vicgpu_abi_version(void) { return VICGPU_ABI_VERSION; }
@@ -344,6 +351,18 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
   if (rc != VICGPU_OK) return fail(rc, why);
   CK(cudaSetDevice(device));
   vicgpu_handle* h = new vicgpu_handle();
+  int crc = create_on_device(h, opt, o, device);
+  if (crc != VICGPU_OK) {
+    vicgpu_destroy(h);
+    return crc;
+  }
+  *out = h;
+  return VICGPU_OK;
+}
+
+}  // extern "C"
+
+static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const Opts& o, int device) {
   h->device = device;
   h->abi = *opt;
   h->o = o;
@@ -362,7 +381,6 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
       green_sms = gp.sms[0];
       fprintf(stderr, "vicgpu: SM partition %d (step) + %d (cell output)\n", gp.sms[0], gp.sms[1]);
     } else {
-      delete h;
       return fail(VICGPU_EUNSUPPORTED, "VICGPU_GREEN: the driver could not split the SMs as asked");
     }
   }
@@ -415,9 +433,10 @@ int vicgpu_create(vicgpu_handle** out, const vicgpu_options* opt, int device) {
     CK(cudaGetDeviceProperties(&prop2, device));
     h->sm_count = green_sms ? green_sms : prop2.multiProcessorCount;
   }
-  *out = h;
   return VICGPU_OK;
 }
+
+extern "C" {
 
 int vicgpu_destroy(vicgpu_handle* h) {
   if (!h) return VICGPU_OK;
@@ -453,6 +472,7 @@ int vicgpu_get_layout(const vicgpu_handle* h, vicgpu_layout* L) {
 
 int vicgpu_set_veglib(vicgpu_handle* h, int nclass, const double* veglib) {
   if (!h || !veglib || nclass < h->o.NVegLibTypes + 4) return fail(VICGPU_EINVAL, "veglib must hold NVegLibTypes + 4 rows");
+  if (h->have_cells && nclass < h->t.nclass) return fail(VICGPU_ESTATE, "a smaller vegetation library after set_cells: call set_cells again");
   CK(cudaSetDevice(h->device));
   cudaFree(h->d_veglib);
   const size_t n = (size_t)nclass * h->o.L.vl_stride;
@@ -465,6 +485,8 @@ int vicgpu_set_veglib(vicgpu_handle* h, int nclass, const double* veglib) {
 
 int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhru, const double* hrupar) {
   if (!h || !cellpar || !hrupar || ncell <= 0 || nhru <= 0) return fail(VICGPU_EINVAL, "bad argument");
+  if (!h->d_veglib) return fail(VICGPU_ESTATE, "set_veglib before set_cells (vegetation indices are checked against it)");
+  if ((long long)ncell > 65535LL * 32) return fail(VICGPU_EUNSUPPORTED, "more than 2,097,120 cells per device (shard the domain)");
   CK(cudaSetDevice(h->device));
   const vicgpu_layout& L = h->o.L;
   // HRU -> cell map must be ascending (hruList order grouped by cell)
@@ -475,7 +497,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     const int c = (int)cd;
     if (cd != (double)c || c < prev || c >= ncell) return fail(VICGPU_EINVAL, "hrupar[HP_cell] must be ascending cell indices in [0, ncell)");
     const int vi = (int)hrupar[(size_t)k * HP_N + HP_vegIndex], b = (int)hrupar[(size_t)k * HP_N + HP_band];
-    if (vi < 0 || (h->t.nclass && vi >= h->t.nclass)) return fail(VICGPU_EINVAL, "hrupar[HP_vegIndex] out of range");
+    if (vi < 0 || vi >= h->t.nclass) return fail(VICGPU_EINVAL, "hrupar[HP_vegIndex] out of range");
     if (b < 0 || b >= h->o.Nbands) return fail(VICGPU_EINVAL, "hrupar[HP_band] out of range");
     prev = c;
     h0[c + 1]++;
@@ -489,6 +511,17 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   const char* deal = getenv("VICGPU_DEAL");
   const bool dealing = deal && atoi(deal) != 0;
   if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru, dealing ? (nhru + h->hru_block - 1) / h->hru_block : 0);
+  // from here on the old domain is gone: a failure below (out of memory on a large domain) must leave a handle that refuses to step
+  h->have_cells = h->have_state = false;
+  h->fnrec = 0;
+  {
+    const double* vl = h->t.veglib;
+    const int nc = h->t.nclass;
+    memset(&h->t, 0, sizeof(h->t));
+    h->t.veglib = vl;
+    h->t.nclass = nc;
+  }
+  h->d_state_cur = nullptr;
   cudaFree(h->d_gmb_cum); cudaFree(h->d_gmb);
   h->d_gmb_cum = h->d_gmb = nullptr;
   cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
