@@ -446,8 +446,11 @@ int vicgpu_set_state(vicgpu_handle *h, const double *hrurec);
 int vicgpu_get_state(vicgpu_handle *h, double *hrurec);
 
 /* ---- forcing: hourly/sub-daily records as produced by initialize_atmos() ---------------- */
-/* forcing [nrec][ncell][L.f_stride]  (var-major inside a record: [FV_*][slot]); copies H2D into the
- * device-resident forcing window that starts at record rec0. */
+/* forcing [nrec][ncell][L.f_stride]  (var-major inside a record: [FV_*][slot]); copies H2D into a
+ * device-resident forcing window that starts at record rec0.  The device keeps the TWO most recently
+ * set windows, and the call returns as soon as the copy is queued: upload block b + 1, then step over
+ * block b, and the transfer overlaps the kernels.  `forcing` must stay untouched until the next call
+ * into the library has returned (with pageable memory the driver has already staged it on return). */
 int vicgpu_set_forcing(vicgpu_handle *h, int rec0, int nrec, const double *forcing);
 
 /* ---- time stepping --------------------------------------------------------------------- */
@@ -460,6 +463,11 @@ int vicgpu_set_forcing(vicgpu_handle *h, int rec0, int nrec, const double *forci
  * out_agg  : NULL or [nout][ncell][L.out_off[N]]   OutputData::aggdata at every completed output
  *            interval inside the block, nout = number of records with step_count == out_step_ratio */
 int vicgpu_step(vicgpu_handle *h, int rec0, int nrec, const int *dmy, double *out_data, double *out_agg);
+/* The same with the outputs narrowed to float32 on the device, as the reference's NetCDF writer stores them
+ * (WriteOutputNetCDF.c:279, 351, 412: plain (float) conversions): half the device-to-host bytes.
+ * Either way the rows travel through two staging buffers on a copy stream, so the transfer of record r
+ * overlaps the kernels of record r + 1. */
+int vicgpu_step_f32(vicgpu_handle *h, int rec0, int nrec, const int *dmy, float *out_data, float *out_agg);
 
 /* mark cells invalid before the run (cells whose initialisation failed on the host, vicNl.c:420-427);
  * status [ncell]: 0 = valid, -999 = skip */

@@ -22,7 +22,10 @@ static void die(const char* m) { fprintf(stderr, "vicport: %s\n", m); exit(2); }
 
 template <int NN>
 static void run_record(const Opts* o, Tables& t, const double* frec, Dmy d, int rec, GlacAccum ga) {
-  for (int h = 0; h < t.nhru; h++) hru_work<NN>(o, t, frec, h, d, rec, ga);
+  if (o->NF == 1)
+    for (int h = 0; h < t.nhru; h++) hru_work<NN, true>(o, t, frec, h, d, rec, ga);
+  else
+    for (int h = 0; h < t.nhru; h++) hru_work<NN, false>(o, t, frec, h, d, rec, ga);
 }
 
 // row-major record r -> column-major row (slot ? slot[r] : r)

@@ -24,7 +24,7 @@ ERRORS = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "EUNSUPPORTED", -4: "ECUDA", 
 SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
-    "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
+    "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_step_f32", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
     "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
 ]
 
@@ -62,6 +62,7 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_get_state.argtypes = [vp, dp]
     lib.vicgpu_set_forcing.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.vicgpu_step.argtypes = [vp, C.c_int, C.c_int, ip, dp, dp]
+    lib.vicgpu_step_f32.argtypes = [vp, C.c_int, C.c_int, ip, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.vicgpu_get_cell_status.argtypes = [vp, ip]
     lib.vicgpu_get_balance_errors.argtypes = [vp, dp]
     lib.vicgpu_get_last_step_timing.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
@@ -166,6 +167,8 @@ class VicGpu:
     def set_forcing(self, rec0, forcing):
         f = _as_f64(forcing)
         assert f.shape[1:] == (self.ncell, self.L.f_stride), f.shape
+        # the upload is asynchronous: the array must outlive it (the library keeps two windows)
+        self._keep = (getattr(self, "_keep", ()) + (f,))[-2:]
         self._chk(self.lib.vicgpu_set_forcing(self.h, int(rec0), int(f.shape[0]), _dptr(f)))
 
     def disagg(self, disagg_raw, daily, want_host=True):
@@ -182,9 +185,18 @@ class VicGpu:
         return (step_count0 + nrec) // self.opt["out_step_ratio"]
 
     def step(self, rec0, nrec, dmy, out_data=None, out_agg=None):
-        """dmy: int32 [nrec+1][5].  out_data / out_agg: preallocated float64 arrays or None."""
+        """dmy: int32 [nrec+1][5].  out_data / out_agg: preallocated float64 (vicgpu_step) or float32 (vicgpu_step_f32: narrowed on
+        the device as the reference's NetCDF writer does) arrays, or None."""
         d = np.ascontiguousarray(dmy, dtype=np.int32)
         assert d.shape[0] >= nrec + 1 and d.shape[1] == 5
+        dts = {a.dtype for a in (out_data, out_agg) if a is not None}
+        assert len(dts) <= 1 and dts <= {np.dtype(np.float64), np.dtype(np.float32)}, dts
+        if dts == {np.dtype(np.float32)}:
+            fp = C.POINTER(C.c_float)
+            od = out_data.ctypes.data_as(fp) if out_data is not None else None
+            oa = out_agg.ctypes.data_as(fp) if out_agg is not None else None
+            self._chk(self.lib.vicgpu_step_f32(self.h, int(rec0), int(nrec), _iptr(d), od, oa))
+            return
         od = _dptr(out_data) if out_data is not None else None
         oa = _dptr(out_agg) if out_agg is not None else None
         self._chk(self.lib.vicgpu_step(self.h, int(rec0), int(nrec), _iptr(d), od, oa))

@@ -55,7 +55,7 @@ VIC_HDI void carry_hru_record(const Tables& t, int h, int hr_stride) {
 }
 
 // h: row of the HRU tables
-template <int NN>
+template <int NN, bool ONE>
 VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec /* [f_stride][ncell] */, int h, Dmy dmy, int rec, GlacAccum ga,
                       PhaseSync ps = PhaseSync{nullptr, 0}) {
   const size_t nh = (size_t)t.nhru;
@@ -80,7 +80,7 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   Hru<NN> hru;
   load_hru<NN>(hru, t.hrurec + hr_off(h, o->L.hr_stride), VIC_HR_TILE, &o->L);
   HruStepDiag d;
-  int e = hru_step<NN>(hru, hp, cx, d);
+  int e = hru_step<NN, ONE>(hru, hp, cx, d);
   if (e == ERROR_I) {
     t.status[cell] = ERROR_I;  // benign race: every writer stores the same value
 #if defined(__CUDA_ARCH__)
@@ -104,85 +104,6 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   dg[0] = d.out_prec * hp.Cv;
   dg[nh] = d.out_rain * hp.Cv;
   dg[2 * nh] = d.out_snow * hp.Cv;
-}
-
-// ---- a block of consecutive records in one launch ------------------------------------------------------------------------------
-// An HRU's record r + 1 depends on nothing but its own record r (and the forcing); only the cell output needs all HRUs of a cell
-// at the same record.  So the CUDA library advances every HRU through up to VICGPU_RECBLOCK_MAX records in ONE launch, keeping the
-// working set in the thread between records and writing the state after each record to its own snapshot buffer; the cell outputs of
-// those records run afterwards from the snapshots.  Warps no longer wait for the slowest warp of the grid after every record (a
-// forest warp with an unlucky root-finder iteration count is 1.5x the average), only once per block of records.
-#define VICGPU_RECBLOCK_MAX 24
-struct RecBlock {
-  int n, rec0;
-  Dmy dmy[VICGPU_RECBLOCK_MAX];
-  unsigned char ga[VICGPU_RECBLOCK_MAX];  // GlacAccum as bits: 1 enabled, 2 reset_first, 4 accumulate, 8 reset_after
-};
-VIC_HD unsigned char pack_ga(const GlacAccum& g) { return (unsigned char)((g.enabled ? 1 : 0) | (g.reset_first ? 2 : 0) | (g.accumulate ? 4 : 0) | (g.reset_after ? 8 : 0)); }
-
-// t.hrurec: state at the start of the block; snap + i * snap_stride: state after record i; hdiag + i * 3 * nhru: step diagnostics.
-// forcing: record rb.rec0 of the window, records `per` doubles apart.  A cell that fails at record r (fail_rec) is frozen from r on;
-// because sibling HRUs may be ahead of the failing one, k_freeze_failed() afterwards makes the snapshots after r equal to snapshot r.
-template <int NN>
-VIC_HDI void hru_block_work(const Opts* o, const Tables& t, const double* forcing, size_t per, const RecBlock& rb, double* snap, size_t snap_stride,
-                            double* hdiag, int h) {
-  const size_t nh = (size_t)t.nhru;
-  Col hpc{t.hrupar + h, nh};
-  const int cell = (int)hpc(HP_cell);
-  Ctx cx;
-  cx.o = o;
-  cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L, Col{t.cellder ? t.cellder + cell : nullptr, (size_t)t.ncell}};
-  cx.vl = VegLib{t.veglib, &o->L};
-  cx.hp = hpc;
-  cx.ps = PhaseSync{nullptr, 0};
-  const HruPar hp = load_hrupar(hpc);
-  Hru<NN> hru;
-  const double* prev = t.hrurec;
-  const size_t hoff = hr_off(h, o->L.hr_stride);
-  load_hru<NN>(hru, prev + hoff, VIC_HR_TILE, &o->L);
-  for (int i = 0; i < rb.n; i++) {
-    const int rec = rb.rec0 + i;
-    double* out = snap + (size_t)i * snap_stride;
-    double* dg = hdiag + (size_t)i * 3 * nh + h;
-    if (t.fail_rec[cell] <= rec) {
-      dg[0] = dg[nh] = dg[2 * nh] = 0;
-      store_hru<NN>(hru, out + hoff, VIC_HR_TILE, &o->L);
-      prev = out;
-      continue;
-    }
-    cx.f = Forcing{Col{forcing + (size_t)i * per + cell, (size_t)t.ncell}, o->L.f_nslot};
-    cx.dmy = rb.dmy[i];
-    cx.rec = rec;
-    HruStepDiag d;
-    const int e = hru_step<NN>(hru, hp, cx, d);
-    if (e == ERROR_I) {
-      t.status[cell] = ERROR_I;
-#if defined(__CUDA_ARCH__)
-      atomicMin(&t.fail_rec[cell], rec);
-#else
-      if (rec < t.fail_rec[cell]) t.fail_rec[cell] = rec;
-#endif
-      dg[0] = dg[nh] = dg[2 * nh] = 0;
-      load_hru<NN>(hru, prev + hoff, VIC_HR_TILE, &o->L);  // the failed step left the working set half updated: back to the last good record
-      store_hru<NN>(hru, out + hoff, VIC_HR_TILE, &o->L);
-      prev = out;
-      continue;
-    }
-    const unsigned char ga = rb.ga[i];
-    if ((ga & 1) && hp.isGlacier) {
-      if (ga & 2) hru.glac.cum_mass_balance = 0;
-      if ((ga & 4) && is_valid(hru.glac.mass_balance)) hru.glac.cum_mass_balance += hru.glac.mass_balance;
-      if (ga & 8) {
-        if (t.gmb_cum) t.gmb_cum[h] = hru.glac.cum_mass_balance;
-        hru.glac.cum_mass_balance = 0;
-      }
-    }
-    store_hru<NN>(hru, out + hoff, VIC_HR_TILE, &o->L);
-    dg[0] = d.out_prec * hp.Cv;
-    dg[nh] = d.out_rain * hp.Cv;
-    dg[2 * nh] = d.out_snow * hp.Cv;
-    prev = out;
-  }
 }
 
 #define VIC_OUT_LOCAL_MAX 512  // doubles of thread-local row (the three-node layout has 365 columns, ten nodes 400)
@@ -279,7 +200,7 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
 // and by cell within a kind, so that the threads of a warp (consecutive rows) take the same branches of the step
 // (surface_fluxes vs surface_fluxes_glac, overstory canopy balance, transpiration vs bare-soil evaporation) and the warps
 // of a block run through the same code.  hrupar_rm: the caller's row-major HRU parameter records.
-inline void bin_hrus(const double* hrupar_rm, int nhru, std::vector<int>& hru_of_slot, std::vector<int>& slot_of_hru, int deal_blocks = 0) {
+inline void bin_hrus(const double* hrupar_rm, int nhru, std::vector<int>& hru_of_slot, std::vector<int>& slot_of_hru) {
   std::vector<long long> key((size_t)nhru);
   for (int k = 0; k < nhru; k++) {
     const double* p = hrupar_rm + (size_t)k * HP_N;
@@ -291,20 +212,6 @@ inline void bin_hrus(const double* hrupar_rm, int nhru, std::vector<int>& hru_of
   hru_of_slot.resize((size_t)nhru);
   for (int k = 0; k < nhru; k++) hru_of_slot[k] = k;
   std::stable_sort(hru_of_slot.begin(), hru_of_slot.end(), [&](int a, int b) { return key[a] < key[b]; });
-  // deal_blocks > 0: the full warps (32 consecutive rows) of the kind-sorted order are dealt round-robin into that many piles and
-  // the piles concatenated, so that every thread block holds a similar mix of cheap and expensive kinds (a block of bare-soil
-  // HRUs finishes long before a block of forest HRUs; with one block per SM the slowest block is the kernel's duration) while a
-  // warp still holds one kind.
-  if (deal_blocks > 1) {
-    const int nfull = nhru / 32;
-    std::vector<int> dealt;
-    dealt.reserve((size_t)nhru);
-    for (int p = 0; p < deal_blocks; p++)
-      for (int w = p; w < nfull; w += deal_blocks)
-        for (int l = 0; l < 32; l++) dealt.push_back(hru_of_slot[(size_t)w * 32 + l]);
-    for (int k = nfull * 32; k < nhru; k++) dealt.push_back(hru_of_slot[k]);
-    hru_of_slot.swap(dealt);
-  }
   slot_of_hru.resize((size_t)nhru);
   for (int s = 0; s < nhru; s++) slot_of_hru[hru_of_slot[s]] = s;
 }

@@ -132,7 +132,7 @@ VIC_HDI int glacier_melt(double Le, double NetShort, double Tgrnd, double Z0_sno
 }
 
 // surface_fluxes_glac.c:6-613.  Returns 0 or ERROR_I.
-template <int NN>
+template <int NN, bool ONE>
 VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, Hru<NN>& hru, const AeroState& as, const double* gauge_correction,
                                 int band, const Ctx& cx, int veg_class, SurfaceFluxOut& out) {
   (void)ice0;
@@ -387,9 +387,10 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
     for (int p = 0; p < N_PET_TYPES; p++) st_pot_evap[p] += step_pot_evap[p];
     N_steps++;
     hidx += 1;
-  } while (hidx < endhidx);
+  } while (!ONE && hidx < endhidx);
 
-  const double N = (double)N_steps;
+  const double N = ONE ? 1.0 : (double)N_steps;
+  auto mean = [&](double x) { return ONE ? x : div_pos(x, N); };
   hru.glac = step_glacier;
   hru.glac.melt = st_melt_glac;
   hru.glac.vapor_flux = st_vapor_flux_glac;
@@ -408,23 +409,23 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
   hru.glac.ice_mass_balance = hru.glac.accumulation - hru.glac.melt - hru.glac.vapor_flux;
   hru.energy = step_energy;
   hru.energy.AlbedoOver = 0 / N;
-  hru.energy.AlbedoUnder = div_pos(st_AlbedoUnder, N);
-  hru.energy.AtmosLatent = div_pos(st_AtmosLatent, N);
-  hru.energy.AtmosLatentSub = div_pos(st_AtmosLatentSub, N);
-  hru.energy.AtmosSensible = div_pos(st_AtmosSensible, N);
+  hru.energy.AlbedoUnder = mean(st_AlbedoUnder);
+  hru.energy.AtmosLatent = mean(st_AtmosLatent);
+  hru.energy.AtmosLatentSub = mean(st_AtmosLatentSub);
+  hru.energy.AtmosSensible = mean(st_AtmosSensible);
   hru.energy.LongOverIn = 0 / N;
-  hru.energy.LongUnderIn = div_pos(st_LongUnderIn, N);
-  hru.energy.LongUnderOut = div_pos(st_LongUnderOut, N);
-  hru.energy.NetLongAtmos = div_pos(st_NetLongAtmos, N);
+  hru.energy.LongUnderIn = mean(st_LongUnderIn);
+  hru.energy.LongUnderOut = mean(st_LongUnderOut);
+  hru.energy.NetLongAtmos = mean(st_NetLongAtmos);
   hru.energy.NetLongOver = 0 / N;
-  hru.energy.NetLongUnder = div_pos(st_NetLongUnder, N);
-  hru.energy.NetShortAtmos = div_pos(st_NetShortAtmos, N);
+  hru.energy.NetLongUnder = mean(st_NetLongUnder);
+  hru.energy.NetShortAtmos = mean(st_NetShortAtmos);
   hru.energy.NetShortGrnd = 0 / N;
   hru.energy.NetShortOver = 0 / N;
-  hru.energy.NetShortUnder = div_pos(st_NetShortUnder, N);
+  hru.energy.NetShortUnder = mean(st_NetShortUnder);
   hru.energy.ShortOverIn = 0 / N;
-  hru.energy.ShortUnderIn = div_pos(st_ShortUnderIn, N);
-  hru.energy.advected_sensible = div_pos(st_advected_sensible, N);
+  hru.energy.ShortUnderIn = mean(st_ShortUnderIn);
+  hru.energy.advected_sensible = mean(st_advected_sensible);
   hru.energy.canopy_advection = 0 / N;
   hru.energy.canopy_latent = 0 / N;
   hru.energy.canopy_latent_sub = 0 / N;
@@ -432,31 +433,31 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
   hru.energy.canopy_sensible = 0 / N;
   hru.energy.deltaH = 0 / N;
   hru.energy.fusion = 0 / N;
-  hru.energy.grnd_flux = div_pos(st_grnd_flux, N);
-  hru.energy.latent = div_pos(st_latent, N);
-  hru.energy.latent_sub = div_pos(st_latent_sub, N);
-  hru.energy.melt_energy = div_pos(st_melt_energy, N);
-  hru.energy.sensible = div_pos(st_sensible, N);
-  hru.energy.glacier_flux = div_pos(st_glacier_flux, N);
-  hru.energy.deltaCC_glac = div_pos(st_deltaCC_glac, N);
-  hru.energy.glacier_melt_energy = div_pos(st_glacier_melt_energy, N);
-  hru.energy.advection = div_pos(st_advection, N);
-  hru.energy.deltaCC = div_pos(st_deltaCC, N);
-  hru.energy.refreeze_energy = div_pos(st_refreeze_energy, N);
-  hru.energy.snow_flux = div_pos(st_snow_flux, N);
+  hru.energy.grnd_flux = mean(st_grnd_flux);
+  hru.energy.latent = mean(st_latent);
+  hru.energy.latent_sub = mean(st_latent_sub);
+  hru.energy.melt_energy = mean(st_melt_energy);
+  hru.energy.sensible = mean(st_sensible);
+  hru.energy.glacier_flux = mean(st_glacier_flux);
+  hru.energy.deltaCC_glac = mean(st_deltaCC_glac);
+  hru.energy.glacier_melt_energy = mean(st_glacier_melt_energy);
+  hru.energy.advection = mean(st_advection);
+  hru.energy.deltaCC = mean(st_deltaCC);
+  hru.energy.refreeze_energy = mean(st_refreeze_energy);
+  hru.energy.snow_flux = mean(st_snow_flux);
   hru.energy.Tcanopy = Tcanopy;
   // the canopy stores of a glacier tile are never touched by the sub-steps
   hru.veg.throughfall = 0.;
   hru.veg.canopyevap = 0.;
   hru.veg.Wdew = wdew_in;
   for (int l = 0; l < NL; l++) hru.cell.layer[l].evap = 0.;
-  if (st_aero_cond_used.surface > 0 && st_aero_cond_used.surface < HUGE_RESIST) hru.cell.aero_surface = 1 / (st_aero_cond_used.surface / N);
+  if (st_aero_cond_used.surface > 0 && st_aero_cond_used.surface < HUGE_RESIST) hru.cell.aero_surface = 1 / (ONE ? st_aero_cond_used.surface : st_aero_cond_used.surface / N);
   else if (st_aero_cond_used.surface >= HUGE_RESIST) hru.cell.aero_surface = 0;
   else hru.cell.aero_surface = HUGE_RESIST;
-  if (st_aero_cond_used.overstory > 0 && st_aero_cond_used.overstory < HUGE_RESIST) hru.cell.aero_overstory = 1 / (st_aero_cond_used.overstory / N);
+  if (st_aero_cond_used.overstory > 0 && st_aero_cond_used.overstory < HUGE_RESIST) hru.cell.aero_overstory = 1 / (ONE ? st_aero_cond_used.overstory : st_aero_cond_used.overstory / N);
   else if (st_aero_cond_used.overstory >= HUGE_RESIST) hru.cell.aero_overstory = 0;
   else hru.cell.aero_overstory = HUGE_RESIST;
-  for (int p = 0; p < N_PET_TYPES; p++) hru.cell.pot_evap[p] = st_pot_evap[p] / N;
+  for (int p = 0; p < N_PET_TYPES; p++) hru.cell.pot_evap[p] = ONE ? st_pot_evap[p] : st_pot_evap[p] / N;
   out.snow_inflow = snow_inflow;
   // glacier water storage: linear reservoir whose coefficient decays with snow depth on the ice
   hru.glac.inflow = ppt + 0.;

@@ -443,9 +443,9 @@ VIC_HDI void mass_release(double* InterceptedSnow, double* TempInterceptionStora
 // snow_intercept.c:81-582 with F == 1.  energy: the sub-step's snow-side energy record;
 // RainFall / SnowFall in mm in and out; LongOverOut is the canopy's downward longwave (becomes
 // the understory's incoming longwave).
-template <int NN>
+template <int NN, class EN>
 VIC_HDI int snow_intercept(double Dt, double LAI, double latent_heat_Le, double LongOverIn, double LongUnderOut, double MaxInt,
-                           double ShortOverIn, double Tcanopy, double bare_albedo, EnergyBal<NN>& energy, SnowPack& snow, VegVar& vv,
+                           double ShortOverIn, double Tcanopy, double bare_albedo, EN& energy, SnowPack& snow, VegVar& vv,
                            double* LongOverOut, const Surf4& Ra, RaUsed& Ra_used, double* RainFall, double* SnowFall,
                            const Surf4& wind_speed, const Surf4& displacement, const Surf4& ref_height, const Surf4& roughness,
                            const VegNow& veg, const SoilET& soil, SoilLayer* layer, double AirDens, double EactAir, double Press, double Vpd,

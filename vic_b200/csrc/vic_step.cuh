@@ -39,7 +39,7 @@ struct HruStepDiag {
 };
 
 // Returns 0 or ERROR_I (the reference then invalidates the whole cell, vicNl.c:545-559).
-template <int NN>
+template <int NN, bool ONE>
 VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag& dg) {
   const Opts& o = *cx.o;
   const CellPar& cp = cx.cp;
@@ -83,7 +83,8 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
   // (calc_veg_params.c:26-37) and the log-profile denominator of the wind correction
   const double height_den = 1.1 * vlog(1 + vpow(0.2 * veg.LAI, 0.25));
   const double wind_den = vlog((o.wind_h - 0.) / soil_rough);
-  Surf4 snap_displacement = as.displacement, snap_ref_height = as.ref_height, snap_roughness = as.roughness, snap_wind_speed = as.displacement;
+  Surf4 snap_displacement, snap_ref_height, snap_roughness, snap_wind_speed;  // the tables as the last evaluation left them (set at p == 0)
+  snap_displacement.set_invalid(); snap_ref_height.set_invalid(); snap_roughness.set_invalid(); snap_wind_speed.set_invalid();
   #pragma unroll 1
   for (int p = 0; p < N_PET_TYPES + 1; p++) {
     const int pet_class = (p < N_PET_TYPES_NON_NAT) ? o.NVegLibTypes + p : veg_class;
@@ -135,8 +136,8 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
     }
     SurfaceFluxOut sf;
     int e;
-    if (hp.isGlacier) e = surface_fluxes_glac<NN>(bare_albedo, ice0, moist0, hru, as, gauge_correction, hp.band, cx, veg_class, sf);
-    else e = surface_fluxes<NN>(overstory, bare_albedo, ice0, moist0, hru, surf_atten, as, gauge_correction, hp.isArtBare, hp.band, cx, veg, soil, veg_class, sf);
+    if (hp.isGlacier) e = surface_fluxes_glac<NN, ONE>(bare_albedo, ice0, moist0, hru, as, gauge_correction, hp.band, cx, veg_class, sf);
+    else e = surface_fluxes<NN, ONE>(overstory, bare_albedo, ice0, moist0, hru, surf_atten, as, gauge_correction, hp.isArtBare, hp.band, cx, veg, soil, veg_class, sf);
     if (e == ERROR_I) return ERROR_I;
     dg.out_prec = sf.out_prec;
     dg.out_rain = sf.out_rain;

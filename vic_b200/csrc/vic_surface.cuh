@@ -379,11 +379,11 @@ struct SolveSnowOut {
 
 // solve_snow.c:7-544.  Returns melt [mm] or ERROR_D.  AlbedoUnder is the HRU's own record
 // (surface_fluxes.c:537 passes &energy->AlbedoUnder), energy the sub-step's snow-side record.
-template <int NN>
+template <int NN, class EN>
 VIC_HDI double solve_snow(bool overstory, double BareAlbedo, double LongUnderOut, double Tcanopy, double Tgrnd, double air_temp, double mu,
                           double prec, double snow_grnd_flux, double* AlbedoUnder, double* latent_heat_Le, const Surf4& aero_resist,
                           RaUsed& aero_resist_used, const AeroState& as, const double* gauge_correction, double* snow_inflow, double* surf_atten,
-                          bool UNSTABLE_SNOW, int dt, int hidx, bool isArtificialBareSoil, int* UnderStory, const Ctx& cx, EnergyBal<NN>& energy,
+                          bool UNSTABLE_SNOW, int dt, int hidx, bool isArtificialBareSoil, int* UnderStory, const Ctx& cx, EN& energy,
                           SoilLayer* layer, SnowPack& snow, VegVar& vv, const VegNow& veg, const SoilET& soil, SolveSnowOut& r) {
   const Opts& o = *cx.o;
   const CellPar& cp = cx.cp;
@@ -416,7 +416,7 @@ VIC_HDI double solve_snow(bool overstory, double BareAlbedo, double LongUnderOut
       if (overstory) {
         r.ShortUnderIn *= (*surf_atten);
         const double ShortOverIn = (1. - (*surf_atten)) * f(FV_shortwave, hidx);
-        int e = snow_intercept<NN>((double)dt * SECPHOUR, veg.LAI, (*latent_heat_Le), f(FV_longwave, hidx), LongUnderOut, veg.Wdmax, ShortOverIn,
+        int e = snow_intercept<NN, EN>((double)dt * SECPHOUR, veg.LAI, (*latent_heat_Le), f(FV_longwave, hidx), LongUnderOut, veg.Wdmax, ShortOverIn,
                                    Tcanopy, BareAlbedo, energy, snow, vv, &r.LongUnderIn, aero_resist, aero_resist_used, &r.rainfall, &r.snowfall,
                                    as.wind_speed, as.displacement, as.ref_height, as.roughness, veg, soil, layer, f(FV_density, hidx),
                                    f(FV_vp, hidx), f(FV_pressure, hidx), f(FV_vpd, hidx), cp, o);
@@ -581,7 +581,10 @@ struct SurfaceFluxOut {
 };
 
 // surface_fluxes.c:17-956.  Returns 0 or ERROR_I.
-template <int NN>
+// ONE: the model step is a single sub-step (NF == 1: every hourly configuration).  The sub-step loop then runs exactly once, so its ~60
+// accumulators are `0.0 + x` at the point of use instead of values kept alive (in thread-local memory) across the solves, and the
+// division by the number of sub-steps (x / 1.0 == x for every x) is dropped.  Same operations on the same values: bit-identical.
+template <int NN, bool ONE>
 VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, double moist0, Hru<NN>& hru, double surf_atten, const AeroState& as,
                            const double* gauge_correction, bool isArtificialBareSoil, int band, const Ctx& cx, const VegNow& veg,
                            const SoilET& soil, int veg_class, SurfaceFluxOut& out) {
@@ -610,7 +613,8 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
   // solve_snow (surface_fluxes.c:433 reads energy->T[0], which the reference only updates after the last sub-step), saved below.
   // Only the snow-side energy record, which evolves separately, is a copy.  A failed step returns ERROR_I and the caller
   // drops the whole working set, so the in-place updates never reach the stored state.
-  EnergyBal<NN> snow_energy = energy;
+  SnowSideEnergy snow_energy;
+  snow_energy.take(energy);
   EnergyBal<NN>& soil_energy = energy;
   const double Tgrnd_step = energy.T[0];
   VegVar snow_vv = hru.veg, soil_vv = hru.veg;
@@ -684,7 +688,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     ss.coverage = coverage;
     ss.delta_coverage = delta_coverage;
     ss.NetLongSnow = 0; ss.NetShortGrnd = 0; ss.NetShortSnow = 0; ss.Torg_snow = 0;
-    double step_melt = solve_snow<NN>(overstory, BareAlbedo, LongUnderOut, Tcanopy, Tgrnd, Tair, hru.mu, step_prec, snow_grnd_flux,
+    double step_melt = solve_snow<NN, SnowSideEnergy>(overstory, BareAlbedo, LongUnderOut, Tcanopy, Tgrnd, Tair, hru.mu, step_prec, snow_grnd_flux,
                                       &energy.AlbedoUnder, &latent_heat_Le, iter_aero_resist, aero_used, as, gauge_correction, &snow_inflow,
                                       &surf_atten, UNSTABLE_SNOW, step_dt, hidx, isArtificialBareSoil, &UnderStory, cx, snow_energy, step_layer,
                                       step_snow, snow_vv, veg, soil, ss);
@@ -827,10 +831,11 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     for (int p = 0; p < N_PET_TYPES; p++) st_pot_evap[p] += iter_pot_evap[p];
     N_steps++;
     hidx += 1;
-  } while (hidx < endhidx);
+  } while (!ONE && hidx < endhidx);
 
   // ---- store the step's results
-  const double N = (double)N_steps;
+  const double N = ONE ? 1.0 : (double)N_steps;
+  auto mean = [&](double x) { return ONE ? x : div_pos(x, N); };
   snow.vapor_flux = st_vapor_flux;
   snow.blowing_flux = st_blowing_flux;
   snow.surface_flux = st_surface_flux;
@@ -838,41 +843,41 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
   out.Melt = st_melt;
   snow.melt = st_melt;
   double ppt = st_ppt;
-  energy.AlbedoOver = div_pos(st_AlbedoOver, N);
-  energy.AlbedoUnder = div_pos(st_AlbedoUnder, N);
-  energy.AtmosLatent = div_pos(st_AtmosLatent, N);
-  energy.AtmosLatentSub = div_pos(st_AtmosLatentSub, N);
-  energy.AtmosSensible = div_pos(st_AtmosSensible, N);
-  energy.LongOverIn = div_pos(st_LongOverIn, N);
-  energy.LongUnderIn = div_pos(st_LongUnderIn, N);
-  energy.LongUnderOut = div_pos(st_LongUnderOut, N);
-  energy.NetLongAtmos = div_pos(st_NetLongAtmos, N);
-  energy.NetLongOver = div_pos(st_NetLongOver, N);
-  energy.NetLongUnder = div_pos(st_NetLongUnder, N);
-  energy.NetShortAtmos = div_pos(st_NetShortAtmos, N);
-  energy.NetShortGrnd = div_pos(st_NetShortGrnd, N);
-  energy.NetShortOver = div_pos(st_NetShortOver, N);
-  energy.NetShortUnder = div_pos(st_NetShortUnder, N);
-  energy.ShortOverIn = div_pos(st_ShortOverIn, N);
-  energy.ShortUnderIn = div_pos(st_ShortUnderIn, N);
-  energy.advected_sensible = div_pos(st_advected_sensible, N);
-  energy.canopy_advection = div_pos(st_canopy_advection, N);
-  energy.canopy_latent = div_pos(st_canopy_latent, N);
-  energy.canopy_latent_sub = div_pos(st_canopy_latent_sub, N);
-  energy.canopy_refreeze = div_pos(st_canopy_refreeze, N);
-  energy.canopy_sensible = div_pos(st_canopy_sensible, N);
-  energy.deltaH = div_pos(st_deltaH, N);
-  energy.fusion = div_pos(st_fusion, N);
-  energy.grnd_flux = div_pos(st_grnd_flux, N);
-  energy.latent = div_pos(st_latent, N);
-  energy.latent_sub = div_pos(st_latent_sub, N);
-  energy.melt_energy = div_pos(st_melt_energy, N);
-  energy.sensible = div_pos(st_sensible, N);
+  energy.AlbedoOver = mean(st_AlbedoOver);
+  energy.AlbedoUnder = mean(st_AlbedoUnder);
+  energy.AtmosLatent = mean(st_AtmosLatent);
+  energy.AtmosLatentSub = mean(st_AtmosLatentSub);
+  energy.AtmosSensible = mean(st_AtmosSensible);
+  energy.LongOverIn = mean(st_LongOverIn);
+  energy.LongUnderIn = mean(st_LongUnderIn);
+  energy.LongUnderOut = mean(st_LongUnderOut);
+  energy.NetLongAtmos = mean(st_NetLongAtmos);
+  energy.NetLongOver = mean(st_NetLongOver);
+  energy.NetLongUnder = mean(st_NetLongUnder);
+  energy.NetShortAtmos = mean(st_NetShortAtmos);
+  energy.NetShortGrnd = mean(st_NetShortGrnd);
+  energy.NetShortOver = mean(st_NetShortOver);
+  energy.NetShortUnder = mean(st_NetShortUnder);
+  energy.ShortOverIn = mean(st_ShortOverIn);
+  energy.ShortUnderIn = mean(st_ShortUnderIn);
+  energy.advected_sensible = mean(st_advected_sensible);
+  energy.canopy_advection = mean(st_canopy_advection);
+  energy.canopy_latent = mean(st_canopy_latent);
+  energy.canopy_latent_sub = mean(st_canopy_latent_sub);
+  energy.canopy_refreeze = mean(st_canopy_refreeze);
+  energy.canopy_sensible = mean(st_canopy_sensible);
+  energy.deltaH = mean(st_deltaH);
+  energy.fusion = mean(st_fusion);
+  energy.grnd_flux = mean(st_grnd_flux);
+  energy.latent = mean(st_latent);
+  energy.latent_sub = mean(st_latent_sub);
+  energy.melt_energy = mean(st_melt_energy);
+  energy.sensible = mean(st_sensible);
   if ((snow.snow != 0.0) || INCLUDE_SNOW) {
-    energy.advection = div_pos(st_advection, N);
-    energy.deltaCC = div_pos(st_deltaCC, N);
-    energy.refreeze_energy = div_pos(st_refreeze_energy, N);
-    energy.snow_flux = div_pos(st_snow_flux, N);
+    energy.advection = mean(st_advection);
+    energy.deltaCC = mean(st_deltaCC);
+    energy.refreeze_energy = mean(st_refreeze_energy);
+    energy.snow_flux = mean(st_snow_flux);
   }
   energy.Tfoliage = snow_energy.Tfoliage;
   energy.Tfoliage_fbflag = snow_energy.Tfoliage_fbflag;
@@ -884,13 +889,13 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     else hru.veg.Wdew = soil_vv.Wdew;
   }
   for (int l = 0; l < NL; l++) cell.layer[l].evap = st_layerevap[l];
-  if (st_aero_cond_used.surface > 0 && st_aero_cond_used.surface < HUGE_RESIST) cell.aero_surface = 1 / (st_aero_cond_used.surface / N);
+  if (st_aero_cond_used.surface > 0 && st_aero_cond_used.surface < HUGE_RESIST) cell.aero_surface = 1 / (ONE ? st_aero_cond_used.surface : st_aero_cond_used.surface / N);
   else if (st_aero_cond_used.surface >= HUGE_RESIST) cell.aero_surface = 0;
   else cell.aero_surface = HUGE_RESIST;
-  if (st_aero_cond_used.overstory > 0 && st_aero_cond_used.overstory < HUGE_RESIST) cell.aero_overstory = 1 / (st_aero_cond_used.overstory / N);
+  if (st_aero_cond_used.overstory > 0 && st_aero_cond_used.overstory < HUGE_RESIST) cell.aero_overstory = 1 / (ONE ? st_aero_cond_used.overstory : st_aero_cond_used.overstory / N);
   else if (st_aero_cond_used.overstory >= HUGE_RESIST) cell.aero_overstory = 0;
   else cell.aero_overstory = HUGE_RESIST;
-  for (int p = 0; p < N_PET_TYPES; p++) cell.pot_evap[p] = st_pot_evap[p] / N;
+  for (int p = 0; p < N_PET_TYPES; p++) cell.pot_evap[p] = ONE ? st_pot_evap[p] : st_pot_evap[p] / N;
   out.snow_inflow = snow_inflow;
 
   // ---- soil column

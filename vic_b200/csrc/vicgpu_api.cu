@@ -41,6 +41,22 @@ __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ 
   }
 }
 
+// The same with the float32 narrowing WriteOutputNetCDF applies to every value it writes (WriteOutputNetCDF.c:279, 351, 412): a plain
+// (float) conversion, round to nearest
+__global__ void k_transpose_f32(const double* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = (float)tile[threadIdx.x][i];
+  }
+}
+
 // The same conversions when the device row of record r is not r (HRU tables are kept binned by kind, vic_engine.cuh bin_hrus):
 // host record r (row-major) <-> device row row_of[r] (column-major).  One thread per element, coalesced on the device side.
 __global__ void k_scatter_rows(const double* __restrict__ in /* [rows][cols] */, double* __restrict__ out /* [cols][rows] */, int rows, int cols,
@@ -114,22 +130,6 @@ __global__ void k_slot_maps(const unsigned long long* __restrict__ keys, int nhr
   slot_of_hru[hru] = s;
 }
 
-// After a block of records: the snapshots of an HRU whose cell failed at record fr (inside the block) are made equal to the
-// snapshot of record fr from there on -- a sibling HRU may have run ahead of the failing one (hru_block_work).
-__global__ void k_freeze_failed(Tables t, int rec0, int n, double* snap, size_t snap_stride, int hr_stride) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= t.nhru) return;
-  const size_t nh = (size_t)t.nhru;
-  const int cell = (int)t.hrupar[(size_t)HP_cell * nh + h];
-  const int fr = t.fail_rec[cell];
-  if (fr < rec0 || fr >= rec0 + n - 1) return;
-  const double* good = snap + (size_t)(fr - rec0) * snap_stride + hr_off(h, hr_stride);
-  for (int i = fr - rec0 + 1; i < n; i++) {
-    double* out = snap + (size_t)i * snap_stride + hr_off(h, hr_stride);
-    for (int k = 0; k < hr_stride; k++) out[(size_t)k * VIC_HR_TILE] = good[(size_t)k * VIC_HR_TILE];
-  }
-}
-
 // FP64 FMA throughput probe: 8 independent chains per thread, nothing but DFMA in the loop
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -176,13 +176,16 @@ int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int ro
   return VICGPU_OK;
 }
 
-int vicgpu_ensure_forcing(vicgpu_handle* h, size_t need) {
-  if (need > h->forcing_cap) {
-    cudaFree(h->d_forcing);
-    h->d_forcing = nullptr;
-    h->forcing_cap = 0;
-    CK(cudaMalloc(&h->d_forcing, need * sizeof(double)));
-    h->forcing_cap = need;
+int vicgpu_ensure_window(vicgpu_handle* h, ForcingWindow& w, size_t need) {
+  if (need > w.cap) {
+    // nothing queued may still read or write the old buffer
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->stream_copy));
+    cudaFree(w.d);
+    w.d = nullptr;
+    w.cap = 0;
+    CK(cudaMalloc(&w.d, need * sizeof(double)));
+    w.cap = need;
   }
   return VICGPU_OK;
 }
@@ -233,11 +236,10 @@ static int download_transposed(vicgpu_handle* h, const double* d_src, double* ho
 }
 
 // ---- state halves ------------------------------------------------------------------------------------------------------------
-// A block of up to `recblock` records is advanced by ONE launch of the step kernel (vic_engine.cuh hru_block_work): it reads the
-// block's input state and writes the state after every record to a snapshot buffer of the half it runs in; the cell outputs of
-// those records then run from the snapshots on the second stream while the next block already runs in the other half.  A half
-// also owns the row order its snapshots are in (the rows are re-sorted by kind and snow state before each block) together with
-// the HRU parameter table in that order.
+// The step kernel of record r reads the state in one half and writes the state after the record into the other half's snapshot, so
+// that the cell output of record r (which reads that snapshot) can run beside the step of record r + 1.  A half also owns the row
+// order its snapshot is in (the rows are re-sorted by kind and snow state every `rebin_every` records) together with the HRU
+// parameter table in that order.
 static void free_half(StateHalf& s) {
   cudaFree(s.in); cudaFree(s.snap); cudaFree(s.hdiag);
   s.in = s.snap = s.hdiag = nullptr;
@@ -274,61 +276,6 @@ static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const do
   h->last_launches += 5 + 2;  // + the radix sort's own passes (counted as two)
   CK(cudaGetLastError());
   return VICGPU_OK;
-}
-
-// ---- SM partition (VICGPU_GREEN=<SMs for the cell output>) -----------------------------------------------------------------------
-// Two green contexts split the device's SMs between the step kernel and the cell-output kernel, so that the output of record r - 1
-// runs beside step r without its blocks sharing an SM (and an L1) with step blocks.  The driver entry points are looked up at run
-// time: the library has no link-time dependency on libcuda.
-struct GreenPartition {
-  CUgreenCtx ctx[2] = {nullptr, nullptr};
-  int sms[2] = {0, 0};
-};
-template <class F>
-static F driver_fn(const char* name) {
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
-  return reinterpret_cast<F>(fn);
-}
-static bool green_streams(int device, int out_sms, int total_sms, int prio_hi, int prio_lo, GreenPartition* gp, cudaStream_t* s_step, cudaStream_t* s_out) {
-  typedef CUresult (*f_devget)(CUdevice*, int);
-  typedef CUresult (*f_getres)(CUdevice, CUdevResource*, CUdevResourceType);
-  typedef CUresult (*f_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
-  typedef CUresult (*f_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
-  typedef CUresult (*f_create)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
-  typedef CUresult (*f_stream)(CUstream*, CUgreenCtx, unsigned int, int);
-  f_devget devget = driver_fn<f_devget>("cuDeviceGet");
-  f_getres getres = driver_fn<f_getres>("cuDeviceGetDevResource");
-  f_split split = driver_fn<f_split>("cuDevSmResourceSplitByCount");
-  f_desc mkdesc = driver_fn<f_desc>("cuDevResourceGenerateDesc");
-  f_create create = driver_fn<f_create>("cuGreenCtxCreate");
-  f_stream mkstream = driver_fn<f_stream>("cuGreenCtxStreamCreate");
-  if (!devget || !getres || !split || !mkdesc || !create || !mkstream) return false;
-  cudaFree(0);  // the primary context exists
-  CUdevice dev;
-  if (devget(&dev, device) != CUDA_SUCCESS) return false;
-  CUdevResource all, part[2];
-  if (getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
-  unsigned int ngroups = 1;
-  const CUresult sr = split(&part[0], &ngroups, &all, &part[1], 0, (unsigned)(total_sms - out_sms));
-  if (sr != CUDA_SUCCESS || ngroups != 1) {
-    fprintf(stderr, "vicgpu: cuDevSmResourceSplitByCount(%d of %u SMs) -> %d, %u groups\n", total_sms - out_sms, all.sm.smCount, (int)sr, ngroups);
-    return false;
-  }
-  if (part[1].sm.smCount == 0) return false;
-  CUstream st[2];
-  const int prio[2] = {prio_hi, prio_lo};
-  for (int k = 0; k < 2; k++) {
-    CUdevResourceDesc d;
-    if (mkdesc(&d, &part[k], 1) != CUDA_SUCCESS) return false;
-    if (create(&gp->ctx[k], d, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-    if (mkstream(&st[k], gp->ctx[k], CU_STREAM_NON_BLOCKING, prio[k]) != CUDA_SUCCESS) return false;
-    gp->sms[k] = (int)part[k].sm.smCount;
-  }
-  *s_step = (cudaStream_t)st[0];
-  *s_out = (cudaStream_t)st[1];
-  return true;
 }
 
 static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const Opts& o, int device);
@@ -368,70 +315,48 @@ static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const O
   h->o = o;
   h->nout = o.L.out_off[VICGPU_N_OUTVARS];
   memset(&h->t, 0, sizeof(h->t));
-  // the HRU step owns the machine: its stream has the highest priority, the cell-output stream the lowest
+  // the HRU step owns the machine: its stream has the highest priority; host <-> device copies run on their own stream
   int prio_lo = 0, prio_hi = 0;
   CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  const char* green = getenv("VICGPU_GREEN");  // SMs set aside for the cell output (two green contexts); 0 / unset: one context
-  int green_sms = 0;
-  if (green && atoi(green) > 0) {
-    cudaDeviceProp gprop;
-    CK(cudaGetDeviceProperties(&gprop, device));
-    GreenPartition gp;
-    if (atoi(green) < gprop.multiProcessorCount && green_streams(device, atoi(green), gprop.multiProcessorCount, prio_hi, prio_lo, &gp, &h->stream, &h->stream_out)) {
-      green_sms = gp.sms[0];
-      fprintf(stderr, "vicgpu: SM partition %d (step) + %d (cell output)\n", gp.sms[0], gp.sms[1]);
-    } else {
-      return fail(VICGPU_EUNSUPPORTED, "VICGPU_GREEN: the driver could not split the SMs as asked");
-    }
-  }
-  if (!green_sms) CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+  CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+  CK(cudaStreamCreateWithPriority(&h->stream_copy, cudaStreamNonBlocking, prio_lo));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
-  // tuning / A-B knobs (environment, read once per handle)
+  for (int k = 0; k < 2; k++) {
+    CK(cudaEventCreateWithFlags(&h->ev_stage_full[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_stage_free[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->fwin[k].ready, cudaEventDisableTiming));
+  }
+  // tuning / A-B knobs (environment, read once per handle; every combination computes the same bits, tests/test_gpu.py)
   const char* wt = getenv("VICGPU_WARPTIME");  // per-warp timers in profiled launches (vicgpu_get_warp_times); they slow the kernel
   h->warp_timing = wt && atoi(wt) != 0;
-  const char* noov = getenv("VICGPU_NOOVERLAP");  // run the cell output in the step's stream
-  h->overlap = !(noov && atoi(noov) != 0);
-  const char* pdl = getenv("VICGPU_PDL");  // 0: cell output on a second stream instead of a programmatic dependent launch
-  h->pdl = !(pdl && atoi(pdl) == 0) && h->overlap && !green_sms;  // a programmatic dependent launch stays in one stream, i.e. one partition
+  const char* noov = getenv("VICGPU_NOOVERLAP");  // 1: the cell output of record r finishes before step r + 1 starts (no dependent launch)
+  h->pdl = !(noov && atoi(noov) != 0);
   const char* sl = getenv("VICGPU_SYNC");  // most clock cycles a warp waits for its block at a phase boundary of the step (0: no rendezvous)
   h->sync_limit = sl ? atoll(sl) : 1000000;  // 0.5 ms: a safety bound, not a tuning parameter (waits end when the group has arrived)
-  const char* rbk = getenv("VICGPU_RECBLOCK");  // records advanced per launch of the step kernel (1 .. VICGPU_RECBLOCK_MAX)
-  h->recblock = rbk ? std::max(1, std::min(VICGPU_RECBLOCK_MAX, atoi(rbk))) : VICGPU_RECBLOCK_MAX;
   const char* nobin = getenv("VICGPU_NOBIN");  // keep the caller's row order (no binning at all)
   h->binned = !(nobin && atoi(nobin) != 0);
   const char* rb = getenv("VICGPU_REBIN");  // records between re-sorts of the rows by (kind, snow); 0: bin by kind once (set_cells)
   h->rebin_every = rb ? atoi(rb) : 24;
   h->rebin = h->binned && h->rebin_every > 0;
-  h->recblock = rbk ? h->recblock : 1;  // default: one record per launch (warps that drift apart lose the shared instruction cache)
-  if (green_sms) h->overlap = true;
-  else if (h->overlap) CK(cudaStreamCreateWithPriority(&h->stream_out, cudaStreamNonBlocking, prio_lo));
-  else h->stream_out = h->stream;
-  CK(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
-  for (int b = 0; b < 2; b++) CK(cudaEventCreateWithFlags(&h->half[b].ev_out, cudaEventDisableTiming));
   CK(cudaMalloc(&h->d_o, sizeof(Opts)));
   CK(cudaMemcpy(h->d_o, &h->o, sizeof(Opts), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_aggtype, VICGPU_N_OUTVARS * sizeof(int)));
   int agg[VICGPU_N_OUTVARS];
   vicgpu_default_aggtypes(agg);
   CK(cudaMemcpy(h->d_aggtype, agg, sizeof(agg), cudaMemcpyHostToDevice));
-  // the step kernel keeps one HRU (about 2 KB) plus its working copies in thread-local memory
-  CK(cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024));
-  {
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    const char* ev = getenv("VICGPU_EVEN");  // 1: round the step grid up to whole blocks per SM (measured: no gain)
-    h->nsm = (ev && atoi(ev) != 0) ? prop.multiProcessorCount : 0;
-  }
+  // The step kernel keeps its working set in thread-local memory; the limit is per device, not per handle: it is raised, never
+  // lowered (another handle or another library in the process may have asked for more), and stays raised after vicgpu_destroy.
+  size_t stack_now = 0;
+  CK(cudaDeviceGetLimit(&stack_now, cudaLimitStackSize));
+  if (stack_now < 24 * 1024) CK(cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
   const char* blk = getenv("VICGPU_BLOCK");  // threads per block of the per-HRU step kernel (multiple of 32, <= VICGPU_HRU_BLOCK_MAX)
   if (blk && atoi(blk) >= 32 && atoi(blk) <= VICGPU_HRU_BLOCK_MAX && atoi(blk) % 32 == 0) {
     h->hru_block = atoi(blk);
     h->hru_block_fixed = true;
-  }
-  {
-    cudaDeviceProp prop2;
-    CK(cudaGetDeviceProperties(&prop2, device));
-    h->sm_count = green_sms ? green_sms : prop2.multiProcessorCount;
   }
   return VICGPU_OK;
 }
@@ -442,23 +367,26 @@ int vicgpu_destroy(vicgpu_handle* h) {
   if (!h) return VICGPU_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->overlap && h->stream_out) cudaStreamSynchronize(h->stream_out);
+  if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
   cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_gmb_cum); cudaFree(h->d_gmb);
   for (int b = 0; b < 2; b++) {
     free_half(h->half[b]);
     free_order(h->order[b]);
-    if (h->half[b].ev_out) cudaEventDestroy(h->half[b].ev_out);
+    cudaFree(h->d_ostage[b]);
+    cudaFree(h->fwin[b].d);
+    if (h->ev_stage_full[b]) cudaEventDestroy(h->ev_stage_full[b]);
+    if (h->ev_stage_free[b]) cudaEventDestroy(h->ev_stage_free[b]);
+    if (h->fwin[b].ready) cudaEventDestroy(h->fwin[b].ready);
   }
   cudaFree(h->d_fail_rec); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]);
   cudaFree(h->d_sort_tmp);
-  cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_forcing); cudaFree(h->d_fstage);
+  cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_fstage);
   cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype);
   cudaFree(h->d_warp_ns);
-  if (h->ev_step) cudaEventDestroy(h->ev_step);
-  if (h->overlap && h->stream_out) cudaStreamDestroy(h->stream_out);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
+  if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return VICGPU_OK;
@@ -504,16 +432,17 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   }
   for (int c = 0; c < ncell; c++) h0[c + 1] += h0[c];
   CK(cudaStreamSynchronize(h->stream));
-  if (h->overlap) CK(cudaStreamSynchronize(h->stream_out));
-  // initial row order: binned by kind (bin_hrus); VICGPU_DEAL=1 deals the warps of a kind over all blocks (measured slower:
-  // blocks of one kind share the instruction cache)
+  CK(cudaStreamSynchronize(h->stream_copy));
+  // initial row order: binned by kind (bin_hrus)
   std::vector<int> hru_of_slot, slot_of_hru;
-  const char* deal = getenv("VICGPU_DEAL");
-  const bool dealing = deal && atoi(deal) != 0;
-  if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru, dealing ? (nhru + h->hru_block - 1) / h->hru_block : 0);
+  if (h->binned) bin_hrus(hrupar, nhru, hru_of_slot, slot_of_hru);
   // from here on the old domain is gone: a failure below (out of memory on a large domain) must leave a handle that refuses to step
   h->have_cells = h->have_state = false;
-  h->fnrec = 0;
+  h->fwin[0].nrec = h->fwin[1].nrec = 0;
+  for (int k = 0; k < 2; k++) {
+    cudaFree(h->d_ostage[k]);
+    h->d_ostage[k] = nullptr;
+  }
   {
     const double* vl = h->t.veglib;
     const int nc = h->t.nclass;
@@ -536,13 +465,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     free_half(h->half[b]);
     free_order(h->order[b]);
   }
-  // records per launch: as many as fit in a third of the free memory (two halves of snapshots), at most `recblock`
   const size_t state_bytes = hr_rows(nhru) * L.hr_stride * sizeof(double);  // whole 32-row tiles
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  int rbn = h->recblock;
-  while (rbn > 1 && 2 * (size_t)rbn * state_bytes > free_b / 3) rbn--;
-  h->rb = rbn;
   CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
   CK(cudaMalloc(&h->d_cellder, (size_t)ncell * VIC_NCELLDER * sizeof(double)));
   CK(cudaMalloc(&h->d_gmb_cum, (size_t)nhru * sizeof(double)));
@@ -556,11 +479,11 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   for (int b = 0; b < 2; b++) {
     StateHalf& s = h->half[b];
     CK(cudaMalloc(&s.in, state_bytes));
-    CK(cudaMalloc(&s.snap, (size_t)h->rb * state_bytes));
+    CK(cudaMalloc(&s.snap, state_bytes));
     CK(cudaMemset(s.in, 0, state_bytes));
-    CK(cudaMemset(s.snap, 0, (size_t)h->rb * state_bytes));
-    CK(cudaMalloc(&s.hdiag, (size_t)h->rb * nhru * 3 * sizeof(double)));
-    CK(cudaMemset(s.hdiag, 0, (size_t)h->rb * nhru * 3 * sizeof(double)));
+    CK(cudaMemset(s.snap, 0, state_bytes));
+    CK(cudaMalloc(&s.hdiag, (size_t)nhru * 3 * sizeof(double)));
+    CK(cudaMemset(s.hdiag, 0, (size_t)nhru * 3 * sizeof(double)));
     RowOrder& r = h->order[b];
     if (b == 0 || h->rebin) {
       CK(cudaMalloc(&r.hrupar, (size_t)nhru * HP_N * sizeof(double)));
@@ -676,17 +599,25 @@ int vicgpu_get_state(vicgpu_handle* h, double* hrurec) {
   return VICGPU_OK;
 }
 
+// The device keeps TWO forcing windows.  vicgpu_set_forcing fills the one that was filled less recently and returns as soon as the
+// copy is queued on the copy stream (the host buffer must stay untouched until the next call into the library returns; pinned host
+// memory makes the copy truly asynchronous), so that the upload of the next block of records overlaps the step over the current one:
+//     set_forcing(block b + 1);  step(block b);  set_forcing(block b + 2);  step(block b + 1); ...
+// vicgpu_step waits (on the device) for the window that holds its records.
 int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forcing) {
   if (!h || !forcing || nrec <= 0 || rec0 < 0) return fail(VICGPU_EINVAL, "bad argument");
   if (!h->have_cells) return fail(VICGPU_ESTATE, "set_cells before set_forcing");
   CK(cudaSetDevice(h->device));
   const size_t per = (size_t)h->t.ncell * h->o.L.f_stride;
-  const size_t need = per * nrec;
-  { int rcf = vicgpu_ensure_forcing(h, need); if (rcf) return rcf; }
+  ForcingWindow& w = h->fwin[h->fwin_next];
+  h->fwin_next ^= 1;
+  w.nrec = 0;
+  { int rcf = vicgpu_ensure_window(h, w, per * nrec); if (rcf) return rcf; }
   // staged in chunks of at most 256 MiB so that the staging buffer stays small next to the window
   const size_t chunk_recs = std::min<size_t>(65535, std::max<size_t>(1, (size_t)(256u << 20) / (per * sizeof(double))));
   const size_t stage_need = per * std::min<size_t>(chunk_recs, (size_t)nrec);
   if (stage_need > h->fstage_cap) {
+    CK(cudaStreamSynchronize(h->stream_copy));
     cudaFree(h->d_fstage);
     h->d_fstage = nullptr;
     h->fstage_cap = 0;
@@ -695,189 +626,121 @@ int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forci
   }
   for (size_t r = 0; r < (size_t)nrec; r += chunk_recs) {
     const int nr = (int)std::min<size_t>(chunk_recs, (size_t)nrec - r);
-    CK(cudaMemcpyAsync(h->d_fstage, forcing + r * per, per * nr * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    dim3 b(32, 8), g((h->o.L.f_stride + 31) / 32, (h->t.ncell + 31) / 32, nr);
-    k_transpose<<<g, b, 0, h->stream>>>(h->d_fstage, h->d_forcing + r * per, h->t.ncell, h->o.L.f_stride);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(h->d_fstage, forcing + r * per, per * nr * sizeof(double), cudaMemcpyHostToDevice, h->stream_copy));
+    int rct = vicgpu_transpose(h, h->d_fstage, w.d + r * per, h->t.ncell, h->o.L.f_stride, nr, h->stream_copy);
+    if (rct) return rct;
   }
-  h->frec0 = rec0;
-  h->fnrec = nrec;
+  CK(cudaEventRecord(w.ready, h->stream_copy));
+  w.rec0 = rec0;
+  w.nrec = nrec;
   return VICGPU_OK;
 }
 
-int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* out_data, double* out_agg) {
+}  // extern "C"
+
+// One output row set [nout][ncell] on the device -> host [ncell][nout] (double, or float32 as the NetCDF writer narrows it), through
+// one of two staging buffers: the transpose runs in the step's stream, the copy on the copy stream, and the staging buffer is handed
+// back with an event, so that the copy of record r overlaps the kernels of record r + 1.
+static int stage_out(vicgpu_handle* h, const double* d_rows, void* host, bool f32) {
+  const int k = h->stage_idx;
+  h->stage_idx ^= 1;
+  const size_t rowsz = (size_t)h->t.ncell * h->nout;
+  CK(cudaStreamWaitEvent(h->stream, h->ev_stage_free[k], 0));
+  if (f32) {
+    dim3 b(32, 8), g((h->t.ncell + 31) / 32, (h->nout + 31) / 32, 1);
+    k_transpose_f32<<<g, b, 0, h->stream>>>(d_rows, (float*)h->d_ostage[k], h->nout, h->t.ncell);
+    h->last_launches++;
+    CK(cudaGetLastError());
+  } else {
+    int rc = vicgpu_transpose(h, d_rows, h->d_ostage[k], h->nout, h->t.ncell, 1, h->stream);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(h->ev_stage_full[k], h->stream));
+  CK(cudaStreamWaitEvent(h->stream_copy, h->ev_stage_full[k], 0));
+  CK(cudaMemcpyAsync(host, h->d_ostage[k], rowsz * (f32 ? sizeof(float) : sizeof(double)), cudaMemcpyDeviceToHost, h->stream_copy));
+  CK(cudaEventRecord(h->ev_stage_free[k], h->stream_copy));
+  return VICGPU_OK;
+}
+
+// ---- one record per launch, cell output as a programmatic dependent launch ---------------------------------------------------------
+// Everything runs in ONE stream: step(r), then output(r-1) launched with programmatic stream serialization.  The output kernel does
+// not wait for step(r) to finish (it reads the state step(r-1) wrote), only for every block of step(r) to be resident
+// (griddepcontrol.launch_dependents at the top of the step kernel); its one-warp blocks then fit beside the step blocks.  Launched
+// from a second stream instead, the output blocks reach the SMs first and the step blocks, which need a whole SM, wait for them:
+// measured 0.3-0.4 ms per record.  step(r+1), an ordinary launch, starts when both have finished (k_cell_output ends with
+// griddepcontrol.wait), which also protects the state buffer output(r-1) reads.
+static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void* out_data, void* out_agg, bool f32) {
   if (!h || !dmy || nrec <= 0) return fail(VICGPU_EINVAL, "bad argument");
   if (!h->have_cells || !h->have_state || !h->d_veglib) return fail(VICGPU_ESTATE, "set_veglib, set_cells and set_state before step");
-  if (rec0 < h->frec0 || rec0 + nrec > h->frec0 + h->fnrec) return fail(VICGPU_ESTATE, "records outside the resident forcing window");
+  const ForcingWindow* fw = nullptr;
+  for (int k = 0; k < 2; k++)
+    if (h->fwin[k].nrec > 0 && rec0 >= h->fwin[k].rec0 && rec0 + nrec <= h->fwin[k].rec0 + h->fwin[k].nrec) fw = &h->fwin[k];
+  if (!fw) return fail(VICGPU_ESTATE, "records outside the resident forcing windows");
   CK(cudaSetDevice(h->device));
   const vicgpu_layout& L = h->o.L;
   const int nhru = h->t.nhru;
   const size_t per = (size_t)h->t.ncell * L.f_stride;
   const size_t rowsz = (size_t)h->t.ncell * h->nout;
-  const size_t snap_stride = hr_rows(nhru) * L.hr_stride;
-  // one warp per block: such a block fits beside a resident step block on every SM (vicgpu_step.inc)
+  const size_t esz = f32 ? sizeof(float) : sizeof(double);
+  // one warp per block: such a block fits beside a resident step block on every SM
   const char* cb = getenv("VICGPU_OUTBLOCK");
   const int B = (cb && atoi(cb) >= 32 && atoi(cb) <= 128) ? atoi(cb) : 32;
   const int cgrid = (h->t.ncell + B - 1) / B;
+  const bool one = h->o.NF == 1;
   h->last_launches = 0;
   int nagg = 0;
   if (out_data || out_agg) {
-    int rc = ensure_stage(h, rowsz);
-    if (rc) return rc;
+    for (int k = 0; k < 2; k++)
+      if (!h->d_ostage[k]) CK(cudaMalloc(&h->d_ostage[k], rowsz * sizeof(double)));
   }
-  const int nblocks = (nrec + h->rb - 1) / h->rb;
   if (h->profiling) {
-    while ((int)h->pev.size() < 2 * nblocks) {
+    while ((int)h->pev.size() < 2 * nrec) {
       cudaEvent_t e;
       CK(cudaEventCreate(&e));
       h->pev.push_back(e);
     }
   }
-  cudaStream_t so = h->stream_out;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  // ---- one record per launch, cell output as a programmatic dependent launch -----------------------------------------------------
-  // Everything runs in ONE stream: step(r), then output(r-1) launched with programmatic stream serialization.  The output kernel does
-  // not wait for step(r) to finish (it reads the state step(r-1) wrote), only for every block of step(r) to be resident
-  // (griddepcontrol.launch_dependents at the top of the step kernel); its one-warp blocks then fit beside the step blocks (160
-  // registers x 384 threads + 128 x 32 = the register file).  Launched from a second stream instead, the output blocks reach the
-  // SMs first and the step blocks, which need a whole SM, wait for them: measured 0.3-0.4 ms per record.  step(r+1), an ordinary
-  // launch, starts when both have finished, which also protects the state buffer output(r-1) reads.
-  if (h->pdl && h->rb == 1) {
-    struct Pending { bool valid; Tables t; const double* frec; int rec, step_count, idx; } pend = {false, h->t, nullptr, 0, 0, 0};
-    auto launch_output = [&](const Pending& p, bool dependent) -> int {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(cgrid);
-      cfg.blockDim = dim3(B);
-      cfg.stream = h->stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = dependent ? 1 : 0;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      CK(cudaLaunchKernelEx(&cfg, k_cell_output, (const Opts*)h->d_o, p.t, p.frec, p.rec, p.step_count));
-      h->last_launches++;
-      if (out_data) {
-        int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1, h->stream);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(out_data + (size_t)p.idx * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      }
-      if (p.step_count == h->o.out_step_ratio) {
-        if (out_agg) {
-          int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1, h->stream);
-          if (rc) return rc;
-          CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        }
-        nagg++;
-        CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), h->stream));
-      }
-      return VICGPU_OK;
-    };
-    CK(cudaEventRecord(h->ev0, h->stream));
-    for (int i = 0; i < nrec; i++) {
-      const int rec = rec0 + i;
-      StateHalf& S = h->half[h->cur_half];
-      StateHalf& D = h->half[h->cur_half ^ 1];
-      const double* input = h->d_state_cur;
-      if (h->rebin && h->recs_since_rebin >= h->rebin_every) {
-        // the pending output still needs the old row order and the state it was launched for: run it now, undeferred
-        if (pend.valid) {
-          int rc = launch_output(pend, false);
-          if (rc) return rc;
-          pend.valid = false;
-        }
-        int rc = rebin_rows(h, h->order[S.ord], h->order[S.ord ^ 1], h->d_state_cur, D.in);
-        if (rc) return rc;
-        D.ord = S.ord ^ 1;
-        input = D.in;
-        h->recs_since_rebin = 0;
-      } else {
-        D.ord = S.ord;
-      }
-      h->recs_since_rebin++;
-      const RowOrder& R = h->order[D.ord];
-      Tables t = h->t;
-      t.hrupar = R.hrupar;
-      t.slot_of_hru = R.slot_of_hru;
-      t.hrurec = input;
-      t.hrurec_out = D.snap;
-      t.hdiag_out = D.hdiag;
-      const int* d = &dmy[i * 5];
-      const Dmy dm = {d[0], d[1], d[2], d[3], d[4]};
-      const GlacAccum ga = glacier_accum_flags(h->o, d, d + 5, rec, &h->glac_started);
-      if (rec == 0) {
-        // storage terms of the initial state: put_data(rec = -nrecs), vicNl.c:524-541
-        Tables t0 = t;
-        t0.hrurec_out = const_cast<double*>(input);
-        k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, t0, nullptr, -1, h->step_count + 1);
-        h->last_launches++;
-      }
-      const double* frec = h->d_forcing + (size_t)(rec - h->frec0) * per;
-      unsigned long long* wns = nullptr;
-      if (h->profiling && h->warp_timing) {
-        const size_t nw = ((size_t)nhru + 31) / 32;
-        if (!h->d_warp_ns) CK(cudaMalloc(&h->d_warp_ns, 2 * nw * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(h->d_warp_ns, 0, 2 * nw * sizeof(unsigned long long), h->stream));
-        wns = h->d_warp_ns;
-      }
-      if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
-      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
-      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
-      h->last_launches++;
-      // the previous record's output rides on this step
-      if (pend.valid) {
-        int rc = launch_output(pend, true);
-        if (rc) return rc;
-      }
-      if (ga.enabled && ga.reset_after) {  // end of a glacier accumulation interval: the cells' mass-balance curves
-        k_cell_gmb<<<(h->t.ncell + 127) / 128, 128, 0, h->stream>>>(h->d_o, t);
-        h->last_launches++;
-      }
-      if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));  // step(r) and the output riding on it
-      h->step_count++;
-      pend.valid = true;
-      pend.t = t;
-      pend.frec = frec;
-      pend.rec = rec;
-      pend.step_count = h->step_count;
-      pend.idx = i;
-      if (h->step_count == h->o.out_step_ratio) h->step_count = 0;
-      h->d_state_cur = D.snap;
-      h->cur_half ^= 1;
-    }
-    if (pend.valid) {
-      int rc = launch_output(pend, false);
+  CK(cudaStreamWaitEvent(h->stream, fw->ready, 0));
+  struct Pending { bool valid; Tables t; const double* frec; int rec, step_count, idx; } pend = {false, h->t, nullptr, 0, 0, 0};
+  auto launch_output = [&](const Pending& p, bool dependent) -> int {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cgrid);
+    cfg.blockDim = dim3(B);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = dependent ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_cell_output, (const Opts*)h->d_o, p.t, p.frec, p.rec, p.step_count));
+    h->last_launches++;
+    if (out_data) {
+      int rc = stage_out(h, h->d_out, (char*)out_data + (size_t)p.idx * rowsz * esz, f32);
       if (rc) return rc;
     }
-    CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
-    float msp = 0;
-    CK(cudaEventElapsedTime(&msp, h->ev0, h->ev1));
-    h->last_ms = msp;
-    if (h->profiling) {
-      for (int i = 0; i < nrec; i++) {
-        float k = 0;
-        CK(cudaEventElapsedTime(&k, h->pev[2 * i], h->pev[2 * i + 1]));
-        h->prof_hru_ms += k;
-        h->prof_hru_launches++;
+    if (p.step_count == h->o.out_step_ratio) {
+      if (out_agg) {
+        int rc = stage_out(h, h->d_agg, (char*)out_agg + (size_t)nagg * rowsz * esz, f32);
+        if (rc) return rc;
       }
+      nagg++;
+      CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), h->stream));
     }
     return VICGPU_OK;
-  }
-
-  for (int blk = 0; blk < nblocks; blk++) {
-    const int i0 = blk * h->rb;
-    const int n = std::min(h->rb, nrec - i0);
-    const int brec0 = rec0 + i0;
+  };
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < nrec; i++) {
+    const int rec = rec0 + i;
     StateHalf& S = h->half[h->cur_half];
     StateHalf& D = h->half[h->cur_half ^ 1];
-    // nothing may still read half D (the cell outputs of the block before the previous one)
-    if (h->overlap) CK(cudaStreamWaitEvent(h->stream, D.ev_out, 0));
     const double* input = h->d_state_cur;
     if (h->rebin && h->recs_since_rebin >= h->rebin_every) {
-      // the other RowOrder is free: the only work that could still use it reads half D, and that is complete (above)
+      // the pending output still needs the old row order and the state it was launched for: run it now, undeferred
+      if (pend.valid) {
+        int rc = launch_output(pend, false);
+        if (rc) return rc;
+        pend.valid = false;
+      }
       int rc = rebin_rows(h, h->order[S.ord], h->order[S.ord ^ 1], h->d_state_cur, D.in);
       if (rc) return rc;
       D.ord = S.ord ^ 1;
@@ -886,33 +749,25 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
     } else {
       D.ord = S.ord;
     }
-    h->recs_since_rebin += n;
+    h->recs_since_rebin++;
     const RowOrder& R = h->order[D.ord];
     Tables t = h->t;
     t.hrupar = R.hrupar;
     t.slot_of_hru = R.slot_of_hru;
     t.hrurec = input;
-    RecBlock rb;
-    rb.n = n;
-    rb.rec0 = brec0;
-    for (int i = 0; i < n; i++) {
-      const int* d = &dmy[(i0 + i) * 5];
-      rb.dmy[i] = Dmy{d[0], d[1], d[2], d[3], d[4]};
-      rb.ga[i] = pack_ga(glacier_accum_flags(h->o, d, d + 5, brec0 + i, &h->glac_started));
-    }
-    if (brec0 == 0) {
+    t.hrurec_out = D.snap;
+    t.hdiag_out = D.hdiag;
+    const int* d = &dmy[i * 5];
+    const Dmy dm = {d[0], d[1], d[2], d[3], d[4]};
+    const GlacAccum ga = glacier_accum_flags(h->o, d, d + 5, rec, &h->glac_started);
+    if (rec == 0) {
       // storage terms of the initial state: put_data(rec = -nrecs), vicNl.c:524-541
-      if (h->overlap) {
-        CK(cudaEventRecord(h->ev_step, h->stream));
-        CK(cudaStreamWaitEvent(so, h->ev_step, 0));
-      }
       Tables t0 = t;
       t0.hrurec_out = const_cast<double*>(input);
-      t0.hdiag_out = D.hdiag;
-      k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t0, nullptr, -1, h->step_count + 1);
+      k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, t0, nullptr, -1, h->step_count + 1);
       h->last_launches++;
     }
-    const double* frec = h->d_forcing + (size_t)(brec0 - h->frec0) * per;
+    const double* frec = fw->d + (size_t)(rec - fw->rec0) * per;
     unsigned long long* wns = nullptr;
     if (h->profiling && h->warp_timing) {
       const size_t nw = ((size_t)nhru + 31) / 32;
@@ -920,78 +775,61 @@ int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* ou
       CK(cudaMemsetAsync(h->d_warp_ns, 0, 2 * nw * sizeof(unsigned long long), h->stream));
       wns = h->d_warp_ns;
     }
-    if (h->profiling) CK(cudaEventRecord(h->pev[2 * blk], h->stream));
-    if (n == 1) {
-      // one record per launch: all warps of the grid start the record together (see the note on the instruction cache in DESIGN.md)
-      t.hrurec_out = D.snap;
-      t.hdiag_out = D.hdiag;
-      const GlacAccum ga = {rb.ga[0] & 1, (rb.ga[0] >> 1) & 1, (rb.ga[0] >> 2) & 1, (rb.ga[0] >> 3) & 1};
-      if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
-      else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
-      else vicgpu_launch_hru_step_nn32(h->d_o, t, frec, rb.dmy[0], brec0, ga, h->hru_block, h->stream, wns, h->nsm, h->sync_limit);
-      h->last_launches++;
-    } else {
-      if (h->o.Nnode <= 3) vicgpu_launch_hru_steps_nn3(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);
-      else if (h->o.Nnode <= 10) vicgpu_launch_hru_steps_nn10(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);
-      else vicgpu_launch_hru_steps_nn32(h->d_o, t, frec, per, rb, D.snap, snap_stride, D.hdiag, h->hru_block, h->stream, wns);
-      k_freeze_failed<<<(nhru + 255) / 256, 256, 0, h->stream>>>(t, brec0, n, D.snap, snap_stride, L.hr_stride);
-      h->last_launches += 2;
+    if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
+    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->sm_count);
+    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->sm_count);
+    else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->sm_count);
+    h->last_launches++;
+    // the previous record's output rides on this step
+    if (pend.valid) {
+      int rc = launch_output(pend, h->pdl);
+      if (rc) return rc;
     }
-    if (h->profiling) CK(cudaEventRecord(h->pev[2 * blk + 1], h->stream));
-    bool interval_end = false;  // a glacier accumulation interval ended inside the block: the step kernel left the balances in gmb_cum
-    for (int i = 0; i < n; i++) interval_end = interval_end || (rb.ga[i] & 8);
-    if (interval_end) {
+    if (ga.enabled && ga.reset_after) {  // end of a glacier accumulation interval: the cells' mass-balance curves
       k_cell_gmb<<<(h->t.ncell + 127) / 128, 128, 0, h->stream>>>(h->d_o, t);
       h->last_launches++;
     }
-    if (h->overlap) {
-      CK(cudaEventRecord(h->ev_step, h->stream));
-      CK(cudaStreamWaitEvent(so, h->ev_step, 0));
-    }
-    // cell outputs of the block's records, from the snapshots
-    for (int i = 0; i < n; i++) {
-      h->step_count++;
-      t.hrurec_out = D.snap + (size_t)i * snap_stride;
-      t.hdiag_out = D.hdiag + (size_t)i * 3 * nhru;
-      k_cell_output<<<cgrid, B, 0, so>>>(h->d_o, t, frec + (size_t)i * per, brec0 + i, h->step_count);
-      h->last_launches++;
-      if (out_data) {
-        int rc = vicgpu_transpose(h, h->d_out, h->d_stage, h->nout, h->t.ncell, 1, so);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(out_data + (size_t)(i0 + i) * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
-      }
-      if (h->step_count == h->o.out_step_ratio) {
-        if (out_agg) {
-          int rc = vicgpu_transpose(h, h->d_agg, h->d_stage, h->nout, h->t.ncell, 1, so);
-          if (rc) return rc;
-          CK(cudaMemcpyAsync(out_agg + (size_t)nagg * rowsz, h->d_stage, rowsz * sizeof(double), cudaMemcpyDeviceToHost, so));
-        }
-        nagg++;
-        CK(cudaMemsetAsync(h->d_agg, 0, rowsz * sizeof(double), so));
-        h->step_count = 0;
-      }
-    }
-    if (h->overlap) CK(cudaEventRecord(D.ev_out, so));
-    h->d_state_cur = D.snap + (size_t)(n - 1) * snap_stride;
+    if (h->profiling) CK(cudaEventRecord(h->pev[2 * i + 1], h->stream));  // step(r) and the output riding on it
+    h->step_count++;
+    pend.valid = true;
+    pend.t = t;
+    pend.frec = frec;
+    pend.rec = rec;
+    pend.step_count = h->step_count;
+    pend.idx = i;
+    if (h->step_count == h->o.out_step_ratio) h->step_count = 0;
+    h->d_state_cur = D.snap;
     h->cur_half ^= 1;
   }
-  if (h->overlap) CK(cudaStreamWaitEvent(h->stream, h->half[h->cur_half].ev_out, 0));
+  if (pend.valid) {
+    int rc = launch_output(pend, false);
+    if (rc) return rc;
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  if (h->overlap) CK(cudaStreamSynchronize(so));
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  h->last_ms = ms;
+  CK(cudaStreamSynchronize(h->stream_copy));
+  float msp = 0;
+  CK(cudaEventElapsedTime(&msp, h->ev0, h->ev1));
+  h->last_ms = msp;
   if (h->profiling) {
-    for (int blk = 0; blk < nblocks; blk++) {
+    for (int i = 0; i < nrec; i++) {
       float k = 0;
-      CK(cudaEventElapsedTime(&k, h->pev[2 * blk], h->pev[2 * blk + 1]));
+      CK(cudaEventElapsedTime(&k, h->pev[2 * i], h->pev[2 * i + 1]));
       h->prof_hru_ms += k;
       h->prof_hru_launches++;
     }
   }
   return VICGPU_OK;
+}
+
+extern "C" {
+
+int vicgpu_step(vicgpu_handle* h, int rec0, int nrec, const int* dmy, double* out_data, double* out_agg) {
+  return step_impl(h, rec0, nrec, dmy, out_data, out_agg, false);
+}
+int vicgpu_step_f32(vicgpu_handle* h, int rec0, int nrec, const int* dmy, float* out_data, float* out_agg) {
+  return step_impl(h, rec0, nrec, dmy, out_data, out_agg, true);
 }
 
 int vicgpu_get_cell_status(vicgpu_handle* h, int* status) {

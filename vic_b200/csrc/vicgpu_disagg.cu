@@ -56,6 +56,12 @@ extern "C" int vicgpu_disagg(vicgpu_handle* h, const vicgpu_disagg_options* dopt
   if (!h->have_cells) return vicgpu_fail(VICGPU_ESTATE, "set_cells before disagg");
   if (dopt->Ndays < 1 || h->abi.nrecs < 1) return vicgpu_fail(VICGPU_EINVAL, "Ndays and nrecs must be positive");
   if (24 % h->abi.dt != 0) return vicgpu_fail(VICGPU_EINVAL, "dt must divide 24");
+  if (h->abi.SNOW_STEP < 1 || h->abi.dt % h->abi.SNOW_STEP != 0 || h->abi.NF != h->abi.dt / h->abi.SNOW_STEP)
+    return vicgpu_fail(VICGPU_EINVAL, "SNOW_STEP must divide dt and NF must be dt / SNOW_STEP");
+  // the per-cell scratch holds (Ndays + 1) local days of hourly values; the records (shifted by the start hour and by up to one
+  // day of time-zone offset, initialize_atmos.c:125-156) must stay inside it
+  if ((long long)h->abi.nrecs * h->abi.dt + dopt->starthour + 24 > ((long long)dopt->Ndays + 1) * 24)
+    return vicgpu_fail(VICGPU_EINVAL, "nrecs * dt + starthour exceeds the Ndays of daily input");
   CK(cudaSetDevice(h->device));
   const vicgpu_layout& L = h->o.L;
   const int ncell = h->t.ncell, nrecs = h->abi.nrecs, Ndays = dopt->Ndays;
@@ -67,11 +73,20 @@ extern "C" int vicgpu_disagg(vicgpu_handle* h, const vicgpu_disagg_options* dopt
   a.s.Ndl = Ndays + 1;
   // forcing window [0, nrecs)
   const size_t per = (size_t)ncell * L.f_stride;
-  int rc = vicgpu_ensure_forcing(h, per * nrecs);
+  // the whole run's forcing becomes window 0; a window uploaded earlier is dropped
+  CK(cudaStreamSynchronize(h->stream_copy));
+  ForcingWindow& w = h->fwin[0];
+  w.nrec = 0;
+  h->fwin[1].nrec = 0;
+  int rc = vicgpu_ensure_window(h, w, per * nrecs);
   if (rc) return rc;
-  a.forcing = h->d_forcing;
+  a.forcing = w.d;
   // daily input: copy, then transpose to [Ndays*4][ncell]
-  double *d_in = nullptr, *d_daily = nullptr, *d_scratch = nullptr;
+  struct DevBuf {  // freed on every return path
+    double* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+  } b_in, b_daily, b_scratch, b_t;
+  double *&d_in = b_in.p, *&d_daily = b_daily.p, *&d_scratch = b_scratch.p;
   const size_t nd4 = (size_t)Ndays * 4;
   CK(cudaMalloc(&d_in, nd4 * ncell * sizeof(double)));
   CK(cudaMalloc(&d_daily, nd4 * ncell * sizeof(double)));
@@ -100,24 +115,22 @@ extern "C" int vicgpu_disagg(vicgpu_handle* h, const vicgpu_disagg_options* dopt
   }
   h->last_launches = 7 * ((ncell + (int)chunk - 1) / (int)chunk) + 1;
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_in);
-  cudaFree(d_scratch);
-  cudaFree(d_daily);
-  h->frec0 = 0;
-  h->fnrec = nrecs;
+  CK(cudaEventRecord(w.ready, h->stream));
+  w.rec0 = 0;
+  w.nrec = nrecs;
+  h->fwin_next = 1;
   if (forcing_out) {
     // [nrecs][f_stride][ncell] -> [nrecs][ncell][f_stride], staged in slabs of records
     const size_t slab_recs = std::min<size_t>((size_t)nrecs, std::min<size_t>(65535, std::max<size_t>(1, ((size_t)256 << 20) / (per * sizeof(double)))));
-    double* d_t = nullptr;
+    double*& d_t = b_t.p;
     CK(cudaMalloc(&d_t, per * slab_recs * sizeof(double)));
     for (size_t r = 0; r < (size_t)nrecs; r += slab_recs) {
       const int nr = (int)std::min<size_t>(slab_recs, (size_t)nrecs - r);
-      rc = vicgpu_transpose(h, h->d_forcing + r * per, d_t, L.f_stride, ncell, nr);
-      if (rc) { cudaFree(d_t); return rc; }
+      rc = vicgpu_transpose(h, w.d + r * per, d_t, L.f_stride, ncell, nr);
+      if (rc) return rc;
       CK(cudaMemcpyAsync(forcing_out + r * per, d_t, per * nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
     }
-    cudaFree(d_t);
   }
   return VICGPU_OK;
 }

@@ -20,10 +20,16 @@ inline int vicgpu_fail(int code, const std::string& msg) {
 // one half of the double-buffered state (vicgpu_api.cu "state halves")
 struct StateHalf {
   double* in = nullptr;      // [hr_stride][nhru] input state of a record block, in this half's row order
-  double* snap = nullptr;    // [rb][hr_stride][nhru] state after each record of the block
-  double* hdiag = nullptr;   // [rb][3][nhru] Cv-weighted out_prec / out_rain / out_snow of each record
+  double* snap = nullptr;    // tiles [hr_stride][32]: state after the record
+  double* hdiag = nullptr;   // [3][nhru] Cv-weighted out_prec / out_rain / out_snow of the record
   int ord = 0;               // which RowOrder its rows are in
-  cudaEvent_t ev_out = nullptr;  // the last cell-output work that reads this half
+};
+// a device-resident window of forcing records [rec0, rec0 + nrec): [nrec][f_stride][ncell]
+struct ForcingWindow {
+  double* d = nullptr;
+  size_t cap = 0;              // doubles allocated
+  int rec0 = 0, nrec = 0;
+  cudaEvent_t ready = nullptr;  // recorded on the copy stream when the window's upload is complete
 };
 // a row order of the HRU tables: the parameter table in that order and the maps row <-> caller's HRU index (null: identity)
 struct RowOrder {
@@ -43,27 +49,30 @@ struct vicgpu_handle {
   int rebin_every = 24, recs_since_rebin = 1 << 30;  // records between re-sorts of the rows
   int cur_half = 0;               // the half whose row order d_state_cur is in
   double* d_state_cur = nullptr;  // current state: half.in after set_state, else the last snapshot of the last block
-  int recblock = VICGPU_RECBLOCK_MAX, rb = 1;  // records per launch: requested, and what fits in memory
-  bool binned = true, rebin = true, overlap = true, pdl = true;
+  bool binned = true, rebin = true, pdl = true;
   int* d_fail_rec = nullptr;
-  cudaStream_t stream = nullptr, stream_out = nullptr;  // HRU step / cell output
-  cudaEvent_t ev_step = nullptr, ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream_copy = nullptr;  // kernels / host <-> device copies
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // output staging: two buffers handed between the kernel stream (transpose) and the copy stream (D2H)
+  double* d_ostage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage_full[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
+  int stage_idx = 0;
+  ForcingWindow fwin[2];
+  int fwin_next = 0;
   double *d_gmb_cum = nullptr, *d_gmb = nullptr;  // glacier mass-balance fit (vic_engine.cuh cell_gmb)
   double *d_veglib = nullptr, *d_cellpar = nullptr, *d_cellder = nullptr, *d_carry = nullptr, *d_out = nullptr, *d_agg = nullptr, *d_stage = nullptr,
-         *d_forcing = nullptr, *d_fstage = nullptr;
-  size_t stage_elems = 0, forcing_cap = 0, fstage_cap = 0;
+         *d_fstage = nullptr;
+  size_t stage_elems = 0, fstage_cap = 0;
   int *d_cell_h0 = nullptr, *d_status = nullptr, *d_aggtype = nullptr;
   int hru_block = VICGPU_HRU_BLOCK;
   bool hru_block_fixed = false;  // set through VICGPU_BLOCK
   int sm_count = 148;
   long long sync_limit = 0;  // PhaseSync::limit
-  int nsm = 0;  // SM count when the step grid is rounded up to whole blocks per SM (0: not)
   // re-binning scratch (vicgpu_api.cu rebin_rows)
   unsigned long long* d_keys[2] = {nullptr, nullptr};
   int* d_oldslot[2] = {nullptr, nullptr};
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
-  int frec0 = 0, fnrec = 0;
   bool have_cells = false, have_state = false, glac_started = false;
   int step_count = 0;
   double last_ms = 0;
@@ -79,6 +88,6 @@ struct vicgpu_handle {
 
 // in: [batch][rows][cols] row-major  ->  out: [batch][cols][rows]   (vicgpu_api.cu)
 int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch, cudaStream_t st = nullptr);
-int vicgpu_ensure_forcing(vicgpu_handle* h, size_t elems);
+int vicgpu_ensure_window(vicgpu_handle* h, ForcingWindow& w, size_t elems);
 
 #endif

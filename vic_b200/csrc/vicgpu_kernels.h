@@ -20,15 +20,9 @@
 #endif
 #define VICGPU_HRU_BLOCK 448
 
-void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0, long long sync_limit = 0);
-void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0, long long sync_limit = 0);
-void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, int nsm = 0, long long sync_limit = 0);
-
-void vicgpu_launch_hru_steps_nn3(const vic::Opts* d_o, const vic::Tables& t, const double* forcing, size_t per, const vic::RecBlock& rb, double* snap,
-                                 size_t snap_stride, double* hdiag, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr);
-void vicgpu_launch_hru_steps_nn10(const vic::Opts* d_o, const vic::Tables& t, const double* forcing, size_t per, const vic::RecBlock& rb, double* snap,
-                                  size_t snap_stride, double* hdiag, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr);
-void vicgpu_launch_hru_steps_nn32(const vic::Opts* d_o, const vic::Tables& t, const double* forcing, size_t per, const vic::RecBlock& rb, double* snap,
-                                  size_t snap_stride, double* hdiag, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr);
+// one: the configuration's model step is a single sub-step (NF == 1)
+void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0);
+void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0);
+void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0);
 
 #endif
