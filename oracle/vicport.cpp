@@ -7,6 +7,7 @@
 // answers stored in the same file.  libvicgpu.so has no path into this code.
 //
 // Usage: vicport <case.bin> <result.bin> [--nrec N]
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -109,14 +110,14 @@ int main(int argc, char** argv) {
       for (int k = 0; k < L.f_stride; k++) frec[(size_t)k * ncell + c] = forcing[((size_t)rec * ncell + c) * L.f_stride + k];
     Dmy d = {dmy[rec * 5 + 0], dmy[rec * 5 + 1], dmy[rec * 5 + 2], dmy[rec * 5 + 3], dmy[rec * 5 + 4]};
     if (rec == 0)
-      for (int c = 0; c < ncell; c++) cell_output(&o, t, nullptr, c, -1, step_count);
+      for (int c = 0; c < ncell; c++) cell_output(o, t, nullptr, c, -1, step_count);
     GlacAccum ga = glacier_accum_flags(o, &dmy[rec * 5], &dmy[(rec + 1) * 5], rec, &started);
     if (o.Nnode <= 3) run_record<3>(&o, t, frec.data(), d, rec, ga);
     else if (o.Nnode <= 10) run_record<10>(&o, t, frec.data(), d, rec, ga);
     else run_record<VICGPU_MAX_NODES>(&o, t, frec.data(), d, rec, ga);
     if (ga.enabled && ga.reset_after)
       for (int c = 0; c < ncell; c++) cell_gmb(&o, t, c);
-    for (int c = 0; c < ncell; c++) cell_output(&o, t, frec.data(), c, rec, step_count);
+    for (int c = 0; c < ncell; c++) cell_output(o, t, frec.data(), c, rec, step_count);
     to_rowmajor(out.data(), ncell, nout, &out_all[(size_t)rec * ncell * nout]);
     while (nd < dump_recs.size() && dump_recs[nd] < rec) nd++;
     if (nd < dump_recs.size() && dump_recs[nd] == rec) {

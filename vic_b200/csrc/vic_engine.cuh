@@ -106,28 +106,43 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   dg[2 * nh] = d.out_snow * hp.Cv;
 }
 
+// put_data of one cell (vic_output.cuh).  Host port: the row is built in the output table itself.  Device: one thread per cell, a
+// few hundred one-warp blocks that all fit beside the resident step blocks (the kernel runs as a programmatic dependent of the next
+// record's step, vicgpu_api.cu); the row is built in a thread-local array (a read-modify-write chain through global memory per
+// statement serialises on the L2 latency) and the HRU records are read in place through the read-only path.
+// Measured alternatives (profiles/r02_summary.md): a warp per cell with the records staged in shared memory and lane 0 reducing them
+// is faster alone (289 us against 352 us serialised at 10,000 cells) but needs 16 resident warps per SM to get there, which do not
+// fit beside the step blocks: the record time went from 570 to 720 us; staging each record in a thread-local array first
+// (16 loads in flight) made the kernel slower (384 us) and the record time 690-940 us.
 #define VIC_OUT_LOCAL_MAX 512  // doubles of thread-local row (the three-node layout has 365 columns, ten nodes 400)
-VIC_HDI void cell_output(const Opts* o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count) {
-  if (rec >= 0 && t.fail_rec[cell] <= rec) {
-    // the reference stops touching an invalid cell (vicNl.c:521); its data row keeps the last values
-    return;
-  }
+VIC_HDI void cell_output(const Opts& o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count) {
+  if (rec >= 0 && t.fail_rec[cell] <= rec) return;  // the reference stops touching an invalid cell (vicNl.c:521): its row keeps the last values
   const size_t nc = (size_t)t.ncell;
-  CellPar cp{Col{t.cellpar + cell, nc}, &o->L};
-  VegLib vl{t.veglib, &o->L};
-  Forcing f{Col{forcing_rec ? forcing_rec + cell : nullptr, nc}, o->L.f_nslot};
+  const int nout = o.L.out_off[VICGPU_N_OUTVARS];
+  CellPar cp{Col{t.cellpar + cell, nc}, &o.L};
+  VegLib vl{t.veglib, &o.L};
+  Forcing f{Col{forcing_rec ? forcing_rec + cell : nullptr, nc}, o.L.f_nslot};
+  RowRW gout{t.out + cell, nc}, agg{t.agg + cell, nc};
 #if defined(__CUDA_ARCH__)
-  const int nout = o->L.out_off[VICGPU_N_OUTVARS];
   double row[VIC_OUT_LOCAL_MAX];
-  if (nout <= VIC_OUT_LOCAL_MAX) {
-    put_data_cell(*o, cp, vl, &f, t.hrurec_out, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count,
-                  t.aggtype, RowRW{t.carry + cell, nc}, RowLocal{row}, RowRW{t.agg + cell, nc});
-    for (int k = 0; k < nout; k++) t.out[(size_t)k * nc + cell] = row[k];
-    return;
-  }
+  RowLocal out{row};
+#else
+  RowRW out = gout;
 #endif
-  put_data_cell(*o, cp, vl, &f, t.hrurec_out, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, t.cell_h0[cell], t.cell_h0[cell + 1], rec, step_count, t.aggtype,
-                RowRW{t.carry + cell, nc}, RowRW{t.out + cell, nc}, RowRW{t.agg + cell, nc});
+  PutDataCtx pc;
+  for (int k = 0; k < nout; k++) out[k] = 0;
+  const int h0 = t.cell_h0[cell], h1 = t.cell_h0[cell + 1];
+  put_data_begin(o, cp, vl, &f, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, h0, h1, rec, out, pc);
+  for (int hh = h0; hh < h1; hh++) {
+    const int h = t.slot_of_hru ? t.slot_of_hru[hh] : hh;
+    put_data_hru(o, cp, vl, RecTile{t.hrurec_out + hr_off(h, o.L.hr_stride)}, t.hrupar, (size_t)t.nhru, h, out, pc);
+  }
+  put_data_finish(o, cp, rec, RowRW{t.carry + cell, nc}, out, pc);
+#if defined(__CUDA_ARCH__)
+  for (int k = 0; k < nout; k++) gout[k] = row[k];
+#endif
+  if (rec < 0) return;
+  put_data_aggregate(o, t.aggtype, step_count, out, agg);
 }
 
 // the cell's mass-balance curve at the end of an accumulation interval (GlacierMassBalanceResult.c:35-72): one point per band

@@ -23,45 +23,56 @@ struct RowRW {
   VIC_HD double& operator[](int k) const { return p[(size_t)k * n]; }
 };
 
-// the row of one cell held in the thread's own memory while it is built up (cell_output on the device): the ~180 variables are
-// accumulated HRU by HRU, and read-modify-write chains through global memory serialise on the L2 latency (one warp per scheduler:
-// nothing hides it).  put_data_cell is inlined into cell_output so that the compiler sees a local array, not a generic pointer.
+// the row of one cell while it is built up on the device: a thread-local array
 struct RowLocal {
   double* p;
   VIC_HD double& operator[](int k) const { return p[k]; }
 };
-
-// out: the cell's row of OutputData::data; agg: its row of aggdata (may be null when rec < 0).
-// hrec/hpar/hdiag are the column-major HRU tables, [h0, h1) the cell's HRUs in hruList order; slot (may be null = identity)
-// maps an HRU to the table row it currently occupies (the device keeps HRUs binned by kind, not by cell).
-// rec < 0 reproduces the storage initialisation call put_data(rec = -nrecs) (vicNl.c:524-541).
-template <class OutRow>
-VIC_HD void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, const Forcing* f, const double* __restrict__ hrec, const double* __restrict__ hpar,
-                          const double* __restrict__ hdiag, size_t nhru, const int* __restrict__ slot, int h0, int h1, int rec, int step_count, const int* aggtype, RowRW carry,
-                          OutRow out, RowRW agg) {
-  const vicgpu_layout& L = o.L;
-  const int NL = VICGPU_NLAYER;
-  const int nout = L.out_off[VICGPU_N_OUTVARS];
-  const int Nbands = o.Nbands;
-#define OUT(v, e) out[L.out_off[VOUT_##v] + (e)]
+// one HRU record, read in place from the tile-major state table
+struct RecTile {
+  const double* p;  // hrec + hr_off(h, hr_stride)
+  VIC_HD double operator()(int k) const {
 #if defined(__CUDA_ARCH__)
-#define HR(k) __ldg(&hrec[hr_off(h, L.hr_stride) + (size_t)(k) * VIC_HR_TILE])
+    return __ldg(p + (size_t)k * VIC_HR_TILE);
 #else
-#define HR(k) hrec[hr_off(h, L.hr_stride) + (size_t)(k) * VIC_HR_TILE]
+    return p[(size_t)k * VIC_HR_TILE];
 #endif
+  }
+};
+
+// what put_data carries from HRU to HRU of a cell
+struct PutDataCtx {
+  double TreeAdjustFactor[VICGPU_MAX_BANDS];
+  double cv_baresoil, cv_veg, cv_overstory, cv_snow, cv_glacier;
+};
+
+#define OUT(v, e) out[L.out_off[VOUT_##v] + (e)]
+#define HR(k) hr(k)
 #define HP(k) hpar[(size_t)(k) * nhru + h]
-  double bandCv[VICGPU_MAX_BANDS], TreeAdjustFactor[VICGPU_MAX_BANDS];
+
+// put_data() is restated in four parts (per cell / per HRU / per cell / aggregation) so that the driver decides where the row and
+// the HRU records live while the cell is reduced (vic_engine.cuh cell_output).
+//
+// Part 1, once per cell: tree-line adjustment factors, the forcing variables and the Cv-weighted precipitation sums.  `out` has been
+// zeroed.  [h0, h1) are the cell's HRUs in hruList order; slot (may be null = identity) maps an HRU to the table row it currently
+// occupies (the device keeps HRUs binned by kind, not by cell).  rec < 0 reproduces the storage initialisation call
+// put_data(rec = -nrecs) (vicNl.c:524-541).
+template <class OutRow>
+VIC_HD void put_data_begin(const Opts& o, const CellPar& cp, const VegLib& vl, const Forcing* f, const double* __restrict__ hpar,
+                           const double* __restrict__ hdiag, size_t nhru, const int* __restrict__ slot, int h0, int h1, int rec, OutRow out, PutDataCtx& pc) {
+  const vicgpu_layout& L = o.L;
+  const int Nbands = o.Nbands;
+  double bandCv[VICGPU_MAX_BANDS];
   for (int b = 0; b < VICGPU_MAX_BANDS; b++) bandCv[b] = 0;
   for (int hh = h0; hh < h1; hh++) {
     const int h = slot ? slot[hh] : hh;
     if (vl.row((int)HP(HP_vegIndex)).overstory()) bandCv[(int)HP(HP_band)] += HP(HP_Cv);
   }
   for (int b = 0; b < Nbands; b++) {
-    if (cp.band(CB_AboveTreeLine, b) != 0.0) TreeAdjustFactor[b] = 1. / (1. - bandCv[b]);
-    else TreeAdjustFactor[b] = 1.;
+    if (cp.band(CB_AboveTreeLine, b) != 0.0) pc.TreeAdjustFactor[b] = 1. / (1. - bandCv[b]);
+    else pc.TreeAdjustFactor[b] = 1.;
   }
-  double cv_baresoil = 0, cv_veg = 0, cv_overstory = 0, cv_snow = 0, cv_glacier = 0;
-  for (int k = 0; k < nout; k++) out[k] = 0;
+  pc.cv_baresoil = pc.cv_veg = pc.cv_overstory = pc.cv_snow = pc.cv_glacier = 0;
   double out_prec = 0, out_rain = 0, out_snow = 0;
   if (rec >= 0) {
     // atmos->out_prec etc. (full_energy.c:425-427): Cv-weighted sums over the HRUs that were stepped
@@ -88,26 +99,33 @@ VIC_HD void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, co
     OUT(VPD, 0) = (*f)(FV_vpd, NR) / 1000.;
     OUT(WIND, 0) = (*f)(FV_wind, NR);
   }
-  for (int hh = h0; hh < h1; hh++) {
-    const int h = slot ? slot[hh] : hh;
+}
+
+// Part 2, once per HRU in hruList order: h is the HRU's table row, hr its record
+template <class Rec, class OutRow>
+VIC_HD void put_data_hru(const Opts& o, const CellPar& cp, const VegLib& vl, Rec hr, const double* __restrict__ hpar, size_t nhru, int h, OutRow out,
+                         PutDataCtx& pc) {
+  const vicgpu_layout& L = o.L;
+  const int NL = VICGPU_NLAYER;
+  {
     const double Cv = HP(HP_Cv);
     const bool isArtBare = HP(HP_isArtBare) != 0.0, HasGlac = HP(HP_isGlacier) != 0.0;
     const bool HasVeg = !(isArtBare || HasGlac);
-    if (!(Cv > 0)) continue;
+    if (!(Cv > 0)) return;
     const int band = (int)HP(HP_band);
     const bool overstory = vl.row((int)HP(HP_vegIndex)).overstory();
     const double ThisAreaFract = cp.band(CB_AreaFract, band);
-    const double ThisTreeAdjust = TreeAdjustFactor[band];
+    const double ThisTreeAdjust = pc.TreeAdjustFactor[band];
     const bool above = cp.band(CB_AboveTreeLine, band) != 0.0;
-    if (!(ThisAreaFract > 0. && (isArtBare || (!above || (above && !overstory))))) continue;
+    if (!(ThisAreaFract > 0. && (isArtBare || (!above || (above && !overstory))))) return;
     OUT(ELEV_BAND, band) = cp.band(CB_BandElev, band);
     const double mu = HR(HR_H_mu);
     const double swq = HR(HR_S_swq);
-    if (HasVeg) cv_veg += Cv * mu * ThisTreeAdjust;
-    else cv_baresoil += Cv * mu * ThisTreeAdjust;
-    if (overstory) cv_overstory += Cv * mu * ThisTreeAdjust;
-    if (swq > 0.0) cv_snow += Cv * mu * ThisTreeAdjust;
-    if (HasGlac) cv_glacier += Cv * mu * ThisTreeAdjust;
+    if (HasVeg) pc.cv_veg += Cv * mu * ThisTreeAdjust;
+    else pc.cv_baresoil += Cv * mu * ThisTreeAdjust;
+    if (overstory) pc.cv_overstory += Cv * mu * ThisTreeAdjust;
+    if (swq > 0.0) pc.cv_snow += Cv * mu * ThisTreeAdjust;
+    if (HasGlac) pc.cv_glacier += Cv * mu * ThisTreeAdjust;
     // ---- water balance terms
     {
       const double AreaFactor = Cv * mu * ThisTreeAdjust * 1.0;
@@ -289,16 +307,23 @@ VIC_HD void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, co
       }
     }
   }
+}
+
+// Part 3, once per cell: derived variables, storage changes, the water / energy balance checks
+template <class OutRow>
+VIC_HD void put_data_finish(const Opts& o, const CellPar& cp, int rec, RowRW carry, OutRow out, const PutDataCtx& pc) {
+  const vicgpu_layout& L = o.L;
+  const int NL = VICGPU_NLAYER;
   // ---- derived variables
-  if (cv_baresoil > 0) OUT(BARESOILT, 0) /= cv_baresoil;
-  if (cv_veg > 0) OUT(VEGT, 0) /= cv_veg;
-  if (cv_overstory > 0) OUT(AERO_COND2, 0) /= cv_overstory;
-  if (cv_snow > 0) {
-    OUT(SALBEDO, 0) /= cv_snow;
-    OUT(SNOW_SURF_TEMP, 0) /= cv_snow;
-    OUT(SNOW_PACK_TEMP, 0) /= cv_snow;
+  if (pc.cv_baresoil > 0) OUT(BARESOILT, 0) /= pc.cv_baresoil;
+  if (pc.cv_veg > 0) OUT(VEGT, 0) /= pc.cv_veg;
+  if (pc.cv_overstory > 0) OUT(AERO_COND2, 0) /= pc.cv_overstory;
+  if (pc.cv_snow > 0) {
+    OUT(SALBEDO, 0) /= pc.cv_snow;
+    OUT(SNOW_SURF_TEMP, 0) /= pc.cv_snow;
+    OUT(SNOW_PACK_TEMP, 0) /= pc.cv_snow;
   }
-  if (cv_glacier > 0) OUT(GLAC_SURF_TEMP, 0) /= cv_glacier;
+  if (pc.cv_glacier > 0) OUT(GLAC_SURF_TEMP, 0) /= pc.cv_glacier;
   OUT(RAD_TEMP, 0) = vpow(OUT(RAD_TEMP, 0), 0.25);
   OUT(AERO_RESIST1, 0) = (OUT(AERO_COND1, 0) > SMALL) ? 1 / OUT(AERO_COND1, 0) : HUGE_RESIST;
   OUT(AERO_RESIST2, 0) = (OUT(AERO_COND2, 0) > SMALL) ? 1 / OUT(AERO_COND2, 0) : HUGE_RESIST;
@@ -367,12 +392,18 @@ VIC_HD void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, co
       if (fabs(error) > fabs(carry[CC_energy_max_error]) && fabs(error) > 0.001) carry[CC_energy_max_error] = error;
     }
   }
-  if (rec < 0) return;
-  // ---- temporal aggregation
-  int v = 0, off = 0;
-  for (v = 0; v < VICGPU_N_OUTVARS; v++) {
+}
+
+// Part 4: temporal aggregation (put_data.c:664-680), resistances from the aggregated conductances, ALMA unit conversions at an
+// output step
+template <class OutRow, class AggRow>
+VIC_HD void put_data_aggregate(const Opts& o, const int* aggtype, int step_count, OutRow out, AggRow agg) {
+  const vicgpu_layout& L = o.L;
+  const int NL = VICGPU_NLAYER;
+  const int dt_sec = o.dt * SECPHOUR;
+  for (int v = 0; v < VICGPU_N_OUTVARS; v++) {
     const int ne = L.out_nelem[v];
-    off = L.out_off[v];
+    const int off = L.out_off[v];
     const int at = aggtype[v];
     for (int i = 0; i < ne; i++) {
       if (at == VICGPU_AGG_END) agg[off + i] = out[off + i];
@@ -400,10 +431,10 @@ VIC_HD void put_data_cell(const Opts& o, const CellPar& cp, const VegLib& vl, co
     AGG(VPD, 0) *= 1000;
 #undef AGG
   }
+}
 #undef OUT
 #undef HR
 #undef HP
-}
 
 }  // namespace vic
 #endif

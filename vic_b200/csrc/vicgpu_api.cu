@@ -41,22 +41,6 @@ __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ 
   }
 }
 
-// The same with the float32 narrowing WriteOutputNetCDF applies to every value it writes (WriteOutputNetCDF.c:279, 351, 412): a plain
-// (float) conversion, round to nearest
-__global__ void k_transpose_f32(const double* __restrict__ in, float* __restrict__ out, int rows, int cols) {
-  __shared__ double tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) out[(size_t)c * rows + r] = (float)tile[threadIdx.x][i];
-  }
-}
-
 // The same conversions when the device row of record r is not r (HRU tables are kept binned by kind, vic_engine.cuh bin_hrus):
 // host record r (row-major) <-> device row row_of[r] (column-major).  One thread per element, coalesced on the device side.
 __global__ void k_scatter_rows(const double* __restrict__ in /* [rows][cols] */, double* __restrict__ out /* [cols][rows] */, int rows, int cols,
@@ -102,7 +86,7 @@ __global__ void k_permute_state(const double* __restrict__ in, double* __restric
 // without snow (dynamic: solve_snow's pack and canopy balances, sub-stepping, evaporation switched off under snow).  Every
 // `rebin_interval` records the rows are re-sorted on the device so that the 32 HRUs of a warp share both.
 __global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __restrict__ hrurec, int nhru, int hr_stride, const int* __restrict__ hru_of_slot,
-                           unsigned long long* __restrict__ keys, int* __restrict__ old_slot) {
+                           unsigned long long* __restrict__ keys, int* __restrict__ old_slot, int fine) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nhru) return;
   const size_t n = (size_t)nhru;
@@ -110,9 +94,18 @@ __global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __re
   if (hrupar[(size_t)HP_isArtBare * n + s] != 0.0) kind |= 1ull << 20;
   if (hrupar[(size_t)HP_isGlacier * n + s] != 0.0) kind |= 1ull << 21;
   const size_t so = hr_off(s, hr_stride);
-  const bool snowy = hrurec[so + (size_t)HR_S_swq * VIC_HR_TILE] > 0.0 || hrurec[so + (size_t)HR_S_snow_canopy * VIC_HR_TILE] > 0.0;
+  const double swq = hrurec[so + (size_t)HR_S_swq * VIC_HR_TILE], canopy = hrurec[so + (size_t)HR_S_snow_canopy * VIC_HR_TILE];
+  unsigned long long regime = (swq > 0.0 || canopy > 0.0) ? 1 : 0;
+  if (fine) {
+    // VICGPU_BINFINE=1: the pack's regime decides which branches of snow_melt / solve_snow run -- no pack on the ground, a pack whose
+    // surface is at the melting point (the balance at 0 C usually closes without a solve) or a cold pack (Brent solve) -- and snow in
+    // the canopy decides whether snow_intercept's canopy balance runs
+    const double ts = hrurec[so + (size_t)HR_S_surf_temp * VIC_HR_TILE];
+    const unsigned long long pack = !(swq > 0.0) ? 0 : ((ts < 0.0) ? 1 : 2);
+    regime = (pack << 1) | (canopy > 0.0 ? 1 : 0);
+  }
   // low 32 bits: the HRU's own index, i.e. cell order within a bin (and a total order: the sort is deterministic)
-  keys[s] = (kind << 33) | ((unsigned long long)(snowy ? 1 : 0) << 32) | (unsigned long long)(unsigned)hru_of_slot[s];
+  keys[s] = (kind << 35) | (regime << 32) | (unsigned long long)(unsigned)hru_of_slot[s];
   old_slot[s] = s;
 }
 // out[c][s] = in[c][src[s]]
@@ -155,8 +148,10 @@ __global__ void k_cell_gmb(const Opts* __restrict__ o, Tables t) {
   cell_gmb(o, t, c);
 }
 
-__global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o, Tables t, const double* __restrict__ forcing_rec, int rec,
-                                                     int step_count) {
+// one thread per cell (vic_engine.cuh cell_output); the options travel as a kernel parameter: the output offsets
+// L.out_off[VOUT_x] are then operands in the constant bank instead of a dependent global load per statement
+__global__ void __launch_bounds__(128) k_cell_output(const __grid_constant__ Opts o, Tables t, const double* __restrict__ forcing_rec, int rec, int step_count,
+                                                     int wait_primary) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < t.ncell) cell_output(o, t, forcing_rec, c, rec, step_count);
   // Launched as a programmatic dependent of step(rec + 1) (vicgpu_step), this grid starts while that step is still running.  It
@@ -164,7 +159,23 @@ __global__ void __launch_bounds__(128) k_cell_output(const Opts* __restrict__ o,
   // cannot change the `fail_rec <= rec` test made here -- so the work above needs no ordering with it.  The wait below is what makes
   // COMPLETION of this grid imply completion of the step grid it rode on: step(rec + 2), the transposes and copies that follow are
   // ordinary launches ordered after this grid only (PTX ISA griddepcontrol.wait).  A no-op for an ordinary launch.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (wait_primary) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// [rows][cols] -> [cols][rows] with the float32 narrowing WriteOutputNetCDF applies to every value it writes (WriteOutputNetCDF.c:279,
+// 351, 412): a plain (float) conversion, round to nearest
+__global__ void k_transpose_f32(const double* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = (float)tile[threadIdx.x][i];
+  }
 }
 
 int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch, cudaStream_t st) {
@@ -257,7 +268,7 @@ static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const do
   const int nhru = h->t.nhru;
   const vicgpu_layout& L = h->o.L;
   const int T = 256, G = (nhru + T - 1) / T;
-  k_bin_keys<<<G, T, 0, h->stream>>>(S.hrupar, src_state, nhru, L.hr_stride, S.hru_of_slot, h->d_keys[0], h->d_oldslot[0]);
+  k_bin_keys<<<G, T, 0, h->stream>>>(S.hrupar, src_state, nhru, L.hr_stride, S.hru_of_slot, h->d_keys[0], h->d_oldslot[0], h->bin_fine ? 1 : 0);
   size_t need = 0;
   CK(cub::DeviceRadixSort::SortPairs(nullptr, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
   if (need > h->sort_tmp_bytes) {
@@ -339,6 +350,15 @@ static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const O
   const char* rb = getenv("VICGPU_REBIN");  // records between re-sorts of the rows by (kind, snow); 0: bin by kind once (set_cells)
   h->rebin_every = rb ? atoi(rb) : 24;
   h->rebin = h->binned && h->rebin_every > 0;
+  const char* pw = getenv("VICGPU_PDLWAIT");  // 0: the dependent cell-output grid does not end with griddepcontrol.wait (A/B only)
+  h->pdl_wait = !(pw && atoi(pw) == 0);
+  // 1: round a step grid smaller than the machine up to one block per SM.  Off by default: the step kernel's duration is set by its
+  // slowest warp, not by how many SMs share the warps, and the SMs a 118-block grid leaves idle are where the dependent cell-output
+  // grid runs (measured at 10,000 cells: record 588 us with 118 blocks, 835 us = step + output back to back with 148)
+  const char* ev = getenv("VICGPU_EVEN");
+  h->even = ev && atoi(ev) != 0;
+  const char* bf = getenv("VICGPU_BINFINE");  // 1: bin by pack regime and canopy snow as well (k_bin_keys)
+  h->bin_fine = bf && atoi(bf) != 0;
   CK(cudaMalloc(&h->d_o, sizeof(Opts)));
   CK(cudaMemcpy(h->d_o, &h->o, sizeof(Opts), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_aggtype, VICGPU_N_OUTVARS * sizeof(int)));
@@ -638,9 +658,9 @@ int vicgpu_set_forcing(vicgpu_handle* h, int rec0, int nrec, const double* forci
 
 }  // extern "C"
 
-// One output row set [nout][ncell] on the device -> host [ncell][nout] (double, or float32 as the NetCDF writer narrows it), through
-// one of two staging buffers: the transpose runs in the step's stream, the copy on the copy stream, and the staging buffer is handed
-// back with an event, so that the copy of record r overlaps the kernels of record r + 1.
+// One set of output rows [nout][ncell] on the device -> host [ncell][nout] (double, or float32 as the NetCDF writer narrows it), through
+// one of two staging buffers: the transpose runs in the step's stream (the next cell-output launch overwrites the rows), the copy on
+// the copy stream, and the staging buffer is handed back with an event, so that the copy of record r overlaps the kernels of record r + 1.
 static int stage_out(vicgpu_handle* h, const double* d_rows, void* host, bool f32) {
   const int k = h->stage_idx;
   h->stage_idx ^= 1;
@@ -682,7 +702,7 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
   const size_t per = (size_t)h->t.ncell * L.f_stride;
   const size_t rowsz = (size_t)h->t.ncell * h->nout;
   const size_t esz = f32 ? sizeof(float) : sizeof(double);
-  // one warp per block: such a block fits beside a resident step block on every SM
+  // cell output: one-warp blocks, such a block fits beside a resident step block on every SM
   const char* cb = getenv("VICGPU_OUTBLOCK");
   const int B = (cb && atoi(cb) >= 32 && atoi(cb) <= 128) ? atoi(cb) : 32;
   const int cgrid = (h->t.ncell + B - 1) / B;
@@ -712,7 +732,7 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
     attr[0].val.programmaticStreamSerializationAllowed = dependent ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, k_cell_output, (const Opts*)h->d_o, p.t, p.frec, p.rec, p.step_count));
+    CK(cudaLaunchKernelEx(&cfg, k_cell_output, h->o, p.t, p.frec, p.rec, p.step_count, h->pdl_wait ? 1 : 0));
     h->last_launches++;
     if (out_data) {
       int rc = stage_out(h, h->d_out, (char*)out_data + (size_t)p.idx * rowsz * esz, f32);
@@ -764,7 +784,7 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
       // storage terms of the initial state: put_data(rec = -nrecs), vicNl.c:524-541
       Tables t0 = t;
       t0.hrurec_out = const_cast<double*>(input);
-      k_cell_output<<<cgrid, B, 0, h->stream>>>(h->d_o, t0, nullptr, -1, h->step_count + 1);
+      k_cell_output<<<cgrid, B, 0, h->stream>>>(h->o, t0, nullptr, -1, h->step_count + 1, 0);
       h->last_launches++;
     }
     const double* frec = fw->d + (size_t)(rec - fw->rec0) * per;
@@ -776,9 +796,9 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
       wns = h->d_warp_ns;
     }
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->sm_count);
-    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->sm_count);
-    else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->sm_count);
+    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0);
+    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0);
+    else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0);
     h->last_launches++;
     // the previous record's output rides on this step
     if (pend.valid) {

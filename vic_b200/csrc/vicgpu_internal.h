@@ -49,7 +49,7 @@ struct vicgpu_handle {
   int rebin_every = 24, recs_since_rebin = 1 << 30;  // records between re-sorts of the rows
   int cur_half = 0;               // the half whose row order d_state_cur is in
   double* d_state_cur = nullptr;  // current state: half.in after set_state, else the last snapshot of the last block
-  bool binned = true, rebin = true, pdl = true;
+  bool binned = true, rebin = true, pdl = true, bin_fine = false, pdl_wait = true, even = false;
   int* d_fail_rec = nullptr;
   cudaStream_t stream = nullptr, stream_copy = nullptr;  // kernels / host <-> device copies
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -18,7 +18,9 @@
 #ifndef VICGPU_STEP_MAXNREG
 #define VICGPU_STEP_MAXNREG 128
 #endif
+#ifndef VICGPU_HRU_BLOCK
 #define VICGPU_HRU_BLOCK 448
+#endif
 
 // one: the configuration's model step is a single sub-step (NF == 1)
 void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0);
