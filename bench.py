@@ -1,17 +1,26 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: cell-timesteps/s of the full-energy hourly VIC cell loop.
+"""Benchmark of the hot path: cell-timesteps/s of the VIC cell loop on B200s, next to the reference's own CPU build.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--cells C] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--cells C] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): FULL_ENERGY=TRUE, QUICK_FLUX=TRUE, 3 soil layers, 3 thermal nodes, 5 vegetation
-tiles (2 overstory + 3 short, + the automatic bare-soil HRU where the tiles do not cover the cell), 1 snow band,
-hourly step, 10,000 cells per GPU.  One bench "step" = one day = 24 hourly records over every cell of the rank
-(240,000 cell-timesteps per GPU); the default K + W = 365 steps is the configuration's full year.
+Workloads (BASELINE.json configs; one bench "step" = one day = 24 hourly records over every cell of the rank):
+  fe_hourly     configs[1]  FULL_ENERGY, QUICK_FLUX, 3 layers, 3 thermal nodes, 5 vegetation tiles (2 overstory + 3 short, + the automatic
+                            bare-soil HRU where the tiles do not cover the cell), 1 snow band, 10,000 cells per GPU.  THE DEFAULT: the
+                            configuration the metric is quoted on; K + W = 365 steps is its full year.
+  frozen_bands  configs[2]  FROZEN_SOIL, QUICK_FLUX FALSE, 10 thermal nodes, 5 snow bands, 100,000 cells per GPU
+  glacier       configs[3]  PCIC glacier mass-balance mode (glacier tiles in the upper bands, 5 bands), 250,000 cells per GPU
+  continental   configs[4]  daily PREC/TMAX/TMIN/WIND in -> mtclim disaggregation on the device (vicgpu_disagg) -> full-energy hourly
+                            steps -> daily float32 aggregates out; 125,000 cells per GPU (1,000,000 over 8 GPUs), one gather of the
+                            last day's aggregates over NCCL at the end, timed separately
 
-Parameters and initial state: bench_data/base_fe_hourly.npz (256 cells produced by the reference's own readers and
-initialisation code, see bench_data/make_base.py) tiled to the domain size with perturbed infiltration / baseflow /
-conductivity parameters; forcing: synthetic hourly weather generated here (seeded).  Cells are independent, so with
-N GPUs every rank owns its own 10,000 cells (weak scaling) and there is no collective on the data path.
+Parameters and initial state: bench_data/base_<config>.npz (256 cells produced by the reference's own readers and initialisation
+code, see bench_data/make_base.py) tiled to the domain size with perturbed infiltration / baseflow / conductivity parameters; forcing:
+synthetic weather generated here (seeded).  Cells are independent, so with N GPUs every rank owns its own cells (weak scaling) and
+there is no collective on the data path.
+
+--impl reference: the reference's own CPU build (oracle/_ref/vic_ref_harness: its unmodified sources, OpenMP cell loop of
+vicNl.c:514-517, -O3) on the box's host cores, timed by the harness's own loop timer exactly as vicNl.c:501, 614-623 times it; for
+fe_hourly on 10,000 synthetic cells of the same generator.
 
 Lines printed (rank 0): one JSON object, see the keys at the bottom of main().
 """
@@ -34,10 +43,23 @@ sys.path.insert(0, ROOT)
 from vic_b200.layout import TABLES, layout_from_options, parse_options  # noqa: E402
 
 RECS_PER_STEP = 24
-BASE_SEED = 20260            # seed of the 16x16 base domain (bench_data/make_base.py)
-# algorithmic bytes per cell-timestep of this configuration (H=5, Nn=3, Tb=1)
-ALGO_BYTES_PER_CELL_STEP = 7.0e3
+BASE_SEED = 20260            # seed of the 16x16 base domains (bench_data/make_base.py)
 SIGMA = 5.6696e-8
+
+# algorithmic bytes per cell-timestep, B = H (2 S_hru + P_hru) + P_cell + F_cell + O_cell:
+#   fe_hourly    H = 5, Nn = 3:            5 (960 + 40) + 1900 + 81 + 13  = 7.0 KB
+#   frozen_bands Nn = 10, 5 bands:          5 (1520 + 40) + 2400 + 81      = 10.3 KB (the survey's figure)
+#   glacier      H = 6.6, Nn = 3, 5 bands:  6.6 (960 + 40) + 2060 + 94     = 8.8 KB
+WORKLOADS = {
+    "fe_hourly": dict(base="fe_hourly", cells=10000, steps=362, warmup=3, algo_bytes=7.0e3, kernel="k_hru_step_nn3", config=1, ref_side=100,
+                      desc="fe_hourly: FULL_ENERGY hourly, QUICK_FLUX, 3 layers, 3 nodes, 5 veg tiles, 1 band"),
+    "frozen_bands": dict(base="frozen_bands", cells=100000, steps=2, warmup=3, algo_bytes=10.3e3, kernel="k_hru_step_nn10", config=2, ref_side=16,
+                         desc="frozen_bands: FROZEN_SOIL, QUICK_FLUX FALSE, 10 thermal nodes, 5 snow bands, hourly"),
+    "glacier": dict(base="glacier", cells=250000, steps=10, warmup=3, algo_bytes=8.8e3, kernel="k_hru_step_nn3", config=3, ref_side=32,
+                    desc="glacier: PCIC glacier mass-balance mode (surface_fluxes_glac), 5 snow bands, hourly"),
+    "continental": dict(base="fe_hourly", cells=125000, steps=10, warmup=3, algo_bytes=7.0e3, kernel="k_hru_step_nn3", config=4, ref_side=100, disagg=True,
+                        desc="continental: mtclim daily->hourly disaggregation on the device + fe_hourly physics, float32 daily aggregates out"),
+}
 
 
 def col(table, name):
@@ -170,61 +192,106 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def run_reference(ncell_sample, ndays, warm_days, threads, seed):
-    """the reference's own CPU implementation (oracle/_ref/vic_ref_harness = its unmodified sources, OpenMP cell loop of
-    vicNl.c:514-517) on the base domain's first cells with the same forcing generator; returns (cell_steps_per_s, seconds)"""
+def run_reference(workload, side, ndays, warm_days, threads, seed=1):
+    """The reference's own CPU implementation (oracle/_ref/vic_ref_harness = its unmodified sources, OpenMP cell loop of
+    vicNl.c:514-517) on side x side synthetic cells of the workload's configuration (vic_b200/synth.py, the generator the base
+    domains of bench_data/ come from) with the bench's hourly forcing generator.  Returns (cell_steps_per_s, seconds, ncell): the
+    harness's own timer around the record loop, exactly what vicNl.c:501, 614-623 report as "Model execution time"; the first
+    warm_days days are run but not timed."""
     import dataclasses
     from vic_b200 import synth
     from vic_b200.casefile import write_case
     harness = os.path.join(ROOT, "oracle", "_ref", "vic_ref_harness")
     if not os.path.exists(harness):
         raise FileNotFoundError(harness)
-    side = 16
-    assert ncell_sample == side * side
-    dom = build_domain(ncell_sample, seed)
+    wl = WORKLOADS[workload]
+    n = side * side
     with tempfile.TemporaryDirectory() as d:
-        cfg = dataclasses.replace(synth.CONFIGS["fe_hourly"], ndays=ndays, out_step=24)
+        cfg = dataclasses.replace(synth.CONFIGS[wl["base"]], ndays=ndays, out_step=24)
         r = synth.generate(d, cfg, side, side, BASE_SEED, forcing=False, threads=threads)
-        L = layout_from_options(parse_options(dom["options_raw"]))
-        f = np.empty((ndays * 24, ncell_sample, L.f_stride))
+        dom = {k: np.array([c[k] for c in r["cells"]]) for k in ("elev", "lat", "avg_temp")}
+        f = np.empty((ndays * 24, n, len(TABLES["forcing"])))
         for day in range(ndays):
             forcing_day(dom, day, seed, f[day * 24:(day + 1) * 24])
         fb = os.path.join(d, "forcing.bin")
         write_case(fb, {"forcing": f})
+        del f
         o = subprocess.run([harness, "-g", r["global_file"], "--forcing-bin", fb, "--time-only", "--threads", str(threads), "--time-from", str(warm_days * 24)],
                            capture_output=True, text=True, check=True).stdout
     line = [x for x in o.splitlines() if x.startswith("run_seconds")][0].split()
-    return float(line[7]), float(line[1])
+    return float(line[7]), float(line[1]), n
+
+
+def cpu_baseline(workload, host_threads):
+    """bounded samples of the workload on the host cores: all threads and one thread"""
+    wl = WORKLOADS[workload]
+    side = wl["ref_side"]
+    if workload in ("fe_hourly", "continental"):
+        v, secs, n = run_reference(workload, side, 5, 1, host_threads)
+        v1, secs1, n1 = run_reference(workload, 32, 3, 1, 1)
+        sample = (f"{n} cells x 96 hourly records (after 24 untimed), {host_threads} OpenMP threads, {secs:.1f} s; one thread: {n1} cells x 48 records, {secs1:.1f} s")
+    else:
+        days = 2 if workload == "frozen_bands" else 3
+        v, secs, n = run_reference(workload, side, days, 1, host_threads)
+        v1, secs1, n1 = run_reference(workload, 8, days, 1, 1)
+        sample = (f"{n} cells x {(days - 1) * 24} hourly records (after 24 untimed), {host_threads} OpenMP threads, {secs:.1f} s; one thread: {n1} cells, {secs1:.1f} s")
+    return {"value": v, "unit": "cell-timesteps/s", "cores": host_threads, "kind": "reference", "value_1thread": v1,
+            "sample": sample + "; reference build oracle/_ref/vic_ref_harness (-O3), synthetic cells of the workload's configuration, the bench's forcing generator, "
+                               "timed by the harness's record-loop timer (vicNl.c:501, 614-623)"}
+
+
+def synth_daily(dom, ndays, seed):
+    """daily PREC [mm], TMAX, TMIN [C], WIND [m/s] per cell: [ncell][ndays][4] (the generator of vic_b200/synth.py, vectorised)"""
+    n = dom["elev"].shape[0]
+    rng = np.random.default_rng([seed, 13])
+    doy = np.arange(ndays)[None, :]
+    tmean = dom["avg_temp"][:, None] + 2.0 + 12.0 * np.sin(2 * np.pi * (doy - 105) / 365.0) - 0.004 * (dom["elev"][:, None] - 1000.0) + rng.normal(0.0, 2.0, (n, ndays))
+    dtr = rng.uniform(6.0, 12.0, (n, ndays))
+    wet = rng.uniform(size=(n, ndays)) < 0.4
+    out = np.empty((n, ndays, 4))
+    out[:, :, 0] = np.round(np.where(wet, rng.gamma(0.6, 6.0, (n, ndays)), 0.0), 4)
+    out[:, :, 1] = np.round(tmean + dtr / 2, 4)
+    out[:, :, 2] = np.round(tmean - dtr / 2, 4)
+    out[:, :, 3] = np.round(rng.uniform(1.0, 5.0, (n, ndays)), 4)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=362)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cells", type=int, default=10000, help="cells per GPU")
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default="fe_hourly", choices=sorted(WORKLOADS))
+    ap.add_argument("--cells", type=int, default=None, help="cells per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
+    wl = WORKLOADS[a.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    K, W = a.steps, max(a.warmup, 0)
+    K = a.steps if a.steps is not None else wl["steps"]
+    W = max(a.warmup if a.warmup is not None else wl["warmup"], 0)
+    cells = a.cells if a.cells is not None else wl["cells"]
     host_threads = os.cpu_count() or 1
-    workload = f"fe_hourly: FULL_ENERGY hourly, QUICK_FLUX, 3 layers, 3 nodes, 5 veg tiles, 1 band, {a.cells} cells/GPU, 1 step = 24 hourly records"
+    workload = f"{wl['desc']}, {cells} cells/GPU (BASELINE configs[{wl['config']}]), 1 step = 24 hourly records"
 
     if a.impl == "reference":
         if rank != 0:
             return
-        ncs = 256
-        v, secs = run_reference(ncs, W + K, W, host_threads, seed=1)
+        # at most 30 days per run: the forcing of 10,000 cells travels to the harness as one file (211 MB per 10 days)
+        side = wl["ref_side"]
+        Kr = min(K, 30 - min(W, 3))
+        Wr = min(W, 3)
+        v, secs, n = run_reference(a.workload, side, Wr + Kr, Wr, host_threads, seed=1)
+        sample = (f"{n} synthetic cells of the workload's configuration x {Kr * 24} hourly records ({Kr} of the {K} steps asked for; {Wr} untimed warm-up days), "
+                  f"reference CPU build (-O3), OpenMP cell loop, {host_threads} threads, harness record-loop timer {secs:.2f} s")
         line = {"impl": "reference", "metric": "cell-timesteps/s", "value": v, "unit": "cell-timesteps/s", "n_gpus": a.gpus, "steps": K, "warmup": W,
-                "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "sample": f"{ncs} cells (the base domain) x {K * 24} hourly records per run; reference CPU build, OpenMP cell loop"},
-                "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": host_threads, "kind": "reference",
-                                 "sample": f"{ncs} cells x {K * 24} records, {host_threads} OpenMP threads"},
+                "ms_per_step": secs / Kr * 1e3 * (cells / n), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "sample": sample},
+                "cpu_baseline": {"value": v, "unit": "cell-timesteps/s", "cores": host_threads, "kind": "reference", "sample": sample},
                 "e2e": {"value": v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -244,29 +311,55 @@ def main():
         torch.cuda.synchronize()
 
     seed = 1 + rank
-    dom = build_domain(a.cells, seed)
-    g = api.VicGpu(dom["options_raw"], device=local_rank)
-    L = g.L
-    g.set_veglib(dom["veglib"])
-    g.set_output_spec(dom["aggtype"])
+    dom = build_domain(cells, seed, wl["base"])
     ndays = W + K
     nrec = ndays * RECS_PER_STEP
     dmy = make_dmy(nrec)
-    # pinned host buffers: the year's forcing and one day's aggregated output
-    fbuf = torch.empty((nrec, a.cells, L.f_stride), dtype=torch.float64, pin_memory=True)
-    fnp = fbuf.numpy()
-    for day in range(ndays):
-        forcing_day(dom, day, seed, fnp[day * 24:(day + 1) * 24])
-    obuf = torch.empty((1, a.cells, L.nout), dtype=torch.float64, pin_memory=True)
+    disagg = bool(wl.get("disagg"))
+    options_raw = dom["options_raw"]
+    if disagg:
+        # the disaggregation fills the forcing window of the whole run: the run is the W + K days of this benchmark
+        opt = parse_options(options_raw)
+        opt["nrecs"] = nrec
+        options_raw = api.options_to_raw(opt)
+    g = api.VicGpu(options_raw, device=local_rank)
+    L = g.L
+    g.set_veglib(dom["veglib"])
+    g.set_output_spec(dom["aggtype"])
+    out_dtype = np.float32 if disagg else np.float64   # continental: the daily aggregates leave as the NetCDF writer stores them
+    obuf = torch.empty((1, cells, L.nout), dtype=torch.float32 if disagg else torch.float64, pin_memory=True)
     onp = obuf.numpy()
 
     def reset():
         g.set_cells(dom["cellpar"], dom["hrupar"])
         g.set_state(dom["hrurec0"])
 
+    disagg_s = None
+    if disagg:
+        gd = dict(np.load(os.path.join(ROOT, "tests", "golden", "fe_hourly_winter.npz")))
+        disagg_raw = gd["disagg_raw"].copy()   # the mtclim options of the synthetic global file (vic_b200/synth.py)
+        disagg_raw[1:6] = (0, 2001, 1, 1, ndays)  # starthour, startyear, startmonth, startday, Ndays
+        dbuf = torch.empty((cells, ndays, 4), dtype=torch.float64, pin_memory=True)
+        daily = dbuf.numpy()
+        daily[:] = synth_daily(dom, ndays, seed)
+        fnp = None
+    else:
+        # pinned host buffer: the run's hourly forcing
+        fbuf = torch.empty((nrec, cells, L.f_stride), dtype=torch.float64, pin_memory=True)
+        fnp = fbuf.numpy()
+        for day in range(ndays):
+            forcing_day(dom, day, seed, fnp[day * 24:(day + 1) * 24])
+
     # ---- leg 1: inputs resident in HBM, device-side daily aggregation, nothing copied back
     reset()
-    g.set_forcing(0, fnp)
+    if disagg:
+        barrier()
+        t0 = time.perf_counter()
+        g.disagg(disagg_raw, daily, want_host=False)
+        barrier()
+        disagg_s = time.perf_counter() - t0
+    else:
+        g.set_forcing(0, fnp)
     for s in range(W):
         g.step(s * 24, 24, dmy[s * 24:s * 24 + 25])
     g.set_profiling(True)
@@ -285,25 +378,48 @@ def main():
     hru_ms, hru_n = g.kernel_profile()
     g.set_profiling(False)
     status = g.cell_status()
-    # ---- leg 2: end to end through the C-ABI with host buffers: per step H2D of the day's forcing + D2H of the daily output
-    e2e = None
+    # ---- leg 2: end to end through the C-ABI with host buffers.  Hourly workloads: per step the H2D of the day's forcing (the upload of
+    # day d + 1 is queued before the step over day d: two device windows) + the D2H of the daily aggregates.  continental: the H2D of
+    # the daily input and its disaggregation are inside the timed region, then per step the D2H of the float32 daily aggregates.
+    e2e_wall = 0.0
     if not a.no_e2e:
         reset()
-        for s in range(W):
-            g.set_forcing(s * 24, fnp[s * 24:s * 24 + 24])
-            g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
+        if disagg:
+            barrier()
+            t0 = time.perf_counter()
+            g.disagg(disagg_raw, daily, want_host=False)
+            for s in range(W + K):
+                g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
+            barrier()
+            e2e_wall = (time.perf_counter() - t0) * K / (W + K)   # the region covers W + K days; K of them are the timed steps' share
+        else:
+            g.set_forcing(0, fnp[0:24])
+            for s in range(W):
+                g.set_forcing((s + 1) * 24, fnp[(s + 1) * 24:(s + 2) * 24])
+                g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
+            barrier()
+            t0 = time.perf_counter()
+            for s in range(W, W + K):
+                if s + 1 < W + K:
+                    g.set_forcing((s + 1) * 24, fnp[(s + 1) * 24:(s + 2) * 24])
+                g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
+            barrier()
+            e2e_wall = time.perf_counter() - t0
+    # ---- the one collective of a multi-GPU run: the gather of the last day's aggregates at the end (not in any timed region above)
+    gather_ms = None
+    if world > 1 and not a.no_e2e:
+        from vic_b200.shard import gather_cells
         barrier()
         t0 = time.perf_counter()
-        for s in range(W, W + K):
-            g.set_forcing(s * 24, fnp[s * 24:s * 24 + 24])
-            g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
+        allrows = gather_cells(onp[0], 0, cells * world)
         barrier()
-        e2e_wall = time.perf_counter() - t0
+        gather_ms = (time.perf_counter() - t0) * 1e3
+        if rank == 0:
+            assert allrows.shape[0] == cells * world
     # max over ranks (vic_b200/shard.py; covered by the world_size-2 gloo test)
     from vic_b200.shard import max_over_ranks
-    dev_s, wall_s, e2e_s = max_over_ranks([dev_ms / 1e3, wall, e2e_wall if not a.no_e2e else 0.0], device="cuda")
-    units = a.cells * RECS_PER_STEP * K * world
-    line = None
+    dev_s, wall_s, e2e_s, dis_s = max_over_ranks([dev_ms / 1e3, wall, e2e_wall, disagg_s or 0.0], device="cuda")
+    units = cells * RECS_PER_STEP * K * world
     if rank == 0:
         peaks = {}
         try:
@@ -311,54 +427,58 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6544.7))
-        recs_per_launch = (K * RECS_PER_STEP) / max(hru_n, 1)   # 1 unless VICGPU_RECBLOCK > 1
-        per_launch_bytes = ALGO_BYTES_PER_CELL_STEP * a.cells * recs_per_launch
+        per_launch_bytes = wl["algo_bytes"] * cells
         hru_avg_s = hru_ms / 1e3 / max(hru_n, 1)
         achieved = per_launch_bytes / hru_avg_s / 1e9
-        traffic, fp64_flop = None, None
+        traffic, fp64_flop, prof_cells = None, None, 10000
         try:  # DRAM bytes and FP64 flops per launch of the same kernel from the committed ncu --set full capture (profiles/)
-            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_hru_step_nn3"]
-            traffic = prof["dram_bytes_per_launch"]
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[f"{wl['kernel']}:{a.workload}"]
+            prof_cells = prof.get("cells", 10000)
+            traffic = prof["dram_bytes_per_launch"] * (cells / prof_cells)
             fp64_flop = prof.get("fp64_flop_per_launch")
         except Exception:
             pass
         fp64 = None
         if fp64_flop:
-            # SURVEY 8(d) asks for the FP64 fraction beside the HBM one: executed DFMA x 2 + DADD + DMUL per launch (ncu, per 10,000 cells)
-            # over the live launch time, against the DFMA throughput measured on this device just now
+            # SURVEY 8(d) asks for the FP64 fraction beside the HBM one: executed DFMA x 2 + DADD + DMUL per launch (ncu) over the live
+            # launch time, against the DFMA throughput measured on this device just now
             try:
                 peak_tf = api.measure_fp64_peak(local_rank)
-                ach_tf = fp64_flop * (a.cells / 10000.0) * recs_per_launch / hru_avg_s / 1e12
+                ach_tf = fp64_flop * (cells / prof_cells) / hru_avg_s / 1e12
                 fp64 = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                        "flop_per_launch": fp64_flop * (a.cells / 10000.0) * recs_per_launch,
+                        "flop_per_launch": fp64_flop * (cells / prof_cells),
                         "peak_source": "vicgpu_measure_fp64_peak (register-resident DFMA loop, best of 5, this run)"}
             except Exception as e:
                 fp64 = {"bound": "fp64", "unavailable": str(e)}
+        state_mb = g.nhru * L.hr_stride * 8 / 1e6
+        cfgd = {"workload": workload, "cells_per_gpu": cells, "hrus_per_gpu": int(g.nhru), "records_per_step": RECS_PER_STEP,
+                "l2": f"no flush: what a record touches (two {state_mb:.0f} MB state buffers, the step kernel's thread-local stack, output rows, forcing) exceeds the "
+                      "126 MB L2" + ("" if state_mb * 2 > 126 else " together") + "; the persistent model state is legitimately cache/HBM resident between records",
+                "timing": "value: sum of CUDA-event device time of the K timed vicgpu_step calls (max over ranks); wall for the same region "
+                          f"{wall_s:.3f} s", "invalid_cells": int((status != 0).sum())}
+        if disagg:
+            cfgd["disagg"] = (f"vicgpu_disagg of {ndays} days x {cells} cells incl. the H2D of the daily input: {dis_s:.3f} s = "
+                              f"{cells * ndays / max(dis_s, 1e-9) / 1e6:.2f} M cell-days/s per GPU (outside `value`, inside `e2e`)")
+        if gather_ms is not None:
+            cfgd["gather"] = f"end-of-run gather of one day's aggregates ({cells * world} cells x {L.nout} x {onp.itemsize} B) to rank 0 over NCCL: {gather_ms:.1f} ms (not in any timed region)"
         line = {"metric": "cell-timesteps/s", "value": units / dev_s, "unit": "cell-timesteps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "cells_per_gpu": a.cells, "hrus_per_gpu": int(g.nhru), "records_per_step": RECS_PER_STEP,
-                           "l2": "no flush: what a record touches (two 76 MB state buffers, 380 MB of thread-local stack, 33 MB of output rows, forcing) exceeds the 126 MB L2; "
-                                 "the persistent model state is legitimately cache/HBM resident between records",
-                           "timing": "value: sum of CUDA-event device time of the K timed vicgpu_step calls (max over ranks); wall for the same region "
-                                     f"{wall_s:.3f} s", "invalid_cells": int((status != 0).sum())},
+                "config": cfgd,
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "k_hru_step_nn3", "avg_launch_us": hru_avg_s * 1e6, "launches_timed": int(hru_n),
+                             "kernel": wl["kernel"], "avg_launch_us": hru_avg_s * 1e6, "launches_timed": int(hru_n),
                              "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6544.7",
                              "kernel_share_of_step": (hru_ms / 1e3) / dev_s if dev_s > 0 else None,
-                             "note": "latency bound (thread-local memory, dependent FP64 chains), not bandwidth bound: see profiles/r01c_summary.md and DESIGN.md section 6"},
+                             "note": "latency bound (thread-local memory, dependent FP64 chains), not bandwidth bound: see profiles/r02_summary.md and DESIGN.md section 6"},
                 "roofline_fp64": fp64,
                 "clocks": cs.summary()}
         if not a.no_e2e:
-            line["e2e"] = {"value": units / e2e_s, "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(24 * a.cells * L.f_stride * 8),
-                           "d2h_bytes_per_step": int(a.cells * L.nout * 8), "seconds": e2e_s}
+            h2d = cells * 4 * 8 if disagg else 24 * cells * L.f_stride * 8
+            line["e2e"] = {"value": units / e2e_s, "unit": "cell-timesteps/s", "h2d_bytes_per_step": int(h2d),
+                           "d2h_bytes_per_step": int(cells * L.nout * onp.itemsize), "seconds": e2e_s}
         if world == 1 and not a.no_cpu_baseline:
             try:
-                sample_days = 30
-                v, secs = run_reference(256, sample_days, 0, host_threads, seed=1)
-                line["cpu_baseline"] = {"value": v, "unit": "cell-timesteps/s", "cores": host_threads, "kind": "reference",
-                                        "sample": f"first 256 cells of the domain x {sample_days * 24} hourly records, same forcing generator; "
-                                                  f"reference build (oracle/_ref/vic_ref_harness), {host_threads} OpenMP threads, {secs:.2f} s"}
+                line["cpu_baseline"] = cpu_baseline(a.workload, host_threads)
             except Exception as e:  # the reference binary is test infrastructure; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "cell-timesteps/s", "cores": host_threads, "kind": "reference", "sample": f"unavailable: {e}"}
         print(json.dumps(line))

@@ -2,10 +2,16 @@
 //
 // The reference's NetCDF writers (WriteOutputNetCDF.c, StateIONetCDF.c) need
 // netcdf-cxx4, which this image does not have.  The oracle build leaves those two
-// files out and supplies inert definitions of the two classes here so that the
-// rest of the reference (which only news/deletes them) links.  Nothing on the
-// dist_prec -> full_energy -> surface_fluxes path calls into them.
+// files out and supplies stand-ins of the two classes here so that the rest of the
+// reference links.  Nothing on the dist_prec -> full_energy -> surface_fluxes path
+// calls into them.  The output writer's stand-in appends OutputData::aggdata of every
+// cell and variable as raw doubles to <RESULT_DIR>/<netCDF output name>.f64 at every
+// output step (the real writer narrows to float32, WriteOutputNetCDF.c:279, useless
+// for bit-level parity): that file is what tests/test_dropin.py compares between the
+// stock vicNl and the GPU drop-in vicNl_gpu.
+#include <cstdio>
 #include <stdexcept>
+#include <string>
 #include "vicNl.h"
 #include "WriteOutputNetCDF.h"
 #include "StateIONetCDF.h"
@@ -17,7 +23,14 @@ void WriteOutputNetCDF::initializeFile(const ProgramState *, const OutputData *)
 void WriteOutputNetCDF::openFile() {}
 void WriteOutputNetCDF::compressFiles() {}
 void WriteOutputNetCDF::write_data_one_cell(std::vector<OutputData *> &, out_data_file_struct *, const int, const int, const ProgramState *) {}
-void WriteOutputNetCDF::write_data_all_cells(std::vector<OutputData *> &, out_data_file_struct *, const int, const ProgramState *) {}
+void WriteOutputNetCDF::write_data_all_cells(std::vector<OutputData *> &all, out_data_file_struct *, const int output_rec, const ProgramState *state) {
+  const std::string path = std::string(state->options.NETCDF_FULL_FILE_PATH) + ".f64";
+  FILE *f = fopen(path.c_str(), output_rec == 0 ? "wb" : "ab");
+  if (!f) throw std::runtime_error("cannot open " + path);
+  for (size_t c = 0; c < all.size(); c++)
+    for (int v = 0; v < N_OUTVAR_TYPES; v++) fwrite(all[c][v].aggdata, sizeof(double), all[c][v].nelem, f);
+  fclose(f);
+}
 void WriteOutputNetCDF::write_header(OutputData *, const dmy_struct *, const ProgramState *) {}
 int WriteOutputNetCDF::getLengthOfTimeDimension(const ProgramState *) { return 0; }
 int WriteOutputNetCDF::getTimeIndex(const dmy_struct *, const int, const ProgramState *) { return 0; }

@@ -1,0 +1,179 @@
+// vicNl_gpu.cpp -- the drop-in: runModel() of the reference's vicNl (vicNl.c:390-654) with the per-cell CPU dispatch
+// (vicNl.c:506-610: put_data(rec = -nrecs), dist_prec, accumulateGlacierMassBalance for every cell and record) replaced by batched
+// calls into libvicgpu.so.  Everything else stays the reference's own code, reached through its own headers: main() and the global
+// parameter file (vicNl.c:36-212), the soil / vegetation / snow-band readers, initializeCell() with the forcing readers,
+// initialize_atmos() and initialize_model_state() (vicNl.c:295-385), the output writer and write_model_state().
+//
+// Build (oracle/Makefile target _ref/vicNl_gpu): the reference's objects + this file + -lvicgpu.  vicNl.c is compiled as it is; its
+// own runModel is made a weak symbol (objcopy --weaken-symbol) so that the definition below is the one main() calls.
+//
+// What this driver does not serve: OUTPUT_FORCE runs (vicNl.c:445-490; the disaggregation itself is vicgpu_disagg).  There is no CPU
+// fallback: without a CUDA device, or with an option the device code does not implement, the run stops with the library's message.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <vector>
+#include "vicNl.h"
+#include "WriteOutputNetCDF.h"
+#include "vicgpu_pack.h"
+
+int initializeCell(cell_info_struct& cell, filep_struct filep, dmy_struct* dmy, filenames_struct filenames, const ProgramState* state);  // vicNl.c:295
+
+static void gpu_check(int rc, const char* what) {
+  if (rc == VICGPU_OK) return;
+  char msg[MAXSTRING];
+  snprintf(msg, sizeof(msg), "libvicgpu: %s failed (%d): %s", what, rc, vicgpu_last_error());
+  vicerror(msg);
+}
+
+void runModel(std::vector<cell_info_struct>& cell_data_structs, filep_struct filep, filenames_struct filenames,
+              out_data_file_struct* out_data_files_template, OutputData* out_data_list, dmy_struct* dmy, ProgramState* state) {
+  if (state->options.OUTPUT_FORCE) vicerror("vicNl_gpu: OUTPUT_FORCE runs are not wired into this driver (the disaggregation itself is vicgpu_disagg)");
+  std::vector<OutputData*> current_output_data;
+  WriteOutputNetCDF* outputwriter = new WriteOutputNetCDF(state);
+  outputwriter->openFile();
+  const int ncell = (int)cell_data_structs.size();
+  const int nrecs = state->global_param.nrecs;
+
+  // ---- per-cell initialisation, as vicNl.c:420-445
+  for (int c = 0; c < ncell; c++) {
+    if (initializeCell(cell_data_structs[c], filep, dmy, filenames, state) == ERROR) cell_data_structs[c].isValid = FALSE;
+    copy_data_file_format(out_data_files_template, cell_data_structs[c].outputFormat->dataFiles, state);
+    make_out_files(&filep, &filenames, &cell_data_structs[c].soil_con, cell_data_structs[c].outputFormat, state);
+    copy_output_data(current_output_data, out_data_list, state);
+  }
+  fprintf(stderr, "Running Model on the GPU...\n");
+  auto t_start = std::chrono::system_clock::now();
+
+  // ---- hand the domain to the device
+  vicgpu_options opt;
+  vicgpu_pack_options(state, &opt);
+  vicgpu_handle* h = NULL;
+  const char* dev = getenv("VICGPU_DEVICE");
+  gpu_check(vicgpu_create(&h, &opt, dev ? atoi(dev) : 0), "vicgpu_create");
+  vicgpu_layout L;
+  gpu_check(vicgpu_get_layout(h, &L), "vicgpu_get_layout");
+  const int nout = L.out_off[VICGPU_N_OUTVARS];
+  {
+    std::vector<double> veglib;
+    vicgpu_pack_veglib(state, &L, veglib);
+    gpu_check(vicgpu_set_veglib(h, (int)(veglib.size() / L.vl_stride), veglib.data()), "vicgpu_set_veglib");
+  }
+  int nhru = 0;
+  for (int c = 0; c < ncell; c++) nhru += (int)cell_data_structs[c].prcp.hruList.size();
+  std::vector<double> hrurec((size_t)nhru * L.hr_stride);
+  std::vector<int> status(ncell);
+  {
+    std::vector<double> cellpar((size_t)ncell * L.cp_stride), hrupar((size_t)nhru * HP_N);
+    int k = 0;
+    for (int c = 0; c < ncell; c++) {
+      vicgpu_pack_cellpar(cell_data_structs[c].soil_con, &L, &cellpar[(size_t)c * L.cp_stride]);
+      status[c] = cell_data_structs[c].isValid ? 0 : ERROR;
+      for (size_t j = 0; j < cell_data_structs[c].prcp.hruList.size(); j++, k++) {
+        vicgpu_pack_hrupar(cell_data_structs[c].prcp.hruList[j], c, &hrupar[(size_t)k * HP_N]);
+        vicgpu_pack_hrurec(cell_data_structs[c].prcp.hruList[j], &L, &hrurec[(size_t)k * L.hr_stride]);
+      }
+    }
+    gpu_check(vicgpu_set_cells(h, ncell, cellpar.data(), nhru, hrupar.data()), "vicgpu_set_cells");
+  }
+  gpu_check(vicgpu_set_cell_status(h, status.data()), "vicgpu_set_cell_status");
+  {
+    std::vector<int> aggtype(N_OUTVAR_TYPES);
+    for (int v = 0; v < N_OUTVAR_TYPES; v++) aggtype[v] = out_data_list[v].aggtype;
+    gpu_check(vicgpu_set_output_spec(h, aggtype.data()), "vicgpu_set_output_spec");
+  }
+  gpu_check(vicgpu_set_state(h, hrurec.data()), "vicgpu_set_state");
+
+  // the record after which the state file is written (vicNl.c:569-577)
+  int state_rec = -1;
+  if (state->options.SAVE_STATE == TRUE)
+    for (int rec = 0; rec < nrecs; rec++)
+      if (dmy[rec].year == state->global_param.stateyear && dmy[rec].month == state->global_param.statemonth && dmy[rec].day == state->global_param.stateday &&
+          (rec + 1 == nrecs || dmy[rec + 1].day != state->global_param.stateday))
+        state_rec = rec;
+
+  // ---- time loop: one call per block of records instead of nrecs x ncell calls of dist_prec()
+  // a block holds at most ~256 MB of packed forcing and never runs past the state-file record
+  const size_t per_rec = (size_t)ncell * L.f_stride;
+  const int Bmax = (int)std::max<size_t>(1, std::min<size_t>((size_t)nrecs, ((size_t)256 << 20) / (per_rec * sizeof(double))));
+  std::vector<double> forcing((size_t)Bmax * per_rec), agg;
+  std::vector<int> dmy5((size_t)(Bmax + 1) * 5), out_recs;
+  for (int rec0 = 0; rec0 < nrecs;) {
+    int n = std::min(Bmax, nrecs - rec0);
+    if (state_rec >= rec0 && state_rec < rec0 + n) n = state_rec - rec0 + 1;
+    for (int r = 0; r < n; r++)
+      for (int c = 0; c < ncell; c++) vicgpu_pack_forcing(cell_data_structs[c].atmos[rec0 + r], &L, &forcing[((size_t)r * ncell + c) * L.f_stride]);
+    for (int r = 0; r <= n; r++) {  // make_dmy() fills nrecs + 1 entries (make_dmy.c:105-127)
+      const dmy_struct& d = dmy[rec0 + r];
+      int* p = &dmy5[(size_t)r * 5];
+      p[0] = d.day; p[1] = d.day_in_year; p[2] = d.hour; p[3] = d.month; p[4] = d.year;
+    }
+    // the output steps inside the block: state->step_count runs exactly as in vicNl.c:512, 596-609
+    out_recs.clear();
+    for (int r = 0; r < n; r++) {
+      state->step_count++;
+      if (state->step_count == state->out_step_ratio) {
+        out_recs.push_back(rec0 + r);
+        state->step_count = 0;
+      }
+    }
+    agg.resize(std::max<size_t>(1, out_recs.size()) * (size_t)ncell * nout);
+    gpu_check(vicgpu_set_forcing(h, rec0, n, forcing.data()), "vicgpu_set_forcing");
+    gpu_check(vicgpu_step(h, rec0, n, dmy5.data(), NULL, out_recs.empty() ? NULL : agg.data()), "vicgpu_step");
+    // cells the step invalidated (dist_prec would have returned ERROR, vicNl.c:545-559)
+    gpu_check(vicgpu_get_cell_status(h, status.data()), "vicgpu_get_cell_status");
+    for (int c = 0; c < ncell; c++)
+      if (status[c] != 0 && cell_data_structs[c].isValid) {
+        cell_data_structs[c].isValid = FALSE;
+        if (state->options.CONTINUEONERROR == TRUE) {
+          fprintf(stderr, "Error processing cell %d (method dist_prec) in records %d-%d.  Cell has been marked as invalid and will be skipped for remainder of model run.  "
+                          "An incomplete output file has been generated, check your inputs before re-running the simulation.\n",
+                  cell_data_structs[c].soil_con.gridcel, rec0, rec0 + n - 1);
+        } else {
+          sprintf(cell_data_structs[c].ErrStr, "Error processing cell %d (method dist_prec) in records %d-%d so the simulation has ended. Check your inputs before re-running the simulation.\n",
+                  cell_data_structs[c].soil_con.gridcel, rec0, rec0 + n - 1);
+          vicerror(cell_data_structs[c].ErrStr);
+        }
+      }
+    // the unchanged output writer consumes OutputData::aggdata (vicNl.c:596-598)
+    for (size_t s = 0; s < out_recs.size(); s++) {
+      if (out_recs[s] < state->global_param.skipyear) continue;
+      for (int c = 0; c < ncell; c++) vicgpu_unpack_outdata(current_output_data[c], &L, &agg[(s * ncell + c) * nout], true);
+      outputwriter->write_data_all_cells(current_output_data, out_data_files_template, out_recs[s] / state->out_step_ratio, state);
+    }
+    // the state file: pull the HRU records (and the glacier mass-balance curves) back into the reference's structs
+    if (state_rec == rec0 + n - 1) {
+      gpu_check(vicgpu_get_state(h, hrurec.data()), "vicgpu_get_state");
+      std::vector<double> gmb((size_t)ncell * 4);
+      gpu_check(vicgpu_get_glacier_fit(h, gmb.data()), "vicgpu_get_glacier_fit");
+      int k = 0;
+      for (int c = 0; c < ncell; c++) {
+        for (size_t j = 0; j < cell_data_structs[c].prcp.hruList.size(); j++, k++)
+          vicgpu_unpack_hrurec(cell_data_structs[c].prcp.hruList[j], &L, &hrurec[(size_t)k * L.hr_stride]);
+        cell_data_structs[c].gmbEquation.b0 = gmb[(size_t)c * 4 + 0];
+        cell_data_structs[c].gmbEquation.b1 = gmb[(size_t)c * 4 + 1];
+        cell_data_structs[c].gmbEquation.b2 = gmb[(size_t)c * 4 + 2];
+        cell_data_structs[c].gmbEquation.fitError = gmb[(size_t)c * 4 + 3];
+        if (cell_data_structs[c].isValid) write_model_state(&cell_data_structs[c], filenames.statefile, state);
+      }
+    }
+    rec0 += n;
+  }
+  gpu_check(vicgpu_destroy(h), "vicgpu_destroy");
+  std::chrono::duration<double> elapsed = std::chrono::system_clock::now() - t_start;
+  fprintf(stderr, "\nVIC model run done. Model execution time (GPU): %.3f seconds\n", elapsed.count());
+
+  // ---- clean-up, as vicNl.c:632-652
+  if (state->param_set.FORCE_FORMAT[0] == NETCDF) close_files(&filep, &filenames, state->options.COMPRESS, state);
+  for (int c = 0; c < ncell; c++) {
+    cell_data_structs[c].writeDebug.cleanup(cell_data_structs[c].prcp.hruList.size(), state);
+    free_atmos(state->global_param.nrecs, &cell_data_structs[c].atmos);
+    delete cell_data_structs[c].outputFormat;
+    free_vegcon(cell_data_structs[c]);
+    free(cell_data_structs[c].soil_con.AreaFract);
+    free(cell_data_structs[c].soil_con.BandElev);
+    free(cell_data_structs[c].soil_con.Tfactor);
+    free(cell_data_structs[c].soil_con.Pfactor);
+    free(cell_data_structs[c].soil_con.AboveTreeLine);
+  }
+}

@@ -230,7 +230,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
             for (cl, cvv, zones, band) in tiles:
                 z = " ".join(f"{d:.2f} {fr:.2f}" for d, fr in zones)
                 veg_lines.append(f"  {cl} {cvv:.4f} {z} {band}")
-            cells.append(dict(id=cid, lat=la, lon=lo, elev=elev))
+            cells.append(dict(id=cid, lat=la, lon=lo, elev=elev, avg_temp=avg_temp))
 
             # --- daily forcing
             if forcing:
