@@ -44,9 +44,11 @@ int main(int argc, char** argv) {
   if (argc < 3) die("usage: vicport case.bin result.bin [--nrec N] [--binned]");
   int nrec_limit = -1;
   bool binned = false;  // keep the HRU tables in the device's binned row order (bin_hrus) instead of the caller's
+  int roles = 0;        // reduce the cell outputs as the device does, three variable groups side by side (vic_engine.cuh cell_output)
   for (int i = 3; i < argc; i++) {
     if (!strcmp(argv[i], "--nrec") && i + 1 < argc) nrec_limit = atoi(argv[++i]);
     if (!strcmp(argv[i], "--binned")) binned = true;
+    if (!strcmp(argv[i], "--roles")) roles = 1;
   }
   std::map<std::string, CaseArray> cs;
   if (!case_read(argv[1], cs)) die("cannot read case file");
@@ -110,14 +112,14 @@ int main(int argc, char** argv) {
       for (int k = 0; k < L.f_stride; k++) frec[(size_t)k * ncell + c] = forcing[((size_t)rec * ncell + c) * L.f_stride + k];
     Dmy d = {dmy[rec * 5 + 0], dmy[rec * 5 + 1], dmy[rec * 5 + 2], dmy[rec * 5 + 3], dmy[rec * 5 + 4]};
     if (rec == 0)
-      for (int c = 0; c < ncell; c++) cell_output(o, t, nullptr, c, -1, step_count);
+      for (int c = 0; c < ncell; c++) cell_output(o, t, nullptr, c, -1, step_count, roles);
     GlacAccum ga = glacier_accum_flags(o, &dmy[rec * 5], &dmy[(rec + 1) * 5], rec, &started);
     if (o.Nnode <= 3) run_record<3>(&o, t, frec.data(), d, rec, ga);
     else if (o.Nnode <= 10) run_record<10>(&o, t, frec.data(), d, rec, ga);
     else run_record<VICGPU_MAX_NODES>(&o, t, frec.data(), d, rec, ga);
     if (ga.enabled && ga.reset_after)
       for (int c = 0; c < ncell; c++) cell_gmb(&o, t, c);
-    for (int c = 0; c < ncell; c++) cell_output(o, t, frec.data(), c, rec, step_count);
+    for (int c = 0; c < ncell; c++) cell_output(o, t, frec.data(), c, rec, step_count, roles);
     to_rowmajor(out.data(), ncell, nout, &out_all[(size_t)rec * ncell * nout]);
     while (nd < dump_recs.size() && dump_recs[nd] < rec) nd++;
     if (nd < dump_recs.size() && dump_recs[nd] == rec) {

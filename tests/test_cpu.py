@@ -44,10 +44,10 @@ def _port_for(flavour, root, base):
     return p
 
 
-def _run_port(port, g, tmp_path, keys=INPUT_KEYS):
+def _run_port(port, g, tmp_path, keys=INPUT_KEYS, extra=()):
     case, out = str(tmp_path / "case.bin"), str(tmp_path / "res.bin")
     write_case(case, {k: g[k] for k in keys})
-    subprocess.run([port, case, out], check=True)
+    subprocess.run([port, case, out, *extra], check=True)
     return read_case(out)
 
 
@@ -70,6 +70,20 @@ def test_port_reproduces_reference_golden(name, flavour, root, tmp_path):
     assert column_report(res["out"][-24:], g["out_ref_tail"], L.out_names)[0][1] == 0.0
     assert integer_mismatches(res["hrurec"], g["hrurec_ref"], L.hru_names) == {}
     assert np.array_equal(res["status"], g["status_ref"])
+    assert np.array_equal(res["balance"], g["balance_ref"], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_cell_output_in_three_variable_groups_is_the_same_reduction(name, root, tmp_path):
+    """the device reduces a cell's outputs with three threads, one per group of output variables (water balance / energy balance /
+    per band), each variable still summed by one thread in hruList order; the host emulation of exactly that (--roles: three passes,
+    rows combined by out_var_group) and the device's binned row order (--binned) must reproduce every bit of all 184 variables"""
+    g = load_golden(name)
+    res = _run_port(_port_for("", root, "vicport"), g, tmp_path, extra=("--roles", "--binned"))
+    L = layout_from_options(parse_options(g["options_raw"]))
+    assert np.array_equal(res["agg"][1:], g["agg_ref"][1:], equal_nan=True), column_report(res["agg"][1:], g["agg_ref"][1:], L.out_names)[:3]
+    assert np.array_equal(res["out"][:24], g["out_ref_head"], equal_nan=True)
+    assert np.array_equal(res["out"][-24:], g["out_ref_tail"], equal_nan=True)
     assert np.array_equal(res["balance"], g["balance_ref"], equal_nan=True)
 
 

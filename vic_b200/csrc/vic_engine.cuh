@@ -106,44 +106,101 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   dg[2 * nh] = d.out_snow * hp.Cv;
 }
 
-// put_data of one cell (vic_output.cuh).  Host port: the row is built in the output table itself.  Device: one thread per cell, a
-// few hundred one-warp blocks that all fit beside the resident step blocks (the kernel runs as a programmatic dependent of the next
-// record's step, vicgpu_api.cu); the row is built in a thread-local array (a read-modify-write chain through global memory per
-// statement serialises on the L2 latency) and the HRU records are read in place through the read-only path.
-// Measured alternatives (profiles/r02_summary.md): a warp per cell with the records staged in shared memory and lane 0 reducing them
-// is faster alone (289 us against 352 us serialised at 10,000 cells) but needs 16 resident warps per SM to get there, which do not
-// fit beside the step blocks: the record time went from 570 to 720 us; staging each record in a thread-local array first
-// (16 loads in flight) made the kernel slower (384 us) and the record time 690-940 us.
-#define VIC_OUT_LOCAL_MAX 512  // doubles of thread-local row (the three-node layout has 365 columns, ten nodes 400)
-VIC_HDI void cell_output(const Opts& o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count) {
+// put_data of one cell (vic_output.cuh), host port: one call does everything, the row is built in the output table itself.
+// roles != 0 emulates the device's three-thread reduction (below) on the host: three passes with separate rows, combined by variable
+// ownership -- the same arithmetic, and the check that out_var_group() agrees with what put_data_hru writes (oracle/vicport --roles).
+VIC_HDI void cell_output(const Opts& o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count, int roles = 0) {
   if (rec >= 0 && t.fail_rec[cell] <= rec) return;  // the reference stops touching an invalid cell (vicNl.c:521): its row keeps the last values
-  const size_t nc = (size_t)t.ncell;
-  const int nout = o.L.out_off[VICGPU_N_OUTVARS];
+  const size_t nc = (size_t)t.ncell, nh = (size_t)t.nhru;
+  const int nout = o.L.out_off[VICGPU_N_OUTVARS], hs = o.L.hr_stride;
   CellPar cp{Col{t.cellpar + cell, nc}, &o.L};
   VegLib vl{t.veglib, &o.L};
   Forcing f{Col{forcing_rec ? forcing_rec + cell : nullptr, nc}, o.L.f_nslot};
-  RowRW gout{t.out + cell, nc}, agg{t.agg + cell, nc};
-#if defined(__CUDA_ARCH__)
-  double row[VIC_OUT_LOCAL_MAX];
-  RowLocal out{row};
-#else
-  RowRW out = gout;
-#endif
+  RowRW out{t.out + cell, nc}, agg{t.agg + cell, nc};
   PutDataCtx pc;
-  for (int k = 0; k < nout; k++) out[k] = 0;
   const int h0 = t.cell_h0[cell], h1 = t.cell_h0[cell + 1];
-  put_data_begin(o, cp, vl, &f, t.hrupar, t.hdiag_out, (size_t)t.nhru, t.slot_of_hru, h0, h1, rec, out, pc);
-  for (int hh = h0; hh < h1; hh++) {
-    const int h = t.slot_of_hru ? t.slot_of_hru[hh] : hh;
-    put_data_hru(o, cp, vl, RecTile{t.hrurec_out + hr_off(h, o.L.hr_stride)}, t.hrupar, (size_t)t.nhru, h, out, pc);
+  if (!roles) {
+    for (int k = 0; k < nout; k++) out[k] = 0;
+    put_data_begin(o, cp, vl, &f, t.hrupar, t.hdiag_out, nh, t.slot_of_hru, h0, h1, rec, out, pc);
+    for (int hh = h0; hh < h1; hh++) {
+      const int h = t.slot_of_hru ? t.slot_of_hru[hh] : hh;
+      put_data_hru<PD_ALL>(o, cp, vl, RecTile{t.hrurec_out + hr_off(h, hs)}, t.hrupar, nh, h, out, pc);
+    }
+  } else {
+#if !defined(__CUDA_ARCH__)
+    std::vector<double> rows((size_t)3 * nout, 0.0);
+    PutDataCtx pcs[3];
+    for (int g = 0; g < 3; g++) {
+      RowLocal row{rows.data() + (size_t)g * nout};
+      put_data_begin(o, cp, vl, &f, t.hrupar, t.hdiag_out, nh, t.slot_of_hru, h0, h1, rec, row, pcs[g]);
+      for (int hh = h0; hh < h1; hh++) {
+        const int h = t.slot_of_hru ? t.slot_of_hru[hh] : hh;
+        const RecTile hr{t.hrurec_out + hr_off(h, hs)};
+        if (g == 0) put_data_hru<PD_WB>(o, cp, vl, hr, t.hrupar, nh, h, row, pcs[g]);
+        else if (g == 1) put_data_hru<PD_EB>(o, cp, vl, hr, t.hrupar, nh, h, row, pcs[g]);
+        else put_data_hru<PD_BAND>(o, cp, vl, hr, t.hrupar, nh, h, row, pcs[g]);
+      }
+    }
+    for (int v = 0; v < VICGPU_N_OUTVARS; v++) {
+      const int grp = out_var_group(v), g = grp == PD_WB ? 0 : grp == PD_EB ? 1 : 2;
+      for (int i = 0; i < o.L.out_nelem[v]; i++) out[o.L.out_off[v] + i] = rows[(size_t)g * nout + o.L.out_off[v] + i];
+    }
+    pc = pcs[0];
+#endif
   }
   put_data_finish(o, cp, rec, RowRW{t.carry + cell, nc}, out, pc);
-#if defined(__CUDA_ARCH__)
-  for (int k = 0; k < nout; k++) gout[k] = row[k];
-#endif
   if (rec < 0) return;
-  put_data_aggregate(o, t.aggtype, step_count, out, agg);
+  put_data_aggregate_vars(o, t.aggtype, out, agg, 0, 1);
+  put_data_aggregate_tail(o, step_count, agg);
 }
+
+#if defined(__CUDACC__)
+// Device: THREE threads per cell, in three warps of a 96-thread block that share 32 cells.  Every output variable is a sum over the
+// cell's HRUs in hruList order -- a sequential chain by definition -- but the variables are independent of each other: warp 0
+// reduces the water-balance terms, warp 1 the energy-balance terms, warp 2 the per-band terms (put_data_hru<PD_*>; each variable is
+// still summed by ONE thread, in the reference's order).  Each thread builds its part of the row in a thread-local array (a
+// read-modify-write chain through global memory per statement serialises on the L2 latency), writes the variables it owns to the
+// output table, and after a block barrier the first thread of the cell runs the derived variables and balance checks on the whole
+// row; the temporal aggregation is dealt over the three threads again.  The kernel runs as a programmatic dependent of the next
+// record's step (vicgpu_api.cu) on the SMs the step grid leaves idle, so what counts is its duration with few warps: one thread per
+// cell took 375 us alone and bounded the record at 590 us (profiles/r02_summary.md).
+#define VIC_OUT_LOCAL_MAX 512  // doubles of thread-local row (the three-node layout has 365 columns, ten nodes 400)
+__device__ __forceinline__ void cell_output_role(const Opts& o, const Tables& t, const double* forcing_rec, int cell, int rec, int step_count, int role, bool live) {
+  const size_t nc = (size_t)t.ncell, nh = (size_t)t.nhru;
+  const int nout = o.L.out_off[VICGPU_N_OUTVARS], hs = o.L.hr_stride;
+  const int c = live ? cell : 0;
+  CellPar cp{Col{t.cellpar + c, nc}, &o.L};
+  VegLib vl{t.veglib, &o.L};
+  Forcing f{Col{forcing_rec ? forcing_rec + c : nullptr, nc}, o.L.f_nslot};
+  RowRW gout{t.out + c, nc}, agg{t.agg + c, nc};
+  PutDataCtx pc;
+  if (live) {
+    double row[VIC_OUT_LOCAL_MAX];
+    RowLocal out{row};
+    for (int k = 0; k < nout; k++) row[k] = 0;
+    const int h0 = t.cell_h0[c], h1 = t.cell_h0[c + 1];
+    put_data_begin(o, cp, vl, &f, t.hrupar, t.hdiag_out, nh, t.slot_of_hru, h0, h1, rec, out, pc);
+    for (int hh = h0; hh < h1; hh++) {
+      const int h = t.slot_of_hru ? t.slot_of_hru[hh] : hh;
+      const RecTile hr{t.hrurec_out + hr_off(h, hs)};
+      if (role == 0) put_data_hru<PD_WB>(o, cp, vl, hr, t.hrupar, nh, h, out, pc);
+      else if (role == 1) put_data_hru<PD_EB>(o, cp, vl, hr, t.hrupar, nh, h, out, pc);
+      else put_data_hru<PD_BAND>(o, cp, vl, hr, t.hrupar, nh, h, out, pc);
+    }
+    const int mine = role == 0 ? PD_WB : role == 1 ? PD_EB : PD_BAND;
+    for (int v = 0; v < VICGPU_N_OUTVARS; v++)
+      if (out_var_group(v) == mine)
+        for (int i = 0; i < o.L.out_nelem[v]; i++) gout[o.L.out_off[v] + i] = row[o.L.out_off[v] + i];
+  }
+  __syncthreads();  // the whole row of every cell of the block is in the output table
+  if (live && role == 0) put_data_finish(o, cp, rec, RowRW{t.carry + c, nc}, gout, pc);
+  if (rec < 0) return;  // (uniform)
+  __syncthreads();
+  if (live) put_data_aggregate_vars(o, t.aggtype, gout, agg, role, 3);
+  __syncthreads();
+  if (live && role == 0) put_data_aggregate_tail(o, step_count, agg);
+}
+#endif
 
 // the cell's mass-balance curve at the end of an accumulation interval (GlacierMassBalanceResult.c:35-72): one point per band
 // elevation that holds glacier HRUs, cumulative balances of HRUs at the same elevation added up, in hruList order

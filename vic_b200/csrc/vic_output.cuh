@@ -101,8 +101,13 @@ VIC_HD void put_data_begin(const Opts& o, const CellPar& cp, const VegLib& vl, c
   }
 }
 
-// Part 2, once per HRU in hruList order: h is the HRU's table row, hr its record
-template <class Rec, class OutRow>
+// Part 2, once per HRU in hruList order: h is the HRU's table row, hr its record.
+// G selects which groups of output variables are accumulated (bits): PD_WB the water-balance terms (collect_wb_terms), PD_EB the
+// energy-balance terms of the cell (collect_eb_terms), PD_BAND the per-band terms.  Every output variable belongs to exactly one
+// group (out_var_group below), so three threads can reduce the three groups of a cell side by side -- each variable is still summed
+// by ONE thread over the HRUs in hruList order -- and PD_ALL in one thread is put_data as the reference runs it.
+enum { PD_WB = 1, PD_EB = 2, PD_BAND = 4, PD_ALL = 7 };
+template <int G, class Rec, class OutRow>
 VIC_HD void put_data_hru(const Opts& o, const CellPar& cp, const VegLib& vl, Rec hr, const double* __restrict__ hpar, size_t nhru, int h, OutRow out,
                          PutDataCtx& pc) {
   const vicgpu_layout& L = o.L;
@@ -118,16 +123,18 @@ VIC_HD void put_data_hru(const Opts& o, const CellPar& cp, const VegLib& vl, Rec
     const double ThisTreeAdjust = pc.TreeAdjustFactor[band];
     const bool above = cp.band(CB_AboveTreeLine, band) != 0.0;
     if (!(ThisAreaFract > 0. && (isArtBare || (!above || (above && !overstory))))) return;
-    OUT(ELEV_BAND, band) = cp.band(CB_BandElev, band);
+    if (G & PD_BAND) OUT(ELEV_BAND, band) = cp.band(CB_BandElev, band);
     const double mu = HR(HR_H_mu);
     const double swq = HR(HR_S_swq);
-    if (HasVeg) pc.cv_veg += Cv * mu * ThisTreeAdjust;
-    else pc.cv_baresoil += Cv * mu * ThisTreeAdjust;
-    if (overstory) pc.cv_overstory += Cv * mu * ThisTreeAdjust;
-    if (swq > 0.0) pc.cv_snow += Cv * mu * ThisTreeAdjust;
-    if (HasGlac) pc.cv_glacier += Cv * mu * ThisTreeAdjust;
+    if (G & PD_WB) {  // the area sums the derived variables of put_data_finish divide by (the thread that reduces PD_WB runs it)
+      if (HasVeg) pc.cv_veg += Cv * mu * ThisTreeAdjust;
+      else pc.cv_baresoil += Cv * mu * ThisTreeAdjust;
+      if (overstory) pc.cv_overstory += Cv * mu * ThisTreeAdjust;
+      if (swq > 0.0) pc.cv_snow += Cv * mu * ThisTreeAdjust;
+      if (HasGlac) pc.cv_glacier += Cv * mu * ThisTreeAdjust;
+    }
     // ---- water balance terms
-    {
+    if (G & PD_WB) {
       const double AreaFactor = Cv * mu * ThisTreeAdjust * 1.0;
       double tmp_evap = 0.0;
       for (int l = 0; l < NL; l++) tmp_evap += HR(VICGPU_HR_LAYER(&L, HRL_evap, l));
@@ -209,9 +216,9 @@ VIC_HD void put_data_hru(const Opts& o, const CellPar& cp, const VegLib& vl, Rec
       }
     }
     // ---- energy balance terms
-    {
+    const bool snowing = HR(HR_S_snow) != 0.0;
+    if (G & PD_EB) {
       const double AreaFactor = Cv * ThisTreeAdjust * 1.0;
-      const bool snowing = HR(HR_S_snow) != 0.0;
       if (o.FROZEN_SOIL) {
         for (int i = 0; i < VICGPU_NFRONTS; i++) {
           const double fd = HR(VICGPU_HR_FRONT(&L, HRF_fdepth, i)), td = HR(VICGPU_HR_FRONT(&L, HRF_tdepth, i));
@@ -268,7 +275,9 @@ VIC_HD void put_data_hru(const Opts& o, const CellPar& cp, const VegLib& vl, Rec
         OUT(GLAC_FLUX, 0) += HR(HR_E_glacier_flux) * AreaFactor;
         OUT(GLAC_MELT_ENERGY, 0) += HR(HR_E_glacier_melt_energy) * AreaFactor;
       }
-      // band-specific
+    }
+    // ---- band-specific terms
+    if (G & PD_BAND) {
       const double bandFactor = Cv * 1.0 / ThisAreaFract;
       OUT(AREA_BAND, band) += (Cv * 1.0);
       OUT(SWE_BAND, band) += swq * bandFactor * 1000.;
@@ -306,6 +315,27 @@ VIC_HD void put_data_hru(const Opts& o, const CellPar& cp, const VegLib& vl, Rec
         OUT(GLAC_OUTFLOW_BAND, band) += HR(HR_G_outflow) * 1000.;
       }
     }
+  }
+}
+
+// the group put_data_hru accumulates an output variable in; variables no HRU term feeds (forcing, derived, lake terms) count as PD_WB
+VIC_HD int out_var_group(int v) {
+  switch (v) {
+#define X(n) case VOUT_##n:
+    X(FDEPTH) X(TDEPTH) X(SURF_FROST_FRAC) X(BARESOILT) X(VEGT) X(SURF_TEMP) X(SOIL_TNODE) X(SURFT_FBFLAG) X(SOILT_FBFLAG) X(SNOWT_FBFLAG)
+    X(TFOL_FBFLAG) X(TCAN_FBFLAG) X(GLAC_TSURF_FBFLAG) X(NET_SHORT) X(NET_LONG) X(IN_LONG) X(ALBEDO) X(LATENT) X(LATENT_SUB) X(SENSIBLE)
+    X(GRND_FLUX) X(DELTAH) X(FUSION) X(ENERGY_ERROR) X(RAD_TEMP) X(DELTACC) X(ADVECTION) X(SNOW_FLUX) X(RFRZ_ENERGY) X(MELT_ENERGY)
+    X(ADV_SENS) X(GLAC_SURF_TEMP) X(GLAC_DELTACC) X(GLAC_FLUX) X(GLAC_MELT_ENERGY)
+    return PD_EB;
+    X(ELEV_BAND) X(AREA_BAND) X(SWE_BAND) X(SNOW_DEPTH_BAND) X(SNOW_CANOPY_BAND) X(SNOW_MELT_BAND) X(SNOW_COVER_BAND) X(DELTACC_BAND)
+    X(ADVECTION_BAND) X(SNOW_FLUX_BAND) X(RFRZ_ENERGY_BAND) X(MELT_ENERGY_BAND) X(ADV_SENS_BAND) X(SNOW_SURFT_BAND) X(SNOW_PACKT_BAND)
+    X(LATENT_SUB_BAND) X(NET_SHORT_BAND) X(NET_LONG_BAND) X(ALBEDO_BAND) X(LATENT_BAND) X(SENSIBLE_BAND) X(GRND_FLUX_BAND)
+    X(GLAC_DELTACC_BAND) X(GLAC_FLUX_BAND) X(GLAC_WAT_STOR_BAND) X(GLAC_AREA_BAND) X(GLAC_MBAL_BAND) X(GLAC_IMBAL_BAND) X(GLAC_ACCUM_BAND)
+    X(GLAC_MELT_BAND) X(GLAC_SUB_BAND) X(GLAC_INFLOW_BAND) X(GLAC_OUTFLOW_BAND)
+    return PD_BAND;
+#undef X
+    default:
+      return PD_WB;
   }
 }
 
@@ -394,14 +424,11 @@ VIC_HD void put_data_finish(const Opts& o, const CellPar& cp, int rec, RowRW car
   }
 }
 
-// Part 4: temporal aggregation (put_data.c:664-680), resistances from the aggregated conductances, ALMA unit conversions at an
-// output step
+// Part 4: temporal aggregation (put_data.c:664-680) of the variables v0, v0 + vstep, ... (independent of each other) ...
 template <class OutRow, class AggRow>
-VIC_HD void put_data_aggregate(const Opts& o, const int* aggtype, int step_count, OutRow out, AggRow agg) {
+VIC_HD void put_data_aggregate_vars(const Opts& o, const int* aggtype, OutRow out, AggRow agg, int v0, int vstep) {
   const vicgpu_layout& L = o.L;
-  const int NL = VICGPU_NLAYER;
-  const int dt_sec = o.dt * SECPHOUR;
-  for (int v = 0; v < VICGPU_N_OUTVARS; v++) {
+  for (int v = v0; v < VICGPU_N_OUTVARS; v += vstep) {
     const int ne = L.out_nelem[v];
     const int off = L.out_off[v];
     const int at = aggtype[v];
@@ -411,6 +438,14 @@ VIC_HD void put_data_aggregate(const Opts& o, const int* aggtype, int step_count
       else if (at == VICGPU_AGG_AVG) agg[off + i] += out[off + i] / o.out_step_ratio;
     }
   }
+}
+// ... and what follows once all variables are aggregated: resistances from the aggregated conductances, ALMA unit conversions at an
+// output step
+template <class AggRow>
+VIC_HD void put_data_aggregate_tail(const Opts& o, int step_count, AggRow agg) {
+  const vicgpu_layout& L = o.L;
+  const int NL = VICGPU_NLAYER;
+  const int dt_sec = o.dt * SECPHOUR;
   agg[L.out_off[VOUT_AERO_RESIST]] = 1 / agg[L.out_off[VOUT_AERO_COND]];
   agg[L.out_off[VOUT_AERO_RESIST1]] = 1 / agg[L.out_off[VOUT_AERO_COND1]];
   agg[L.out_off[VOUT_AERO_RESIST2]] = 1 / agg[L.out_off[VOUT_AERO_COND2]];

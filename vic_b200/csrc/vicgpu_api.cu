@@ -148,12 +148,14 @@ __global__ void k_cell_gmb(const Opts* __restrict__ o, Tables t) {
   cell_gmb(o, t, c);
 }
 
-// one thread per cell (vic_engine.cuh cell_output); the options travel as a kernel parameter: the output offsets
-// L.out_off[VOUT_x] are then operands in the constant bank instead of a dependent global load per statement
-__global__ void __launch_bounds__(128) k_cell_output(const __grid_constant__ Opts o, Tables t, const double* __restrict__ forcing_rec, int rec, int step_count,
-                                                     int wait_primary) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < t.ncell) cell_output(o, t, forcing_rec, c, rec, step_count);
+// three threads per cell in three warps of a 96-thread block (vic_engine.cuh cell_output_role); the options travel as a kernel
+// parameter: the output offsets L.out_off[VOUT_x] are then operands in the constant bank instead of a dependent global load each
+__global__ void __launch_bounds__(96) k_cell_output(const __grid_constant__ Opts o, Tables t, const double* __restrict__ forcing_rec, int rec, int step_count,
+                                                    int wait_primary) {
+  const int role = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool live = c < t.ncell && !(rec >= 0 && t.fail_rec[c] <= rec);
+  cell_output_role(o, t, forcing_rec, c, rec, step_count, role, live);
   // Launched as a programmatic dependent of step(rec + 1) (vicgpu_step), this grid starts while that step is still running.  It
   // reads only what step(rec) left behind -- hru_work of step(rec + 1) writes the OTHER state half, and its atomicMin on fail_rec
   // cannot change the `fail_rec <= rec` test made here -- so the work above needs no ordering with it.  The wait below is what makes
@@ -702,10 +704,9 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
   const size_t per = (size_t)h->t.ncell * L.f_stride;
   const size_t rowsz = (size_t)h->t.ncell * h->nout;
   const size_t esz = f32 ? sizeof(float) : sizeof(double);
-  // cell output: one-warp blocks, such a block fits beside a resident step block on every SM
-  const char* cb = getenv("VICGPU_OUTBLOCK");
-  const int B = (cb && atoi(cb) >= 32 && atoi(cb) <= 128) ? atoi(cb) : 32;
-  const int cgrid = (h->t.ncell + B - 1) / B;
+  // cell output: three warps (the three variable groups) per 32 cells
+  const int B = 96;
+  const int cgrid = (h->t.ncell + 31) / 32;
   const bool one = h->o.NF == 1;
   h->last_launches = 0;
   int nagg = 0;

@@ -6,12 +6,14 @@
 #include "vic_engine.cuh"
 
 // Thread block and register budget of the per-HRU step kernel.  The kernel is latency bound, so what counts is
-// how many warps an SM can interleave: at 128 registers an SM holds 16 warps.  Measured on the 10,000-cell workload (us per launch,
-// winter / spring / summer / autumn week): 160 registers x 384 threads 890 / 935 / 808 / --; 128 x 448: 823 / 908 / 672 / 942;
-// 128 x 512: 847 / 943 / 681 / 991; 96 x 640: 896 / -- / 766; 80 x 768: 951 / -- / 821; 64 x 1024: 996 / -- / 877.  The default block is 448
-// threads (14 warps, leaving room for two one-warp blocks of the cell-output kernel on the same SM) while that covers the domain in
-// one wave, else 512.  Blocks this large also keep the warps of one kind (binned rows) on one SM, which is what the instruction
-// cache needs.
+// how many warps an SM can interleave: at 128 registers an SM holds 16 warps.  Measured on the 10,000-cell workload in round 1 (us per
+// launch, winter / spring / summer / autumn week): 160 registers x 384 threads 890 / 935 / 808 / --; 128 x 448: 823 / 908 / 672 / 942;
+// 128 x 512: 847 / 943 / 681 / 991; 96 x 640: 896 / -- / 766; 80 x 768: 951 / -- / 821; 64 x 1024: 996 / -- / 877; round 2, 168 x 384:
+// 686 against 717 for 128 x 448 with the same cell-output kernel.
+// Block size: the dependent cell-output grid (vicgpu_api.cu) never shares an SM with a resident step block in practice -- it runs
+// on the SMs the step grid leaves idle -- so the step grid should be as small as the register file allows: 512-thread blocks put the
+// 1,647 warps of the 10,000-cell domain on 103 SMs and leave 45 to the output grid (record time, winter week: 512 threads 553 us,
+// 448 threads / 118 blocks 615 us, 384 / 138 blocks 609 us with the step slowed by co-resident output blocks; profiles/r02_summary.md).
 #ifndef VICGPU_HRU_BLOCK_MAX
 #define VICGPU_HRU_BLOCK_MAX 512
 #endif
@@ -19,7 +21,7 @@
 #define VICGPU_STEP_MAXNREG 128
 #endif
 #ifndef VICGPU_HRU_BLOCK
-#define VICGPU_HRU_BLOCK 448
+#define VICGPU_HRU_BLOCK 512
 #endif
 
 // one: the configuration's model step is a single sub-step (NF == 1)
