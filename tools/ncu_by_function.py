@@ -22,7 +22,7 @@ for l in elf.splitlines():
     elif on:
         p = l.split()
         # out-of-line device functions are named $<kernel>$<function>; keep those of the single-record kernel k_hru_step_nn*
-        if len(p) >= 7 and p[3] == "0x2" and p[6].startswith("$") and os.environ.get("NCU_KERNEL", "k_hru_step_nn") in p[6].split("$")[1]:
+        if len(p) >= 7 and p[3] == "0x2" and p[6].startswith("$") and os.environ.get("NCU_KERNEL", "k_hru_step_nn3ILb1") in p[6].split("$")[1]:
             syms.append((int(p[1], 16), int(p[2], 16), p[6]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:k_hru_step", "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))

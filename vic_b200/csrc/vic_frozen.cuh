@@ -58,7 +58,7 @@ VIC_HD double layer_array_as_node(const CellPar& cp, int layer_field, int node_f
 template <int NN>
 VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double* Tfbcount, const double* kappa, const double* Cs,
                             const double* moist, double deltat, const double* ice, double Dp, int Nnodes, int* FIRST_SOLN, int NOFLUX,
-                            int EXP_TRANS, const CellPar& cp, const Opts& o) {
+                            int EXP_TRANS, const CellPar& cp, const Opts& o, int* work = nullptr) {
   const int MAXIT = 1000;
   double A[NN], B[NN], C[NN], D[NN], E[NN], Tlast[NN];
   FIRST_SOLN[0] = 0;
@@ -126,6 +126,7 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
         eq.expt = layer_array_as_node(cp, CL_expt, CN_expt_node, j);
         eq.ice0 = ice[j]; eq.A = A[j]; eq.B = B[j]; eq.C = C[j]; eq.D = D[j]; eq.E = E[j]; eq.EXP_TRANS = EXP_TRANS; eq.node = j;
         T[j] = root_brent(T0[j] - (SOIL_DT), T0[j] + (SOIL_DT), eq);
+        if (work) *work += 16;  // cost estimate of this HRU-step (vic_engine.cuh hru_work): a frozen-node solve is ~16 surface-residual evaluations' worth
         if (result_is_error(T[j])) {
           if (o.TFALLBACK) {
             T[j] = T0[j];

@@ -86,7 +86,7 @@ __global__ void k_permute_state(const double* __restrict__ in, double* __restric
 // without snow (dynamic: solve_snow's pack and canopy balances, sub-stepping, evaporation switched off under snow).  Every
 // `rebin_interval` records the rows are re-sorted on the device so that the 32 HRUs of a warp share both.
 __global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __restrict__ hrurec, int nhru, int hr_stride, const int* __restrict__ hru_of_slot,
-                           unsigned long long* __restrict__ keys, int* __restrict__ old_slot, int fine) {
+                           unsigned long long* __restrict__ keys, int* __restrict__ old_slot, int fine, const int* __restrict__ cost, int cost_mode) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nhru) return;
   const size_t n = (size_t)nhru;
@@ -104,8 +104,18 @@ __global__ void k_bin_keys(const double* __restrict__ hrupar, const double* __re
     const unsigned long long pack = !(swq > 0.0) ? 0 : ((ts < 0.0) ? 1 : 2);
     regime = (pack << 1) | (canopy > 0.0 ? 1 : 0);
   }
+  // VICGPU_BINCOST: the cost of the row's last step (residual evaluations + frozen-node solves, HruStepDiag::work) in powers of two.
+  // A warp costs what its slowest lane costs, so rows of similar cost share warps: mode 1 sorts by cost inside a (kind, regime) bin,
+  // mode 2 sorts by cost FIRST (the frozen-soil configuration, where an HRU with frozen nodes costs 10-100 times one without and
+  // the code path is the same for all of them).
+  unsigned long long bucket = 0;
+  if (cost_mode && cost) {
+    int c = cost[s];
+    while (c > 0 && bucket < 15) { c >>= 1; bucket++; }
+  }
   // low 32 bits: the HRU's own index, i.e. cell order within a bin (and a total order: the sort is deterministic)
-  keys[s] = (kind << 35) | (regime << 32) | (unsigned long long)(unsigned)hru_of_slot[s];
+  if (cost_mode == 2) keys[s] = (bucket << 58) | (kind << 35) | (regime << 32) | (unsigned long long)(unsigned)hru_of_slot[s];
+  else keys[s] = (kind << 39) | (regime << 36) | (bucket << 32) | (unsigned long long)(unsigned)hru_of_slot[s];
   old_slot[s] = s;
 }
 // out[c][s] = in[c][src[s]]
@@ -270,7 +280,7 @@ static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const do
   const int nhru = h->t.nhru;
   const vicgpu_layout& L = h->o.L;
   const int T = 256, G = (nhru + T - 1) / T;
-  k_bin_keys<<<G, T, 0, h->stream>>>(S.hrupar, src_state, nhru, L.hr_stride, S.hru_of_slot, h->d_keys[0], h->d_oldslot[0], h->bin_fine ? 1 : 0);
+  k_bin_keys<<<G, T, 0, h->stream>>>(S.hrupar, src_state, nhru, L.hr_stride, S.hru_of_slot, h->d_keys[0], h->d_oldslot[0], h->bin_fine ? 1 : 0, h->d_cost, h->bin_cost);
   size_t need = 0;
   CK(cub::DeviceRadixSort::SortPairs(nullptr, need, h->d_keys[0], h->d_keys[1], h->d_oldslot[0], h->d_oldslot[1], nhru, 0, 64, h->stream));
   if (need > h->sort_tmp_bytes) {
@@ -359,6 +369,11 @@ static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const O
   // grid runs (measured at 10,000 cells: record 588 us with 118 blocks, 835 us = step + output back to back with 148)
   const char* ev = getenv("VICGPU_EVEN");
   h->even = ev && atoi(ev) != 0;
+  // rows binned by the cost of their last step as well (k_bin_keys): 0 off, 1 inside a (kind, regime) bin, 2 cost first; -1 (default):
+  // decided in vicgpu_set_cells from the configuration and the domain size
+  const char* bc = getenv("VICGPU_BINCOST");
+  h->bin_cost_env = bc ? atoi(bc) : -1;
+  h->rebin_env = rb != nullptr;
   const char* bf = getenv("VICGPU_BINFINE");  // 1: bin by pack regime and canopy snow as well (k_bin_keys)
   h->bin_fine = bf && atoi(bf) != 0;
   CK(cudaMalloc(&h->d_o, sizeof(Opts)));
@@ -404,7 +419,7 @@ int vicgpu_destroy(vicgpu_handle* h) {
   cudaFree(h->d_sort_tmp);
   cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_fstage);
   cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype);
-  cudaFree(h->d_warp_ns);
+  cudaFree(h->d_warp_ns); cudaFree(h->d_cost);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
@@ -478,6 +493,8 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
   h->d_cellder = nullptr;
   cudaFree(h->d_fail_rec); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]); cudaFree(h->d_warp_ns);
+  cudaFree(h->d_cost);
+  h->d_cost = nullptr;
   h->d_cellpar = h->d_carry = h->d_out = h->d_agg = nullptr;
   h->d_cell_h0 = h->d_status = h->d_fail_rec = nullptr;
   h->d_keys[0] = h->d_keys[1] = nullptr;
@@ -490,6 +507,8 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   const size_t state_bytes = hr_rows(nhru) * L.hr_stride * sizeof(double);  // whole 32-row tiles
   CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
   CK(cudaMalloc(&h->d_cellder, (size_t)ncell * VIC_NCELLDER * sizeof(double)));
+  CK(cudaMalloc(&h->d_cost, (size_t)nhru * sizeof(int)));
+  CK(cudaMemset(h->d_cost, 0, (size_t)nhru * sizeof(int)));
   CK(cudaMalloc(&h->d_gmb_cum, (size_t)nhru * sizeof(double)));
   CK(cudaMemset(h->d_gmb_cum, 0, (size_t)nhru * sizeof(double)));
   CK(cudaMalloc(&h->d_gmb, (size_t)ncell * 4 * sizeof(double)));
@@ -548,9 +567,15 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   CK(cudaStreamSynchronize(h->stream));
   rc = upload_transposed(h, hrupar, h->order[0].hrupar, nhru, HP_N, h->order[0].hru_of_slot);
   if (rc) return rc;
+  // Cost binning pays only when the domain runs in many waves (the step kernel of a one-wave domain ends when its slowest HRU does,
+  // however the rows are packed: measured 60 -> 74 ms per record at 10,000 frozen-soil cells) and only where the cost varies by orders
+  // of magnitude between HRUs: the soil-thermal-profile configurations, 100,000 cells 0.287 -> 0.353 M cell-timesteps/s with a re-sort
+  // every other record.  For the quick-flux configurations it is neutral (profiles/r02_summary.md).
+  h->bin_cost = h->bin_cost_env >= 0 ? h->bin_cost_env : ((!h->o.QUICK_FLUX && (long long)nhru > 8LL * h->sm_count * VICGPU_HRU_BLOCK_MAX) ? 2 : 0);
+  if (h->bin_cost == 2 && !h->rebin_env) h->rebin_every = 2;
   if (!h->hru_block_fixed) h->hru_block = ((long long)nhru <= (long long)h->sm_count * VICGPU_HRU_BLOCK) ? VICGPU_HRU_BLOCK : VICGPU_HRU_BLOCK_MAX;
   h->t.ncell = ncell; h->t.nhru = nhru;
-  h->t.gmb_cum = h->d_gmb_cum; h->t.gmb = h->d_gmb;
+  h->t.gmb_cum = h->d_gmb_cum; h->t.gmb = h->d_gmb; h->t.cost = h->d_cost;
   h->t.cellpar = h->d_cellpar; h->t.cellder = h->d_cellder; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
   h->t.status = h->d_status; h->t.carry = h->d_carry; h->t.out = h->d_out; h->t.agg = h->d_agg; h->t.aggtype = h->d_aggtype;
   h->cur_half = 0;

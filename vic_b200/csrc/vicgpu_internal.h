@@ -51,6 +51,9 @@ struct vicgpu_handle {
   double* d_state_cur = nullptr;  // current state: half.in after set_state, else the last snapshot of the last block
   bool binned = true, rebin = true, pdl = true, bin_fine = false, pdl_wait = true, even = false;
   int* d_fail_rec = nullptr;
+  int* d_cost = nullptr;  // [nhru] cost estimate of each row's last step (Tables::cost)
+  int bin_cost = 0, bin_cost_env = -1;  // VICGPU_BINCOST
+  bool rebin_env = false;
   cudaStream_t stream = nullptr, stream_copy = nullptr;  // kernels / host <-> device copies
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // output staging: two buffers handed between the kernel stream (transpose) and the copy stream (D2H)
