@@ -511,6 +511,11 @@ int vicgpu_get_glacier_fit(vicgpu_handle *h, double *gmb);
  * timed with CUDA events (best of 5) -- the denominator of the FP64 roofline fraction bench.py reports. */
 int vicgpu_measure_fp64_peak(int device, double *tflops);
 
+/* measurement aid for the kernel-structure decision: device time [us] of one pass that does what every
+ * additional kernel boundary inside the step would add -- load the HRU record, load and store `nframe` doubles per HRU of values
+ * live across the boundary, store the record -- over the current domain, averaged over `reps` launches.  Does not change the state. */
+int vicgpu_measure_phase_tax(vicgpu_handle *h, int nframe, int reps, double *us_per_pass);
+
 /* measurement aid: with profiling on, every launch of the per-HRU step kernel inside vicgpu_step is bracketed
  * by CUDA events on the library's stream; get_kernel_profile returns the summed duration and the launch count
  * since profiling was switched on. */

@@ -199,15 +199,15 @@ def test_call_order_errors():
     gp.close()
 
 
-@pytest.mark.parametrize("ncell,nrec", [(10000, 48), (100000, 24)])
-def test_full_size_domain_properties(ncell, nrec):
+@pytest.mark.parametrize("base,ncell,nrec", [("fe_hourly", 10000, 48), ("fe_hourly", 100000, 24), ("glacier", 10000, 48), ("frozen_bands", 10000, 24)])
+def test_full_size_domain_properties(base, ncell, nrec):
     """BASELINE-size domains (configs[1]: 10,000 cells; configs[2]-size: 100,000), through properties that do not need the reference
     to run at that size: (1) cells are independent, so the first 256 cells of the big domain -- the unperturbed base domain the
     reference itself is timed on -- must give bit-identical outputs and state whether they are advanced alone or inside the big domain
     (different row binning, different block placement, different re-sort decisions); (2) the reference's own closure check holds in every
     cell: |water balance error| of a step < 1e-5 mm (calc_water_energy_balance_errors.c:33-43); (3) no cell is flagged invalid."""
     import bench
-    dom = bench.build_domain(ncell, 1)
+    dom = bench.build_domain(ncell, 1, base)
     nb = 256
     h_nb = int(np.searchsorted(dom["hrupar"][:, TABLES["hpar"].index("HP_cell")], nb))
 

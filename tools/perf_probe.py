@@ -43,6 +43,8 @@ kms, kn = g.kernel_profile()
 env = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("VICGPU_"))
 print(f"PROBE {a.tag} {a.config} [{env}] cells={a.cells} hrus={g.nhru} ms_per_step={ms / a.steps:.3f} hru_kernel_us={kms / max(kn, 1) * 1e3:.1f} "
       f"cell_steps_per_s={a.cells * 24 * a.steps / (ms / 1e3):.4g} state_sum={np.nansum(g.get_state()):.17g}", flush=True)
+if os.environ.get("PROBE_PHASE_TAX"):
+    print("PHASETAX", a.config, "cells", a.cells, " ".join(f"nframe={n}:{g.phase_tax(n):.1f}us" for n in (0, 64, 128, 192)), flush=True)
 if os.environ.get("VICGPU_WARPTIME"):
     t0, t1, kind = g.warp_times()
     dur = (t1 - t0) / 1e3

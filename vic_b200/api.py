@@ -25,7 +25,7 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_step_f32", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
+    "vicgpu_get_last_step_timing", "vicgpu_measure_phase_tax", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
 ]
 
 
@@ -67,13 +67,16 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_get_balance_errors.argtypes = [vp, dp]
     lib.vicgpu_get_last_step_timing.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.vicgpu_disagg.argtypes = [vp, vp, dp, dp]
+    if hasattr(lib, "vicgpu_measure_phase_tax") or not os.environ.get("VICGPU_LIB"):  # (an older A/B build may lack it)
+        lib.vicgpu_measure_phase_tax.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.vicgpu_set_profiling.argtypes = [vp, C.c_int]
     lib.vicgpu_get_kernel_profile.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.vicgpu_get_warp_times.argtypes = [vp, dp, dp, C.c_int]
     lib.vicgpu_get_glacier_fit.argtypes = [vp, dp]
     lib.vicgpu_measure_fp64_peak.argtypes = [C.c_int, dp]
     for s in SYMBOLS:
-        getattr(lib, s)
+        if not os.environ.get("VICGPU_LIB"):
+            getattr(lib, s)
     _lib = lib
     return lib
 
@@ -235,6 +238,12 @@ class VicGpu:
         if n < 0:
             self._chk(n)
         return t[:, 0], t[:, 1], k
+
+    def phase_tax(self, nframe, reps=20):
+        """device time [us] of one record-in / frame-in-out / record-out pass over the domain (vicgpu_measure_phase_tax)"""
+        v = C.c_double()
+        self._chk(self.lib.vicgpu_measure_phase_tax(self.h, int(nframe), int(reps), C.byref(v)))
+        return v.value
 
     def last_step_timing(self):
         ms = C.c_double()

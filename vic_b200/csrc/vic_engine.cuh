@@ -37,7 +37,7 @@ struct Tables {
   double* out;            // [nout][ncell]  OutputData::data of the current record
   double* agg;            // [nout][ncell]  OutputData::aggdata
   const int* aggtype;     // [N_OUTVARS]
-  int* cost;              // [nhru] or null: cost estimate of each row's last step (HruStepDiag::work), read by the row binning only
+  int* cost;              // [nhru] or null: cost estimate of each row's last step (vic_frozen.cuh vic_count_work), read by the row binning only
   double* gmb_cum;        // [nhru] glacier.cum_mass_balance of an HRU at the end of the last accumulation interval, before its reset
   double* gmb;            // [4][ncell] b0, b1, b2, fitError of the cell's mass-balance curve (GraphingEquation), or null
 };
@@ -105,7 +105,13 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   dg[0] = d.out_prec * hp.Cv;
   dg[nh] = d.out_rain * hp.Cv;
   dg[2 * nh] = d.out_snow * hp.Cv;
-  if (t.cost) t.cost[h] = d.work;
+#if defined(VIC_WORK_BUFFER) && defined(__CUDA_ARCH__)
+  if (t.cost && vic_work_buf) {  // the step's cost estimate (vic_frozen.cuh vic_count_work), for the row binning only
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    t.cost[h] = vic_work_buf[g];
+    vic_work_buf[g] = 0;
+  }
+#endif
 }
 
 // put_data of one cell (vic_output.cuh), host port: one call does everything, the row is built in the output table itself.

@@ -20,6 +20,22 @@
 
 namespace vic {
 
+// Cost estimate for the row binning of the soil-thermal-profile configurations (vicgpu_api.cu k_bin_keys): the number of frozen-node
+// solves of the thread's current HRU-step, counted into a per-thread slot of a device buffer that the translation unit of the step
+// kernel owns (vicgpu_step.inc defines VIC_WORK_BUFFER for the 10- and 32-node kernels only; hru_work moves the count to
+// Tables::cost).  A side channel on purpose: threading a counter through the signatures of the surface solve cost the 3-node kernel
+// 11 % (profiles/r02_summary.md).  No physics reads it.
+#if defined(VIC_WORK_BUFFER) && defined(__CUDACC__)
+static __device__ int* vic_work_buf = nullptr;
+#endif
+VIC_HD void vic_count_work(int n) {
+#if defined(VIC_WORK_BUFFER) && defined(__CUDA_ARCH__)
+  if (vic_work_buf) vic_work_buf[blockIdx.x * blockDim.x + threadIdx.x] += n;
+#else
+  (void)n;
+#endif
+}
+
 struct SoilThermalEqn {
   double TL, TU, T0, moist, max_moist, bubble, expt, ice0, A, B, C, D, E;
   int EXP_TRANS, node;
@@ -58,7 +74,7 @@ VIC_HD double layer_array_as_node(const CellPar& cp, int layer_field, int node_f
 template <int NN>
 VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double* Tfbcount, const double* kappa, const double* Cs,
                             const double* moist, double deltat, const double* ice, double Dp, int Nnodes, int* FIRST_SOLN, int NOFLUX,
-                            int EXP_TRANS, const CellPar& cp, const Opts& o, int* work = nullptr) {
+                            int EXP_TRANS, const CellPar& cp, const Opts& o) {
   const int MAXIT = 1000;
   double A[NN], B[NN], C[NN], D[NN], E[NN], Tlast[NN];
   FIRST_SOLN[0] = 0;
@@ -126,7 +142,7 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
         eq.expt = layer_array_as_node(cp, CL_expt, CN_expt_node, j);
         eq.ice0 = ice[j]; eq.A = A[j]; eq.B = B[j]; eq.C = C[j]; eq.D = D[j]; eq.E = E[j]; eq.EXP_TRANS = EXP_TRANS; eq.node = j;
         T[j] = root_brent(T0[j] - (SOIL_DT), T0[j] + (SOIL_DT), eq);
-        if (work) *work += 16;  // cost estimate of this HRU-step (vic_engine.cuh hru_work): a frozen-node solve is ~16 surface-residual evaluations' worth
+        vic_count_work(1);
         if (result_is_error(T[j])) {
           if (o.TFALLBACK) {
             T[j] = T0[j];

@@ -36,7 +36,6 @@ VIC_HD HruPar load_hrupar(const Col& hp) {
 // output (atmos->out_prec / out_rain / out_snow, full_energy.c:425-427)
 struct HruStepDiag {
   double out_prec, out_rain, out_snow;
-  int work;  // cost estimate of the step (residual evaluations + frozen-node solves): no physics reads it, the device bins rows by it
 };
 
 // Returns 0 or ERROR_I (the reference then invalidates the whole cell, vicNl.c:545-559).
@@ -45,7 +44,6 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
   const Opts& o = *cx.o;
   const CellPar& cp = cx.cp;
   dg.out_prec = dg.out_rain = dg.out_snow = 0;
-  dg.work = 0;
   if (!((hp.Cv > 0.0) || (hp.isGlacier && o.GLACIER_DYNAMICS && hp.Cv >= 0.0))) return 0;
   const int month0 = cx.dmy.month - 1;
   const double AreaFract = cp.band(CB_AreaFract, hp.band);
@@ -137,13 +135,11 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
       soil.root[l] = hp.root[l];
     }
     SurfaceFluxOut sf;
-    sf.work = 0;
     int e;
     if (hp.isGlacier) e = surface_fluxes_glac<NN, ONE>(bare_albedo, ice0, moist0, hru, as, gauge_correction, hp.band, cx, veg_class, sf);
     else e = surface_fluxes<NN, ONE>(overstory, bare_albedo, ice0, moist0, hru, surf_atten, as, gauge_correction, hp.isArtBare, hp.band, cx, veg, soil, veg_class, sf);
     if (e == ERROR_I) return ERROR_I;
     dg.out_prec = sf.out_prec;
-    dg.work = sf.work;
     dg.out_rain = sf.out_rain;
     dg.out_snow = sf.out_snow;
     // root-zone moisture and wetness

@@ -49,7 +49,6 @@ struct SurfEB {
   double t1_k1, t1_b, t1_c, t1_den, gf_k1, gf_k2e, sc_lg;
   int sc_lg_ok;
   EvapMemo* memo;  // the caller's (the functor itself must not have its address taken, or its members stay in memory)
-  int work;                 // cost estimate: residual evaluations (+ the frozen-node solves inside them), for the row binning only
   double Tsnow_surf_final;  // what Tsnow_surf restarts from at the evaluation after the solve
   VIC_HD void before_final() { Tsnow_surf = Tsnow_surf_final; }
 
@@ -91,7 +90,6 @@ struct SurfEB {
   VIC_HD double eval(double Ts) {
     const double TMean = Ts;
     const double Tmp = TMean + KELVIN;
-    work++;
     if (snow_coverage > 0 && !INCLUDE_SNOW) en->snow_flux = (kappa_snow * (Tsnow_surf - TMean));
     else if (INCLUDE_SNOW) {
       en->snow_flux = 0;
@@ -105,7 +103,7 @@ struct SurfEB {
     } else {
       T_node[0] = TMean;
       int Error = solve_T_profile<NN>(Tnew_node, T_node, Tnew_fbflag, Tnew_fbcount, kappa_node, Cs_node, moist_node, delta_t, ice_node, dp,
-                                      Nnodes, FIRST_SOLN, NOFLUX, EXP_TRANS, *cp, *o, &work);
+                                      Nnodes, FIRST_SOLN, NOFLUX, EXP_TRANS, *cp, *o);
       if (Error == ERROR_I) return ERROR_D;
       T1 = Tnew_node[1];
       if (GRND_FLUX_TYPE == GF_406) en->grnd_flux = cover * (kappa1 / D1 * (T1 - TMean));
@@ -193,8 +191,7 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
                                     const Surf4& displacement, double* melt, double* ppt, double rainfall, const Surf4& ref_height,
                                     const Surf4& roughness, const Surf4& wind_speed, int INCLUDE_SNOW, int UnderStory, int dt, int overstory,
                                     bool isArtificialBareSoil, double atmos_density, double atmos_pressure, EnergyBal<NN>& energy, SoilLayer* layer,
-                                    SnowPack& snow, VegVar& vv, const VegNow& veg, const SoilET& soil, const CellPar& cp, const Opts& o,
-                                    int* work = nullptr) {
+                                    SnowPack& snow, VegVar& vv, const VegNow& veg, const SoilET& soil, const CellPar& cp, const Opts& o) {
   (void)coldcontent;
   const int Nnodes = o.Nnode;
   int FIRST_SOLN[2] = {1, 1};
@@ -249,7 +246,6 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   EvapMemo memo;
   eb.memo = &memo;
   eb.Tsnow_surf_final = snow.surf_temp;
-  eb.work = 0;
   eb.prepare();
 
   // The solve (FULL_ENERGY) and the evaluation at the accepted temperature -- in the reference a fresh functor, i.e. Tsnow_surf restarts
@@ -277,7 +273,6 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   fin.f_final = 0.;
   fin.fell_back = 0;
   Tsurf = root_brent_ss_impl<true>(T_lower, T_upper, call, &fin);
-  if (work) *work += eb.work;
   if (o.FULL_ENERGY && !fin.fell_back && result_is_error(Tsurf)) return ERROR_D;  // the solve failed and TFALLBACK is off
   if (fin.fell_back) {
     Tsurf_fbflag = 1;
@@ -583,7 +578,6 @@ VIC_HDI double solve_snow(bool overstory, double BareAlbedo, double LongUnderOut
 
 struct SurfaceFluxOut {
   double out_prec, out_rain, out_snow, Melt, snow_inflow;
-  int work;  // cost estimate of the step (residual evaluations), for the row binning only
 };
 
 // surface_fluxes.c:17-956.  Returns 0 or ERROR_I.
@@ -659,7 +653,6 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
   for (int p = 0; p < N_PET_TYPES; p++) st_pot_evap[p] = 0;
   double snow_inflow = 0;
   out.out_prec = out.out_rain = out.out_snow = 0;
-  out.work = 0;
   int N_steps = 0;
   double latent_heat_Le = 0, delta_coverage = 0;
 
@@ -719,7 +712,7 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
                                             step_snow.coverage, (prev_depth + step_snow.depth) / 2., BareAlbedo, surf_atten, iter_aero_resist,
                                             aero_used, as.displacement, &step_melt, &step_ppt, ss.rainfall, as.ref_height, as.roughness,
                                             as.wind_speed, INCLUDE_SNOW, UnderStory, step_dt, (int)overstory, isArtificialBareSoil,
-                                            f(FV_density, hidx), f(FV_pressure, hidx), soil_energy, step_layer, step_snow, soil_vv, veg, soil, cp, o, &out.work);
+                                            f(FV_density, hidx), f(FV_pressure, hidx), soil_energy, step_layer, step_snow, soil_vv, veg, soil, cp, o);
     if ((int)Tsurf == ERROR_I) return ERROR_I;
     if (INCLUDE_SNOW) step_ppt += step_melt;
 

@@ -174,7 +174,7 @@ VIC_HD size_t hr_rows(int nhru) { return ((size_t)nhru + 31) / 32 * 32; }
 // first, then the chunk's stores -- so that the memory round trips of a chunk overlap (a member-by-member copy compiles to
 // load, store, load, store ... and pays one round trip per column).
 #include <stddef.h>
-#define VIC_XFER_CHUNK 32
+#define VIC_XFER_CHUNK 16
 
 // columns col0 .. col0+count-1 of my record row  ->  dst[0 .. count)
 VIC_HD void cols_to_local(const double* __restrict__ rec, size_t n, int col0, int count, double* __restrict__ dst) {

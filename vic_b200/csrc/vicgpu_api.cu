@@ -419,7 +419,7 @@ int vicgpu_destroy(vicgpu_handle* h) {
   cudaFree(h->d_sort_tmp);
   cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_fstage);
   cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype);
-  cudaFree(h->d_warp_ns); cudaFree(h->d_cost);
+  cudaFree(h->d_warp_ns); cudaFree(h->d_cost); cudaFree(h->d_work);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
@@ -509,6 +509,16 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   CK(cudaMalloc(&h->d_cellder, (size_t)ncell * VIC_NCELLDER * sizeof(double)));
   CK(cudaMalloc(&h->d_cost, (size_t)nhru * sizeof(int)));
   CK(cudaMemset(h->d_cost, 0, (size_t)nhru * sizeof(int)));
+  {
+    // per-thread cost counters of the step kernel (vic_frozen.cuh): one slot per thread of the largest grid the launcher makes
+    cudaFree(h->d_work);
+    h->d_work = nullptr;
+    const size_t slots = ((size_t)nhru / 32 + (size_t)h->sm_count + 2) * VICGPU_HRU_BLOCK_MAX;
+    CK(cudaMalloc(&h->d_work, slots * sizeof(int)));
+    CK(cudaMemset(h->d_work, 0, slots * sizeof(int)));
+    const int rcw = h->o.Nnode <= 3 ? vicgpu_set_work_buffer_nn3(h->d_work) : h->o.Nnode <= 10 ? vicgpu_set_work_buffer_nn10(h->d_work) : vicgpu_set_work_buffer_nn32(h->d_work);
+    if (rcw != 0) return fail(VICGPU_ECUDA, "cudaMemcpyToSymbol(vic_work_buf)");
+  }
   CK(cudaMalloc(&h->d_gmb_cum, (size_t)nhru * sizeof(double)));
   CK(cudaMemset(h->d_gmb_cum, 0, (size_t)nhru * sizeof(double)));
   CK(cudaMalloc(&h->d_gmb, (size_t)ncell * 4 * sizeof(double)));
@@ -971,6 +981,35 @@ int vicgpu_measure_fp64_peak(int device, double* tflops) {
   cudaEventDestroy(e1);
   cudaFree(d);
   *tflops = best;
+  return VICGPU_OK;
+}
+
+int vicgpu_measure_phase_tax(vicgpu_handle* h, int nframe, int reps, double* us_per_pass) {
+  if (!h || !us_per_pass || nframe < 0 || reps < 1) return fail(VICGPU_EINVAL, "bad argument");
+  if (!h->have_state) return fail(VICGPU_ESTATE, "no state set");
+  CK(cudaSetDevice(h->device));
+  double* frame = nullptr;
+  CK(cudaMalloc(&frame, std::max<size_t>(1, (size_t)nframe * h->t.nhru) * sizeof(double)));
+  CK(cudaMemsetAsync(frame, 0, std::max<size_t>(1, (size_t)nframe * h->t.nhru) * sizeof(double), h->stream));
+  Tables t = h->t;
+  t.hrupar = h->order[h->half[h->cur_half].ord].hrupar;
+  t.hrurec = h->d_state_cur;
+  t.hrurec_out = h->half[h->cur_half ^ 1].in;  // scratch between steps: a re-sort overwrites it completely before anything reads it
+  auto launch = [&]() {
+    if (h->o.Nnode <= 3) vicgpu_launch_hru_pass_nn3(h->d_o, t, frame, nframe, h->hru_block, h->stream);
+    else if (h->o.Nnode <= 10) vicgpu_launch_hru_pass_nn10(h->d_o, t, frame, nframe, h->hru_block, h->stream);
+    else vicgpu_launch_hru_pass_nn32(h->d_o, t, frame, nframe, h->hru_block, h->stream);
+  };
+  launch();  // warm-up
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int r = 0; r < reps; r++) launch();
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  cudaFree(frame);
+  *us_per_pass = (double)ms * 1e3 / reps;
   return VICGPU_OK;
 }
 

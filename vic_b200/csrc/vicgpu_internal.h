@@ -52,6 +52,7 @@ struct vicgpu_handle {
   bool binned = true, rebin = true, pdl = true, bin_fine = false, pdl_wait = true, even = false;
   int* d_fail_rec = nullptr;
   int* d_cost = nullptr;  // [nhru] cost estimate of each row's last step (Tables::cost)
+  int* d_work = nullptr;  // per-thread cost counters of the step kernel (vic_frozen.cuh vic_count_work)
   int bin_cost = 0, bin_cost_env = -1;  // VICGPU_BINCOST
   bool rebin_env = false;
   cudaStream_t stream = nullptr, stream_copy = nullptr;  // kernels / host <-> device copies
