@@ -93,6 +93,7 @@ int main(int argc, char** argv) {
   t.ncell = ncell; t.nhru = nhru; t.nclass = (int)cs["veglib"].dims[0];
   t.veglib = cs["veglib"].f64.data(); t.cellpar = cellpar.data(); t.cellder = cellder.data(); t.hrupar = hrupar.data(); t.hrurec = hrurec.data(); t.hrurec_out = hrurec.data(); t.hdiag_out = hdiag.data();
   t.cost = nullptr;
+  t.aero = nullptr;  // the host port evaluates the aerodynamic geometry every record (vic_step.cuh aero_geom)
   t.cell_h0 = cell_h0.data(); t.status = status.data(); t.gmb_cum = gmb_cum.data(); t.gmb = gmb.data(); t.fail_rec = fail_rec.data(); t.carry = carry.data(); t.out = out.data(); t.agg = agg.data();
   t.aggtype = cs["aggtype"].i32.data();
   t.slot_of_hru = slot;

@@ -12,11 +12,15 @@
 
 namespace vic {
 
+// CalcAerodynamic() is a geometry part -- the profile of a unit wind over the land cover -- followed by a scaling with the wind at
+// the reference height (CalcAerodynamic.c:240-270).  The geometry depends only on the land cover's monthly parameters and the
+// cell's roughness lengths, not on the forcing or the state: calc_aerodynamic_geom() is evaluated once per HRU and month on the
+// device (AeroGeom, vic_step.cuh) and calc_aerodynamic_wind() every record; calc_aerodynamic() is the two in sequence, the
+// reference's operations in the reference's order.
 // returns 0 or ERROR_I
-VIC_HDI int calc_aerodynamic(bool OverStory, double Height, double Trunk, double Z0_SNOW, double Z0_SOIL, double n,
-                             Surf4& aero_resist, Surf4& wind_speed, Surf4& displacement, Surf4& ref_height, Surf4& roughness) {
+VIC_HDI int calc_aerodynamic_geom(bool OverStory, double Height, double Trunk, double Z0_SNOW, double Z0_SOIL, double n,
+                                  Surf4& aero_resist, Surf4& wind_speed, Surf4& displacement, Surf4& ref_height, Surf4& roughness) {
   double d_Lower, d_Upper, Uh, Ut, Uw, Z0_Lower, Z0_Upper, Zt, Zw;
-  const double tmp_wind = wind_speed[SNOW_FREE];
   const double K2 = von_K * von_K;
   if (!OverStory) {
     Z0_Lower = roughness[SNOW_FREE];
@@ -92,6 +96,11 @@ VIC_HDI int calc_aerodynamic(bool OverStory, double Height, double Trunk, double
     roughness[GLACIER_SURF] = Z0_Lower;
     displacement[GLACIER_SURF] = 0.;
   }
+  return 0;
+}
+
+// the wind at the reference height scales the unit-wind profile (CalcAerodynamic.c:240-270)
+VIC_HD void calc_aerodynamic_wind(double tmp_wind, Surf4& aero_resist, Surf4& wind_speed) {
   if (tmp_wind > 0.) {
     wind_speed[SNOW_FREE] *= tmp_wind;
     aero_resist[SNOW_FREE] /= tmp_wind;
@@ -108,6 +117,14 @@ VIC_HDI int calc_aerodynamic(bool OverStory, double Height, double Trunk, double
     if (is_valid(wind_speed[GLACIER_SURF])) wind_speed[GLACIER_SURF] *= tmp_wind;
     aero_resist[GLACIER_SURF] = HUGE_RESIST;
   }
+}
+
+VIC_HDI int calc_aerodynamic(bool OverStory, double Height, double Trunk, double Z0_SNOW, double Z0_SOIL, double n,
+                             Surf4& aero_resist, Surf4& wind_speed, Surf4& displacement, Surf4& ref_height, Surf4& roughness) {
+  const double tmp_wind = wind_speed[SNOW_FREE];
+  if (calc_aerodynamic_geom(OverStory, Height, Trunk, Z0_SNOW, Z0_SOIL, n, aero_resist, wind_speed, displacement, ref_height, roughness) == ERROR_I)
+    return ERROR_I;
+  calc_aerodynamic_wind(tmp_wind, aero_resist, wind_speed);
   return 0;
 }
 

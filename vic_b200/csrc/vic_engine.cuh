@@ -38,6 +38,7 @@ struct Tables {
   double* agg;            // [nout][ncell]  OutputData::aggdata
   const int* aggtype;     // [N_OUTVARS]
   int* cost;              // [nhru] or null: cost estimate of each row's last step (vic_frozen.cuh vic_count_work), read by the row binning only
+  const double* aero;     // [VIC_AERO_NCOL][nhru] per-month aerodynamic geometry of each row (vic_step.cuh AeroGeom, kernel k_hru_aero), or null
   double* gmb_cum;        // [nhru] glacier.cum_mass_balance of an HRU at the end of the last accumulation interval, before its reset
   double* gmb;            // [4][ncell] b0, b1, b2, fitError of the cell's mass-balance curve (GraphingEquation), or null
 };
@@ -58,7 +59,7 @@ VIC_HDI void carry_hru_record(const Tables& t, int h, int hr_stride) {
 // h: row of the HRU tables
 template <int NN, bool ONE>
 VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec /* [f_stride][ncell] */, int h, Dmy dmy, int rec, GlacAccum ga,
-                      PhaseSync ps = PhaseSync{nullptr, 0}) {
+                      PhaseSync ps = PhaseSync{nullptr, 0}, const double* fstage = nullptr, int fstage_n = 0) {
   const size_t nh = (size_t)t.nhru;
   Col hpc{t.hrupar + h, nh};
   const int cell = (int)hpc(HP_cell);
@@ -73,13 +74,18 @@ VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec 
   cx.cp = CellPar{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L, Col{t.cellder ? t.cellder + cell : nullptr, (size_t)t.ncell}};
   cx.vl = VegLib{t.veglib, &o->L};
   cx.hp = hpc;
-  cx.f = Forcing{Col{forcing_rec + cell, (size_t)t.ncell}, o->L.f_nslot};
+  // fstage: this thread's column of the forcing record staged in shared memory by the kernel (vicgpu_step.inc), stride fstage_n
+  cx.f = fstage ? Forcing{Col{fstage, (size_t)fstage_n}, o->L.f_nslot} : Forcing{Col{forcing_rec + cell, (size_t)t.ncell}, o->L.f_nslot};
+  cx.aero = Col{t.aero ? t.aero + h : nullptr, nh};
   cx.dmy = dmy;
   cx.rec = rec;
   cx.ps = ps;
   const HruPar hp = load_hrupar(hpc);
   Hru<NN> hru;
   load_hru<NN>(hru, t.hrurec + hr_off(h, o->L.hr_stride), VIC_HR_TILE, &o->L);
+#if defined(VIC_FORCING_SMEM) && defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");  // the staged forcing column is in shared memory (issued before the record load)
+#endif
   HruStepDiag d;
   int e = hru_step<NN, ONE>(hru, hp, cx, d);
   if (e == ERROR_I) {

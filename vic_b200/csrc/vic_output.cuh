@@ -32,11 +32,7 @@ struct RowLocal {
 struct RecTile {
   const double* p;  // hrec + hr_off(h, hr_stride)
   VIC_HD double operator()(int k) const {
-#if defined(__CUDA_ARCH__)
-    return __ldg(p + (size_t)k * VIC_HR_TILE);
-#else
-    return p[(size_t)k * VIC_HR_TILE];
-#endif
+    return VIC_REC_LD(p + (size_t)k * VIC_HR_TILE);
   }
 };
 

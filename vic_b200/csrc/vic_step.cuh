@@ -32,6 +32,134 @@ VIC_HD HruPar load_hrupar(const Col& hp) {
   return p;
 }
 
+// ---- aerodynamic tables ---------------------------------------------------------------------------------------------------------
+// The seven CalcAerodynamic() evaluations of full_energy.c:302-354 split into the part that depends only on the HRU's land cover in
+// the current month (AeroGeom: logarithms and exponentials of roughness lengths and canopy heights, ~25 vlog/vexp/vpow per HRU-step
+// when recomputed every record) and the scaling with the record's wind (aero_apply).  The device evaluates aero_geom once per HRU
+// and month into a table (kernel k_hru_aero, vicgpu_api.cu) and hru_step loads it; without a table (host port) hru_step calls
+// aero_geom itself -- the same operations in the same order either way.
+#define VIC_AERO_NCOL 53
+struct AeroGeom {
+  double v[VIC_AERO_NCOL];
+  VIC_HD double& R0(int p, int s) { return v[p * 4 + s]; }             // aero_resist[p][s] of a unit wind
+  VIC_HD double R0(int p, int s) const { return v[p * 4 + s]; }
+  VIC_HD double& wind_corr(int p) { return v[28 + p]; }                 // reference-height wind / forcing wind
+  VIC_HD double wind_corr(int p) const { return v[28 + p]; }
+  VIC_HD double* U0() { return v + 35; }                                // the shared tables as the last evaluation leaves them
+  VIC_HD double* displacement() { return v + 39; }
+  VIC_HD double* ref_height() { return v + 43; }
+  VIC_HD double* roughness() { return v + 47; }
+  VIC_HD const double* U0() const { return v + 35; }
+  VIC_HD const double* displacement() const { return v + 39; }
+  VIC_HD const double* ref_height() const { return v + 43; }
+  VIC_HD const double* roughness() const { return v + 47; }
+  VIC_HD double& valid() { return v[51]; }                              // bit p*4+s: wind_speed[s] is valid after evaluation p
+  VIC_HD double valid() const { return v[51]; }
+  VIC_HD double& err() { return v[52]; }                                // != 0: an evaluation returned ERROR
+  VIC_HD double err() const { return v[52]; }
+};
+
+VIC_HDI void aero_geom(const VegLib& vl, const CellPar& cp, const Opts& o, bool isGlacier, int veg_class, int month0, const VegNow& veg, AeroGeom& g) {
+  (void)isGlacier;
+  for (int k = 0; k < VIC_AERO_NCOL; k++) g.v[k] = 0;
+  Surf4 displacement, roughness, ref_height, wind_speed, resist, prev_resist;
+  displacement.set_invalid(); roughness.set_invalid(); ref_height.set_invalid(); wind_speed.set_invalid(); prev_resist.set_invalid();
+  const double wind_h = veg.wind_h;
+  const double soil_rough = cp(CP_rough);
+  double in_prev[7] = {-1, 0, 0, 0, 0, 0, 0};
+  // terms of the loop below that do not depend on the land cover: the leaf-area factor of calc_veg_height()
+  // (calc_veg_params.c:26-37) and the log-profile denominator of the wind correction
+  const double height_den = 1.1 * vlog(1 + vpow(0.2 * veg.LAI, 0.25));
+  const double wind_den = vlog((o.wind_h - 0.) / soil_rough);
+  Surf4 snap_displacement, snap_ref_height, snap_roughness, snap_wind_speed;  // the tables as the last evaluation left them (set at p == 0)
+  snap_displacement.set_invalid(); snap_ref_height.set_invalid(); snap_roughness.set_invalid(); snap_wind_speed.set_invalid();
+  unsigned valid = 0, prev_valid = 0;
+  #pragma unroll 1
+  for (int p = 0; p < N_PET_TYPES + 1; p++) {
+    const int pet_class = (p < N_PET_TYPES_NON_NAT) ? o.NVegLibTypes + p : veg_class;
+    VegRow r = vl.row(pet_class);
+    if (pet_class == o.GLACIER_ID) roughness[SNOW_FREE] = cp(CP_GLAC_ROUGH);
+    else roughness[SNOW_FREE] = r.m(VM_roughness, month0);
+    displacement[SNOW_FREE] = r.m(VM_displacement, month0);
+    const bool overstory = r.overstory();
+    if (p >= N_PET_TYPES_NON_NAT && roughness[SNOW_FREE] == 0) roughness[SNOW_FREE] = soil_rough;
+    const double height = displacement[SNOW_FREE] / height_den;
+    if (displacement[SNOW_FREE] < wind_h) ref_height[SNOW_FREE] = wind_h;
+    else ref_height[SNOW_FREE] = displacement[SNOW_FREE] + wind_h + roughness[SNOW_FREE];
+    // bring the forcing wind from its nominal height to the reference height (log profile over open ground)
+    g.wind_corr(p) = vlog((ref_height[SNOW_FREE] - 0.) / soil_rough) / wind_den;
+    wind_speed.set_invalid();
+    resist.set_invalid();
+    // calc_aerodynamic_geom is a pure function of the values just set (every shared entry is overwritten), so when a land cover
+    // repeats the previous one (the two bare reference covers; the tile's own cover three times) the previous results are
+    // reused bit for bit instead of being recomputed.
+    const double in_now[7] = {(double)overstory, height, r.s(VL_trunk_ratio), r.s(VL_wind_atten), roughness[SNOW_FREE], displacement[SNOW_FREE],
+                              ref_height[SNOW_FREE]};
+    bool same = (p > 0);
+    for (int k = 0; k < 7; k++) same = same && (in_now[k] == in_prev[k]);
+    unsigned now_valid;
+    if (same) {
+      resist = prev_resist;
+      now_valid = prev_valid;
+      displacement = snap_displacement; ref_height = snap_ref_height; roughness = snap_roughness; wind_speed = snap_wind_speed;
+    } else {
+      int e = calc_aerodynamic_geom(overstory, height, r.s(VL_trunk_ratio), cp(CP_snow_rough), soil_rough, r.s(VL_wind_atten), resist, wind_speed,
+                                    displacement, ref_height, roughness);
+      if (e == ERROR_I) {
+        g.err() = 1;
+        return;
+      }
+      now_valid = 0;
+      for (int sidx = 0; sidx < 4; sidx++)
+        if (is_valid(wind_speed[sidx])) now_valid |= 1u << sidx;
+      for (int k = 0; k < 7; k++) in_prev[k] = in_now[k];
+      prev_resist = resist;
+      prev_valid = now_valid;
+      snap_displacement = displacement; snap_ref_height = ref_height; snap_roughness = roughness; snap_wind_speed = wind_speed;
+    }
+    for (int sidx = 0; sidx < 4; sidx++) g.R0(p, sidx) = resist[sidx];
+    valid |= now_valid << (4 * p);
+  }
+  for (int sidx = 0; sidx < 4; sidx++) {
+    g.U0()[sidx] = wind_speed[sidx];
+    g.displacement()[sidx] = displacement[sidx];
+    g.ref_height()[sidx] = ref_height[sidx];
+    g.roughness()[sidx] = roughness[sidx];
+  }
+  g.valid() = (double)valid;
+}
+
+// my row of the per-month table [VIC_AERO_NCOL][nhru]
+VIC_HD void load_aero_geom(const Col& c, AeroGeom& g) {
+#pragma unroll
+  for (int k = 0; k < VIC_AERO_NCOL; k++) g.v[k] = c(k);
+}
+
+// the record's wind scales the unit-wind tables: what the seven calc_aerodynamic() calls leave behind
+VIC_HD void aero_apply(const AeroGeom& g, double wind_NR, AeroState& as) {
+  const unsigned valid = (unsigned)g.valid();
+  const double nanv = vnan();
+#pragma unroll
+  for (int p = 0; p < N_PET_TYPES + 1; p++) {
+    const double tmp_wind = wind_NR * g.wind_corr(p);
+    Surf4 ws;
+#pragma unroll
+    for (int sidx = 0; sidx < 4; sidx++) {
+      as.aero_resist[p][sidx] = g.R0(p, sidx);
+      const bool ok = (valid >> (4 * p + sidx)) & 1u;
+      ws[sidx] = (p == N_PET_TYPES) ? g.U0()[sidx] : (ok ? 1.0 : nanv);
+    }
+    calc_aerodynamic_wind(tmp_wind, as.aero_resist[p], ws);
+    if (p == N_PET_TYPES) as.wind_speed = ws;
+  }
+#pragma unroll
+  for (int sidx = 0; sidx < 4; sidx++) {
+    as.displacement[sidx] = g.displacement()[sidx];
+    as.ref_height[sidx] = g.ref_height()[sidx];
+    as.roughness[sidx] = g.roughness()[sidx];
+  }
+}
+
 // per-HRU diagnostics of the step that are not part of the HRU record but feed the cell
 // output (atmos->out_prec / out_rain / out_snow, full_energy.c:425-427)
 struct HruStepDiag {
@@ -62,66 +190,23 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
   }
   const int veg_class = hp.vegIndex;
   const VegNow veg = veg_now(cx.vl, veg_class, month0);
-  const double wind_h = veg.wind_h;
   double surf_atten = vexp(-veg.rad_atten * veg.LAI);
   double moist0 = 0, ice0 = 0;
   prepare_full_energy<NN>(hru, cp, AreaFract, o, &moist0, &ice0);
   const double bare_albedo = hp.isGlacier ? cp(CP_GLAC_ALBEDO) : veg.albedo;
 
-  // aerodynamic resistances: 4 reference land covers, then the tile's own cover three times
-  // (natural vegetation, natural vegetation without canopy resistance, current)
+  // aerodynamic resistances: 4 reference land covers, then the tile's own cover three times (natural vegetation, natural vegetation
+  // without canopy resistance, current).  The wind-independent part comes from the per-month table when the kernel has one.
+  AeroGeom ag;
+#if defined(__CUDA_ARCH__) && !defined(VIC_NO_AERO_TABLE)
+  load_aero_geom(cx.aero, ag);  // (no run-time alternative on the device: `ag` must not have its address taken, or it lives in local memory)
+#else
+  aero_geom(cx.vl, cp, o, hp.isGlacier, veg_class, month0, veg, ag);
+#endif
+  if (ag.err() != 0.0) return ERROR_I;
   AeroState as;
-  as.displacement.set_invalid();
-  as.roughness.set_invalid();
-  as.ref_height.set_invalid();
-  double height = 0;
-  bool overstory = false;
-  const double soil_rough = cp(CP_rough);
-  const double wind_NR = cx.f(FV_wind, o.NR);
-  double in_prev[8] = {-1, 0, 0, 0, 0, 0, 0, 0};
-  // terms of the loop below that do not depend on the land cover: the leaf-area factor of calc_veg_height()
-  // (calc_veg_params.c:26-37) and the log-profile denominator of the wind correction
-  const double height_den = 1.1 * vlog(1 + vpow(0.2 * veg.LAI, 0.25));
-  const double wind_den = vlog((o.wind_h - 0.) / soil_rough);
-  Surf4 snap_displacement, snap_ref_height, snap_roughness, snap_wind_speed;  // the tables as the last evaluation left them (set at p == 0)
-  snap_displacement.set_invalid(); snap_ref_height.set_invalid(); snap_roughness.set_invalid(); snap_wind_speed.set_invalid();
-  #pragma unroll 1
-  for (int p = 0; p < N_PET_TYPES + 1; p++) {
-    const int pet_class = (p < N_PET_TYPES_NON_NAT) ? o.NVegLibTypes + p : veg_class;
-    VegRow r = cx.vl.row(pet_class);
-    if (pet_class == o.GLACIER_ID) as.roughness[SNOW_FREE] = cp(CP_GLAC_ROUGH);
-    else as.roughness[SNOW_FREE] = r.m(VM_roughness, month0);
-    as.displacement[SNOW_FREE] = r.m(VM_displacement, month0);
-    overstory = r.overstory();
-    if (p >= N_PET_TYPES_NON_NAT && as.roughness[SNOW_FREE] == 0) as.roughness[SNOW_FREE] = soil_rough;
-    height = as.displacement[SNOW_FREE] / height_den;
-    if (as.displacement[SNOW_FREE] < wind_h) as.ref_height[SNOW_FREE] = wind_h;
-    else as.ref_height[SNOW_FREE] = as.displacement[SNOW_FREE] + wind_h + as.roughness[SNOW_FREE];
-    // bring the forcing wind from its nominal height to the reference height (log profile over open ground)
-    const double wind_corr = vlog((as.ref_height[SNOW_FREE] - 0.) / soil_rough) / wind_den;
-    as.wind_speed[SNOW_FREE] = wind_NR * wind_corr;
-    as.wind_speed[CANOPY_OVER] = vnan();
-    as.wind_speed[SNOW_COVERED] = vnan();
-    as.wind_speed[GLACIER_SURF] = vnan();
-    as.aero_resist[p].set_invalid();
-    // calc_aerodynamic is a pure function of the values just set (every shared entry is overwritten), so when
-    // a land cover repeats the previous one (the two bare reference covers; the tile's own cover three times)
-    // the previous results are reused bit for bit instead of being recomputed.
-    const double in_now[8] = {(double)overstory, height, r.s(VL_trunk_ratio), r.s(VL_wind_atten), as.roughness[SNOW_FREE],
-                              as.displacement[SNOW_FREE], as.ref_height[SNOW_FREE], as.wind_speed[SNOW_FREE]};
-    bool same = (p > 0);
-    for (int k = 0; k < 8; k++) same = same && (in_now[k] == in_prev[k]);
-    if (same) {
-      as.aero_resist[p] = as.aero_resist[p - 1];
-      as.displacement = snap_displacement; as.ref_height = snap_ref_height; as.roughness = snap_roughness; as.wind_speed = snap_wind_speed;
-    } else {
-      int e = calc_aerodynamic(overstory, height, r.s(VL_trunk_ratio), cp(CP_snow_rough), soil_rough, r.s(VL_wind_atten), as.aero_resist[p],
-                               as.wind_speed, as.displacement, as.ref_height, as.roughness);
-      if (e == ERROR_I) return ERROR_I;
-      for (int k = 0; k < 8; k++) in_prev[k] = in_now[k];
-      snap_displacement = as.displacement; snap_ref_height = as.ref_height; snap_roughness = as.roughness; snap_wind_speed = as.wind_speed;
-    }
-  }
+  aero_apply(ag, cx.f(FV_wind, o.NR), as);
+  const bool overstory = veg.overstory;
   if (AreaFract > 0) {
     hru.cell.aero_surface = as.aero_resist[N_PET_TYPES][SNOW_FREE];
     hru.cell.aero_overstory = as.aero_resist[N_PET_TYPES][CANOPY_OVER];

@@ -76,7 +76,13 @@ struct CellPar {
 struct Forcing {
   Col c;
   int nslot;
-  VIC_HD double operator()(int var, int slot) const { return c(var * nslot + slot); }
+  VIC_HD double operator()(int var, int slot) const {
+#if defined(VIC_FORCING_SMEM) && defined(__CUDA_ARCH__)
+    return c.p[(size_t)(var * nslot + slot) * c.n];  // may point into shared memory (vicgpu_step.inc): a generic load, not ld.global.nc
+#else
+    return c(var * nslot + slot);
+#endif
+  }
 };
 
 struct Dmy {
@@ -175,6 +181,19 @@ VIC_HD size_t hr_rows(int nhru) { return ((size_t)nhru + 31) / 32 * 32; }
 // load, store, load, store ... and pays one round trip per column).
 #include <stddef.h>
 #define VIC_XFER_CHUNK 16
+// The HRU records stream through the step once per record (read from one state half, written to the other) while the step's own
+// thread-local working set is re-read thousands of times: with -DVIC_STATE_CS the record transfers carry the evict-first hint
+// (ld.global.cs / st.global.cs) so that they do not push the stack lines out of L2.
+#if defined(VIC_STATE_CS) && defined(__CUDA_ARCH__)
+#define VIC_REC_LD(ptr) __ldcs(ptr)
+#define VIC_REC_ST(ptr, v) __stcs((ptr), (v))
+#elif defined(__CUDA_ARCH__)
+#define VIC_REC_LD(ptr) __ldg(ptr)
+#define VIC_REC_ST(ptr, v) (*(ptr) = (v))
+#else
+#define VIC_REC_LD(ptr) (*(ptr))
+#define VIC_REC_ST(ptr, v) (*(ptr) = (v))
+#endif
 
 // columns col0 .. col0+count-1 of my record row  ->  dst[0 .. count)
 VIC_HD void cols_to_local(const double* __restrict__ rec, size_t n, int col0, int count, double* __restrict__ dst) {
@@ -184,11 +203,7 @@ VIC_HD void cols_to_local(const double* __restrict__ rec, size_t n, int col0, in
 #pragma unroll
     for (int j = 0; j < VIC_XFER_CHUNK; j++) {
       if (k + j < count) {
-#if defined(__CUDA_ARCH__)
-        r[j] = __ldg(rec + (size_t)(col0 + k + j) * n);
-#else
-        r[j] = rec[(size_t)(col0 + k + j) * n];
-#endif
+        r[j] = VIC_REC_LD(rec + (size_t)(col0 + k + j) * n);
       }
     }
 #pragma unroll
@@ -205,7 +220,7 @@ VIC_HD void local_to_cols(const double* __restrict__ src, double* __restrict__ r
       if (k + j < count) r[j] = src[k + j];
 #pragma unroll
     for (int j = 0; j < VIC_XFER_CHUNK; j++)
-      if (k + j < count) rec[(size_t)(col0 + k + j) * n] = r[j];
+      if (k + j < count) VIC_REC_ST(rec + (size_t)(col0 + k + j) * n, r[j]);
   }
 }
 
@@ -233,7 +248,7 @@ VIC_HDI void load_hru(Hru<NN>& h, const double* __restrict__ rec, size_t n, cons
   cols_to_local(rec, n, G::nE + G::nS, G::nC, reinterpret_cast<double*>(&h.cell));
   cols_to_local(rec, n, G::nE + G::nS + G::nC, G::nV, reinterpret_cast<double*>(&h.veg));
   cols_to_local(rec, n, G::nE + G::nS + G::nC + G::nV, G::nG, reinterpret_cast<double*>(&h.glac));
-  h.mu = rec[(size_t)HR_H_mu * n];
+  h.mu = VIC_REC_LD(rec + (size_t)HR_H_mu * n);
   // layers: record [field][layer], working set layer[i].field
   {
     double r[HRL_N * VICGPU_NLAYER];
@@ -260,7 +275,7 @@ VIC_HDI void store_hru(const Hru<NN>& h, double* __restrict__ rec, size_t n, con
   local_to_cols(reinterpret_cast<const double*>(&h.cell), rec, n, G::nE + G::nS, G::nC);
   local_to_cols(reinterpret_cast<const double*>(&h.veg), rec, n, G::nE + G::nS + G::nC, G::nV);
   local_to_cols(reinterpret_cast<const double*>(&h.glac), rec, n, G::nE + G::nS + G::nC + G::nV, G::nG);
-  rec[(size_t)HR_H_mu * n] = h.mu;
+  VIC_REC_ST(rec + (size_t)HR_H_mu * n, h.mu);
   {
     double r[HRL_N * VICGPU_NLAYER];
     for (int i = 0; i < VICGPU_NLAYER; i++) {
@@ -295,6 +310,7 @@ struct Ctx {
   VegLib vl;
   Col hp;        // my HRU parameter row
   Forcing f;     // my cell's forcing record of the current model step
+  Col aero;      // my row of the per-month aerodynamic table (vic_step.cuh AeroGeom); p == nullptr: none, hru_step computes it
   Dmy dmy;
   int rec;
   PhaseSync ps;

@@ -152,6 +152,23 @@ __global__ void k_derive_cells(const Opts* __restrict__ o, const double* __restr
 }
 
 // the cells' glacier mass-balance curves at the end of an accumulation interval (vic_engine.cuh cell_gmb)
+// The wind-independent part of the seven CalcAerodynamic() evaluations of every row (vic_step.cuh AeroGeom) for the month `month0`:
+// run when the month or the row order changes, read by every step of the month.
+__global__ void __launch_bounds__(128) k_hru_aero(const Opts* __restrict__ o, Tables t, double* __restrict__ aero, int month0) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= t.nhru) return;
+  const size_t nh = (size_t)t.nhru;
+  Col hpc{t.hrupar + h, nh};
+  const int cell = (int)hpc(HP_cell);
+  const CellPar cp{Col{t.cellpar + cell, (size_t)t.ncell}, &o->L, Col{nullptr, 0}};
+  const VegLib vl{t.veglib, &o->L};
+  const int veg_class = (int)hpc(HP_vegIndex);
+  const VegNow veg = veg_now(vl, veg_class, month0);
+  AeroGeom g;
+  aero_geom(vl, cp, *o, hpc(HP_isGlacier) != 0.0, veg_class, month0, veg, g);
+  for (int k = 0; k < VIC_AERO_NCOL; k++) aero[(size_t)k * nh + h] = g.v[k];
+}
+
 __global__ void k_cell_gmb(const Opts* __restrict__ o, Tables t) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= t.ncell) return;
@@ -374,6 +391,13 @@ static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const O
   const char* bc = getenv("VICGPU_BINCOST");
   h->bin_cost_env = bc ? atoi(bc) : -1;
   h->rebin_env = rb != nullptr;
+  const char* lp = getenv("VICGPU_L2PERSIST");  // MB of L2 set aside for the cell-parameter table (persisting access-policy window), 0: off
+  h->l2_persist_mb = lp ? atoi(lp) : 0;
+#if defined(VIC_NO_AERO_TABLE)
+  h->aero_cache = false;  // A/B build: the step kernel evaluates the aerodynamic geometry every record
+#else
+  h->aero_cache = true;
+#endif
   const char* bf = getenv("VICGPU_BINFINE");  // 1: bin by pack regime and canopy snow as well (k_bin_keys)
   h->bin_fine = bf && atoi(bf) != 0;
   CK(cudaMalloc(&h->d_o, sizeof(Opts)));
@@ -405,6 +429,7 @@ int vicgpu_destroy(vicgpu_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
+  cudaFree(h->d_aero);
   cudaFree(h->d_o); cudaFree(h->d_veglib); cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_gmb_cum); cudaFree(h->d_gmb);
   for (int b = 0; b < 2; b++) {
     free_half(h->half[b]);
@@ -445,6 +470,7 @@ int vicgpu_set_veglib(vicgpu_handle* h, int nclass, const double* veglib) {
   CK(cudaMemcpy(h->d_veglib, veglib, n * sizeof(double), cudaMemcpyHostToDevice));
   h->t.veglib = h->d_veglib;
   h->t.nclass = nclass;
+  h->aero_month = -1;
   return VICGPU_OK;
 }
 
@@ -490,6 +516,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   h->d_state_cur = nullptr;
   cudaFree(h->d_gmb_cum); cudaFree(h->d_gmb);
   h->d_gmb_cum = h->d_gmb = nullptr;
+  cudaFree(h->d_aero); h->d_aero = nullptr;
   cudaFree(h->d_cellpar); cudaFree(h->d_cellder); cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_cell_h0); cudaFree(h->d_status);
   h->d_cellder = nullptr;
   cudaFree(h->d_fail_rec); cudaFree(h->d_keys[0]); cudaFree(h->d_keys[1]); cudaFree(h->d_oldslot[0]); cudaFree(h->d_oldslot[1]); cudaFree(h->d_warp_ns);
@@ -506,6 +533,8 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   }
   const size_t state_bytes = hr_rows(nhru) * L.hr_stride * sizeof(double);  // whole 32-row tiles
   CK(cudaMalloc(&h->d_cellpar, (size_t)ncell * L.cp_stride * sizeof(double)));
+  if (h->aero_cache) CK(cudaMalloc(&h->d_aero, (size_t)nhru * VIC_AERO_NCOL * sizeof(double)));
+  h->aero_month = -1;
   CK(cudaMalloc(&h->d_cellder, (size_t)ncell * VIC_NCELLDER * sizeof(double)));
   CK(cudaMalloc(&h->d_cost, (size_t)nhru * sizeof(int)));
   CK(cudaMemset(h->d_cost, 0, (size_t)nhru * sizeof(int)));
@@ -585,9 +614,24 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   if (h->bin_cost == 2 && !h->rebin_env) h->rebin_every = 2;
   if (!h->hru_block_fixed) h->hru_block = ((long long)nhru <= (long long)h->sm_count * VICGPU_HRU_BLOCK) ? VICGPU_HRU_BLOCK : VICGPU_HRU_BLOCK_MAX;
   h->t.ncell = ncell; h->t.nhru = nhru;
-  h->t.gmb_cum = h->d_gmb_cum; h->t.gmb = h->d_gmb; h->t.cost = h->d_cost;
+  h->t.gmb_cum = h->d_gmb_cum; h->t.gmb = h->d_gmb; h->t.cost = h->d_cost; h->t.aero = nullptr;
   h->t.cellpar = h->d_cellpar; h->t.cellder = h->d_cellder; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
   h->t.status = h->d_status; h->t.carry = h->d_carry; h->t.out = h->d_out; h->t.agg = h->d_agg; h->t.aggtype = h->d_aggtype;
+  if (h->l2_persist_mb > 0) {
+    // The cell-parameter table is read column by column all through the step (227 columns, 18 MB at 10,000 cells) while 300+ MB of
+    // state and stack stream through L2 per record: a persisting window keeps it resident (measurement knob, off by default).
+    int maxwin = 0;
+    CK(cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, h->device));
+    const size_t want = (size_t)h->l2_persist_mb << 20, bytes = (size_t)ncell * L.cp_stride * sizeof(double);
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    cudaStreamAttrValue av = {};
+    av.accessPolicyWindow.base_ptr = h->d_cellpar;
+    av.accessPolicyWindow.num_bytes = bytes < (size_t)maxwin ? bytes : (size_t)maxwin;
+    av.accessPolicyWindow.hitRatio = (float)(want >= av.accessPolicyWindow.num_bytes ? 1.0 : (double)want / (double)av.accessPolicyWindow.num_bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+  }
   h->cur_half = 0;
   h->d_state_cur = h->half[0].in;
   h->have_cells = true;
@@ -623,6 +667,7 @@ int vicgpu_set_cell_status(vicgpu_handle* h, const int* status) {
 int vicgpu_set_state(vicgpu_handle* h, const double* hrurec) {
   if (!h || !hrurec) return fail(VICGPU_EINVAL, "null argument");
   if (!h->have_cells) return fail(VICGPU_ESTATE, "set_cells before set_state");
+  h->aero_month = -1;  // the rows return to the order of the first half
   CK(cudaSetDevice(h->device));
   StateHalf& s = h->half[h->cur_half];
   {
@@ -802,6 +847,7 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
       D.ord = S.ord ^ 1;
       input = D.in;
       h->recs_since_rebin = 0;
+      h->aero_month = -1;  // the table is in row order
     } else {
       D.ord = S.ord;
     }
@@ -815,6 +861,14 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
     t.hdiag_out = D.hdiag;
     const int* d = &dmy[i * 5];
     const Dmy dm = {d[0], d[1], d[2], d[3], d[4]};
+    if (h->d_aero) {
+      if (h->aero_month != dm.month) {
+        k_hru_aero<<<(nhru + 127) / 128, 128, 0, h->stream>>>(h->d_o, t, h->d_aero, dm.month - 1);
+        h->last_launches++;
+        h->aero_month = dm.month;
+      }
+      t.aero = h->d_aero;
+    } else t.aero = nullptr;
     const GlacAccum ga = glacier_accum_flags(h->o, d, d + 5, rec, &h->glac_started);
     if (rec == 0) {
       // storage terms of the initial state: put_data(rec = -nrecs), vicNl.c:524-541
@@ -832,9 +886,9 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
       wns = h->d_warp_ns;
     }
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0);
-    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0);
-    else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0);
+    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
+    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
+    else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
     h->last_launches++;
     // the previous record's output rides on this step
     if (pend.valid) {

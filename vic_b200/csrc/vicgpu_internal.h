@@ -71,6 +71,10 @@ struct vicgpu_handle {
   int hru_block = VICGPU_HRU_BLOCK;
   bool hru_block_fixed = false;  // set through VICGPU_BLOCK
   int sm_count = 148;
+  int l2_persist_mb = 0;  // VICGPU_L2PERSIST
+  bool aero_cache = true;   // VICGPU_AEROCACHE
+  double* d_aero = nullptr;  // [VIC_AERO_NCOL][nhru] aerodynamic geometry of every row for month aero_month (k_hru_aero), in the current row order
+  int aero_month = -1;
   long long sync_limit = 0;  // PhaseSync::limit
   // re-binning scratch (vicgpu_api.cu rebin_rows)
   unsigned long long* d_keys[2] = {nullptr, nullptr};

@@ -16,42 +16,18 @@
 // 448 threads / 118 blocks 615 us, 384 / 138 blocks 609 us with the step slowed by co-resident output blocks; profiles/r02_summary.md).
 #ifndef VICGPU_HRU_BLOCK_MAX
 #define VICGPU_HRU_BLOCK_MAX 512
-int vicgpu_set_work_buffer_nn3(int* buf);
-int vicgpu_set_work_buffer_nn10(int* buf);
-int vicgpu_set_work_buffer_nn32(int* buf);
-// measurement aid: record in, nframe live values in and out, record out (vicgpu_measure_phase_tax)
-void vicgpu_launch_hru_pass_nn3(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-void vicgpu_launch_hru_pass_nn10(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-void vicgpu_launch_hru_pass_nn32(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-
 #endif
 #ifndef VICGPU_STEP_MAXNREG
 #define VICGPU_STEP_MAXNREG 128
-int vicgpu_set_work_buffer_nn3(int* buf);
-int vicgpu_set_work_buffer_nn10(int* buf);
-int vicgpu_set_work_buffer_nn32(int* buf);
-// measurement aid: record in, nframe live values in and out, record out (vicgpu_measure_phase_tax)
-void vicgpu_launch_hru_pass_nn3(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-void vicgpu_launch_hru_pass_nn10(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-void vicgpu_launch_hru_pass_nn32(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-
 #endif
 #ifndef VICGPU_HRU_BLOCK
 #define VICGPU_HRU_BLOCK 512
-int vicgpu_set_work_buffer_nn3(int* buf);
-int vicgpu_set_work_buffer_nn10(int* buf);
-int vicgpu_set_work_buffer_nn32(int* buf);
-// measurement aid: record in, nframe live values in and out, record out (vicgpu_measure_phase_tax)
-void vicgpu_launch_hru_pass_nn3(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-void vicgpu_launch_hru_pass_nn10(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-void vicgpu_launch_hru_pass_nn32(const vic::Opts* d_o, const vic::Tables& t, double* frame, int nframe, int block, cudaStream_t s);
-
 #endif
 
 // one: the configuration's model step is a single sub-step (NF == 1)
-void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0);
-void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0);
-void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0);
+void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0);
+void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0);
+void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0);
 
 int vicgpu_set_work_buffer_nn3(int* buf);
 int vicgpu_set_work_buffer_nn10(int* buf);
