@@ -130,6 +130,20 @@ VIC_HD double div_pos(double a, double b) {
   return z ? a : q;
 }
 
+// a / b for any b, exactly, when the numerator is often an exact zero (dry canopy, no ice, no rain): +-0 / b is +-0 with the sign of
+// the operands for every b except 0 and NaN, which go through the divider as they are
+VIC_HD double div_zn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  const bool z = (a == 0.0) && (b > 0.0 || b < 0.0);
+  double n = z ? 1.0 : a;
+  asm volatile("" : "+d"(n));
+  const double q = n / b;
+  return z ? (b > 0.0 ? a : -a) : q;
+#else
+  return a / b;
+#endif
+}
+
 VIC_HD double vnan() {
 #if defined(__CUDA_ARCH__)
   return __longlong_as_double(0x7ff8000000000000LL);

@@ -59,7 +59,7 @@ VIC_HDI void carry_hru_record(const Tables& t, int h, int hr_stride) {
 // h: row of the HRU tables
 template <int NN, bool ONE>
 VIC_HDI void hru_work(const Opts* o, const Tables& t, const double* forcing_rec /* [f_stride][ncell] */, int h, Dmy dmy, int rec, GlacAccum ga,
-                      PhaseSync ps = PhaseSync{nullptr, 0}, const double* fstage = nullptr, int fstage_n = 0) {
+                      PhaseSync ps = PhaseSync{nullptr, 0, 0}, const double* fstage = nullptr, int fstage_n = 0) {
   const size_t nh = (size_t)t.nhru;
   Col hpc{t.hrupar + h, nh};
   const int cell = (int)hpc(HP_cell);

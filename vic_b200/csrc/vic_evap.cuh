@@ -101,13 +101,13 @@ VIC_HD void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doubl
   }
   const double moist2 = layer[NL - 1].moist - layer[NL - 1].soil_ice;
   avail_moist[NL - 1] = moist2;
-  const double wet_canopy = 1.0 - f * pow23_m(memo, 1, (Wdew / veg.Wdmax));
+  const double wet_canopy = 1.0 - f * pow23_m(memo, 1, div_zn(Wdew, veg.Wdmax));
   // (1 - root) is evaluated in single precision by the reference (float operand)
   const double one_minus_rootN = (double)(1.0f - s.root[NL - 1]);
   if ((moist1 >= Wcr1 && moist2 >= s.Wcr[NL - 1] && Wcr1 > 0.) || (moist1 >= Wcr1 && one_minus_rootN >= 0.5) ||
       (moist2 >= s.Wcr[NL - 1] && s.root[NL - 1] >= 0.5)) {
     double rc = calc_rc_m(memo, 0, veg.rmin, net_short, veg.RGL, air_temp, vpd, veg.LAI, 1.0);
-    double evap = penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t / SEC_PER_DAY * wet_canopy;
+    double evap = div_pos(penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t, SEC_PER_DAY) * wet_canopy;
     double root_sum = 1.0, spare_evap = 0.0;
     #pragma unroll
     for (int i = 0; i < NL; i++) {
@@ -134,7 +134,7 @@ VIC_HD void transpiration(SoilLayer* layer, const VegNow& veg, double rad, doubl
       else gsm_inv = 0.0;
       if (gsm_inv > 0.0) {
         double rc = calc_rc_m(memo, 1 + i, veg.rmin, net_short, veg.RGL, air_temp, vpd, veg.LAI, gsm_inv);
-        layerevap[i] = penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t / SEC_PER_DAY * (double)s.root[i] * wet_canopy;
+        layerevap[i] = div_pos(penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t, SEC_PER_DAY) * (double)s.root[i] * wet_canopy;
       } else layerevap[i] = 0.0;
     }
   }
@@ -169,7 +169,7 @@ VIC_HD double canopy_evap(SoilLayer* layer, VegVar& vv, bool CALC_EVAP, const Ve
     tmp_Wdew = veg.Wdmax;
   }
   double rc = calc_rc(0.0, net_short, veg.RGL, air_temp, vpd, veg.LAI, 1.0, false);
-  double canopyevap = pow23_m(memo, 0, (tmp_Wdew / veg.Wdmax)) * penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t / SEC_PER_DAY;
+  double canopyevap = div_pos(pow23_m(memo, 0, div_zn(tmp_Wdew, veg.Wdmax)) * penman_m(memo, air_temp, elevation, rad, vpd, ra, rc, veg.rarc) * delta_t, SEC_PER_DAY);
   double f;
   if (canopyevap > 0.0 && delta_t == SEC_PER_DAY) f = vmin(1.0, ((tmp_Wdew + ppt) / canopyevap));
   else if (canopyevap > 0.0) f = vmin(1.0, ((tmp_Wdew) / canopyevap));
@@ -201,7 +201,7 @@ VIC_HD double arno_evap(SoilLayer* layer, double rad, double air_temp, double vp
   double tmp, ratio, as, evap;
   double moist = layer[0].moist - layer[0].soil_ice;
   if (moist > max_moist) moist = max_moist;
-  double Epot = penman_m(memo, air_temp, elevation, rad, vpd, ra, 0.0, 0.0) * delta_t / SEC_PER_DAY;
+  double Epot = div_pos(penman_m(memo, air_temp, elevation, rad, vpd, ra, 0.0, 0.0) * delta_t, SEC_PER_DAY);
   int kind;
   double beta_asp = 0;
   if (memo && memo->arno_ok) {

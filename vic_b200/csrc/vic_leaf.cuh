@@ -74,7 +74,7 @@ VIC_HD PenmanPre penman_pre(double tair, double elevation) {
   return p;
 }
 VIC_HD double penman_eval(const PenmanPre& p, double rad, double vpd, double ra, double rc, double rarc) {
-  double evap = (p.slope * rad + p.r_air * CP_PM * vpd / ra) / (p.lv * (p.slope + p.gamma * (1 + (rc + rarc) / ra))) * SEC_PER_DAY;
+  double evap = (p.slope * rad + p.r_air * CP_PM * vpd / ra) / (p.lv * (p.slope + p.gamma * (1 + div_zn(rc + rarc, ra)))) * SEC_PER_DAY;
   if (vpd >= 0.0 && evap < 0.0) evap = 0.0;
   return evap;
 }

@@ -134,7 +134,7 @@ VIC_HDI int runoff(SoilCol& cell, EnergyBal<NN>& energy, const CellPar& cp, doub
   cell.asat = 0;
   double baseflow = 0, runoff_v, A;
   const int dt = o.dt;
-  for (int l = 0; l < NL; l++) evap[l] = cell.layer[l].evap / (double)dt;
+  for (int l = 0; l < NL; l++) evap[l] = div_pos(cell.layer[l].evap, (double)dt);  // (dt >= 1)
   double inflow = ppt;
   for (int l = 0; l < NL; l++) {
     Ksat[l] = cp.layer(CL_Ksat, l) / 24.;
@@ -145,8 +145,8 @@ VIC_HDI int runoff(SoilCol& cell, EnergyBal<NN>& energy, const CellPar& cp, doub
   }
   for (int l = 0; l < NL; l++) mm_tmp[l] = (liq[l] + ice[l]);
   compute_runoff_and_asat(cp, mm_tmp, inflow, &A, &runoff_v);
-  const double tmp_dt_runoff = runoff_v / (double)dt;
-  const double dt_inflow = inflow / (double)dt;
+  const double tmp_dt_runoff = div_pos(runoff_v, (double)dt);
+  const double dt_inflow = div_pos(inflow, (double)dt);
   const double Dsmax = cp(CP_Dsmax) / 24.;
   const double Ds = cp(CP_Ds), Ws = cp(CP_Ws), c_exp = cp(CP_c);
   for (int time_step = 0; time_step < dt; time_step++) {
@@ -365,7 +365,7 @@ VIC_HDI void prepare_full_energy(Hru<NN>& h, const CellPar& cp, double AreaFract
     for (int l = 0; l < 2; l++) {
       const double dl = cp.layer(CL_depth, l);
       const double moist = h.cell.layer[l].moist / dl / 1000;
-      const double ice = h.cell.layer[l].soil_ice / dl / 1000;
+      const double ice = div_pos(div_zn(h.cell.layer[l].soil_ice, dl), 1000);
       const double kappa = soil_conductivity_pre(moist, moist - ice, cell_kpre(cp, l));
       const double Cs = volumetric_heat_capacity(cp.layer(CL_bulk_density, l) / cp.layer(CL_soil_density, l), moist - ice, ice, cp.layer(CL_organic, l));
       if (l == 0) { h.energy.kappa0 = kappa; h.energy.Cs0 = Cs; }

@@ -302,6 +302,7 @@ VIC_HDI void store_hru(const Hru<NN>& h, double* __restrict__ rec, size_t n, con
 struct PhaseSync {
   unsigned* count;  // [VIC_NPHASE + 2] in shared memory, zeroed at kernel start: arrivals per phase, then the two groups' sizes; null: off
   long long limit;  // clock cycles a warp is prepared to wait
+  unsigned mask;    // bit p: rendezvous at phase boundary p (VICGPU_SYNCMASK, A/B knob; all by default)
 };
 
 struct Ctx {
@@ -327,7 +328,7 @@ struct Ctx {
   }
   VIC_HD void rendezvous(int phase, int group) const {
 #if defined(__CUDA_ARCH__)
-    if (!ps.count) return;
+    if (!ps.count || !((ps.mask >> phase) & 1u)) return;
     const unsigned m = __activemask();
     if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
       atomicAdd(&ps.count[phase], 1u);

@@ -373,7 +373,8 @@ static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const O
   const char* noov = getenv("VICGPU_NOOVERLAP");  // 1: the cell output of record r finishes before step r + 1 starts (no dependent launch)
   h->pdl = !(noov && atoi(noov) != 0);
   const char* sl = getenv("VICGPU_SYNC");  // most clock cycles a warp waits for its block at a phase boundary of the step (0: no rendezvous)
-  h->sync_limit = sl ? atoll(sl) : 1000000;  // 0.5 ms: a safety bound, not a tuning parameter (waits end when the group has arrived)
+  const char* sm = getenv("VICGPU_SYNCMASK");  // phase boundaries at which the warps of a block wait for each other (bit per phase; A/B knob)
+  h->sync_limit = ((sl ? atoll(sl) : 1000000) & 0x00ffffffffffffffll) | ((long long)((sm ? atoi(sm) : 0x7f) & 0x7f) << 56);  // 0.5 ms: a safety bound, not a tuning parameter (waits end when the group has arrived)
   const char* nobin = getenv("VICGPU_NOBIN");  // keep the caller's row order (no binning at all)
   h->binned = !(nobin && atoi(nobin) != 0);
   const char* rb = getenv("VICGPU_REBIN");  // records between re-sorts of the rows by (kind, snow); 0: bin by kind once (set_cells)
