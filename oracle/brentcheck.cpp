@@ -1,6 +1,6 @@
 // oracle/brentcheck.cpp -- TEST INFRASTRUCTURE ONLY.
-// Drives root_brent (the restatement of root_brent.c:97-335 with its ~15 residual call sites) and root_brent_ss (the same control
-// flow as a state machine around one call site) with random residuals -- monotone and non-monotone, with and without regions where
+// Drives root_brent (the restatement of root_brent.c:97-335 with its ~15 residual call sites), root_brent_ss (the same control
+// flow as a state machine around one call site) and the resumable brent_begin / brent_advance with random residuals -- monotone and non-monotone, with and without regions where
 // the residual is undefined (ERROR), with and without a sign change in the first bracket -- and requires the two to evaluate the
 // residual at exactly the same points in the same order and to return the same value.  Prints "cases N mismatches M ..." (tests/test_cpu.py).
 #include <cstdio>
@@ -50,6 +50,17 @@ int main() {
     const double xa = root_brent(lo, hi, r);
     r.trace = &tb;
     const double xb = root_brent_ss(lo, hi, r);
+    // the resumable machine (brent_begin / brent_advance), driven the way vic_frozen.cuh drives it
+    std::vector<double> tc;
+    r.trace = &tc;
+    BrentStep bs;
+    brent_begin(bs, lo, hi);
+    while (!brent_advance(bs, r(bs.x))) {}
+    const double xc = bs.res;
+    if (!((memcmp(&xa, &xc, 8) == 0) && ta.size() == tc.size() && (ta.empty() || memcmp(ta.data(), tc.data(), ta.size() * 8) == 0))) {
+      if (mism < 5) fprintf(stderr, "stepper mismatch: case %d lo %.17g hi %.17g  ret %.17g vs %.17g  evals %zu vs %zu\n", t, lo, hi, xa, xc, ta.size(), tc.size());
+      mism++;
+    }
     cases++;
     if (xa == ERROR_D) errs++;
     if (ta.size() > 2 && (ta[2] == lo - 10 || ta[2] == 0.5 * (lo + hi))) expansions++;

@@ -345,5 +345,168 @@ VIC_HD double root_brent_ss(double LowerBound, double UpperBound, F& f) {
   return root_brent_ss_impl<false>(LowerBound, UpperBound, f, (BrentFinal*)nullptr);
 }
 
+
+// The same solver once more, as a RESUMABLE machine: the caller owns the residual evaluations.  brent_begin() names the first point,
+// the caller evaluates the residual there and hands the value to brent_advance(), which either names the next point (returns false)
+// or finishes (returns true, BrentStep::res is what root_brent would have returned).  Same points, same order, same result as
+// root_brent / root_brent_ss (oracle/brentcheck.cpp compares all three).  It exists for the soil thermal profile (vic_frozen.cuh):
+// there a lane of a warp works through hundreds of small solves -- one per frozen node and sweep -- and with a resumable machine
+// every lane can be at a different node, sweep and iteration while the warp still shares the one expensive call site, the residual.
+struct BrentStep {
+  double a, b, c, d, e, fa, fb, fc, last_bad, last_good, x, res;
+  int which_err, i, j, st;
+};
+VIC_HD void brent_begin(BrentStep& s, double LowerBound, double UpperBound) {
+  s.a = LowerBound; s.b = UpperBound; s.c = 0; s.d = 0; s.e = 0; s.fa = 0; s.fb = 0; s.fc = 0; s.last_bad = 0; s.last_good = 0;
+  s.which_err = 0; s.i = 0; s.j = 0; s.st = 0; s.res = 0;
+  s.x = s.a;
+}
+VIC_HD bool brent_advance(BrentStep& s, double fx) {
+  const int MAXTRIES = 5, MAXITER = 1000;
+  const double MACHEPS = 3e-8, TSTEP = 10, T = 1e-7;
+  double m, p, q, r, sv, tol;
+  switch (s.st) {
+    case 0:
+      s.fa = fx;
+      s.x = s.b;
+      s.st = 1;
+      return false;
+    case 1:
+      s.fb = fx;
+      if (s.fa == ERROR_D && s.fb == ERROR_D) { s.res = (ERROR_D); return true; }
+      if (s.fa == ERROR_D || s.fb == ERROR_D) {
+        if (s.fa == ERROR_D) { s.which_err = -1; s.last_bad = s.a; s.last_good = s.b; }
+        else { s.which_err = 1; s.last_good = s.a; s.last_bad = s.b; }
+        s.c = 0.5 * (s.last_bad + s.last_good);
+        s.x = s.c;
+        s.j = 0;
+        s.st = 2;
+        return false;
+      }
+      s.j = 0;
+      goto expand_check;
+    case 2:  // bisection towards the good bound while the residual is undefined
+      s.fc = fx;
+      if (s.fc == ERROR_D && s.j < MAXITER) {
+        s.last_bad = s.c;
+        s.c = 0.5 * (s.last_bad + s.last_good);
+        s.x = s.c;
+        s.j++;
+        return false;
+      }
+      if (s.fc == ERROR_D) { s.res = (ERROR_D); return true; }
+      if (s.which_err == -1) { s.a = s.c; s.fa = s.fc; } else { s.b = s.c; s.fb = s.fc; }
+      s.j = 0;
+      goto expand_check;
+    case 4:
+      s.fa = fx;
+      s.x = s.b;
+      s.st = 5;
+      return false;
+    case 5:
+      s.fb = fx;
+      s.j++;
+      goto expand_check;
+    case 6:
+      s.fb = fx;
+      if (s.fb == ERROR_D) { s.res = (ERROR_D); return true; }
+      s.last_good = s.a;
+      s.c = 0.5 * (s.last_good + s.last_bad);
+      s.x = s.c;
+      s.i = 0;
+      s.st = 8;
+      return false;
+    case 7:
+      s.fa = fx;
+      if (s.fa == ERROR_D) { s.res = (ERROR_D); return true; }
+      s.last_good = s.b;
+      s.c = 0.5 * (s.last_good + s.last_bad);
+      s.x = s.c;
+      s.i = 0;
+      s.st = 8;
+      return false;
+    case 8:
+      s.fc = fx;
+      if (s.fc == ERROR_D && s.i < MAXITER) {
+        s.last_bad = s.c;
+        s.c = 0.5 * (s.last_bad + s.last_good);
+        s.x = s.c;
+        s.i++;
+        return false;
+      }
+      if (s.fc == ERROR_D) { s.res = (ERROR_D); return true; }
+      if (s.which_err == -1) { s.a = s.c; s.fa = s.fc; } else { s.b = s.c; s.fb = s.fc; }
+      s.j++;
+      goto expand_check;
+    default:  // 10: an iteration of the main loop has evaluated f(b)
+      s.fb = fx;
+      if (s.fb == ERROR_D) { s.res = (ERROR_D); return true; }
+      s.i++;
+      goto main_top;
+  }
+expand_check:
+  if ((s.fa * s.fb) >= 0 && s.j < MAXTRIES) {
+    if (s.which_err == 0) {
+      s.a -= TSTEP;
+      s.b += TSTEP;
+      s.x = s.a;
+      s.st = 4;
+    } else if (s.which_err == -1) {
+      s.b += TSTEP;
+      s.x = s.b;
+      s.st = 6;
+    } else {
+      s.a -= TSTEP;
+      s.x = s.a;
+      s.st = 7;
+    }
+    return false;
+  }
+  if ((s.fa * s.fb) >= 0) { s.res = (ERROR_D); return true; }
+  s.fc = s.fb;
+  s.i = 0;
+main_top:
+  if (s.i >= MAXITER) { s.res = (ERROR_D); return true; }
+  if (s.fb * s.fc > 0) {
+    s.c = s.a;
+    s.fc = s.fa;
+    s.d = s.b - s.a;
+    s.e = s.d;
+  }
+  if (fabs(s.fc) < fabs(s.fb)) {
+    s.a = s.b; s.b = s.c; s.c = s.a;
+    s.fa = s.fb; s.fb = s.fc; s.fc = s.fa;
+  }
+  tol = 2 * MACHEPS * fabs(s.b) + T;
+  m = 0.5 * (s.c - s.b);
+  if (fabs(m) <= tol || s.fb == 0) { s.res = (s.b); return true; }
+  if (fabs(s.e) < tol || fabs(s.fa) <= fabs(s.fb)) {
+    s.d = m;
+    s.e = s.d;
+  } else {
+    sv = s.fb / s.fa;
+    if (s.a == s.c) {
+      p = 2 * m * sv;
+      q = 1 - sv;
+    } else {
+      q = s.fa / s.fc;
+      r = s.fb / s.fc;
+      p = sv * (2 * m * q * (q - r) - (s.b - s.a) * (r - 1));
+      q = (q - 1) * (r - 1) * (sv - 1);
+    }
+    if (p > 0) q = -q; else p = -p;
+    sv = s.e;
+    s.e = s.d;
+    if ((2 * p) < (3 * m * q - fabs(tol * q)) && p < fabs(0.5 * sv * q)) s.d = p / q;
+    else { s.d = m; s.e = s.d; }
+  }
+  s.a = s.b;
+  s.fa = s.fb;
+  s.b += (fabs(s.d) > tol) ? s.d : ((m > 0) ? tol : -tol);
+  s.x = s.b;
+  s.st = 10;
+  return false;
+}
+
 }  // namespace vic
 #endif

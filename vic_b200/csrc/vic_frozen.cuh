@@ -39,7 +39,9 @@ VIC_HD void vic_count_work(int n) {
 struct SoilThermalEqn {
   double TL, TU, T0, moist, max_moist, bubble, expt, ice0, A, B, C, D, E;
   int EXP_TRANS, node;
-  VIC_HDI double operator()(double T) {
+  VIC_HDI double operator()(double T) { return eval(T); }
+  // (inlined into the single call site of the lane-asynchronous sweeps, solve_T_profile)
+  VIC_HD double eval(double T) {
     double ice;
     if (T < 0.) {
       ice = moist - maximum_unfrozen_water(T, max_moist, bubble, expt);
@@ -122,6 +124,7 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
   const int HIST = 8;
   double Th[HIST][NN];     // temperatures after the last HIST sweeps
   unsigned fbh[HIST];      // nodes whose Brent solve fell back, per sweep
+#if !defined(VIC_FROZEN_ASYNC)
   while (!Done && ItCount < MAXIT) {
     ItCount++;
     unsigned fbmask = 0;
@@ -192,6 +195,116 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
     for (int j = 0; j < Nnodes; j++) Th[ItCount % HIST][j] = T[j];
     fbh[ItCount % HIST] = fbmask;
   }
+#else
+  // Lane-asynchronous form of the same sweeps (-DVIC_FROZEN_ASYNC; measured, NOT the default).  In lock-step form (above) the threads
+  // of a warp walk the nodes together and at every node wait for the lanes whose node is frozen to finish a Brent solve of 5-15
+  // residual evaluations: 6.8 of 32 lanes are active per instruction on the 100,000-cell frozen-soil workload.  Here every
+  // thread keeps its own cursor (sweep, node, state of the node's solve: BrentStep) and the loop body is ONE residual evaluation --
+  // the single expensive call site (maximum_unfrozen_water's pow) -- preceded by whatever cheap work brings the thread to its next
+  // evaluation (explicit nodes, end-of-sweep bookkeeping).  A thread is busy as long as it has evaluations left, wherever the other
+  // lanes are; the operations of each thread and their order are exactly those of the lock-step form (bit-identical on the frozen-soil
+  // parity tests, CPU port and GPU).  Result (profiles/r02_summary.md): the residual's pow runs at 12.6 lanes instead of 6.9 and half
+  // as often per warp, but the machine's own bookkeeping now runs at 5.6 lanes -- the lanes of a warp do not differ in WHERE their
+  // frozen nodes are but in WHETHER they have expensive (non-converging) profiles this record at all -- and the record takes 316 ms
+  // instead of 282 ms at 100,000 cells (58 instead of 60 ms at 10,000).
+  {
+    const int jend = NOFLUX ? Nnodes : Nnodes - 1;
+    int j = jend;          // cursor; jend = "between sweeps"
+    bool started = false, in_solve = false;
+    unsigned fbmask = 0;
+    double maxdiff = threshold, oldT = 0;
+    BrentStep bs;
+    SoilThermalEqn eq;
+    for (;;) {
+      while (!in_solve) {
+        if (j >= jend) {
+          if (started) {  // end of a sweep
+            if (maxdiff <= threshold) Done = true;
+            bool cycle = false;
+            if (!Done && ItCount >= 6 && ItCount < MAXIT) {
+              // exact repeat of an earlier iterate?  (period p: the state after this sweep equals the state p sweeps ago)
+              int period = 0;
+              for (int p = 1; p < HIST && p < ItCount && period == 0; p++) {
+                bool same = true;
+                for (int k = 0; k < Nnodes && same; k++) same = (T[k] == Th[(ItCount - p) % HIST][k]) && !(T[k] != T[k]);
+                if (same) period = p;
+              }
+              if (period > 0) {
+                for (int k = 0; k < Nnodes; k++) Th[ItCount % HIST][k] = T[k];
+                fbh[ItCount % HIST] = fbmask;
+                // sweeps ItCount+1 .. MAXIT repeat sweeps ItCount-period+1 .. ItCount: position q of the cycle comes up once for every
+                // k = q, q + period, ... below the number of skipped sweeps (the counts are small integers held in doubles: adding the
+                // number of visits at once is the same as adding 1 that many times)
+                const int skipped = MAXIT - ItCount;
+                for (int q = 0; q < period && q < skipped; q++) {
+                  const unsigned m = fbh[(ItCount - period + 1 + q) % HIST];
+                  if (m) {
+                    const int visits = (skipped - q + period - 1) / period;
+                    for (int k = 0; k < Nnodes; k++)
+                      if (m & (1u << k)) {
+                        Tfbflag[k] = 1;
+                        Tfbcount[k] += visits;
+                      }
+                  }
+                }
+                const int last = ItCount - period + 1 + (MAXIT - ItCount - 1) % period;
+                for (int k = 0; k < Nnodes; k++) T[k] = Th[last % HIST][k];
+                ItCount = MAXIT;
+                cycle = true;
+              }
+            }
+            if (!cycle) {
+              for (int k = 0; k < Nnodes; k++) Th[ItCount % HIST][k] = T[k];
+              fbh[ItCount % HIST] = fbmask;
+            }
+          }
+          if (Done || ItCount >= MAXIT) goto sweeps_done;
+          started = true;
+          ItCount++;
+          fbmask = 0;
+          maxdiff = threshold;
+          j = 1;
+        }
+        const bool bottom = (j == Nnodes - 1);  // only reached with NOFLUX: the node below is the node itself
+        oldT = T[j];
+        const double Tdn = bottom ? T[j] : T[j + 1];
+        if (T[j] >= 0 || !frozen_on) {
+          if (!EXP_TRANS) T[j] = (A[j] * T0[j] + B[j] * (Tdn - T[j - 1]) + C[j] * Tdn + D[j] * T[j - 1] + E[j] * (0. - ice[j])) / (A[j] + C[j] + D[j]);
+          else T[j] = (A[j] * T0[j] + B[j] * (Tdn - T[j - 1]) + C[j] * (Tdn + T[j - 1]) - D[j] * (Tdn - T[j - 1]) + E[j] * (0. - ice[j])) / (A[j] + 2. * C[j]);
+          const double diff = fabs(oldT - T[j]);
+          if (diff > maxdiff) maxdiff = diff;
+          j++;
+        } else {
+          eq.TL = Tdn; eq.TU = T[j - 1]; eq.T0 = T0[j]; eq.moist = moist[j];
+          eq.max_moist = layer_array_as_node(cp, CL_max_moist, CN_max_moist_node, j);
+          eq.bubble = layer_array_as_node(cp, CL_bubble, CN_bubble_node, j);
+          eq.expt = layer_array_as_node(cp, CL_expt, CN_expt_node, j);
+          eq.ice0 = ice[j]; eq.A = A[j]; eq.B = B[j]; eq.C = C[j]; eq.D = D[j]; eq.E = E[j]; eq.EXP_TRANS = EXP_TRANS; eq.node = j;
+          brent_begin(bs, T0[j] - (SOIL_DT), T0[j] + (SOIL_DT));
+          in_solve = true;
+        }
+      }
+      // one residual evaluation of this thread's current node solve
+      if (brent_advance(bs, eq.eval(bs.x))) {
+        T[j] = bs.res;
+        vic_count_work(1);
+        if (result_is_error(T[j])) {
+          if (o.TFALLBACK) {
+            T[j] = T0[j];
+            Tfbflag[j] = 1;
+            Tfbcount[j] += 1;
+            fbmask |= 1u << j;
+          } else return ERROR_I;
+        }
+        const double diff = fabs(oldT - T[j]);
+        if (diff > maxdiff) maxdiff = diff;
+        j++;
+        in_solve = false;
+      }
+    }
+  sweeps_done:;
+  }
+#endif
   if (o.TFALLBACK) {
     // "cold nose" repair (frozen_soil.c:470-484)
     for (int j = 1; j < Nnodes - 1; j++) {
