@@ -116,8 +116,8 @@ int main(int argc, char** argv) {
     if (rec == 0)
       for (int c = 0; c < ncell; c++) cell_output(o, t, nullptr, c, -1, step_count, roles);
     GlacAccum ga = glacier_accum_flags(o, &dmy[rec * 5], &dmy[(rec + 1) * 5], rec, &started);
-    if (o.Nnode <= 3) run_record<3>(&o, t, frec.data(), d, rec, ga);
-    else if (o.Nnode <= 10) run_record<10>(&o, t, frec.data(), d, rec, ga);
+    if (vic_node_width(o) == 3) run_record<3>(&o, t, frec.data(), d, rec, ga);
+    else if (vic_node_width(o) == 10) run_record<10>(&o, t, frec.data(), d, rec, ga);
     else run_record<VICGPU_MAX_NODES>(&o, t, frec.data(), d, rec, ga);
     if (ga.enabled && ga.reset_after)
       for (int c = 0; c < ncell; c++) cell_gmb(&o, t, c);

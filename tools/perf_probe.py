@@ -22,8 +22,15 @@ ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--start-day", type=int, default=0)
 ap.add_argument("--tag", default="")
 ap.add_argument("--config", default="fe_hourly", help="fe_hourly | frozen_bands | glacier (bench_data/base_<config>.npz)")
+ap.add_argument("--set", action="append", default=[], metavar="OPTION=VALUE", help="override an option of the base domain, e.g. --set IMPLICIT=1")
 a = ap.parse_args()
 dom = bench.build_domain(a.cells, 1, a.config)
+if a.set:
+    opt = api.parse_options(dom["options_raw"])
+    for kv in a.set:
+        k, v = kv.split("=")
+        opt[k] = type(opt[k])(float(v))
+    dom["options_raw"] = api.options_to_raw(opt)
 g = api.VicGpu(dom["options_raw"], device=0)
 g.set_veglib(dom["veglib"]); g.set_output_spec(dom["aggtype"]); g.set_cells(dom["cellpar"], dom["hrupar"]); g.set_state(dom["hrurec0"])
 nd = a.warmup + a.steps

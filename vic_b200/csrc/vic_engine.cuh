@@ -266,7 +266,6 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   if (a.BLOWING) { *why = "BLOWING is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.CORRPREC) { *why = "CORRPREC is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.LAKES) { *why = "LAKES is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
-  if (a.IMPLICIT) { *why = "IMPLICIT is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.QUICK_SOLVE) { *why = "QUICK_SOLVE is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.GLACIER_DYNAMICS) { *why = "GLACIER_DYNAMICS is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.COMPUTE_TREELINE) { *why = "COMPUTE_TREELINE is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
@@ -280,6 +279,12 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   o.gaDay = a.glacierAccumStartDay; o.gaInterval = a.glacierAccumInterval; o.wind_h = a.wind_h;
   vicgpu_layout_init(&o.L, &a);
   return VICGPU_OK;
+}
+
+// which instantiation (thermal-node array width) steps a configuration: 3, 10 or 32
+inline int vic_node_width(const Opts& o) {
+  if (o.Nnode <= 3 && !(o.IMPLICIT && !o.QUICK_FLUX)) return 3;
+  return o.Nnode <= 10 ? 10 : 32;
 }
 
 // Binning (host): the rows of the HRU tables are ordered by kind -- glacier / artificial bare soil / vegetation class --

@@ -328,5 +328,206 @@ VIC_HDI int solve_T_profile(double* T, const double* T0, double* Tfbflag, double
   return 0;
 }
 
+
+// ---- IMPLICIT: Newton-Raphson solution of the whole profile (frozen_soil.c:229-301 solve_T_profile_implicit, :540-803
+// NewtonRaphsonMethod::fda_heat_eqn; newt_raph_func_fast.c:17-220 compute / fdjac3 / tridiag) ------------------------------------
+// The residual of the implicit finite-difference heat equation at the n unknown nodes.  focus == -1 evaluates all of them; the
+// Jacobian (fdjac3) perturbs one unknown and re-evaluates only that node and its neighbours (focus >= 0), reading what the last
+// all-node evaluation left in ice_new / Cs_new / kappa_new -- static arrays in upstream VIC 4.1.2, members here (the oracle gives
+// the reference's copies `static thread_local`, oracle/Makefile patch 3): an all-node evaluation rewrites every entry a later
+// single-node evaluation reads except kappa_new[n + 1] without NOFLUX, which nobody ever writes (zero, as a static is).
+// max_moist / bubble / expt are the per-LAYER arrays indexed per NODE, as in the explicit scheme (header, (2)).
+template <int NN>
+struct FdaHeat {
+  const double *T0, *moist, *ice, *kappa, *Cs;
+  const CellPar* cp;
+  double deltat, Ts, Tb, Bexp;
+  int NOFLUX, EXP_TRANS;
+  double ice_new[NN + 2], Cs_new[NN + 2], kappa_new[NN + 2];
+
+  VIC_HD void node_props(int i, int lidx) {
+    kappa_new[i] = soil_conductivity_pre(moist[i], moist[i] - ice_new[i], cell_kpre(*cp, lidx));
+    Cs_new[i] = volumetric_heat_capacity(cp->layer(CL_bulk_density, lidx) / cp->layer(CL_soil_density, lidx), moist[i] - ice_new[i], ice_new[i],
+                                         cp->layer(CL_organic, lidx));
+  }
+  VIC_HD double new_ice(double T, int i) const {
+    if (T < 0) {
+      double v = moist[i] - maximum_unfrozen_water(T, layer_array_as_node(*cp, CL_max_moist, CN_max_moist_node, i),
+                                                   layer_array_as_node(*cp, CL_bubble, CN_bubble_node, i),
+                                                   layer_array_as_node(*cp, CL_expt, CN_expt_node, i));
+      if (v < 0) v = 0;
+      return v;
+    }
+    return 0;
+  }
+  // the equation of unknown i (node i + 1); first: the i == 0 || i == 1 restriction of the cold-nose fix in single-node mode
+  VIC_HD double node_residual(const double* T_2, int n, int i, bool nose_everywhere) const {
+    double DT, DT_up, DT_down, T_up, Dkappa;
+    if (i == 0) {
+      DT = T_2[i + 1] - Ts; DT_up = T_2[i] - Ts; DT_down = T_2[i + 1] - T_2[i]; T_up = Ts;
+    } else if (i == n - 1) {
+      DT = Tb - T_2[i - 1]; DT_up = T_2[i] - T_2[i - 1]; DT_down = Tb - T_2[i]; T_up = T_2[i - 1];
+    } else {
+      DT = T_2[i + 1] - T_2[i - 1]; DT_up = T_2[i] - T_2[i - 1]; DT_down = T_2[i + 1] - T_2[i]; T_up = T_2[i - 1];
+    }
+    if (i < n - 1) Dkappa = kappa_new[i + 2] - kappa_new[i];
+    else if (!NOFLUX) Dkappa = kappa_new[i + 2] - kappa_new[i];
+    else Dkappa = kappa_new[i + 1] - kappa_new[i];
+    const double storage_term = Cs_new[i + 1] * (T_2[i] - T0[i + 1]) / deltat + T_2[i] * (Cs_new[i + 1] - Cs[i + 1]) / deltat;
+    double flux_term1, flux_term2;
+    if (!EXP_TRANS) {
+      const double al = cp->node(CN_alpha, i);
+      flux_term1 = Dkappa / al * DT / al;
+      flux_term2 = kappa_new[i + 1] * (DT_down / cp->node(CN_gamma, i) - DT_up / cp->node(CN_beta, i)) / (0.5 * al);
+    } else {
+      const double z1 = cp->node(CN_Zsum_node, i + 1) + 1.;
+      flux_term1 = Dkappa / 2. * DT / 2. / (Bexp * z1) / (Bexp * z1);
+      flux_term2 = kappa_new[i + 1] * ((DT_down - DT_up) / (Bexp * z1) / (Bexp * z1) - DT / 2. / (Bexp * z1 * z1));
+    }
+    if (nose_everywhere || i == 0 || i == 1) {
+      if (fabs(DT) > 5. && (T_2[i] < T_2[i + 1] && T_2[i] < T_up)) {  // cold nose
+        if ((flux_term1 < 0 && flux_term2 > 0) && fabs(flux_term1) > fabs(flux_term2)) flux_term1 = 0;
+      }
+    }
+    const double flux_term = flux_term1 + flux_term2;
+    const double phase_term = ice_density * Lf * (ice_new[i + 1] - ice[i + 1]) / deltat;
+    return flux_term + phase_term - storage_term;
+  }
+  VIC_HD void eval(const double* T_2, double* res, int n, int focus) {
+    const int Nlayers = VICGPU_NLAYER;
+    int lidx = 0;
+    double Lsum = 0.;
+    bool PAST_BOTTOM = false;
+    if (focus == -1) {
+      for (int i = 0; i < n + 1; i++) {
+        kappa_new[i] = kappa[i];
+        if (i >= 1) {
+          ice_new[i] = new_ice(T_2[i - 1], i);
+          Cs_new[i] = Cs[i];
+          if (ice_new[i] != ice[i]) node_props(i, lidx);
+        }
+        if (cp->node(CN_Zsum_node, i) > Lsum + cp->layer(CL_depth, lidx) && !PAST_BOTTOM) {
+          Lsum += cp->layer(CL_depth, lidx);
+          lidx++;
+          if (lidx == Nlayers) {
+            PAST_BOTTOM = true;
+            lidx = Nlayers - 1;
+          }
+        }
+      }
+      // (the cold-nose test of the all-node evaluation looks at T_2[i + 1] of the last unknown too: one past the unknowns, i.e. the
+      // caller's array element after them -- T[Nnodes - 1] without NOFLUX; see solve_T_profile_implicit)
+      for (int i = 0; i < n; i++) res[i] = node_residual(T_2, n, i, true);
+    } else {
+      const int left = (focus == 0) ? 0 : focus - 1, right = (focus == n - 1) ? n - 1 : focus + 1;
+      for (int i = left; i <= right; i++) ice_new[i + 1] = new_ice(T_2[i], i + 1);
+      for (int i = 0; i <= right + 1; i++) {
+        if (i >= left + 1) {
+          if (ice_new[i] != ice[i]) node_props(i, lidx);
+        }
+        if (cp->node(CN_Zsum_node, i) > Lsum + cp->layer(CL_depth, lidx) && !PAST_BOTTOM) {
+          Lsum += cp->layer(CL_depth, lidx);
+          lidx++;
+          if (lidx == Nlayers) {
+            PAST_BOTTOM = true;
+            lidx = Nlayers - 1;
+          }
+        }
+      }
+      for (int i = left; i <= right; i++) res[i] = node_residual(T_2, n, i, false);
+    }
+  }
+};
+
+// tridiagonal solve, newt_raph_func_fast.c:180-220 (a: sub-, b: main, c: super-diagonal; r: right-hand side in, solution out)
+VIC_HD void nr_tridiag(double* a, double* b, double* c, double* r, int n) {
+  double factor = b[0];
+  b[0] = 1.0;
+  c[0] = c[0] / factor;
+  r[0] = r[0] / factor;
+  for (int j = 1; j < n; j++) {
+    factor = a[j];
+    a[j] = a[j] - b[j - 1] * factor;
+    b[j] = b[j] - c[j - 1] * factor;
+    r[j] = r[j] - r[j - 1] * factor;
+    factor = b[j];
+    b[j] = 1.0;
+    c[j] = c[j] / factor;
+    r[j] = r[j] / factor;
+  }
+  for (int j = n - 2; j >= 0; j--) {
+    factor = c[j];
+    c[j] = c[j] - b[j + 1] * factor;
+    r[j] = r[j] - r[j + 1] * factor;
+    factor = b[j];
+    r[j] = r[j] / factor;
+  }
+}
+
+// Returns 0 (T holds the new profile) or 1 (no convergence in 150 trials: the caller falls back to the explicit scheme,
+// func_surf_energy_bal.c:212-221).
+template <int NN>
+VIC_HDI int solve_T_profile_implicit(double* T, const double* T0, const double* kappa, const double* Cs, const double* moist, double deltat,
+                                     const double* ice, double Dp, int Nnodes, int* FIRST_SOLN, int NOFLUX, int EXP_TRANS, const CellPar& cp) {
+  const int MAXTRIAL = 150;
+  const double TOLX = 1e-4, TOLF = 1e-1, R_MAX = 2.0, R_MIN = -5.0, RELAX1 = 0.9, RELAX2 = 0.7, RELAX3 = 0.2, EPS2 = 1e-4;
+  if (FIRST_SOLN[0]) FIRST_SOLN[0] = 0;
+  const int n = NOFLUX ? Nnodes - 1 : Nnodes - 2;
+  FdaHeat<NN> fda;
+  fda.T0 = T0; fda.moist = moist; fda.ice = ice; fda.kappa = kappa; fda.Cs = Cs; fda.cp = &cp;
+  fda.deltat = deltat; fda.NOFLUX = NOFLUX; fda.EXP_TRANS = EXP_TRANS;
+  fda.Bexp = 0;
+  if (EXP_TRANS) fda.Bexp = NOFLUX ? vlog(Dp + 1.) / (double)(n) : vlog(Dp + 1.) / (double)(n + 1);
+  fda.Ts = T0[0];
+  fda.Tb = NOFLUX ? T0[n] : T0[n + 1];
+  for (int i = 0; i < NN + 2; i++) fda.ice_new[i] = fda.Cs_new[i] = fda.kappa_new[i] = 0;
+  double* x = &T[1];
+  for (int i = 0; i < n; i++) x[i] = T0[i + 1];
+  double fvec[NN], f[NN], p[NN], a[NN], b[NN], c[NN];
+  for (int i = 0; i < NN; i++) fvec[i] = f[i] = p[i] = a[i] = b[i] = c[i] = 0;
+  int Error = 1;
+  for (int k = 0; k < MAXTRIAL; k++) {
+    fda.eval(x, fvec, n, -1);
+    double errf = 0.0;
+    for (int i = 0; i < n; i++) errf += fabs(fvec[i]);
+    if (errf <= TOLF) {
+      Error = 0;
+      break;
+    }
+    // forward-difference Jacobian, tridiagonal part only (fdjac3)
+    for (int j = 0; j < n; j++) {
+      const double temp = x[j];
+      double h = EPS2 * fabs(temp);
+      if (h == 0) h = EPS2;
+      x[j] = temp + h;
+      h = x[j] - temp;
+      fda.eval(x, f, n, j);
+      x[j] = temp;
+      b[j] = (f[j] - fvec[j]) / h;
+      if (j != 0) c[j - 1] = (f[j - 1] - fvec[j - 1]) / h;
+      if (j != n - 1) a[j + 1] = (f[j + 1] - fvec[j + 1]) / h;
+    }
+    for (int i = 0; i < n; i++) p[i] = -fvec[i];
+    nr_tridiag(a, b, c, p, n);
+    double errx = 0.0;
+    for (int i = 0; i < n; i++) {
+      errx += fabs(p[i]);
+      if (k > 10 && k <= 20 && x[i] < R_MAX && x[i] > R_MIN) x[i] += p[i] * RELAX1;
+      else if (k > 20 && k <= 60 && x[i] < R_MAX && x[i] > R_MIN) x[i] += p[i] * RELAX2;
+      else if (k > 60 && x[i] < R_MAX && x[i] > R_MIN) x[i] += p[i] * RELAX3;
+      else x[i] += p[i];
+    }
+    if (errx <= TOLX) {
+      Error = 0;
+      break;
+    }
+  }
+  if (Error == 0) {
+    T[0] = T0[0];
+    if (!NOFLUX) T[Nnodes - 1] = T0[Nnodes - 1];
+  }
+  return Error;
+}
+
 }  // namespace vic
 #endif

@@ -26,7 +26,7 @@ struct SurfEB {
   const SoilET* soil;
   // what the residual reads of *o, *cp, *veg and the aerodynamic tables, copied once per solve (prepare) so that an evaluation
   // does not chase pointers: each of these was two or three dependent thread-local / global loads per evaluation
-  int QUICK_FLUX, GRND_FLUX_TYPE, FS_FROZEN;
+  int QUICK_FLUX, GRND_FLUX_TYPE, FS_FROZEN, IMPLICIT;
   double elevation, b_infilt, depth0, resid_moist0, veg_LAI, ws_under, ra_under, zref_under, disp_under, rough_under;
   // scalars captured by value
   int VEG, UnderStory, overstory, INCLUDE_SNOW, NOFLUX, EXP_TRANS, SNOWING, Nnodes;
@@ -58,6 +58,7 @@ struct SurfEB {
     sc_lg = 0;
     t1_k1 = t1_b = t1_c = t1_den = gf_k1 = gf_k2e = 0;
     QUICK_FLUX = o->QUICK_FLUX;
+    IMPLICIT = o->IMPLICIT;
     GRND_FLUX_TYPE = o->GRND_FLUX_TYPE;
     FS_FROZEN = (((*cp)(CP_FS_ACTIVE) != 0.0) && o->FROZEN_SOIL) ? 1 : 0;
     elevation = (*cp)(CP_elevation);
@@ -102,8 +103,19 @@ struct SurfEB {
       else en->grnd_flux = cover * (gf_k1 * (T1 - TMean) + (gf_k2e * (T2 - T1))) / 2.;
     } else {
       T_node[0] = TMean;
-      int Error = solve_T_profile<NN>(Tnew_node, T_node, Tnew_fbflag, Tnew_fbcount, kappa_node, Cs_node, moist_node, delta_t, ice_node, dp,
-                                      Nnodes, FIRST_SOLN, NOFLUX, EXP_TRANS, *cp, *o);
+      // IMPLICIT: Newton-Raphson on the whole profile first; the explicit sweeps are its fallback (func_surf_energy_bal.c:192-221)
+      int Error = 0;
+      // (not compiled into the three-node kernel, which exists for the QUICK_FLUX configurations: vic_node_width() sends an IMPLICIT
+      // configuration with three nodes to the ten-node instantiation)
+      if constexpr (NN > 3) {
+        if (IMPLICIT) Error = solve_T_profile_implicit<NN>(Tnew_node, T_node, kappa_node, Cs_node, moist_node, delta_t, ice_node, dp, Nnodes, FIRST_SOLN,
+                                                           NOFLUX, EXP_TRANS, *cp);
+      }
+      if (!IMPLICIT || Error == 1) {
+        if (IMPLICIT) FIRST_SOLN[0] = 1;
+        Error = solve_T_profile<NN>(Tnew_node, T_node, Tnew_fbflag, Tnew_fbcount, kappa_node, Cs_node, moist_node, delta_t, ice_node, dp,
+                                    Nnodes, FIRST_SOLN, NOFLUX, EXP_TRANS, *cp, *o);
+      }
       if (Error == ERROR_I) return ERROR_D;
       T1 = Tnew_node[1];
       if (GRND_FLUX_TYPE == GF_406) en->grnd_flux = cover * (kappa1 / D1 * (T1 - TMean));
@@ -195,9 +207,10 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   (void)coldcontent;
   const int Nnodes = o.Nnode;
   int FIRST_SOLN[2] = {1, 1};
-  double Tnew_node[NN], Tnew_fbflag[NN], Tnew_fbcount[NN];
+  double Tnew_node[NN + 1], Tnew_fbflag[NN], Tnew_fbcount[NN];  // (+1: the implicit scheme's cold-nose test reads one element past the unknowns)
   double Tsurf_fbflag = 0, Tsurf_fbcount = 0;
   for (int n = 0; n < NN; n++) { Tnew_fbflag[n] = 0; Tnew_fbcount[n] = 0; Tnew_node[n] = 0; }
+  Tnew_node[NN] = 0;
   int VEG;
   if (!isArtificialBareSoil) VEG = (veg.LAI > 0.0) ? 1 : 0;
   else VEG = 0;

@@ -546,7 +546,7 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
     const size_t slots = ((size_t)nhru / 32 + (size_t)h->sm_count + 2) * VICGPU_HRU_BLOCK_MAX;
     CK(cudaMalloc(&h->d_work, slots * sizeof(int)));
     CK(cudaMemset(h->d_work, 0, slots * sizeof(int)));
-    const int rcw = h->o.Nnode <= 3 ? vicgpu_set_work_buffer_nn3(h->d_work) : h->o.Nnode <= 10 ? vicgpu_set_work_buffer_nn10(h->d_work) : vicgpu_set_work_buffer_nn32(h->d_work);
+    const int rcw = vic_node_width(h->o) == 3 ? vicgpu_set_work_buffer_nn3(h->d_work) : vic_node_width(h->o) == 10 ? vicgpu_set_work_buffer_nn10(h->d_work) : vicgpu_set_work_buffer_nn32(h->d_work);
     if (rcw != 0) return fail(VICGPU_ECUDA, "cudaMemcpyToSymbol(vic_work_buf)");
   }
   CK(cudaMalloc(&h->d_gmb_cum, (size_t)nhru * sizeof(double)));
@@ -887,8 +887,8 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
       wns = h->d_warp_ns;
     }
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-    if (h->o.Nnode <= 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
-    else if (h->o.Nnode <= 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
+    if (vic_node_width(h->o) == 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
+    else if (vic_node_width(h->o) == 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
     else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
     h->last_launches++;
     // the previous record's output rides on this step
@@ -1051,8 +1051,8 @@ int vicgpu_measure_phase_tax(vicgpu_handle* h, int nframe, int reps, double* us_
   t.hrurec = h->d_state_cur;
   t.hrurec_out = h->half[h->cur_half ^ 1].in;  // scratch between steps: a re-sort overwrites it completely before anything reads it
   auto launch = [&]() {
-    if (h->o.Nnode <= 3) vicgpu_launch_hru_pass_nn3(h->d_o, t, frame, nframe, h->hru_block, h->stream);
-    else if (h->o.Nnode <= 10) vicgpu_launch_hru_pass_nn10(h->d_o, t, frame, nframe, h->hru_block, h->stream);
+    if (vic_node_width(h->o) == 3) vicgpu_launch_hru_pass_nn3(h->d_o, t, frame, nframe, h->hru_block, h->stream);
+    else if (vic_node_width(h->o) == 10) vicgpu_launch_hru_pass_nn10(h->d_o, t, frame, nframe, h->hru_block, h->stream);
     else vicgpu_launch_hru_pass_nn32(h->d_o, t, frame, nframe, h->hru_block, h->stream);
   };
   launch();  // warm-up

@@ -56,6 +56,8 @@ CONFIGS = {
     "fe_hourly": Config("fe_hourly"),
     # configs[2]: frozen soil + 5 bands, QUICK_FLUX=FALSE, 10 nodes
     "frozen_bands": Config("frozen_bands", frozen_soil=True, quick_flux=False, nodes=10, nbands=5),
+    # the same with the implicit (Newton-Raphson, tridiagonal) soil-temperature solver, explicit scheme as its fallback
+    "frozen_implicit": Config("frozen_implicit", frozen_soil=True, quick_flux=False, nodes=10, nbands=5, implicit=True),
     # configs[3]: PCIC glacier mass-balance mode
     "glacier": Config("glacier", glacier=True, nbands=5),
     # the same with glacier HRUs in four bands of every cell: exercises accumulateGlacierMassBalance's quadratic fit
