@@ -209,6 +209,8 @@ __global__ void k_transpose_f32(const double* __restrict__ in, float* __restrict
 
 int vicgpu_transpose(vicgpu_handle* h, const double* d_in, double* d_out, int rows, int cols, int batch, cudaStream_t st) {
   if (!st) st = h->stream;
+  // the tile rows ride on gridDim.y: 65,535 x 32 = 2,097,120 rows (cells of a shard, or columns of a table) per launch
+  if ((rows + 31) / 32 > 65535 || batch > 65535) return vicgpu_fail(VICGPU_EUNSUPPORTED, "more than 2,097,120 cells per device: shard the domain (vic_b200/shard.py)");
   dim3 b(32, 8), g((cols + 31) / 32, (rows + 31) / 32, batch);
   k_transpose<<<g, b, 0, st>>>(d_in, d_out, rows, cols);
   h->last_launches++;
