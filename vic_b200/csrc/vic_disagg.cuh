@@ -112,6 +112,25 @@ VIC_HDI void disagg_solar(const CellPar& cp, const DisaggOpts& d, const DisaggSc
   const double optam[21] = {2.90, 3.05, 3.21, 3.39, 3.69, 3.82, 4.07, 4.37, 4.72, 5.12, 5.60, 6.18, 6.88, 7.77, 8.90, 10.39, 12.44, 15.36, 19.79, 26.96, 30.00};
   const double site_elev = (double)(float)cp(CP_elevation);
   const LocalTime lt = local_time(cp, d);
+  // The reference fills the tables for the whole year whatever the length of the run (mtclim_vic.c:1345); what is read afterwards are
+  // the entries of the run's local days only (disagg_daily: D_yday).  A window of a few days -- the continental bench disaggregates
+  // two weeks at a time -- therefore skips the other days of year: 30-second stepping through ~350 unused days was the whole cost
+  // of a short call.  The skipped entries of the scratch are never read.
+  {
+    const int month_days_[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    int day_in_year = lt.local_startday;
+    for (int m = 1; m < lt.local_startmonth; m++) {
+      int dim = month_days_[m - 1];
+      if (lt.local_startyear % 4 == 0 && m == 2) dim++;
+      day_in_year += dim;
+    }
+    // indices used: (day_in_year - 1 + k) for k < Ndays_local, with the calendar's wrap after day 365 / 366; two days of margin
+    const int first = day_in_year - 1, span = lt.Ndays_local + 2;
+    if (span < 365) {
+      const int dist = ((i - first) % 365 + 365) % 365;
+      if (dist >= span && dist < 365 - 2) return;
+    }
+  }
   const double t1 = 1.0 - (LR_STD * site_elev) / T_STD;
   const double t2 = G_STD / (LR_STD * (R / MA));
   const double pratio = vpow(t1, t2);
