@@ -237,7 +237,8 @@ def test_full_size_domain_properties(base, ncell, nrec):
 
 
 @pytest.mark.parametrize("env", [{"VICGPU_NOOVERLAP": "1"}, {"VICGPU_NOBIN": "1"}, {"VICGPU_REBIN": "0"}, {"VICGPU_REBIN": "1"}, {"VICGPU_SYNC": "50000"},
-                                 {"VICGPU_SYNC": "0"}, {"VICGPU_BLOCK": "128"}, {"VICGPU_BLOCK": "512"}, {"VICGPU_OUTBLOCK": "128"}, {"VICGPU_EVEN": "1"}, {"VICGPU_BINFINE": "1"}, {"VICGPU_PDLWAIT": "0"}, {"VICGPU_BINCOST": "1"}, {"VICGPU_BINCOST": "2", "VICGPU_REBIN": "1"}],
+                                 {"VICGPU_SYNC": "0"}, {"VICGPU_BLOCK": "128"}, {"VICGPU_BLOCK": "512"}, {"VICGPU_OUTBLOCK": "128"}, {"VICGPU_EVEN": "1"}, {"VICGPU_BINFINE": "1"}, {"VICGPU_PDLWAIT": "0"}, {"VICGPU_BINCOST": "1"}, {"VICGPU_BINCOST": "2", "VICGPU_REBIN": "1"},
+                                 {"VICGPU_BALANCE": "0"}, {"VICGPU_BALANCE": "100", "VICGPU_REBIN": "2"}, {"VICGPU_SYNCMASK": "4"}],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_every_launch_mode_gives_the_same_bits(env, monkeypatch):
     """the tuning / A-B knobs of libvicgpu.so (read from the environment at vicgpu_create) change how the work is laid out and launched --

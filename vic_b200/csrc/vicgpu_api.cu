@@ -320,6 +320,75 @@ static int rebin_rows(vicgpu_handle* h, const RowOrder& S, RowOrder& D, const do
   return VICGPU_OK;
 }
 
+// ---- balanced blocks (single-wave domains) -------------------------------------------------------------------------------------
+// The warps of kind k run in blocks of kind_n[k] warps (16 = the register file's worth, the initial layout).  upload_block_layout
+// turns kind_n into the table the kernel reads; balance_blocks updates kind_n from the measured warp durations of a launch with the
+// current layout: a warp gets ~10 us faster per co-resident warp it loses (profiles/r02_summary.md, domain-size sweep), so every kind
+// is moved towards the common duration T that makes the blocks fit the SMs the cell-output grid does not need.
+static int upload_block_layout(vicgpu_handle* h) {
+  const int nw = (int)h->warp_kind.size();
+  h->h_block_w0.clear();
+  for (int w = 0; w < nw;) {
+    h->h_block_w0.push_back(w);
+    w += std::max(1, std::min(h->kind_n[h->warp_kind[w]], VICGPU_HRU_BLOCK_MAX / 32));
+  }
+  h->h_block_w0.push_back(nw);
+  h->nb_balanced = (int)h->h_block_w0.size() - 1;
+  cudaFree(h->d_block_w0);
+  h->d_block_w0 = nullptr;
+  CK(cudaMalloc(&h->d_block_w0, h->h_block_w0.size() * sizeof(int)));
+  CK(cudaMemcpy(h->d_block_w0, h->h_block_w0.data(), h->h_block_w0.size() * sizeof(int), cudaMemcpyHostToDevice));
+  h->bal_measured = false;
+  h->bal_measure_next = true;
+  return VICGPU_OK;
+}
+
+static int balance_blocks(vicgpu_handle* h) {
+  const int nw = (int)h->warp_kind.size(), nk = (int)h->kind_n.size();
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<unsigned long long> ns((size_t)2 * nw);
+  CK(cudaMemcpy(ns.data(), h->d_warp_ns, ns.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::vector<double> sum((size_t)nk, 0.0);
+  std::vector<int> cnt((size_t)nk, 0), wk((size_t)nk, 0);
+  for (int w = 0; w < nw; w++) {
+    wk[h->warp_kind[w]]++;
+    if (ns[2 * w + 1] > ns[2 * w] && ns[2 * w] != 0) {
+      sum[h->warp_kind[w]] += (double)(ns[2 * w + 1] - ns[2 * w]) / 1e3;
+      cnt[h->warp_kind[w]]++;
+    }
+  }
+  const double c_us = 10.0;   // duration a warp gains per co-resident warp less
+  const int nmax = VICGPU_HRU_BLOCK_MAX / 32, nmin = 6;
+  const int nb_max = std::max(1, h->sm_count - h->bal_reserve);  // (the rest is left to the dependent cell-output grid)
+  std::vector<double> t((size_t)nk, 0.0);
+  double lo = 1e30, hi = 0;
+  for (int k = 0; k < nk; k++) {
+    if (!cnt[k]) continue;
+    t[k] = sum[k] / cnt[k];
+    lo = std::min(lo, t[k] - c_us * nmax);
+    hi = std::max(hi, t[k] + c_us * nmax);
+  }
+  if (hi <= 0) return VICGPU_OK;  // nothing measured
+  auto n_of = [&](int k, double T) {
+    if (!cnt[k]) return h->kind_n[k];
+    int n = (int)floor(h->kind_n[k] + (T - t[k]) / c_us);
+    n = std::max(h->kind_n[k] - 2, std::min(h->kind_n[k] + 2, n));  // damped: at most two warps per update
+    return std::max(nmin, std::min(nmax, n));
+  };
+  auto blocks = [&](double T) {
+    int nb = 0;
+    for (int k = 0; k < nk; k++) nb += (wk[k] + n_of(k, T) - 1) / n_of(k, T);
+    return nb;
+  };
+  for (int it = 0; it < 40; it++) {  // smallest common duration whose blocks fit
+    const double mid = 0.5 * (lo + hi);
+    if (blocks(mid) <= nb_max) hi = mid; else lo = mid;
+  }
+  if (blocks(hi) > nb_max) return VICGPU_OK;  // (cannot happen: at T = hi every kind is at 16 warps, the initial layout)
+  for (int k = 0; k < nk; k++) h->kind_n[k] = n_of(k, hi);
+  return upload_block_layout(h);
+}
+
 static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const Opts& o, int device);
 
 extern "C" {
@@ -401,6 +470,9 @@ static int create_on_device(vicgpu_handle* h, const vicgpu_options* opt, const O
 #else
   h->aero_cache = true;
 #endif
+  const char* bl = getenv("VICGPU_BALANCE");  // SMs left to the cell-output grid by the balanced step grid; 0: blocks of equal warp counts (A/B)
+  h->bal_reserve = bl ? atoi(bl) : 28;
+  h->balance = h->bal_reserve > 0;
   const char* bf = getenv("VICGPU_BINFINE");  // 1: bin by pack regime and canopy snow as well (k_bin_keys)
   h->bin_fine = bf && atoi(bf) != 0;
   CK(cudaMalloc(&h->d_o, sizeof(Opts)));
@@ -447,7 +519,7 @@ int vicgpu_destroy(vicgpu_handle* h) {
   cudaFree(h->d_sort_tmp);
   cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_agg); cudaFree(h->d_stage); cudaFree(h->d_fstage);
   cudaFree(h->d_cell_h0); cudaFree(h->d_status); cudaFree(h->d_aggtype);
-  cudaFree(h->d_warp_ns); cudaFree(h->d_cost); cudaFree(h->d_work);
+  cudaFree(h->d_warp_ns); cudaFree(h->d_cost); cudaFree(h->d_work); cudaFree(h->d_block_w0);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev) cudaEventDestroy(e);
@@ -616,6 +688,35 @@ int vicgpu_set_cells(vicgpu_handle* h, int ncell, const double* cellpar, int nhr
   h->bin_cost = h->bin_cost_env >= 0 ? h->bin_cost_env : ((!h->o.QUICK_FLUX && (long long)nhru > 8LL * h->sm_count * VICGPU_HRU_BLOCK_MAX) ? 2 : 0);
   if (h->bin_cost == 2 && !h->rebin_env) h->rebin_every = 2;
   if (!h->hru_block_fixed) h->hru_block = ((long long)nhru <= (long long)h->sm_count * VICGPU_HRU_BLOCK) ? VICGPU_HRU_BLOCK : VICGPU_HRU_BLOCK_MAX;
+  // balanced blocks: rows sorted by kind first (so that a warp's kind never changes), re-sorted regularly (the layout is revised then),
+  // the whole domain resident at once with SMs to spare, default block size, no per-warp profiling requested
+  h->bal_active = h->balance && h->binned && h->rebin && h->bin_cost != 2 && !h->warp_timing && !h->even && h->hru_block == VICGPU_HRU_BLOCK_MAX &&
+                  (long long)nhru <= (long long)(h->sm_count - h->bal_reserve) * VICGPU_HRU_BLOCK_MAX * 15 / 16;
+  h->warp_kind.clear();
+  h->kind_n.clear();
+  cudaFree(h->d_block_w0);
+  h->d_block_w0 = nullptr;
+  if (h->bal_active) {
+    const int nw = (nhru + 31) / 32;
+    std::vector<long long> keys;
+    h->warp_kind.resize((size_t)nw);
+    for (int w = 0; w < nw; w++) {
+      const double* pr = hrupar + (size_t)hru_of_slot[(size_t)w * 32] * HP_N;
+      long long kind = (long long)pr[HP_vegIndex];
+      if (pr[HP_isArtBare] != 0.0) kind += 1000000;
+      if (pr[HP_isGlacier] != 0.0) kind += 2000000;
+      size_t k = 0;
+      while (k < keys.size() && keys[k] != kind) k++;
+      if (k == keys.size()) keys.push_back(kind);
+      h->warp_kind[(size_t)w] = (int)k;
+    }
+    h->kind_n.assign(keys.size(), VICGPU_HRU_BLOCK_MAX / 32);
+    cudaFree(h->d_warp_ns);
+    h->d_warp_ns = nullptr;
+    CK(cudaMalloc(&h->d_warp_ns, 2 * (size_t)nw * sizeof(unsigned long long)));
+    int rcb = upload_block_layout(h);
+    if (rcb) return rcb;
+  }
   h->t.ncell = ncell; h->t.nhru = nhru;
   h->t.gmb_cum = h->d_gmb_cum; h->t.gmb = h->d_gmb; h->t.cost = h->d_cost; h->t.aero = nullptr;
   h->t.cellpar = h->d_cellpar; h->t.cellder = h->d_cellder; h->t.cell_h0 = h->d_cell_h0; h->t.fail_rec = h->d_fail_rec;
@@ -845,6 +946,10 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
         if (rc) return rc;
         pend.valid = false;
       }
+      if (h->bal_active && h->bal_measured) {  // the layout is revised when the rows are re-sorted: once a day
+        int rcb = balance_blocks(h);
+        if (rcb) return rcb;
+      }
       int rc = rebin_rows(h, h->order[S.ord], h->order[S.ord ^ 1], h->d_state_cur, D.in);
       if (rc) return rc;
       D.ord = S.ord ^ 1;
@@ -888,10 +993,19 @@ static int step_impl(vicgpu_handle* h, int rec0, int nrec, const int* dmy, void*
       CK(cudaMemsetAsync(h->d_warp_ns, 0, 2 * nw * sizeof(unsigned long long), h->stream));
       wns = h->d_warp_ns;
     }
+    const bool bal_time = h->bal_active && h->bal_measure_next && !wns;
+    if (bal_time) {
+      CK(cudaMemsetAsync(h->d_warp_ns, 0, 2 * (((size_t)nhru + 31) / 32) * sizeof(unsigned long long), h->stream));
+      wns = h->d_warp_ns;
+      h->bal_measure_next = false;
+      h->bal_measured = true;
+    }
+    const int* bw0 = h->bal_active ? h->d_block_w0 : nullptr;
+    const int nbw0 = h->nb_balanced;
     if (h->profiling) CK(cudaEventRecord(h->pev[2 * i], h->stream));
-    if (vic_node_width(h->o) == 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
-    else if (vic_node_width(h->o) == 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
-    else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride);
+    if (vic_node_width(h->o) == 3) vicgpu_launch_hru_step_nn3(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride, bw0, nbw0);
+    else if (vic_node_width(h->o) == 10) vicgpu_launch_hru_step_nn10(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride, bw0, nbw0);
+    else vicgpu_launch_hru_step_nn32(h->d_o, one, t, frec, dm, rec, ga, h->hru_block, h->stream, wns, h->sync_limit, h->even ? h->sm_count : 0, L.f_stride, bw0, nbw0);
     h->last_launches++;
     // the previous record's output rides on this step
     if (pend.valid) {

@@ -75,6 +75,18 @@ struct vicgpu_handle {
   bool aero_cache = true;   // VICGPU_AEROCACHE
   double* d_aero = nullptr;  // [VIC_AERO_NCOL][nhru] aerodynamic geometry of every row for month aero_month (k_hru_aero), in the current row order
   int aero_month = -1;
+  // Balanced blocks of a single-wave domain (vicgpu_api.cu balance_blocks): the step kernel of a domain that fits the machine at once
+  // ends when its slowest block does, and the land-cover kinds differ by 30 % in duration; kinds that run long get fewer warps per block
+  bool balance = true;                 // VICGPU_BALANCE
+  int bal_reserve = 28;
+  bool bal_active = false;             // this domain is balanced (binned by kind first, one wave)
+  bool bal_measured = false;           // d_warp_ns holds the warp times of a launch with the current layout
+  bool bal_measure_next = false;       // time the warps of the next launch
+  std::vector<int> warp_kind;          // [nwarp] dense index of the kind of each warp's first row (static: the kind is the first sort key)
+  std::vector<int> kind_n;             // [nkind] warps per block of each kind in the current layout
+  std::vector<int> h_block_w0;         // [nb + 1] first warp of each block
+  int* d_block_w0 = nullptr;
+  int nb_balanced = 0;
   long long sync_limit = 0;  // PhaseSync::limit
   // re-binning scratch (vicgpu_api.cu rebin_rows)
   unsigned long long* d_keys[2] = {nullptr, nullptr};

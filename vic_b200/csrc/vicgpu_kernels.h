@@ -25,9 +25,9 @@
 #endif
 
 // one: the configuration's model step is a single sub-step (NF == 1)
-void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0);
-void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0);
-void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0);
+void vicgpu_launch_hru_step_nn3(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0, const int* block_w0 = nullptr, int nb_w0 = 0);
+void vicgpu_launch_hru_step_nn10(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0, const int* block_w0 = nullptr, int nb_w0 = 0);
+void vicgpu_launch_hru_step_nn32(const vic::Opts* d_o, bool one, const vic::Tables& t, const double* frec, vic::Dmy d, int rec, vic::GlacAccum ga, int block, cudaStream_t s, unsigned long long* warp_ns = nullptr, long long sync_limit = 0, int nsm = 0, int f_stride = 0, const int* block_w0 = nullptr, int nb_w0 = 0);
 
 int vicgpu_set_work_buffer_nn3(int* buf);
 int vicgpu_set_work_buffer_nn10(int* buf);
