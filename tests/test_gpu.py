@@ -69,7 +69,9 @@ def _reference_case(harness, cfgname, nlat, nlon, ndays, seed, tmp_path):
     cfg = dataclasses.replace(synth.CONFIGS[cfgname], ndays=ndays)
     r = synth.generate(str(tmp_path / "in"), cfg, nlat, nlon, seed)
     case = str(tmp_path / "case.bin")
-    subprocess.run([harness, "-g", r["global_file"], "-o", case, "--dump-every", "240"], check=True, stdout=subprocess.DEVNULL)
+    # (the cells are independent: the reference's OpenMP cell loop over all host threads computes the same bits as one thread)
+    subprocess.run([harness, "-g", r["global_file"], "-o", case, "--dump-every", "240", "--threads", str(os.cpu_count() or 1)], check=True,
+                   stdout=subprocess.DEVNULL)
     return read_case(case)
 
 
