@@ -334,10 +334,10 @@ static int upload_block_layout(vicgpu_handle* h) {
   }
   h->h_block_w0.push_back(nw);
   h->nb_balanced = (int)h->h_block_w0.size() - 1;
-  cudaFree(h->d_block_w0);
-  h->d_block_w0 = nullptr;
-  CK(cudaMalloc(&h->d_block_w0, h->h_block_w0.size() * sizeof(int)));
-  CK(cudaMemcpy(h->d_block_w0, h->h_block_w0.data(), h->h_block_w0.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // (at most one block per warp: the table is allocated once per domain, in vicgpu_set_cells; the copy is ordered behind the launches
+  // that still read the old table and h_block_w0 stays untouched until the next revision, a day of records later)
+  if (!h->d_block_w0) CK(cudaMalloc(&h->d_block_w0, ((size_t)nw + 1) * sizeof(int)));
+  CK(cudaMemcpyAsync(h->d_block_w0, h->h_block_w0.data(), h->h_block_w0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   h->bal_measured = false;
   h->bal_measure_next = true;
   return VICGPU_OK;
