@@ -34,6 +34,8 @@ GOLDEN = {
     "wb_daily": ("wb_daily", dict(ndays=120), 2, 2, 13, 30),
     "frozen_bands": ("frozen_bands", dict(ndays=8, out_step=24), 2, 2, 14, 48),
     "glacier": ("glacier", dict(ndays=10, out_step=24), 2, 2, 15, 48),
+    # IMPLICIT TRUE: Newton-Raphson soil-temperature solver with the explicit scheme as fallback (third oracle patch, oracle/Makefile)
+    "frozen_implicit": ("frozen_implicit", dict(ndays=8, out_step=24), 2, 2, 16, 48),
 }
 
 
