@@ -35,10 +35,12 @@ struct SurfEB {
   double surf_atten, vp, vpd, Wdew, rainfall, latent_heat_Le, Advection, OldTSurf, TPack, Tsnow_surf, kappa_snow, melt_energy;
   double snow_coverage, snow_density, snow_swq, snow_water;
   const Surf4 *displacement, *aero_resist, *ref_height, *roughness, *wind_speed;
-  // in/out
-  RaUsed* aero_resist_used;
-  EnergyBal<NN>* en;  // deltaCC, refreeze_energy, deltaH, fusion, grnd_flux, latent, latent_sub, sensible, snow_flux, error
-  SnowPack* sn;       // vapor_flux, blowing_flux, surface_flux
+  // in/out, BY VALUE: what an evaluation writes of the HRU's energy record, snow pack and the resistances in use.  The caller copies
+  // them in before the solve and back after the last evaluation (calc_surf_energy_bal); written through pointers into the HRU they
+  // were ~20 thread-local stores and reloads per evaluation, and every such store made the compiler reload whatever else it held.
+  struct EnOut { double snow_flux, grnd_flux, deltaH, fusion, deltaCC, refreeze_energy, latent, latent_sub, sensible, error; } en;
+  struct SnOut { double vapor_flux, blowing_flux, surface_flux; } sn;
+  RaUsed aero_resist_used;
   double *Cs_node, *T_node, *Tnew_node, *Tnew_fbflag, *Tnew_fbcount, *ice_node, *kappa_node, *moist_node;
   SoilLayer* layer;
   VegVar* vv;
@@ -91,16 +93,16 @@ struct SurfEB {
   VIC_HD double eval(double Ts) {
     const double TMean = Ts;
     const double Tmp = TMean + KELVIN;
-    if (snow_coverage > 0 && !INCLUDE_SNOW) en->snow_flux = (kappa_snow * (Tsnow_surf - TMean));
+    if (snow_coverage > 0 && !INCLUDE_SNOW) en.snow_flux = (kappa_snow * (Tsnow_surf - TMean));
     else if (INCLUDE_SNOW) {
-      en->snow_flux = 0;
+      en.snow_flux = 0;
       Tsnow_surf = TMean;
-    } else en->snow_flux = 0;
+    } else en.snow_flux = 0;
     const double cover = (snow_coverage + (1. - snow_coverage) * surf_atten);
     if (QUICK_FLUX) {
       T1 = (t1_k1 * (TMean) + t1_b + t1_c) / t1_den;
-      if (GRND_FLUX_TYPE == GF_406) en->grnd_flux = cover * (gf_k1 * (T1 - TMean));
-      else en->grnd_flux = cover * (gf_k1 * (T1 - TMean) + (gf_k2e * (T2 - T1))) / 2.;
+      if (GRND_FLUX_TYPE == GF_406) en.grnd_flux = cover * (gf_k1 * (T1 - TMean));
+      else en.grnd_flux = cover * (gf_k1 * (T1 - TMean) + (gf_k2e * (T2 - T1))) / 2.;
     } else {
       T_node[0] = TMean;
       // IMPLICIT: Newton-Raphson on the whole profile first; the explicit sweeps are its fallback (func_surf_energy_bal.c:192-221)
@@ -118,31 +120,31 @@ struct SurfEB {
       }
       if (Error == ERROR_I) return ERROR_D;
       T1 = Tnew_node[1];
-      if (GRND_FLUX_TYPE == GF_406) en->grnd_flux = cover * (kappa1 / D1 * (T1 - TMean));
-      else en->grnd_flux = cover * (kappa1 / D1 * (T1 - TMean) + (kappa2 / D2 * (Tnew_node[2] - T1))) / 2.;
+      if (GRND_FLUX_TYPE == GF_406) en.grnd_flux = cover * (kappa1 / D1 * (T1 - TMean));
+      else en.grnd_flux = cover * (kappa1 / D1 * (T1 - TMean) + (kappa2 / D2 * (Tnew_node[2] - T1))) / 2.;
     }
-    if (GRND_FLUX_TYPE == GF_FULL) en->deltaH = cover * (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1, delta_t) / 2.);
-    else en->deltaH = (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1, delta_t) / 2.);
+    if (GRND_FLUX_TYPE == GF_FULL) en.deltaH = cover * (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1, delta_t) / 2.);
+    else en.deltaH = (div_pos(Cs1 * ((Ts_old + T1_old) - (TMean + T1)) * D1, delta_t) / 2.);
     if (FS_FROZEN) {
       double ice;
       if ((TMean + T1) / 2. < 0.) {
         ice = moist - maximum_unfrozen_water((TMean + T1) / 2., max_moist, bubble, expt);
         if (ice < 0.) ice = 0.;
       } else ice = 0.;
-      if (GRND_FLUX_TYPE == GF_FULL) en->fusion = cover * (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
-      else en->fusion = (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
+      if (GRND_FLUX_TYPE == GF_FULL) en.fusion = cover * (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
+      else en.fusion = (-ice_density * Lf * (ice0 - ice) * D1 / delta_t);
     }
     if (INCLUDE_SNOW) {
-      if (TMean > 0) en->deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (0 - OldTSurf), delta_t);
-      else en->deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (TMean - OldTSurf), delta_t);
-      en->refreeze_energy = div_pos((snow_water * Lf * snow_density), delta_t);
-      en->deltaCC *= snow_coverage;
-      en->refreeze_energy *= snow_coverage;
+      if (TMean > 0) en.deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (0 - OldTSurf), delta_t);
+      else en.deltaCC = div_pos(CH_ICE * (snow_swq - snow_water) * (TMean - OldTSurf), delta_t);
+      en.refreeze_energy = div_pos((snow_water * Lf * snow_density), delta_t);
+      en.deltaCC *= snow_coverage;
+      en.refreeze_energy *= snow_coverage;
     }
     const double LongBareOut = STEFAN_B * Tmp * Tmp * Tmp * Tmp;
     if (INCLUDE_SNOW) NetLongSnow = (LongSnowIn - snow_coverage * LongBareOut);
     NetLongBare = (LongBareIn - (1. - snow_coverage) * LongBareOut);
-    const double NetBareRad = (NetShortBare + NetLongBare + en->grnd_flux + en->deltaH + en->fusion);
+    const double NetBareRad = (NetShortBare + NetLongBare + en.grnd_flux + en.deltaH + en.fusion);
     const double ws = ws_under;
     if (ws > 0.0) {
       // the displacement height is dropped under a snowing overstory (func_surf_energy_bal.c:280-296); which case applies is fixed for the solve
@@ -151,44 +153,44 @@ struct SurfEB {
         sc_lg = vlog((Zr - dr) / rough_under);
         sc_lg_ok = 1;
       }
-      aero_resist_used->surface = ra_under / stability_correction_lg(Zr, dr, TMean, Tair, ws, sc_lg);
-    } else aero_resist_used->surface = HUGE_RESIST;
+      aero_resist_used.surface = ra_under / stability_correction_lg(Zr, dr, TMean, Tair, ws, sc_lg);
+    } else aero_resist_used.surface = HUGE_RESIST;
     double Evap;
     if (VEG && !SNOWING && veg_LAI > 0) {
-      Evap = canopy_evap(layer, *vv, true, *veg, Wdew, delta_t, NetBareRad, vpd, NetShortBare, Tair, aero_resist_used->overstory,
+      Evap = canopy_evap(layer, *vv, true, *veg, Wdew, delta_t, NetBareRad, vpd, NetShortBare, Tair, aero_resist_used.overstory,
                          elevation, rainfall, *soil, memo);
     } else if (!SNOWING) {
       Evap = arno_evap(layer, NetBareRad, Tair, vpd, depth0, max_moist * depth0 * 1000., elevation,
-                       b_infilt, aero_resist_used->surface, delta_t, resid_moist0, memo);
+                       b_infilt, aero_resist_used.surface, delta_t, resid_moist0, memo);
     } else Evap = 0.;
-    en->latent = -RHO_W * latent_heat_Le * Evap;
-    en->latent_sub = 0.;
+    en.latent = -RHO_W * latent_heat_Le * Evap;
+    en.latent_sub = 0.;
     if (INCLUDE_SNOW) {
-      double VaporMassFlux = div_pos(sn->vapor_flux * ice_density, delta_t);
-      double BlowingMassFlux = div_pos(sn->blowing_flux * ice_density, delta_t);
-      double SurfaceMassFlux = div_pos(sn->surface_flux * ice_density, delta_t);
+      double VaporMassFlux = div_pos(sn.vapor_flux * ice_density, delta_t);
+      double BlowingMassFlux = div_pos(sn.blowing_flux * ice_density, delta_t);
+      double SurfaceMassFlux = div_pos(sn.surface_flux * ice_density, delta_t);
       double tl, tls;
-      latent_heat_from_snow(atmos_density, vp, latent_heat_Le, atmos_pressure, aero_resist_used->surface, TMean, vpd, &tl, &tls, &VaporMassFlux,
+      latent_heat_from_snow(atmos_density, vp, latent_heat_Le, atmos_pressure, aero_resist_used.surface, TMean, vpd, &tl, &tls, &VaporMassFlux,
                             &BlowingMassFlux, &SurfaceMassFlux);
-      en->latent += tl * snow_coverage;
-      en->latent_sub = tls * snow_coverage;
-      sn->vapor_flux = div_pos(VaporMassFlux * delta_t, ice_density);
-      sn->blowing_flux = div_pos(BlowingMassFlux * delta_t, ice_density);
-      sn->surface_flux = div_pos(SurfaceMassFlux * delta_t, ice_density);
-    } else en->latent *= (1. - snow_coverage);
+      en.latent += tl * snow_coverage;
+      en.latent_sub = tls * snow_coverage;
+      sn.vapor_flux = div_pos(VaporMassFlux * delta_t, ice_density);
+      sn.blowing_flux = div_pos(BlowingMassFlux * delta_t, ice_density);
+      sn.surface_flux = div_pos(SurfaceMassFlux * delta_t, ice_density);
+    } else en.latent *= (1. - snow_coverage);
     if (snow_coverage < 1 || INCLUDE_SNOW) {
-      en->sensible = atmos_density * Cp * (Tair - (TMean)) / aero_resist_used->surface;
-      if (!INCLUDE_SNOW) en->sensible *= (1. - snow_coverage);
-    } else en->sensible = 0.;
-    double error = (NetBareRad + NetShortGrnd + NetShortSnow + emissivity * NetLongSnow) + en->sensible + (en->latent + en->latent_sub) +
-                   en->snow_flux * snow_coverage + melt_energy + Advection - en->deltaCC;
+      en.sensible = atmos_density * Cp * (Tair - (TMean)) / aero_resist_used.surface;
+      if (!INCLUDE_SNOW) en.sensible *= (1. - snow_coverage);
+    } else en.sensible = 0.;
+    double error = (NetBareRad + NetShortGrnd + NetShortSnow + emissivity * NetLongSnow) + en.sensible + (en.latent + en.latent_sub) +
+                   en.snow_flux * snow_coverage + melt_energy + Advection - en.deltaCC;
     if (INCLUDE_SNOW) {
-      if (Tsnow_surf == 0.0 && error > -(en->refreeze_energy)) {
-        en->refreeze_energy = -error;
+      if (Tsnow_surf == 0.0 && error > -(en.refreeze_energy)) {
+        en.refreeze_energy = -error;
         error = 0.0;
-      } else error += en->refreeze_energy;
+      } else error += en.refreeze_energy;
     }
-    en->error = error;
+    en.error = error;
     return error;
   }
 };
@@ -250,8 +252,11 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   eb.kappa_snow = kappa_snow; eb.melt_energy = melt_energy; eb.snow_coverage = snow_coverage; eb.snow_density = snow.density; eb.snow_swq = snow.swq;
   eb.snow_water = snow.surf_water;
   eb.displacement = &displacement; eb.aero_resist = &aero_resist; eb.ref_height = &ref_height; eb.roughness = &roughness; eb.wind_speed = &wind_speed;
-  eb.aero_resist_used = &aero_resist_used;
-  eb.en = &energy; eb.sn = &snow;
+  eb.aero_resist_used = aero_resist_used;
+  eb.en.snow_flux = energy.snow_flux; eb.en.grnd_flux = energy.grnd_flux; eb.en.deltaH = energy.deltaH; eb.en.fusion = energy.fusion;
+  eb.en.deltaCC = energy.deltaCC; eb.en.refreeze_energy = energy.refreeze_energy; eb.en.latent = energy.latent; eb.en.latent_sub = energy.latent_sub;
+  eb.en.sensible = energy.sensible; eb.en.error = energy.error;
+  eb.sn.vapor_flux = snow.vapor_flux; eb.sn.blowing_flux = snow.blowing_flux; eb.sn.surface_flux = snow.surface_flux;
   eb.Cs_node = energy.Cs_node; eb.T_node = energy.T; eb.Tnew_node = Tnew_node; eb.Tnew_fbflag = Tnew_fbflag; eb.Tnew_fbcount = Tnew_fbcount;
   eb.ice_node = energy.ice; eb.kappa_node = energy.kappa_node; eb.moist_node = energy.moist;
   eb.layer = layer; eb.vv = &vv; eb.FIRST_SOLN = FIRST_SOLN;
@@ -286,6 +291,12 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   fin.f_final = 0.;
   fin.fell_back = 0;
   Tsurf = root_brent_ss_impl<true>(T_lower, T_upper, call, &fin);
+  // what the last evaluation left behind
+  aero_resist_used = eb.aero_resist_used;
+  energy.snow_flux = eb.en.snow_flux; energy.grnd_flux = eb.en.grnd_flux; energy.deltaH = eb.en.deltaH; energy.fusion = eb.en.fusion;
+  energy.deltaCC = eb.en.deltaCC; energy.refreeze_energy = eb.en.refreeze_energy; energy.latent = eb.en.latent; energy.latent_sub = eb.en.latent_sub;
+  energy.sensible = eb.en.sensible; energy.error = eb.en.error;
+  snow.vapor_flux = eb.sn.vapor_flux; snow.blowing_flux = eb.sn.blowing_flux; snow.surface_flux = eb.sn.surface_flux;
   if (o.FULL_ENERGY && !fin.fell_back && result_is_error(Tsurf)) return ERROR_D;  // the solve failed and TFALLBACK is off
   if (fin.fell_back) {
     Tsurf_fbflag = 1;
