@@ -268,7 +268,9 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   if (a.LAKES) { *why = "LAKES is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.QUICK_SOLVE) { *why = "QUICK_SOLVE is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.GLACIER_DYNAMICS) { *why = "GLACIER_DYNAMICS is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
-  if (a.COMPUTE_TREELINE) { *why = "COMPUTE_TREELINE is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  // COMPUTE_TREELINE: the host's initialize_atmos() decides which bands lie above the treeline (compute_treeline.c) and hands the flags
+  // over in cellpar (CB_AboveTreeLine); the device side of the option is put_data's treatment of those bands (vic_output.cuh).
+  // vicgpu_disagg refuses it: the decision needs the July temperatures of the whole forcing record.
   if (a.dt < 1 || a.SNOW_STEP < 1 || a.NF < 1 || a.out_step_ratio < 1) { *why = "bad time-step options"; return VICGPU_EINVAL; }
   o.Nnode = a.Nnode; o.Nbands = a.Nbands; o.dt = a.dt; o.SNOW_STEP = a.SNOW_STEP; o.NR = a.NR; o.NF = a.NF; o.nrecs = a.nrecs;
   o.out_step_ratio = a.out_step_ratio; o.FULL_ENERGY = a.FULL_ENERGY; o.FROZEN_SOIL = a.FROZEN_SOIL; o.QUICK_FLUX = a.QUICK_FLUX;

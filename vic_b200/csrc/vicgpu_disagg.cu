@@ -54,6 +54,7 @@ extern "C" int vicgpu_disagg(vicgpu_handle* h, const vicgpu_disagg_options* dopt
   if (!h || !dopt || !daily) return vicgpu_fail(VICGPU_EINVAL, "null argument");
   if (dopt->abi_version != VICGPU_ABI_VERSION) return vicgpu_fail(VICGPU_EINVAL, "abi_version mismatch");
   if (!h->have_cells) return vicgpu_fail(VICGPU_ESTATE, "set_cells before disagg");
+  if (h->abi.COMPUTE_TREELINE) return vicgpu_fail(VICGPU_EUNSUPPORTED, "COMPUTE_TREELINE with device-side disaggregation: compute_treeline() is not implemented on the device");
   if (dopt->Ndays < 1 || h->abi.nrecs < 1) return vicgpu_fail(VICGPU_EINVAL, "Ndays and nrecs must be positive");
   if (24 % h->abi.dt != 0) return vicgpu_fail(VICGPU_EINVAL, "dt must divide 24");
   if (h->abi.SNOW_STEP < 1 || h->abi.dt % h->abi.SNOW_STEP != 0 || h->abi.NF != h->abi.dt / h->abi.SNOW_STEP)

@@ -58,6 +58,9 @@ CONFIGS = {
     "frozen_bands": Config("frozen_bands", frozen_soil=True, quick_flux=False, nodes=10, nbands=5),
     # the same with the implicit (Newton-Raphson, tridiagonal) soil-temperature solver, explicit scheme as its fallback
     "frozen_implicit": Config("frozen_implicit", frozen_soil=True, quick_flux=False, nodes=10, nbands=5, implicit=True),
+    # full energy with 5 bands and COMPUTE_TREELINE: the reference marks the bands whose mean July air temperature is below 10 C
+    # (compute_treeline.c) and put_data leaves the overstory tiles of those bands out of the cell averages (put_data.c:205, 290)
+    "treeline": Config("treeline", nbands=5, startday=182, extra_global=["COMPUTE_TREELINE 10"]),
     # configs[3]: PCIC glacier mass-balance mode
     "glacier": Config("glacier", glacier=True, nbands=5),
     # the same with glacier HRUs in four bands of every cell: exercises accumulateGlacierMassBalance's quadratic fit
