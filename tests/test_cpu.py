@@ -155,6 +155,30 @@ def test_optimised_reference_build_computes_the_same_bits(ref_harness, root, tmp
             assert np.array_equal(cases[0][k], cases[1][k], equal_nan=True), (cfgname, k)
 
 
+SOIL_THERMAL_OPTIONS = [dict(exp_trans=True), dict(noflux=True), dict(exp_trans=True, noflux=True), dict(implicit=True, exp_trans=True),
+                        dict(implicit=True, noflux=True), dict(implicit=True, exp_trans=True, noflux=True)]
+
+
+@pytest.mark.parametrize("over", SOIL_THERMAL_OPTIONS, ids=lambda o: "+".join(sorted(o)))
+def test_soil_thermal_options_against_reference(over, ref_harness, vicport, tmp_path):
+    """EXP_TRANS (exponential node spacing), NO_FLUX (zero-flux bottom boundary) and IMPLICIT in every combination, frozen soil with ten
+    nodes and five bands, 5 winter days: the host build of the kernels' headers against the reference, bit for bit"""
+    import dataclasses
+    from vic_b200 import synth
+    cfg = dataclasses.replace(synth.CONFIGS["frozen_bands"], ndays=5, **over)
+    r = synth.generate(str(tmp_path / "in"), cfg, 2, 2, 333)
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "res.bin")
+    subprocess.run([ref_harness, "-g", r["global_file"], "-o", case, "--dump-every", "96", "--threads", "4"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([vicport, case, out], check=True)
+    c, res = read_case(case), read_case(out)
+    opt = parse_options(c["options_raw"])
+    assert (opt["EXP_TRANS"], opt["NOFLUX"], opt["IMPLICIT"]) == (int(over.get("exp_trans", False)), int(over.get("noflux", False)), int(over.get("implicit", False)))
+    assert np.array_equal(res["out"], c["out_ref"], equal_nan=True)
+    assert np.array_equal(res["hrurec"], c["hrurec_ref"], equal_nan=True)
+    assert np.array_equal(res["balance"], c["balance_ref"], equal_nan=True)
+    assert np.array_equal(res["status"], c["status_ref"])
+
+
 def _failing_case(harness, tmp_path):
     """frozen soil without TFALLBACK: every failed solve is an error, and each of the nine cells is invalidated somewhere in the
     first day (vicNl.c:545-559), at a different record"""

@@ -90,6 +90,20 @@ def test_bit_exact_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref
     annual_totals_match(res["out"], c["out_ref"], list(L.out_names))
 
 
+@pytest.mark.parametrize("over", [dict(exp_trans=True, noflux=True), dict(implicit=True, exp_trans=True, noflux=True)], ids=lambda o: "+".join(sorted(o)))
+def test_soil_thermal_options_against_reference_build(over, ref_harness, tmp_path):
+    """EXP_TRANS + NO_FLUX with the explicit and with the IMPLICIT soil-temperature scheme (frozen soil, ten nodes, five bands), 4 winter days"""
+    cfg = dataclasses.replace(synth.CONFIGS["frozen_bands"], ndays=4, **over)
+    r = synth.generate(str(tmp_path / "in"), cfg, 2, 2, 333)
+    case = str(tmp_path / "case.bin")
+    subprocess.run([ref_harness, "-g", r["global_file"], "-o", case, "--dump-every", "48", "--threads", "4"], check=True, stdout=subprocess.DEVNULL)
+    c = read_case(case)
+    res = api.run_case(c, device=0)
+    assert np.array_equal(res["out"], c["out_ref"], equal_nan=True)
+    assert np.array_equal(res["hrurec"], c["hrurec_ref"], equal_nan=True)
+    assert np.array_equal(res["status"], c["status_ref"])
+
+
 def test_thousand_cells_against_reference_build(ref_harness, tmp_path):
     """1,024 cells (5,400 HRUs: every land-cover kind, many warps, re-binning by snow state) x 60 days against the reference
     build: daily aggregates of all 184 variables, the state, balance errors and status bit-identical"""
