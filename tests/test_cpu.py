@@ -156,12 +156,14 @@ def test_optimised_reference_build_computes_the_same_bits(ref_harness, root, tmp
 
 
 SOIL_THERMAL_OPTIONS = [dict(exp_trans=True), dict(noflux=True), dict(exp_trans=True, noflux=True), dict(implicit=True, exp_trans=True),
-                        dict(implicit=True, noflux=True), dict(implicit=True, exp_trans=True, noflux=True)]
+                        dict(implicit=True, noflux=True), dict(implicit=True, exp_trans=True, noflux=True), dict(quick_solve=True),
+                        dict(quick_solve=True, exp_trans=True, noflux=True)]
 
 
 @pytest.mark.parametrize("over", SOIL_THERMAL_OPTIONS, ids=lambda o: "+".join(sorted(o)))
 def test_soil_thermal_options_against_reference(over, ref_harness, vicport, tmp_path):
-    """EXP_TRANS (exponential node spacing), NO_FLUX (zero-flux bottom boundary) and IMPLICIT in every combination, frozen soil with ten
+    """EXP_TRANS (exponential node spacing), NO_FLUX (zero-flux bottom boundary) and IMPLICIT in every combination, QUICK_SOLVE (search on the
+    nodes above the thaw depth, second search on the whole profile when the surface changes sign), frozen soil with ten
     nodes and five bands, 5 winter days: the host build of the kernels' headers against the reference, bit for bit"""
     import dataclasses
     from vic_b200 import synth
@@ -172,7 +174,7 @@ def test_soil_thermal_options_against_reference(over, ref_harness, vicport, tmp_
     subprocess.run([vicport, case, out], check=True)
     c, res = read_case(case), read_case(out)
     opt = parse_options(c["options_raw"])
-    assert (opt["EXP_TRANS"], opt["NOFLUX"], opt["IMPLICIT"]) == (int(over.get("exp_trans", False)), int(over.get("noflux", False)), int(over.get("implicit", False)))
+    assert (opt["EXP_TRANS"], opt["NOFLUX"], opt["IMPLICIT"], opt["QUICK_SOLVE"]) == tuple(int(over.get(k, False)) for k in ("exp_trans", "noflux", "implicit", "quick_solve"))
     assert np.array_equal(res["out"], c["out_ref"], equal_nan=True)
     assert np.array_equal(res["hrurec"], c["hrurec_ref"], equal_nan=True)
     assert np.array_equal(res["balance"], c["balance_ref"], equal_nan=True)
@@ -302,7 +304,7 @@ def test_unsupported_options_are_rejected():
     opt = parse_options(g["options_raw"])
     assert api.parse_options(api.options_to_raw(opt)) == opt
     lib = api.load_library()
-    for key in ("DIST_PRCP", "BLOWING", "LAKES", "CORRPREC", "QUICK_SOLVE"):
+    for key in ("DIST_PRCP", "BLOWING", "LAKES", "CORRPREC", "GLACIER_DYNAMICS"):
         o = dict(opt)
         o[key] = 1
         raw = api.options_to_raw(o)

@@ -90,9 +90,11 @@ def test_bit_exact_against_reference_build(cfgname, nlat, nlon, ndays, seed, ref
     annual_totals_match(res["out"], c["out_ref"], list(L.out_names))
 
 
-@pytest.mark.parametrize("over", [dict(exp_trans=True, noflux=True), dict(implicit=True, exp_trans=True, noflux=True)], ids=lambda o: "+".join(sorted(o)))
+@pytest.mark.parametrize("over", [dict(exp_trans=True, noflux=True), dict(implicit=True, exp_trans=True, noflux=True), dict(quick_solve=True)],
+                         ids=lambda o: "+".join(sorted(o)))
 def test_soil_thermal_options_against_reference_build(over, ref_harness, tmp_path):
-    """EXP_TRANS + NO_FLUX with the explicit and with the IMPLICIT soil-temperature scheme (frozen soil, ten nodes, five bands), 4 winter days"""
+    """EXP_TRANS + NO_FLUX with the explicit and with the IMPLICIT soil-temperature scheme, and QUICK_SOLVE (frozen soil, ten nodes, five
+    bands), 4 winter days"""
     cfg = dataclasses.replace(synth.CONFIGS["frozen_bands"], ndays=4, **over)
     r = synth.generate(str(tmp_path / "in"), cfg, 2, 2, 333)
     case = str(tmp_path / "case.bin")

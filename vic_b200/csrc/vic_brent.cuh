@@ -134,14 +134,16 @@ struct BrentFinal {
   double fallback_x, nosolve_x;
   double lo = 0, hi = 0;  // PRE: the bracket, set by `decide`
   double f_final;  // out: the residual at the returned point
-  int fell_back;   // out: 1 when the solve failed and fallback_x was used
+  int fell_back;   // out: how many solves failed and took fallback_x (0 or 1; up to 2 with RESOLVE)
 };
 
 struct BrentNoDecide {
   VIC_HD void operator()(double) const {}
 };
 
-template <bool FINAL, bool PRE = false, class F, class D = BrentNoDecide>
+// RESOLVE: after a solve (and its fallback) the functor is asked whether it wants the same bracket solved once more with whatever it has
+// changed about itself in the meantime (f.resolve(x): QUICK_SOLVE's second pass over the full node profile, calc_surf_energy_bal.c:400-475).
+template <bool FINAL, bool PRE = false, bool RESOLVE = false, class F, class D = BrentNoDecide>
 VIC_HD double root_brent_ss_impl(double LowerBound, double UpperBound, F& f, BrentFinal* fin, bool pre = false, double x_pre = 0,
                                  D decide = D()) {
   const int MAXTRIES = 5, MAXITER = 1000;
@@ -330,7 +332,16 @@ VIC_HD double root_brent_ss_impl(double LowerBound, double UpperBound, F& f, Bre
       if (result_is_error(res)) {
         if (!fin->allow_fallback) return res;
         res = fin->fallback_x;
-        fin->fell_back = 1;
+        fin->fell_back += 1;
+      }
+      if constexpr (RESOLVE) {
+        if (f.resolve(res)) {
+          a = LowerBound; b = UpperBound; c = 0; d = 0; e = 0; fa = 0; fb = 0; fc = 0; last_bad = 0; last_good = 0;
+          which_err = 0; i = 0; j = 0;
+          x = a;
+          st = 0;
+          continue;
+        }
       }
       if (!fin->do_final || (fin->final_needs_valid && !is_valid(res))) return res;
       f.before_final();

@@ -266,7 +266,10 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   if (a.BLOWING) { *why = "BLOWING is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.CORRPREC) { *why = "CORRPREC is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.LAKES) { *why = "LAKES is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
-  if (a.QUICK_SOLVE) { *why = "QUICK_SOLVE is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  // QUICK_SOLVE + IMPLICIT: fda_heat_eqn reads kappa_new[n + 1], which no evaluation of the same solve writes; with QUICK_SOLVE the number
+  // of unknowns n changes between the searches of a step, so that entry holds what an earlier solve with more unknowns -- of whichever
+  // HRU or cell the thread handled before -- left in the (static) array: the reference's answer depends on its OpenMP schedule.
+  if (a.QUICK_SOLVE && a.IMPLICIT && !a.QUICK_FLUX) { *why = "QUICK_SOLVE with IMPLICIT has no defined answer in the reference"; return VICGPU_EUNSUPPORTED; }
   if (a.GLACIER_DYNAMICS) { *why = "GLACIER_DYNAMICS is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   // COMPUTE_TREELINE: the host's initialize_atmos() decides which bands lie above the treeline (compute_treeline.c) and hands the flags
   // over in cellpar (CB_AboveTreeLine); the device side of the option is put_data's treatment of those bands (vic_output.cuh).
@@ -285,7 +288,7 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
 
 // which instantiation (thermal-node array width) steps a configuration: 3, 10 or 32
 inline int vic_node_width(const Opts& o) {
-  if (o.Nnode <= 3 && !(o.IMPLICIT && !o.QUICK_FLUX)) return 3;
+  if (o.Nnode <= 3 && !((o.IMPLICIT || o.QUICK_SOLVE) && !o.QUICK_FLUX)) return 3;
   return o.Nnode <= 10 ? 10 : 32;
 }
 

@@ -52,7 +52,28 @@ struct SurfEB {
   int sc_lg_ok;
   EvapMemo* memo;  // the caller's (the functor itself must not have its address taken, or its members stay in memory)
   double Tsnow_surf_final;  // what Tsnow_surf restarts from at the evaluation after the solve
-  VIC_HD void before_final() { Tsnow_surf = Tsnow_surf_final; }
+  // QUICK_SOLVE (calc_surf_energy_bal.c:289-314, 400-475, 484-486): the search runs on the nodes above the thaw depth only, a second search
+  // on the whole profile follows when the surface changes sign, and the evaluation at the accepted temperature always uses the whole profile
+  int qs_pass, Nnodes_full, NOFLUX_full;  // qs_pass: 0 = option off, 1 = reduced-node search running, 2 = over
+  VIC_HD void before_final() {
+    Tsnow_surf = Tsnow_surf_final;
+    if (qs_pass) {
+      Nnodes = Nnodes_full;
+      FIRST_SOLN[0] = 1;
+    }
+  }
+  VIC_HD bool resolve(double Tsurf) {
+    if (qs_pass != 1) return false;
+    qs_pass = 2;
+    if (Ts_old * Tsurf < 0) {
+      Nnodes = Nnodes_full;
+      NOFLUX = NOFLUX_full;
+      FIRST_SOLN[0] = 1;
+      Tsnow_surf = Tsnow_surf_final;  // (a fresh functor in the reference)
+      return true;
+    }
+    return false;
+  }
 
   VIC_HD void prepare() {
     memo->reset();
@@ -268,8 +289,7 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
 
   // The solve (FULL_ENERGY) and the evaluation at the accepted temperature -- in the reference a fresh functor, i.e. Tsnow_surf restarts
   // from snow.surf_temp -- go through the one residual call site of root_brent_ss_impl, so the residual is inlined here and the
-  // solve's constants live in registers.  QUICK_SOLVE (reduced-node first pass, calc_surf_energy_bal.c:289-314, 400-475) is rejected
-  // at create time.
+  // solve's constants live in registers.  QUICK_SOLVE's second search (SurfEB::resolve) goes through the same call site.
   double T_lower, T_upper;
   if (INCLUDE_SNOW) {
     T_lower = energy.T[0] - SURF_DT;
@@ -282,7 +302,27 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
     SurfEB<NN>& f;
     VIC_HD double operator()(double x) { return f.eval(x); }
     VIC_HD void before_final() { f.before_final(); }
+    VIC_HD bool resolve(double x) { return f.resolve(x); }
   } call{eb};
+  eb.qs_pass = 0; eb.Nnodes_full = Nnodes; eb.NOFLUX_full = o.NOFLUX;
+  if constexpr (NN > 3) {
+    if (o.QUICK_SOLVE && !o.QUICK_FLUX) {
+      if (o.FULL_ENERGY) {
+        // iterate on the nodes down to four below the thaw front (or three, or all: calc_surf_energy_bal.c:289-300), open bottom, linear grid
+        int tmpNnodes = 0;
+        for (int nidx = Nnodes - 5; nidx >= 0; nidx--)
+          if (energy.T[nidx] >= 0 && energy.T[nidx + 1] < 0) tmpNnodes = nidx + 1;
+        if (tmpNnodes == 0) {
+          if (energy.T[0] <= 0 && energy.T[1] >= 0) tmpNnodes = Nnodes;
+          else tmpNnodes = 3;
+        } else tmpNnodes += 4;
+        eb.Nnodes = tmpNnodes;
+        eb.NOFLUX = 0;
+        eb.EXP_TRANS = 0;
+      }
+      eb.qs_pass = 1;
+    }
+  }
   BrentFinal fin;
   fin.do_solve = o.FULL_ENERGY != 0;
   fin.allow_fallback = o.TFALLBACK != 0;
@@ -290,7 +330,7 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   fin.nosolve_x = Tair;
   fin.f_final = 0.;
   fin.fell_back = 0;
-  Tsurf = root_brent_ss_impl<true>(T_lower, T_upper, call, &fin);
+  Tsurf = root_brent_ss_impl<true, false, (NN > 3)>(T_lower, T_upper, call, &fin);
   // what the last evaluation left behind
   aero_resist_used = eb.aero_resist_used;
   energy.snow_flux = eb.en.snow_flux; energy.grnd_flux = eb.en.grnd_flux; energy.deltaH = eb.en.deltaH; energy.fusion = eb.en.fusion;
@@ -300,7 +340,7 @@ VIC_HDI double calc_surf_energy_bal(double latent_heat_Le, double LongUnderIn, d
   if (o.FULL_ENERGY && !fin.fell_back && result_is_error(Tsurf)) return ERROR_D;  // the solve failed and TFALLBACK is off
   if (fin.fell_back) {
     Tsurf_fbflag = 1;
-    Tsurf_fbcount += 1;
+    Tsurf_fbcount += fin.fell_back;
   }
   const double error = fin.f_final;
   if (error == ERROR_D) return ERROR_D;

@@ -44,6 +44,7 @@ class Config:
     implicit: bool = False
     exp_trans: bool = False
     noflux: bool = False
+    quick_solve: bool = False
     out_step: int = 0  # OUT_STEP [h]; 0 = every model step
     startday: int = 1  # day of January the run (and the forcing files) start on
     extra_global: list = field(default_factory=list)
@@ -277,7 +278,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
           f"FULL_ENERGY {tf(cfg.full_energy)}", f"FROZEN_SOIL {tf(cfg.frozen_soil)}",
           f"QUICK_FLUX {tf(cfg.quick_flux)}", f"NO_FLUX {tf(cfg.noflux)}",
           f"IMPLICIT {tf(cfg.implicit)}", f"EXP_TRANS {tf(cfg.exp_trans)}",
-          "QUICK_SOLVE FALSE", "SNOW_ALBEDO USACE", "SNOW_DENSITY DENS_BRAS", "BLOWING FALSE",
+          f"QUICK_SOLVE {tf(cfg.quick_solve)}", "SNOW_ALBEDO USACE", "SNOW_DENSITY DENS_BRAS", "BLOWING FALSE",
           "DIST_PRCP FALSE", "CORRPREC FALSE", "MIN_WIND_SPEED 0.1", "CONTINUEONERROR TRUE",
           "TFALLBACK TRUE", "COMPUTE_TREELINE FALSE", "EQUAL_AREA FALSE", f"RESOLUTION {res}",
           "AERO_RESIST_CANSNOW AR_406_FULL", "GRND_FLUX_TYPE GF_410", "PLAPSE TRUE",
