@@ -98,7 +98,7 @@ def test_disagg_port_reproduces_reference_forcing(name, flavour, root, tmp_path)
     assert np.array_equal(f, g["forcing"])
 
 
-YEAR_CASES = [("fe_hourly", 4, 4, 365, 101), ("wb_daily", 5, 5, 365, 102), ("glacier", 4, 4, 365, 103), ("frozen_bands", 2, 2, 40, 104), ("frozen_implicit", 2, 2, 120, 105), ("treeline", 3, 3, 40, 901)]
+YEAR_CASES = [("fe_hourly", 4, 4, 365, 101), ("wb_daily", 5, 5, 365, 102), ("glacier", 4, 4, 365, 103), ("frozen_bands", 2, 2, 40, 104), ("frozen_implicit", 2, 2, 120, 105), ("treeline", 3, 3, 40, 901), ("fe_corrprec", 3, 3, 40, 555)]
 ANNUAL_VARS = ("RUNOFF", "BASEFLOW", "EVAP", "SWE", "GLAC_MBAL", "GLAC_IMBAL")
 
 
@@ -304,7 +304,7 @@ def test_unsupported_options_are_rejected():
     opt = parse_options(g["options_raw"])
     assert api.parse_options(api.options_to_raw(opt)) == opt
     lib = api.load_library()
-    for key in ("DIST_PRCP", "BLOWING", "LAKES", "CORRPREC", "GLACIER_DYNAMICS"):
+    for key in ("DIST_PRCP", "BLOWING", "LAKES", "GLACIER_DYNAMICS"):
         o = dict(opt)
         o[key] = 1
         raw = api.options_to_raw(o)

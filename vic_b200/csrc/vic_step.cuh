@@ -175,8 +175,16 @@ VIC_HDI int hru_step(Hru<NN>& hru, const HruPar& hp, const Ctx& cx, HruStepDiag&
   if (!((hp.Cv > 0.0) || (hp.isGlacier && o.GLACIER_DYNAMICS && hp.Cv >= 0.0))) return 0;
   const int month0 = cx.dmy.month - 1;
   const double AreaFract = cp.band(CB_AreaFract, hp.band);
-  // CORRPREC is rejected at create time: no gauge correction
-  const double gauge_correction[2] = {1, 1};
+  // gauge undercatch (CORRPREC, full_energy.c:185-194, correct_precip.c:10-47: WMO equations for the shielded 8-inch gauge, wind
+  // brought to the gauge height of 1 m over bare ground and over snow); [0] rain, [1] snow
+  double gauge_correction[2] = {1, 1};
+  if (o.CORRPREC && cx.f(FV_prec, o.NR) > 0) {
+    const double wind = cx.f(FV_wind, o.NR), rough = cp(CP_rough), snow_rough = cp(CP_snow_rough);
+    double gauge_wind = wind * (vlog((1.0 + rough) / rough) / vlog(o.wind_h / rough));
+    gauge_correction[0] = 100. / vexp(4.606 - 0.041 * vpow(gauge_wind, 0.69));
+    gauge_wind = wind * (vlog((1.0 + snow_rough) / snow_rough) / vlog(o.wind_h / snow_rough));
+    gauge_correction[1] = 100. / vexp(4.606 - 0.036 * vpow(gauge_wind, 1.75));
+  }
   if (AreaFract > 0) {
     hru.energy.shortwave = 0;
     hru.energy.longwave = 0.;

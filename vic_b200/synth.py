@@ -45,6 +45,7 @@ class Config:
     exp_trans: bool = False
     noflux: bool = False
     quick_solve: bool = False
+    corrprec: bool = False
     out_step: int = 0  # OUT_STEP [h]; 0 = every model step
     startday: int = 1  # day of January the run (and the forcing files) start on
     extra_global: list = field(default_factory=list)
@@ -62,6 +63,8 @@ CONFIGS = {
     # full energy with 5 bands and COMPUTE_TREELINE: the reference marks the bands whose mean July air temperature is below 10 C
     # (compute_treeline.c) and put_data leaves the overstory tiles of those bands out of the cell averages (put_data.c:205, 290)
     "treeline": Config("treeline", nbands=5, startday=182, extra_global=["COMPUTE_TREELINE 10"]),
+    # full energy with the gauge-undercatch correction of the precipitation (CORRPREC, correct_precip.c)
+    "fe_corrprec": Config("fe_corrprec", corrprec=True),
     # configs[3]: PCIC glacier mass-balance mode
     "glacier": Config("glacier", glacier=True, nbands=5),
     # the same with glacier HRUs in four bands of every cell: exercises accumulateGlacierMassBalance's quadratic fit
@@ -279,7 +282,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
           f"QUICK_FLUX {tf(cfg.quick_flux)}", f"NO_FLUX {tf(cfg.noflux)}",
           f"IMPLICIT {tf(cfg.implicit)}", f"EXP_TRANS {tf(cfg.exp_trans)}",
           f"QUICK_SOLVE {tf(cfg.quick_solve)}", "SNOW_ALBEDO USACE", "SNOW_DENSITY DENS_BRAS", "BLOWING FALSE",
-          "DIST_PRCP FALSE", "CORRPREC FALSE", "MIN_WIND_SPEED 0.1", "CONTINUEONERROR TRUE",
+          "DIST_PRCP FALSE", f"CORRPREC {tf(cfg.corrprec)}", "MIN_WIND_SPEED 0.1", "CONTINUEONERROR TRUE",
           "TFALLBACK TRUE", "COMPUTE_TREELINE FALSE", "EQUAL_AREA FALSE", f"RESOLUTION {res}",
           "AERO_RESIST_CANSNOW AR_406_FULL", "GRND_FLUX_TYPE GF_410", "PLAPSE TRUE",
           "MTCLIM_SWE_CORR TRUE", "VP_ITER VP_ITER_ALWAYS", "VP_INTERP TRUE", "LW_TYPE LW_TVA",
