@@ -98,7 +98,7 @@ def test_disagg_port_reproduces_reference_forcing(name, flavour, root, tmp_path)
     assert np.array_equal(f, g["forcing"])
 
 
-YEAR_CASES = [("fe_hourly", 4, 4, 365, 101), ("wb_daily", 5, 5, 365, 102), ("glacier", 4, 4, 365, 103), ("frozen_bands", 2, 2, 40, 104), ("frozen_implicit", 2, 2, 120, 105), ("treeline", 3, 3, 40, 901), ("fe_corrprec", 3, 3, 40, 555)]
+YEAR_CASES = [("fe_hourly", 4, 4, 365, 101), ("wb_daily", 5, 5, 365, 102), ("glacier", 4, 4, 365, 103), ("frozen_bands", 2, 2, 40, 104), ("frozen_implicit", 2, 2, 120, 105), ("treeline", 3, 3, 40, 901), ("fe_corrprec", 3, 3, 40, 555), ("glacier_dyn", 3, 3, 40, 666)]
 ANNUAL_VARS = ("RUNOFF", "BASEFLOW", "EVAP", "SWE", "GLAC_MBAL", "GLAC_IMBAL")
 
 
@@ -125,6 +125,11 @@ def test_year_long_bit_exact_against_glibc_reference(cfgname, nlat, nlon, ndays,
     subprocess.run([vicport, case, out], check=True)
     c, res = read_case(case), read_case(out)
     L = layout_from_options(parse_options(c["options_raw"]))
+    if cfgname == "glacier_dyn":  # GLACIER_DYNAMICS: there must be glacier HRUs of zero area, and they must have been stepped
+        from vic_b200.layout import TABLES
+        hp, names = c["hrupar"], TABLES["hpar"]
+        zero = (hp[:, names.index("HP_isGlacier")] != 0) & (hp[:, names.index("HP_Cv")] == 0)
+        assert zero.any() and not np.array_equal(c["hrurec0"][zero], c["hrurec_ref"][-1][zero], equal_nan=True)
     if cfgname == "treeline":  # COMPUTE_TREELINE must have put some bands above the treeline (cellpar CB_AboveTreeLine: the last Nbands columns)
         assert c["cellpar"][:, -cfg.nbands:].sum() > 0
     assert np.array_equal(res["out"], c["out_ref"], equal_nan=True), column_report(res["out"], c["out_ref"], L.out_names)[:3]
@@ -304,7 +309,7 @@ def test_unsupported_options_are_rejected():
     opt = parse_options(g["options_raw"])
     assert api.parse_options(api.options_to_raw(opt)) == opt
     lib = api.load_library()
-    for key in ("DIST_PRCP", "BLOWING", "LAKES", "GLACIER_DYNAMICS"):
+    for key in ("DIST_PRCP", "BLOWING", "LAKES"):
         o = dict(opt)
         o[key] = 1
         raw = api.options_to_raw(o)

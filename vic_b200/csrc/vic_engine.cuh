@@ -269,7 +269,8 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   // of unknowns n changes between the searches of a step, so that entry holds what an earlier solve with more unknowns -- of whichever
   // HRU or cell the thread handled before -- left in the (static) array: the reference's answer depends on its OpenMP schedule.
   if (a.QUICK_SOLVE && a.IMPLICIT && !a.QUICK_FLUX) { *why = "QUICK_SOLVE with IMPLICIT has no defined answer in the reference"; return VICGPU_EUNSUPPORTED; }
-  if (a.GLACIER_DYNAMICS) { *why = "GLACIER_DYNAMICS is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
+  // GLACIER_DYNAMICS: glacier HRUs of zero area are stepped like the others (full_energy.c:220, 389; vic_step.cuh hru_step); the coupling
+  // that changes their area between runs is host-side
   // COMPUTE_TREELINE: the host's initialize_atmos() decides which bands lie above the treeline (compute_treeline.c) and hands the flags
   // over in cellpar (CB_AboveTreeLine); the device side of the option is put_data's treatment of those bands (vic_output.cuh).
   // vicgpu_disagg refuses it: the decision needs the July temperatures of the whole forcing record.

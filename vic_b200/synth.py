@@ -46,6 +46,7 @@ class Config:
     noflux: bool = False
     quick_solve: bool = False
     corrprec: bool = False
+    glacier_dynamics: bool = False  # GLACIER_DYNAMICS TRUE, and the glacier tile of every other cell has zero area (a placeholder the glacier model may grow)
     out_step: int = 0  # OUT_STEP [h]; 0 = every model step
     startday: int = 1  # day of January the run (and the forcing files) start on
     extra_global: list = field(default_factory=list)
@@ -69,6 +70,8 @@ CONFIGS = {
     "glacier": Config("glacier", glacier=True, nbands=5),
     # the same with glacier HRUs in four bands of every cell: exercises accumulateGlacierMassBalance's quadratic fit
     "glacier_multi": Config("glacier_multi", glacier=True, nbands=5, glacier_tiles=4),
+    # glacier mode with GLACIER_DYNAMICS: zero-area glacier tiles are stepped too (full_energy.c:220, 389)
+    "glacier_dyn": Config("glacier_dyn", glacier=True, nbands=5, glacier_dynamics=True),
     # configs[4] (first half): OUTPUT_FORCE disaggregation only
     "disagg": Config("disagg", output_force=True),
 }
@@ -235,6 +238,11 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
                 else:
                     zones = [(0.10, 0.30), (0.50, 0.50), (1.00, 0.20)]
                 tiles.append((int(cl), float(cv[k]), zones, band))
+            if cfg.glacier_dynamics and cfg.glacier and (len(cells) % 2 == 0):
+                # zero-area glacier tile: its area goes to the first tile
+                gi = [k for k, tl in enumerate(tiles) if tl[0] == GLACIER_ID][0]
+                tiles[0] = (tiles[0][0], round(tiles[0][1] + tiles[gi][1], 4), tiles[0][2], tiles[0][3])
+                tiles[gi] = (tiles[gi][0], 0.0, tiles[gi][2], tiles[gi][3])
             veg_lines.append(f"{cid} {len(tiles)}")
             for (cl, cvv, zones, band) in tiles:
                 z = " ".join(f"{d:.2f} {fr:.2f}" for d, fr in zones)
@@ -288,7 +296,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
           "MTCLIM_SWE_CORR TRUE", "VP_ITER VP_ITER_ALWAYS", "VP_INTERP TRUE", "LW_TYPE LW_TVA",
           "LW_CLOUD LW_CLOUD_DEARDORFF", f"PARALLEL_THREADS {threads}"]
     if cfg.glacier:
-        g += [f"GLACIER_ID {GLACIER_ID}", "GLACIER_DYNAMICS FALSE",
+        g += [f"GLACIER_ID {GLACIER_ID}", f"GLACIER_DYNAMICS {tf(cfg.glacier_dynamics)}",
               f"GLACIER_ACCUM_START_YEAR {d0.year}", "GLACIER_ACCUM_START_MONTH 1",
               "GLACIER_ACCUM_START_DAY 2", "GLACIER_ACCUM_INTERVAL 1"]
     else:
