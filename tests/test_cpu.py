@@ -98,7 +98,8 @@ def test_disagg_port_reproduces_reference_forcing(name, flavour, root, tmp_path)
     assert np.array_equal(f, g["forcing"])
 
 
-YEAR_CASES = [("fe_hourly", 4, 4, 365, 101), ("wb_daily", 5, 5, 365, 102), ("glacier", 4, 4, 365, 103), ("frozen_bands", 2, 2, 40, 104), ("frozen_implicit", 2, 2, 120, 105), ("treeline", 3, 3, 40, 901), ("fe_corrprec", 3, 3, 40, 555), ("glacier_dyn", 3, 3, 40, 666)]
+YEAR_CASES = [("fe_hourly", 4, 4, 365, 101), ("wb_daily", 5, 5, 365, 102), ("glacier", 4, 4, 365, 103), ("frozen_bands", 2, 2, 40, 104), ("frozen_implicit", 2, 2, 120, 105), ("treeline", 3, 3, 40, 901), ("fe_corrprec", 3, 3, 40, 555), ("glacier_dyn", 3, 3, 40, 666), ("fe_blowing", 3, 3, 60, 777),
+              ("glacier_blowing", 3, 3, 20, 777)]
 ANNUAL_VARS = ("RUNOFF", "BASEFLOW", "EVAP", "SWE", "GLAC_MBAL", "GLAC_IMBAL")
 
 
@@ -130,6 +131,8 @@ def test_year_long_bit_exact_against_glibc_reference(cfgname, nlat, nlon, ndays,
         hp, names = c["hrupar"], TABLES["hpar"]
         zero = (hp[:, names.index("HP_isGlacier")] != 0) & (hp[:, names.index("HP_Cv")] == 0)
         assert zero.any() and not np.array_equal(c["hrurec0"][zero], c["hrurec_ref"][-1][zero], equal_nan=True)
+    if cfgname.endswith("_blowing"):  # BLOWING must have sublimated some blowing snow
+        assert (c["out_ref"][:, :, list(L.out_names).index("SUB_BLOWING")] != 0).any()
     if cfgname == "treeline":  # COMPUTE_TREELINE must have put some bands above the treeline (cellpar CB_AboveTreeLine: the last Nbands columns)
         assert c["cellpar"][:, -cfg.nbands:].sum() > 0
     assert np.array_equal(res["out"], c["out_ref"], equal_nan=True), column_report(res["out"], c["out_ref"], L.out_names)[:3]
@@ -309,7 +312,7 @@ def test_unsupported_options_are_rejected():
     opt = parse_options(g["options_raw"])
     assert api.parse_options(api.options_to_raw(opt)) == opt
     lib = api.load_library()
-    for key in ("DIST_PRCP", "BLOWING", "LAKES"):
+    for key in ("DIST_PRCP", "LAKES"):
         o = dict(opt)
         o[key] = 1
         raw = api.options_to_raw(o)

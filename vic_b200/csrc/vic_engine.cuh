@@ -263,7 +263,6 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   if (a.Nnode < 3 || a.Nnode > VICGPU_MAX_NODES) { *why = "Nnode out of range"; return VICGPU_EUNSUPPORTED; }
   if (a.Nbands < 1 || a.Nbands > VICGPU_MAX_BANDS) { *why = "Nbands out of range"; return VICGPU_EUNSUPPORTED; }
   if (a.DIST_PRCP) { *why = "DIST_PRCP is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
-  if (a.BLOWING) { *why = "BLOWING is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   if (a.LAKES) { *why = "LAKES is not implemented on the device"; return VICGPU_EUNSUPPORTED; }
   // QUICK_SOLVE + IMPLICIT: fda_heat_eqn reads kappa_new[n + 1], which no evaluation of the same solve writes; with QUICK_SOLVE the number
   // of unknowns n changes between the searches of a step, so that entry holds what an earlier solve with more unknowns -- of whichever
@@ -280,7 +279,7 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
   o.QUICK_SOLVE = a.QUICK_SOLVE; o.IMPLICIT = a.IMPLICIT; o.EXP_TRANS = a.EXP_TRANS; o.NOFLUX = a.NOFLUX; o.GRND_FLUX_TYPE = a.GRND_FLUX_TYPE;
   o.AERO_RESIST_CANSNOW = a.AERO_RESIST_CANSNOW; o.SNOW_ALBEDO = a.SNOW_ALBEDO; o.SNOW_DENSITY = a.SNOW_DENSITY; o.TEMP_TH_TYPE = a.TEMP_TH_TYPE;
   o.TFALLBACK = a.TFALLBACK; o.GLACIER_ID = a.GLACIER_ID; o.GLACIER_DYNAMICS = a.GLACIER_DYNAMICS; o.MOISTFRACT = a.MOISTFRACT;
-  o.ALMA_OUTPUT = a.ALMA_OUTPUT; o.NVegLibTypes = a.NVegLibTypes; o.CORRPREC = a.CORRPREC; o.gaYear = a.glacierAccumStartYear; o.gaMonth = a.glacierAccumStartMonth;
+  o.ALMA_OUTPUT = a.ALMA_OUTPUT; o.NVegLibTypes = a.NVegLibTypes; o.CORRPREC = a.CORRPREC; o.BLOWING = a.BLOWING; o.gaYear = a.glacierAccumStartYear; o.gaMonth = a.glacierAccumStartMonth;
   o.gaDay = a.glacierAccumStartDay; o.gaInterval = a.glacierAccumInterval; o.wind_h = a.wind_h;
   vicgpu_layout_init(&o.L, &a);
   return VICGPU_OK;
@@ -288,7 +287,7 @@ inline int opts_from_abi(const vicgpu_options& a, Opts& o, const char** why) {
 
 // which instantiation (thermal-node array width) steps a configuration: 3, 10 or 32
 inline int vic_node_width(const Opts& o) {
-  if (o.Nnode <= 3 && !((o.IMPLICIT || o.QUICK_SOLVE) && !o.QUICK_FLUX)) return 3;
+  if (o.Nnode <= 3 && !((o.IMPLICIT || o.QUICK_SOLVE) && !o.QUICK_FLUX) && !o.BLOWING) return 3;
   return o.Nnode <= 10 ? 10 : 32;
 }
 

@@ -175,7 +175,19 @@ VIC_HDI int surface_fluxes_glac(double BareAlbedo, double ice0, double moist0, H
     double rainfall = gauge_correction[0] * rainOnly * cp(CP_PADJ_R);
     const double step_out_prec = snowfall + rainfall, step_out_rain = rainfall, step_out_snow = snowfall;
     const double Tgrnd = GLAC_TEMP;
+    // mass flux of blowing snow (surface_fluxes_glac.c:261-275); as in surface_fluxes, not in the three-node kernel
     step_snow.blowing_flux = 0.0;
+    if constexpr (NN > 3) {
+      if (o.BLOWING && step_snow.swq > 0.) {
+        const double Ls = (677. - 0.07 * step_snow.surf_temp) * JOULESPCAL * GRAMSPKG;
+        step_snow.blowing_flux = blow::calc_blowing_snow((double)step_dt, Tair, (int)step_snow.last_snow, step_snow.surf_water, as.wind_speed[SNOW_COVERED], Ls,
+                                                         f(FV_density, hidx), f(FV_vp, hidx), as.roughness[SNOW_COVERED], step_snow.depth,
+                                                         (float)cx.hp(HP_lag_one), (float)cx.hp(HP_sigma_slope), cx.hp(HP_isArtBare) != 0.0,
+                                                         (float)cx.hp(HP_fetch), as.displacement[CANOPY_OVER], as.roughness[CANOPY_OVER], &step_snow.transport);
+        if ((int)step_snow.blowing_flux == ERROR_I) return ERROR_I;
+        step_snow.blowing_flux *= step_dt * SECPHOUR / RHO_W;
+      }
+    }
     const Surf4& temp_aero_resist = as.aero_resist[N_PET_TYPES];
     RaUsed aero_used;
     aero_used.surface = hru.cell.aero_surface;

@@ -14,6 +14,7 @@
 #include "vic_snow.cuh"
 #include "vic_soil.cuh"
 #include "vic_frozen.cuh"
+#include "vic_blowing.cuh"
 
 namespace vic {
 
@@ -727,7 +728,20 @@ VIC_HDI int surface_fluxes(bool overstory, double BareAlbedo, double ice0, doubl
     const double Tcanopy = Tair;
     const double VPcanopy = f(FV_vp, hidx);
     const double VPDcanopy = f(FV_vpd, hidx);
-    step_snow.blowing_flux = 0.0;  // BLOWING is rejected at create time (surface_fluxes.c:440-453)
+    // mass flux of blowing snow (surface_fluxes.c:440-453); not compiled into the three-node kernel (vic_node_width sends BLOWING configurations
+    // to the ten-node instantiation)
+    step_snow.blowing_flux = 0.0;
+    if constexpr (NN > 3) {
+      if (!overstory && o.BLOWING && step_snow.swq > 0.) {
+        const double Ls = (677. - 0.07 * step_snow.surf_temp) * JOULESPCAL * GRAMSPKG;
+        step_snow.blowing_flux = blow::calc_blowing_snow((double)step_dt, Tair, (int)step_snow.last_snow, step_snow.surf_water, as.wind_speed[SNOW_COVERED], Ls,
+                                                         f(FV_density, hidx), f(FV_vp, hidx), as.roughness[SNOW_COVERED], step_snow.depth,
+                                                         (float)cx.hp(HP_lag_one), (float)cx.hp(HP_sigma_slope), isArtificialBareSoil, (float)cx.hp(HP_fetch),
+                                                         as.displacement[CANOPY_OVER], as.roughness[CANOPY_OVER], &step_snow.transport);
+        if ((int)step_snow.blowing_flux == ERROR_I) return ERROR_I;
+        step_snow.blowing_flux *= step_dt * SECPHOUR / RHO_W;  // m per time step
+      }
+    }
     int UnderStory = SURF_UNSET;
     const double snow_grnd_flux = -snow_flux;
 

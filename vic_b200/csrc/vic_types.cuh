@@ -20,7 +20,7 @@ struct Opts {
   int Nnode, Nbands, dt, SNOW_STEP, NR, NF, nrecs, out_step_ratio;
   int FULL_ENERGY, FROZEN_SOIL, QUICK_FLUX, QUICK_SOLVE, IMPLICIT, EXP_TRANS, NOFLUX;
   int GRND_FLUX_TYPE, AERO_RESIST_CANSNOW, SNOW_ALBEDO, SNOW_DENSITY, TEMP_TH_TYPE, TFALLBACK;
-  int GLACIER_ID, GLACIER_DYNAMICS, MOISTFRACT, ALMA_OUTPUT, NVegLibTypes, CORRPREC;
+  int GLACIER_ID, GLACIER_DYNAMICS, MOISTFRACT, ALMA_OUTPUT, NVegLibTypes, CORRPREC, BLOWING;
   int gaYear, gaMonth, gaDay, gaInterval;
   double wind_h;
   vicgpu_layout L;

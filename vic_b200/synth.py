@@ -46,6 +46,7 @@ class Config:
     noflux: bool = False
     quick_solve: bool = False
     corrprec: bool = False
+    blowing: bool = False  # BLOWING TRUE: every vegetation tile carries sigma_slope, lag_one, fetch (read_vegparam.c:172-190)
     glacier_dynamics: bool = False  # GLACIER_DYNAMICS TRUE, and the glacier tile of every other cell has zero area (a placeholder the glacier model may grow)
     out_step: int = 0  # OUT_STEP [h]; 0 = every model step
     startday: int = 1  # day of January the run (and the forcing files) start on
@@ -66,6 +67,9 @@ CONFIGS = {
     "treeline": Config("treeline", nbands=5, startday=182, extra_global=["COMPUTE_TREELINE 10"]),
     # full energy with the gauge-undercatch correction of the precipitation (CORRPREC, correct_precip.c)
     "fe_corrprec": Config("fe_corrprec", corrprec=True),
+    # full energy with sublimation of blowing snow (BLOWING, CalcBlowingSnow.c)
+    "fe_blowing": Config("fe_blowing", blowing=True),
+    "glacier_blowing": Config("glacier_blowing", glacier=True, nbands=5, blowing=True),
     # configs[3]: PCIC glacier mass-balance mode
     "glacier": Config("glacier", glacier=True, nbands=5),
     # the same with glacier HRUs in four bands of every cell: exercises accumulateGlacierMassBalance's quadratic fit
@@ -246,7 +250,8 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
             veg_lines.append(f"{cid} {len(tiles)}")
             for (cl, cvv, zones, band) in tiles:
                 z = " ".join(f"{d:.2f} {fr:.2f}" for d, fr in zones)
-                veg_lines.append(f"  {cl} {cvv:.4f} {z} {band}")
+                bl = f" {rng.uniform(0.02, 0.12):.4f} {rng.uniform(0.80, 0.98):.3f} {rng.uniform(200.0, 3000.0):.1f}" if cfg.blowing else ""
+                veg_lines.append(f"  {cl} {cvv:.4f} {z}{bl} {band}")
             cells.append(dict(id=cid, lat=la, lon=lo, elev=elev, avg_temp=avg_temp))
 
             # --- daily forcing
@@ -289,7 +294,7 @@ def generate(outdir, config: Config | str, nlat=4, nlon=4, seed=1234, threads=1,
           f"FULL_ENERGY {tf(cfg.full_energy)}", f"FROZEN_SOIL {tf(cfg.frozen_soil)}",
           f"QUICK_FLUX {tf(cfg.quick_flux)}", f"NO_FLUX {tf(cfg.noflux)}",
           f"IMPLICIT {tf(cfg.implicit)}", f"EXP_TRANS {tf(cfg.exp_trans)}",
-          f"QUICK_SOLVE {tf(cfg.quick_solve)}", "SNOW_ALBEDO USACE", "SNOW_DENSITY DENS_BRAS", "BLOWING FALSE",
+          f"QUICK_SOLVE {tf(cfg.quick_solve)}", "SNOW_ALBEDO USACE", "SNOW_DENSITY DENS_BRAS", f"BLOWING {tf(cfg.blowing)}",
           "DIST_PRCP FALSE", f"CORRPREC {tf(cfg.corrprec)}", "MIN_WIND_SPEED 0.1", "CONTINUEONERROR TRUE",
           "TFALLBACK TRUE", "COMPUTE_TREELINE FALSE", "EQUAL_AREA FALSE", f"RESOLUTION {res}",
           "AERO_RESIST_CANSNOW AR_406_FULL", "GRND_FLUX_TYPE GF_410", "PLAPSE TRUE",
