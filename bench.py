@@ -55,6 +55,11 @@ WORKLOADS = {
                       desc="fe_hourly: FULL_ENERGY hourly, QUICK_FLUX, 3 layers, 3 nodes, 5 veg tiles, 1 band"),
     "frozen_bands": dict(base="frozen_bands", cells=100000, steps=2, warmup=3, algo_bytes=10.3e3, kernel="k_hru_step_nn10", config=2, ref_side=16,
                          desc="frozen_bands: FROZEN_SOIL, QUICK_FLUX FALSE, 10 thermal nodes, 5 snow bands, hourly"),
+    # the same domain with the reference's own speed option for frozen soils: the surface-temperature search runs on the nodes above the thaw
+    # depth, the whole profile is solved once at the accepted temperature (QUICK_SOLVE, calc_surf_energy_bal.c:289-314, 400-475)
+    "frozen_quick_solve": dict(base="frozen_bands", synth="frozen_quick_solve", set={"QUICK_SOLVE": 1}, cells=100000, steps=5, warmup=3, algo_bytes=10.3e3,
+                               kernel="k_hru_step_nn10", config=2, ref_side=16,
+                               desc="frozen_quick_solve: frozen_bands with QUICK_SOLVE TRUE (FROZEN_SOIL, QUICK_FLUX FALSE, 10 thermal nodes, 5 snow bands, hourly)"),
     "glacier": dict(base="glacier", cells=250000, steps=10, warmup=3, algo_bytes=8.8e3, kernel="k_hru_step_nn3", config=3, ref_side=32,
                     desc="glacier: PCIC glacier mass-balance mode (surface_fluxes_glac), 5 snow bands, hourly"),
     "continental": dict(base="fe_hourly", cells=125000, steps=10, warmup=3, algo_bytes=7.0e3, kernel="k_hru_step_nn3", config=4, ref_side=100, disagg=True,
@@ -207,7 +212,7 @@ def run_reference(workload, side, ndays, warm_days, threads, seed=1):
     wl = WORKLOADS[workload]
     n = side * side
     with tempfile.TemporaryDirectory() as d:
-        cfg = dataclasses.replace(synth.CONFIGS[wl["base"]], ndays=ndays, out_step=24)
+        cfg = dataclasses.replace(synth.CONFIGS[wl.get("synth", wl["base"])], ndays=ndays, out_step=24)
         r = synth.generate(d, cfg, side, side, BASE_SEED, forcing=False, threads=threads)
         dom = {k: np.array([c[k] for c in r["cells"]]) for k in ("elev", "lat", "avg_temp")}
         f = np.empty((ndays * 24, n, len(TABLES["forcing"])))
@@ -231,7 +236,7 @@ def cpu_baseline(workload, host_threads):
         v1, secs1, n1 = run_reference(workload, 32, 3, 1, 1)
         sample = (f"{n} cells x 96 hourly records (after 24 untimed), {host_threads} OpenMP threads, {secs:.1f} s; one thread: {n1} cells x 48 records, {secs1:.1f} s")
     else:
-        days = 2 if workload == "frozen_bands" else 3
+        days = 2 if workload.startswith("frozen") else 3
         v, secs, n = run_reference(workload, side, days, 1, host_threads)
         v1, secs1, n1 = run_reference(workload, 8, days, 1, 1)
         sample = (f"{n} cells x {(days - 1) * 24} hourly records (after 24 untimed), {host_threads} OpenMP threads, {secs:.1f} s; one thread: {n1} cells, {secs1:.1f} s")
@@ -312,6 +317,10 @@ def main():
 
     seed = 1 + rank
     dom = build_domain(cells, seed, wl["base"])
+    if wl.get("set"):  # option overrides of the base domain
+        opt = api.parse_options(dom["options_raw"])
+        opt.update(wl["set"])
+        dom["options_raw"] = api.options_to_raw(opt)
     ndays = W + K
     nrec = ndays * RECS_PER_STEP
     dmy = make_dmy(nrec)

@@ -70,6 +70,7 @@ CONFIGS = {
     # full energy with sublimation of blowing snow (BLOWING, CalcBlowingSnow.c)
     "fe_blowing": Config("fe_blowing", blowing=True),
     "glacier_blowing": Config("glacier_blowing", glacier=True, nbands=5, blowing=True),
+    "frozen_quick_solve": Config("frozen_quick_solve", frozen_soil=True, quick_flux=False, nodes=10, nbands=5, quick_solve=True),
     # configs[3]: PCIC glacier mass-balance mode
     "glacier": Config("glacier", glacier=True, nbands=5),
     # the same with glacier HRUs in four bands of every cell: exercises accumulateGlacierMassBalance's quadratic fit
