@@ -56,3 +56,84 @@ def test_stock_vicNl_runs_and_writes_state(tmp_path):
     out, state, err = _run("vicNl", "fe_hourly", tmp_path, "cpu", 2, 2, 505)
     assert "VIC model run done" in err
     assert out.size > 0 and len(state) > 1000
+
+
+# ---- the drop-in's loader (vic_b200/host/vicgpu_fastread.h) ------------------------------------------------
+def _records(path, lines_after_header):
+    """split a per-cell parameter file into its records: header line + lines_after_header(header) lines"""
+    lines = open(path).read().splitlines(keepends=True)
+    recs, i = [], 0
+    while i < len(lines):
+        if not lines[i].strip():
+            i += 1
+            continue
+        n = 1 + lines_after_header(lines[i])
+        recs.append(lines[i:i + n])
+        i += n
+    return recs
+
+
+def _shuffle_parameter_files(indir, seed, with_decoys):
+    """vegetation and snow-band records in another order than the soil file's cells; optionally a second, different record of an
+    existing cell number further down (the reference takes the FIRST match, read_vegparam.c:117) and a snow-band file that lacks one
+    cell (read_snowband.c:49-54: warning, one band)"""
+    rng = np.random.default_rng(seed)
+    glob = open(os.path.join(indir, "global.txt")).read()
+    per_tile = 2 if "VEGPARAM_LAI TRUE" in glob.replace("\t", " ") else 1
+    vp = os.path.join(indir, "vegparam.txt")
+    recs = _records(vp, lambda h: int(h.split()[1]) * per_tile)
+    order = rng.permutation(len(recs))
+    out = [recs[k] for k in order]
+    if with_decoys:
+        a, b = recs[0], recs[1]
+        out.append([a[0].split()[0] + " " + " ".join(b[0].split()[1:]) + "\n"] + b[1:])  # cell of record 0 with record 1's tiles
+    open(vp, "w").write("".join("".join(r) for r in out))
+    sb = os.path.join(indir, "snowband.txt")
+    if os.path.exists(sb):
+        recs = _records(sb, lambda h: 0)
+        order = rng.permutation(len(recs))
+        out = [recs[k] for k in order]
+        if with_decoys:
+            out = out[:-1] + [[out[0][0].split()[0] + " " + " ".join(out[1][0].split()[1:]) + "\n"]]
+        open(sb, "w").write("".join("".join(r) for r in out))
+
+
+@pytest.mark.parametrize("cfgname,decoys", [("frozen_bands", False), ("frozen_bands", True), ("fe_blowing", False), ("glacier", True)])
+def test_indexed_parameter_lookups_match_the_reference_scans(cfgname, decoys, tmp_path):
+    """read_vegparam / read_snowband behind the one-pass index and the O(N log N) initGrid against the reference's own scans
+    (oracle/_ref/readercheck): HRU lists, band tables and grid geometry of every cell bit-identical, records in shuffled order"""
+    exe = os.path.join(REF, "readercheck")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (oracle/Makefile)")
+    cfg = dataclasses.replace(synth.CONFIGS[cfgname], ndays=1)
+    r = synth.generate(str(tmp_path / "in"), cfg, 7, 9, 808)
+    _shuffle_parameter_files(r["dir"], 5, decoys)
+    o = subprocess.run([exe, "-g", r["global_file"]], capture_output=True, text=True)
+    assert o.returncode == 0 and "identical" in o.stdout, o.stdout[-2000:]
+    assert "ncell 63 " in o.stdout and "compared 63 " in o.stdout
+
+
+def test_reference_physics_behind_the_indexed_loader(tmp_path):
+    """the reference's executable with the drop-in's loader linked in (oracle/_ref/vicNl_fastread: read_vegparam, read_snowband and
+    initGrid replaced, everything else -- its runModel on the CPU included -- untouched) against the stock vicNl on shuffled
+    parameter files: output stream and state file identical byte for byte; VICGPU_STOCK_READERS=1 switches the scans back"""
+    def run(exe, tag, env=None):
+        p = os.path.join(REF, exe)
+        if not os.path.exists(p):
+            pytest.skip(f"{p} not built (oracle/Makefile)")
+        res = tmp_path / f"res_{tag}"
+        res.mkdir()
+        cfg = dataclasses.replace(synth.CONFIGS["frozen_bands"], ndays=2, out_step=24,
+                                  extra_global=["STATENAME state", "STATEYEAR 2001", "STATEMONTH 1", "STATEDAY 2", "STATE_FORMAT ASCII"])
+        r = synth.generate(str(tmp_path / f"in_{tag}"), cfg, 2, 3, 606, result_dir=str(res))
+        _shuffle_parameter_files(r["dir"], 6, False)
+        o = subprocess.run([p, "-g", r["global_file"]], cwd=str(res), capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+        assert o.returncode == 0, o.stderr[-2000:]
+        return np.fromfile(res / "results.nc.f64", dtype=np.float64), (res / "_2001-01-02").read_bytes()
+
+    out0, st0 = run("vicNl", "stock")
+    out1, st1 = run("vicNl_fastread", "fast")
+    out2, st2 = run("vicNl_fastread", "fast_stockscan", {"VICGPU_STOCK_READERS": "1"})
+    half = out0.size // 2  # (first output step: uninitialised aggdata in the reference, see above)
+    assert out0.size > 0 and np.array_equal(out0[half:], out1[half:], equal_nan=True) and np.array_equal(out0[half:], out2[half:], equal_nan=True)
+    assert len(st0) > 1000 and st0 == st1 == st2
