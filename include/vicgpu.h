@@ -501,6 +501,27 @@ typedef struct vicgpu_disagg_options {
  * (the OUTPUT_FORCE use).  Needs vicgpu_set_cells (latitude, longitude, time zone, elevation, slope, aspect, horizons,
  * annual precipitation, band temperature factors, rain/snow thresholds are cell parameters). */
 int vicgpu_disagg(vicgpu_handle *h, const vicgpu_disagg_options *dopt, const double *daily, double *forcing_out);
+/* The same from TIME-MAJOR daily input, daily_tm [Ndays][4][ncell]: the layout a (time, lat, lon) forcing file yields when it is
+ * read the way it is stored (vicgpu_nc_read_slab below), and the layout the device kernels use, so the upload needs no transpose.
+ * Same forcing, bit for bit. */
+int vicgpu_disagg_tm(vicgpu_handle *h, const vicgpu_disagg_options *dopt, const double *daily_tm, double *forcing_out);
+
+/* ---- NetCDF forcing ingestion (stands in for read_atmos_data()'s NetCDF branch, read_atmos_data.c:109-338) ---------------
+ * Host-side and device-free.  The reference pulls one cell's time series per call out of the (time, lat, lon) variables with a
+ * strided nc_get_varm_*: Ncell x Nvar passes over the file.  These entry points read each (lat, lon) grid once, in file order,
+ * and gather the modelled cells: out [nt][nvar][ncell].  Cell lookup (first exact match of the float/double "lat" / "lon"
+ * coordinate), the (time, lat, lon) requirement and the value conversions (NC_SHORT / inverse_scale_factor or * scale_factor with
+ * the attribute as float, NC_FLOAT and NC_DOUBLE as they are, anything else an error) are the reference's.  Containers: NetCDF
+ * classic CDF-1 and CDF-2 (parsed by vic_b200/host/vicgpu_ncslab.h); a NetCDF-4/HDF5 file is refused with VICGPU_EUNSUPPORTED. */
+typedef struct vicgpu_ncfile vicgpu_ncfile;
+int vicgpu_nc_open(vicgpu_ncfile **nc, const char *path);
+int vicgpu_nc_close(vicgpu_ncfile *nc);
+/* lengths of the "time", "lat" and "lon" coordinate variables' dimensions */
+int vicgpu_nc_dims(vicgpu_ncfile *nc, long long *ntime, long long *nlat, long long *nlon);
+/* varnames [nvar]: the file's variable names (the reference maps FORCE_TYPE names through ProgramState::forcing_mapping);
+ * lat, lng [ncell]: (double)soil_con.lat / .lng of the modelled cells; time steps [t0, t0 + nt) (t0 = the reference's skip_recs) */
+int vicgpu_nc_read_slab(vicgpu_ncfile *nc, int nvar, const char *const *varnames, long long t0, long long nt, int ncell,
+                        const double *lat, const double *lng, double *out);
 
 /* accumulateGlacierMassBalance()'s per-cell result (vicNl.c:563, cell_info_struct::gmbEquation, written to the state file by
  * write_model_state.c:153-156): gmb[ncell][4] = b0, b1, b2, fitError of the quadratic fitted to (band elevation, cumulative mass

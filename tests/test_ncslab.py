@@ -1,0 +1,161 @@
+"""NetCDF forcing ingestion: vicgpu_nc_* (include/vicgpu.h; vic_b200/host/vicgpu_ncslab.h) reads a (time, lat, lon)
+forcing file as time-major slabs [time][variable][cell].  The reference's NetCDF branch (read_atmos_data.c:109-338) needs libnetcdf,
+which this image does not have, so it cannot be run as the oracle here; the expected values below are its documented conversions
+applied with numpy to the arrays the files were written from (files written by scipy.io.netcdf_file, an independent implementation
+of the classic format)."""
+import os
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from vic_b200 import api
+
+VARS = ["pr", "tasmax", "tasmin", "wind"]
+
+
+def _write(path, version, record_time, nt=7, nlat=3, nlon=5, seed=0, extra_int=False, dup_lat=False):
+    rng = np.random.default_rng(seed)
+    lat = (48.03125 + 0.0625 * np.arange(nlat)).astype(np.float64)
+    if dup_lat:
+        lat[-1] = lat[0]
+    lon = (-121.96875 + 0.0625 * np.arange(nlon)).astype(np.float32)  # a float coordinate variable
+    data = {
+        "pr": rng.integers(0, 4000, (nt, nlat, nlon)).astype(np.int16),
+        "tasmax": rng.integers(-3000, 3500, (nt, nlat, nlon)).astype(np.int16),
+        "tasmin": rng.normal(0, 10, (nt, nlat, nlon)).astype(np.float32),
+        "wind": rng.gamma(2.0, 2.0, (nt, nlat, nlon)).astype(np.float64),
+    }
+    f = netcdf_file(path, "w", version=version)
+    f.createDimension("time", None if record_time else nt)
+    f.createDimension("lat", nlat)
+    f.createDimension("lon", nlon)
+    v = f.createVariable("time", "d", ("time",))
+    v[:] = np.arange(nt, dtype=np.float64)
+    v = f.createVariable("lat", "d", ("lat",))
+    v[:] = lat
+    v = f.createVariable("lon", "f", ("lon",))
+    v[:] = lon
+    v = f.createVariable("pr", "h", ("time", "lat", "lon"))
+    v[:] = data["pr"]
+    v.scale_factor = np.float32(0.025)
+    v.units = "mm"
+    v = f.createVariable("tasmax", "h", ("time", "lat", "lon"))
+    v[:] = data["tasmax"]
+    v.inverse_scale_factor = np.float64(100.0)
+    v.scale_factor = np.float32(7.0)
+    v = f.createVariable("tasmin", "f", ("time", "lat", "lon"))
+    v[:] = data["tasmin"]
+    v = f.createVariable("wind", "d", ("time", "lat", "lon"))
+    v[:] = data["wind"]
+    if extra_int:
+        v = f.createVariable("count", "i", ("time", "lat", "lon"))
+        v[:] = np.zeros((nt, nlat, nlon), dtype=np.int32)
+    f.close()
+    return lat, lon.astype(np.float64), data
+
+
+def _expected(data, t0, nt, ii, jj):
+    """read_atmos_data.c:226-310, value for value"""
+    sl = (slice(t0, t0 + nt), ii, jj)
+    return np.stack([
+        data["pr"][sl].astype(np.float64) * np.float64(np.float32(0.025)),     # scale_factor, as float
+        data["tasmax"][sl].astype(np.float64) / np.float64(np.float32(100.0)),  # inverse_scale_factor wins when both are present
+        data["tasmin"][sl].astype(np.float64),
+        data["wind"][sl],
+    ], axis=1)
+
+
+@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("record_time", [True, False])
+def test_time_major_slab_matches_the_reference_conversions(version, record_time, tmp_path):
+    path = str(tmp_path / "forcing.nc")
+    lat, lon, data = _write(path, version, record_time, seed=version)
+    # modelled cells: a subset of the grid in another order than the file's
+    ii = np.array([2, 0, 1, 2, 0, 1, 1])
+    jj = np.array([4, 0, 3, 1, 2, 2, 0])
+    with api.NcForcing(path) as nc:
+        assert (nc.ntime, nc.nlat, nc.nlon) == (7, 3, 5)
+        got = nc.read_slab(VARS, 0, 7, lat[ii], lon[jj])
+        assert got.shape == (7, 4, 7) and np.array_equal(got, _expected(data, 0, 7, ii, jj))
+        # a window that starts at the reference's skip_recs, variables in another order
+        got = nc.read_slab(VARS[::-1], 2, 3, lat[ii], lon[jj])
+        assert np.array_equal(got, _expected(data, 2, 3, ii, jj)[:, ::-1])
+
+
+def test_first_exact_match_of_a_repeated_coordinate(tmp_path):
+    path = str(tmp_path / "forcing.nc")
+    lat, lon, data = _write(path, 1, True, dup_lat=True)
+    with api.NcForcing(path) as nc:
+        got = nc.read_slab(["wind"], 0, 7, lat[[2]], lon[[1]])  # lat[2] == lat[0]: the reference stops at index 0 (:176-181)
+    assert np.array_equal(got[:, 0, 0], data["wind"][:, 0, 1])
+
+
+def test_errors_are_the_references(tmp_path):
+    path = str(tmp_path / "forcing.nc")
+    lat, lon, _ = _write(path, 2, True, extra_int=True)
+    with api.NcForcing(path) as nc:
+        with pytest.raises(api.VicGpuError, match="no exactly matching grid point"):
+            nc.read_slab(VARS, 0, 7, np.array([lat[0] + 1e-9]), lon[:1])
+        with pytest.raises(api.VicGpuError, match="type not supported"):
+            nc.read_slab(["count"], 0, 7, lat[:1], lon[:1])
+        with pytest.raises(api.VicGpuError, match="the file has 7"):
+            nc.read_slab(VARS, 5, 3, lat[:1], lon[:1])
+        with pytest.raises(api.VicGpuError, match="no variable 'snowfall'"):
+            nc.read_slab(["snowfall"], 0, 1, lat[:1], lon[:1])
+        with pytest.raises(api.VicGpuError, match="not .time, lat, lon."):
+            nc.read_slab(["lat"], 0, 1, lat[:1], lon[:1])
+    hdf = str(tmp_path / "nc4.nc")
+    open(hdf, "wb").write(b"\x89HDF\r\n\x1a\n" + bytes(64))
+    with pytest.raises(api.VicGpuError) as e:
+        api.NcForcing(hdf)
+    assert e.value.code == -3 and "NetCDF-4" in str(e.value)
+    with pytest.raises(api.VicGpuError):
+        api.NcForcing(str(tmp_path / "missing.nc"))
+
+
+def test_large_grid_in_file_order(tmp_path):
+    """every cell of an 89 x 121 grid over 40 days, record variables with padded (odd-sized short) slabs"""
+    path = str(tmp_path / "forcing.nc")
+    lat, lon, data = _write(path, 2, True, nt=40, nlat=89, nlon=121, seed=3)
+    ii, jj = [a.ravel() for a in np.meshgrid(np.arange(89), np.arange(121), indexing="ij")]
+    with api.NcForcing(path) as nc:
+        got = nc.read_slab(VARS, 0, 40, lat[ii], lon[jj])
+    assert np.array_equal(got, _expected(data, 0, 40, ii, jj))
+
+
+@pytest.mark.gpu
+def test_disagg_from_a_netcdf_file_gives_the_reference_forcing(tmp_path):
+    """daily PREC / TMAX / TMIN / WIND of the golden case written to a NetCDF file, read back as a time-major slab and handed to
+    vicgpu_disagg_tm: the hourly forcing is the reference's initialize_atmos() output bit for bit (the cell-major vicgpu_disagg too)"""
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fe_hourly_winter.npz")))
+    daily = g["daily"]  # [ncell][Ndays][4]
+    ncell, ndays, _ = daily.shape
+    path = str(tmp_path / "daily.nc")
+    lat = 40.0 + 0.5 * np.arange(ncell)
+    f = netcdf_file(path, "w", version=2)
+    f.createDimension("time", None)
+    f.createDimension("lat", ncell)
+    f.createDimension("lon", 1)
+    v = f.createVariable("time", "d", ("time",))
+    v[:] = np.arange(ndays, dtype=np.float64)
+    v = f.createVariable("lat", "d", ("lat",))
+    v[:] = lat
+    v = f.createVariable("lon", "d", ("lon",))
+    v[:] = np.array([-120.0])
+    for k, name in enumerate(VARS):
+        v = f.createVariable(name, "d", ("time", "lat", "lon"))
+        v[:] = daily[:, :, k].T[:, :, None]
+    f.close()
+    with api.NcForcing(path) as nc:
+        slab = nc.read_slab(VARS, 0, ndays, lat, np.full(ncell, -120.0))
+    assert np.array_equal(slab, daily.transpose(1, 2, 0))
+    gp = api.VicGpu(g["options_raw"])
+    gp.set_veglib(g["veglib"])
+    gp.set_cells(g["cellpar"], g["hrupar"])
+    gp.set_output_spec(g["aggtype"])
+    gp.set_state(g["hrurec0"])
+    f_tm = gp.disagg_tm(g["disagg_raw"], slab)
+    f_cm = gp.disagg(g["disagg_raw"], daily)
+    gp.close()
+    assert np.array_equal(f_tm, g["forcing"]) and np.array_equal(f_cm, g["forcing"])

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_step_f32", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_measure_phase_tax", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
+    "vicgpu_get_last_step_timing", "vicgpu_measure_phase_tax", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_disagg_tm", "vicgpu_nc_open", "vicgpu_nc_close", "vicgpu_nc_dims", "vicgpu_nc_read_slab", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
 ]
 
 
@@ -67,6 +67,11 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_get_balance_errors.argtypes = [vp, dp]
     lib.vicgpu_get_last_step_timing.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.vicgpu_disagg.argtypes = [vp, vp, dp, dp]
+    lib.vicgpu_disagg_tm.argtypes = [vp, vp, dp, dp]
+    lib.vicgpu_nc_open.argtypes = [C.POINTER(vp), C.c_char_p]
+    lib.vicgpu_nc_close.argtypes = [vp]
+    lib.vicgpu_nc_dims.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 3
+    lib.vicgpu_nc_read_slab.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.c_longlong, C.c_longlong, C.c_int, dp, dp, dp]
     if hasattr(lib, "vicgpu_measure_phase_tax") or not os.environ.get("VICGPU_LIB"):  # (an older A/B build may lack it)
         lib.vicgpu_measure_phase_tax.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.vicgpu_set_profiling.argtypes = [vp, C.c_int]
@@ -182,6 +187,15 @@ class VicGpu:
         assert d.shape == (self.ncell, int(raw[5]), 4), d.shape
         out = np.empty((self.opt["nrecs"], self.ncell, self.L.f_stride), dtype=np.float64) if want_host else None
         self._chk(self.lib.vicgpu_disagg(self.h, raw.ctypes.data_as(C.c_void_p), _dptr(d), _dptr(out) if want_host else None))
+        return out
+
+    def disagg_tm(self, disagg_raw, daily_tm, want_host=True):
+        """the same from time-major input daily_tm [Ndays][4][ncell] (what NcForcing.read_slab returns): vicgpu_disagg_tm"""
+        raw = np.ascontiguousarray(disagg_raw, dtype=np.int32)
+        d = _as_f64(daily_tm)
+        assert d.shape == (int(raw[5]), 4, self.ncell), d.shape
+        out = np.empty((self.opt["nrecs"], self.ncell, self.L.f_stride), dtype=np.float64) if want_host else None
+        self._chk(self.lib.vicgpu_disagg_tm(self.h, raw.ctypes.data_as(C.c_void_p), _dptr(d), _dptr(out) if want_host else None))
         return out
 
     def n_output_steps(self, nrec, step_count0=0):
@@ -302,3 +316,44 @@ def run_case(case, device=0, nrec=None, want_out=True, block=None):
         return res
     finally:
         g.close()
+
+
+class NcForcing:
+    """A NetCDF (classic CDF-1 / CDF-2) forcing file read as time-major slabs through the library's host-side reader
+    (vicgpu_nc_*, include/vicgpu.h; stands in for read_atmos_data.c:109-338).  No device needed."""
+
+    def __init__(self, path):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.vicgpu_nc_open(C.byref(self.h), os.fsencode(path))
+        if rc != 0:
+            raise VicGpuError(rc, self.lib.vicgpu_last_error().decode())
+        n = [C.c_longlong() for _ in range(3)]
+        rc = self.lib.vicgpu_nc_dims(self.h, *[C.byref(x) for x in n])
+        if rc != 0:
+            msg = self.lib.vicgpu_last_error().decode()
+            self.close()
+            raise VicGpuError(rc, msg)
+        self.ntime, self.nlat, self.nlon = (int(x.value) for x in n)
+
+    def read_slab(self, varnames, t0, nt, lat, lng):
+        """-> float64 [nt][len(varnames)][ncell]; lat / lng: the cells' (double)(float) coordinates"""
+        la, lo = _as_f64(lat), _as_f64(lng)
+        assert la.shape == lo.shape and la.ndim == 1
+        out = np.empty((int(nt), len(varnames), la.shape[0]), dtype=np.float64)
+        names = (C.c_char_p * len(varnames))(*[v.encode() for v in varnames])
+        rc = self.lib.vicgpu_nc_read_slab(self.h, len(varnames), names, int(t0), int(nt), int(la.shape[0]), _dptr(la), _dptr(lo), _dptr(out))
+        if rc != 0:
+            raise VicGpuError(rc, self.lib.vicgpu_last_error().decode())
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.vicgpu_nc_close(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -50,7 +50,14 @@ inline unsigned blocks_for(size_t n) { return (unsigned)((n + 127) / 128); }
 
 }  // namespace
 
+static int disagg_impl(vicgpu_handle* h, const vicgpu_disagg_options* dopt, const double* daily, double* forcing_out, bool time_major);
 extern "C" int vicgpu_disagg(vicgpu_handle* h, const vicgpu_disagg_options* dopt, const double* daily, double* forcing_out) {
+  return disagg_impl(h, dopt, daily, forcing_out, false);
+}
+extern "C" int vicgpu_disagg_tm(vicgpu_handle* h, const vicgpu_disagg_options* dopt, const double* daily_tm, double* forcing_out) {
+  return disagg_impl(h, dopt, daily_tm, forcing_out, true);
+}
+static int disagg_impl(vicgpu_handle* h, const vicgpu_disagg_options* dopt, const double* daily, double* forcing_out, bool time_major) {
   if (!h || !dopt || !daily) return vicgpu_fail(VICGPU_EINVAL, "null argument");
   if (dopt->abi_version != VICGPU_ABI_VERSION) return vicgpu_fail(VICGPU_EINVAL, "abi_version mismatch");
   if (!h->have_cells) return vicgpu_fail(VICGPU_ESTATE, "set_cells before disagg");
@@ -89,11 +96,15 @@ extern "C" int vicgpu_disagg(vicgpu_handle* h, const vicgpu_disagg_options* dopt
   } b_in, b_daily, b_scratch, b_t;
   double *&d_in = b_in.p, *&d_daily = b_daily.p, *&d_scratch = b_scratch.p;
   const size_t nd4 = (size_t)Ndays * 4;
-  CK(cudaMalloc(&d_in, nd4 * ncell * sizeof(double)));
   CK(cudaMalloc(&d_daily, nd4 * ncell * sizeof(double)));
-  CK(cudaMemcpyAsync(d_in, daily, nd4 * ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  rc = vicgpu_transpose(h, d_in, d_daily, ncell, (int)nd4, 1);
-  if (rc) return rc;
+  if (time_major) {  // [Ndays][4][ncell] is the device layout: straight copy
+    CK(cudaMemcpyAsync(d_daily, daily, nd4 * ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CK(cudaMalloc(&d_in, nd4 * ncell * sizeof(double)));
+    CK(cudaMemcpyAsync(d_in, daily, nd4 * ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = vicgpu_transpose(h, d_in, d_daily, ncell, (int)nd4, 1);
+    if (rc) return rc;
+  }
   a.daily = d_daily;
   // scratch for a chunk of cells: bounded to ~8 GiB
   const size_t per_cell = a.s.per_cell();
