@@ -523,6 +523,29 @@ int vicgpu_nc_dims(vicgpu_ncfile *nc, long long *ntime, long long *nlat, long lo
 int vicgpu_nc_read_slab(vicgpu_ncfile *nc, int nvar, const char *const *varnames, long long t0, long long nt, int ncell,
                         const double *lat, const double *lng, double *out);
 
+/* ---- lake-ice surface solve as a batch operator ------------------------------------------------------
+ * ice_melt() (ice_melt.c:30-585) with its residual IceEnergyBalance::calculate (IceEnergyBalance.c:60-175) and icerad()
+ * (lakes.eb.c:1092-1151) for n independent lake-ice columns, one device thread each; bit-identical to the reference's ice_melt().
+ * The lake model around it (solve_lake, water_balance: lakes.eb.c) is not built -- vicgpu_create still rejects LAKES TRUE -- so
+ * this entry point serves a host-side lake loop that batches its cells' ice solves, and pins the residual the survey lists.
+ * in  [n][VICGPU_ICE_NIN]  arguments and the members of snow_data_struct / lake_var_struct the function reads
+ * out [n][VICGPU_ICE_NOUT] return code (0 or -999), the save_* results, and the members it writes
+ * Arguments of the reference's signature that its body never reads (displacement, surf_atten, fracprv) are not carried;
+ * options.BLOWING is taken as FALSE (ice_melt.c:239-258 not served); tfallback = options.TFALLBACK. */
+#define VICGPU_ICE_IN(X) \
+  X(z2) X(aero_resist) X(latent_heat_Le) X(Z0) X(rainfall) X(snowfall) X(wind) X(Tcutoff) X(air_temp) X(net_short) X(longwave) \
+  X(density) X(pressure) X(vpd) X(vp) X(swq) X(surf_temp) X(pack_temp) X(pack_water) X(surf_water) X(vapor_flux) X(surface_flux) \
+  X(surf_temp_fbflag) X(surf_temp_fbcount) X(ice_water_eq) X(areai) X(hice) X(volume)
+#define VICGPU_ICE_OUT(X) \
+  X(rc) X(aero_resist_used) X(melt) X(advection) X(deltaCC) X(SnowFlux) X(latent) X(sensible) X(Qnet) X(refreeze_energy) X(LWnet) \
+  X(swq) X(surf_temp) X(pack_temp) X(pack_water) X(surf_water) X(vapor_flux) X(blowing_flux) X(surface_flux) X(surf_temp_fbflag) \
+  X(surf_temp_fbcount) X(coverage) X(mass_error) X(coldcontent) X(ice_water_eq) X(volume)
+#define VICGPU_ICE_ENUM_IN(n) ICEIN_##n,
+#define VICGPU_ICE_ENUM_OUT(n) ICEOUT_##n,
+enum { VICGPU_ICE_IN(VICGPU_ICE_ENUM_IN) VICGPU_ICE_NIN };
+enum { VICGPU_ICE_OUT(VICGPU_ICE_ENUM_OUT) VICGPU_ICE_NOUT };
+int vicgpu_ice_melt(int device, int n, int delta_t, int tfallback, const double *in, double *out);
+
 /* accumulateGlacierMassBalance()'s per-cell result (vicNl.c:563, cell_info_struct::gmbEquation, written to the state file by
  * write_model_state.c:153-156): gmb[ncell][4] = b0, b1, b2, fitError of the quadratic fitted to (band elevation, cumulative mass
  * balance of the cell's glacier HRUs) at the end of the last completed accumulation interval; 0, 0, 0, -1 before the first. */

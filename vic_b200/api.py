@@ -25,7 +25,7 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_step_f32", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_measure_phase_tax", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_disagg_tm", "vicgpu_nc_open", "vicgpu_nc_close", "vicgpu_nc_dims", "vicgpu_nc_read_slab", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
+    "vicgpu_get_last_step_timing", "vicgpu_measure_phase_tax", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_disagg_tm", "vicgpu_nc_open", "vicgpu_nc_close", "vicgpu_nc_dims", "vicgpu_nc_read_slab", "vicgpu_ice_melt", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
 ]
 
 
@@ -68,6 +68,7 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_get_last_step_timing.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
     lib.vicgpu_disagg.argtypes = [vp, vp, dp, dp]
     lib.vicgpu_disagg_tm.argtypes = [vp, vp, dp, dp]
+    lib.vicgpu_ice_melt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]
     lib.vicgpu_nc_open.argtypes = [C.POINTER(vp), C.c_char_p]
     lib.vicgpu_nc_close.argtypes = [vp]
     lib.vicgpu_nc_dims.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 3
@@ -316,6 +317,26 @@ def run_case(case, device=0, nrec=None, want_out=True, block=None):
         return res
     finally:
         g.close()
+
+
+# columns of vicgpu_ice_melt's records (VICGPU_ICE_IN / VICGPU_ICE_OUT, include/vicgpu.h; tests/test_lakeice.py checks the order)
+ICE_IN = ("z2 aero_resist latent_heat_Le Z0 rainfall snowfall wind Tcutoff air_temp net_short longwave density pressure vpd vp swq surf_temp pack_temp "
+          "pack_water surf_water vapor_flux surface_flux surf_temp_fbflag surf_temp_fbcount ice_water_eq areai hice volume").split()
+ICE_OUT = ("rc aero_resist_used melt advection deltaCC SnowFlux latent sensible Qnet refreeze_energy LWnet swq surf_temp pack_temp pack_water surf_water "
+           "vapor_flux blowing_flux surface_flux surf_temp_fbflag surf_temp_fbcount coverage mass_error coldcontent ice_water_eq volume").split()
+
+
+def ice_melt(columns, delta_t, tfallback=True, device=0):
+    """the reference's ice_melt() (ice_melt.c:30-585) for a batch of lake-ice columns on the device: columns [n][len(ICE_IN)] ->
+    [n][len(ICE_OUT)] (vicgpu_ice_melt, include/vicgpu.h)"""
+    lib = load_library()
+    a = _as_f64(columns)
+    assert a.ndim == 2 and a.shape[1] == len(ICE_IN), a.shape
+    out = np.empty((a.shape[0], len(ICE_OUT)), dtype=np.float64)
+    rc = lib.vicgpu_ice_melt(int(device), int(a.shape[0]), int(delta_t), int(bool(tfallback)), _dptr(a), _dptr(out))
+    if rc != 0:
+        raise VicGpuError(rc, (lib.vicgpu_last_error() or b"").decode())
+    return out
 
 
 class NcForcing:
