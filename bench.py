@@ -245,6 +245,9 @@ def cpu_baseline(workload, host_threads):
                                "timed by the harness's record-loop timer (vicNl.c:501, 614-623)"}
 
 
+NC_VARS = ["pr", "tasmax", "tasmin", "wind"]
+
+
 def synth_daily(dom, ndays, seed):
     """daily PREC [mm], TMAX, TMIN [C], WIND [m/s] per cell: [ncell][ndays][4] (the generator of vic_b200/synth.py, vectorised)"""
     n = dom["elev"].shape[0]
@@ -272,6 +275,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--forcing-nc", action="store_true",
+                    help="continental only: the e2e leg takes its daily forcing from a NetCDF (classic) file through vicgpu_nc_read_slab + vicgpu_disagg_tm")
     a = ap.parse_args()
     wl = WORKLOADS[a.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -352,6 +357,31 @@ def main():
         daily = dbuf.numpy()
         daily[:] = synth_daily(dom, ndays, seed)
         fnp = None
+        nc_path = None
+        if a.forcing_nc:
+            # the same daily forcing as a (time, lat, lon) NetCDF file of doubles (written once, untimed, by an independent implementation of
+            # the format); cell c sits at grid point (c // nlon, c % nlon) of a grid with a few unmodelled points at the end
+            from scipy.io import netcdf_file
+            nlon = int(np.ceil(np.sqrt(cells)))
+            nlat = (cells + nlon - 1) // nlon
+            glat, glon = 30.0 + 0.0625 * np.arange(nlat), -130.0 + 0.0625 * np.arange(nlon)
+            nc_path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"vicgpu_bench_daily_{os.getpid()}.nc")
+            f = netcdf_file(nc_path, "w", version=2)
+            f.createDimension("time", None)
+            f.createDimension("lat", nlat)
+            f.createDimension("lon", nlon)
+            for name, vals in (("time", np.arange(ndays, dtype=np.float64)), ("lat", glat), ("lon", glon)):
+                v = f.createVariable(name, "d", (name,))
+                v[:] = vals
+            grid = np.zeros((ndays, nlat * nlon))
+            for k, name in enumerate(NC_VARS):
+                grid[:, :cells] = daily[:, :, k].T
+                v = f.createVariable(name, "d", ("time", "lat", "lon"))
+                v[:] = grid.reshape(ndays, nlat, nlon)
+            f.close()
+            cell_lat, cell_lon = glat[np.arange(cells) // nlon], glon[np.arange(cells) % nlon]
+            tmbuf = torch.empty((ndays, 4, cells), dtype=torch.float64, pin_memory=True)
+            daily_tm = tmbuf.numpy()
     else:
         # pinned host buffer: the run's hourly forcing
         fbuf = torch.empty((nrec, cells, L.f_stride), dtype=torch.float64, pin_memory=True)
@@ -396,7 +426,14 @@ def main():
         if disagg:
             barrier()
             t0 = time.perf_counter()
-            g.disagg(disagg_raw, daily, want_host=False)
+            if nc_path:
+                t1 = time.perf_counter()
+                with api.NcForcing(nc_path) as nc:
+                    nc.read_slab(NC_VARS, 0, ndays, cell_lat, cell_lon, out=daily_tm)
+                nc_read_s = time.perf_counter() - t1
+                g.disagg_tm(disagg_raw, daily_tm, want_host=False)
+            else:
+                g.disagg(disagg_raw, daily, want_host=False)
             for s in range(W + K):
                 g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
             barrier()
@@ -414,6 +451,8 @@ def main():
                 g.step(s * 24, 24, dmy[s * 24:s * 24 + 25], None, onp)
             barrier()
             e2e_wall = time.perf_counter() - t0
+    if disagg and nc_path:
+        os.remove(nc_path)
     # ---- the one collective of a multi-GPU run: the gather of the last day's aggregates at the end (not in any timed region above)
     gather_ms = None
     if world > 1 and not a.no_e2e:
@@ -468,6 +507,11 @@ def main():
         if disagg:
             cfgd["disagg"] = (f"vicgpu_disagg of {ndays} days x {cells} cells incl. the H2D of the daily input: {dis_s:.3f} s = "
                               f"{cells * ndays / max(dis_s, 1e-9) / 1e6:.2f} M cell-days/s per GPU (outside `value`, inside `e2e`)")
+        if disagg and a.forcing_nc and not a.no_e2e:
+            assert np.array_equal(daily_tm, daily.transpose(1, 2, 0))  # what came out of the file is what went in
+            cfgd["forcing_nc"] = (f"e2e leg: daily forcing read from a NetCDF classic (CDF-2) file of doubles, {ndays} x 4 grids of {nlat} x {nlon}, by vicgpu_nc_read_slab "
+                                  f"into a pinned [day][variable][cell] buffer ({nc_read_s:.3f} s = {cells * ndays / max(nc_read_s, 1e-9) / 1e6:.1f} M cell-days/s, one host "
+                                  "thread, file in the page cache), then vicgpu_disagg_tm; both inside the e2e region")
         if gather_ms is not None:
             cfgd["gather"] = f"end-of-run gather of one day's aggregates ({cells * world} cells x {L.nout} x {onp.itemsize} B) to rank 0 over NCCL: {gather_ms:.1f} ms (not in any timed region)"
         line = {"metric": "cell-timesteps/s", "value": units / dev_s, "unit": "cell-timesteps/s", "n_gpus": world, "steps": K, "warmup": W,

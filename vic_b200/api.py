@@ -357,11 +357,14 @@ class NcForcing:
             raise VicGpuError(rc, msg)
         self.ntime, self.nlat, self.nlon = (int(x.value) for x in n)
 
-    def read_slab(self, varnames, t0, nt, lat, lng):
-        """-> float64 [nt][len(varnames)][ncell]; lat / lng: the cells' (double)(float) coordinates"""
+    def read_slab(self, varnames, t0, nt, lat, lng, out=None):
+        """-> float64 [nt][len(varnames)][ncell] (into `out` when given, e.g. a pinned buffer); lat / lng: the cells' (double)(float) coordinates"""
         la, lo = _as_f64(lat), _as_f64(lng)
         assert la.shape == lo.shape and la.ndim == 1
-        out = np.empty((int(nt), len(varnames), la.shape[0]), dtype=np.float64)
+        shape = (int(nt), len(varnames), la.shape[0])
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        assert out.shape == shape and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
         names = (C.c_char_p * len(varnames))(*[v.encode() for v in varnames])
         rc = self.lib.vicgpu_nc_read_slab(self.h, len(varnames), names, int(t0), int(nt), int(la.shape[0]), _dptr(la), _dptr(lo), _dptr(out))
         if rc != 0:
