@@ -81,272 +81,284 @@ struct IceMeltOut {
   double aero_resist_used, melt, advection, deltaCC, SnowFlux, latent, sensible, Qnet, refreeze_energy, LWnet;
 };
 
+// The slab that lies on the lake water, in metres of water equivalent: snow over lake ice, cut into a surface layer that exchanges
+// energy with the air (at most LK_MAX_SURFACE_SWE thick, snow first) and the pack below it.  ice_melt.c keeps these as a dozen loose
+// locals; here they travel together through the phases of the sub-step.
+struct IceSlab {
+  double top;        // surface layer
+  double pack_snow;  // snow below the surface layer
+  double pack_ice;   // lake ice below the surface layer
+  double snow;       // all frozen snow (surface layer + pack)
+  double lake;       // all lake ice
+  double all;        // snow + lake
+  double top_cc;     // cold content of the surface layer [J/m2]
+  double pack_cc;    // cold content of the pack
+
+  // ice_melt.c:139-160: cut the slab at the surface-layer thickness
+  VIC_HD void cut(double top_temp, double pack_temp) {
+    all = snow + lake;
+    top = all > LK_MAX_SURFACE_SWE ? LK_MAX_SURFACE_SWE : all;
+    if (top <= snow) {
+      pack_snow = snow - top;
+      pack_ice = lake;
+    } else {
+      pack_snow = 0.;
+      pack_ice = all - top;
+    }
+    top_cc = CH_ICE * top * top_temp;
+    pack_cc = CH_ICE * (pack_snow + pack_ice) * pack_temp;
+  }
+  // ice_melt.c:162-205: new snow lands on the surface layer; what no longer fits moves down with its share of cold content
+  VIC_HD void snowfall(double fall, double air_temp) {
+    const double fall_cc = air_temp > 0.0 ? 0.0 : CH_ICE * fall * air_temp;
+    if (fall > (LK_MAX_SURFACE_SWE - top)) {
+      const double down = top + fall - LK_MAX_SURFACE_SWE;
+      double down_cc;
+      if (down > top) down_cc = top_cc + (fall - LK_MAX_SURFACE_SWE) / fall * fall_cc;
+      else down_cc = down / top * top_cc;
+      top = LK_MAX_SURFACE_SWE;
+      top_cc += fall_cc - down_cc;
+      pack_snow += down;
+      pack_cc += down_cc;
+    } else {
+      top += fall;
+      top_cc += fall_cc;
+    }
+    snow += fall;
+    all += fall;
+  }
+  VIC_HD double top_temp() const { return top > 0.0 ? top_cc / (CH_ICE * top) : 0.0; }
+  VIC_HD double pack_temp() const { return pack_snow + pack_ice > 0.0 ? pack_cc / (CH_ICE * (pack_snow + pack_ice)) : 0.0; }
+};
+
 // ice_melt.c:30-585.  Returns 0, or ERROR_I when the surface solve fails and TFALLBACK is off (outputs then undefined, as in the reference).
-VIC_HDI int ice_melt(double z2, double aero_resist, double latent_heat_Le, IceSnow& snow, IceLake& lake, int delta_t, double Z0, double rainfall,
+VIC_HDI int ice_melt(double z2, double aero_resist, double latent_heat_Le, IceSnow& sn, IceLake& lk, int delta_t, double Z0, double rainfall,
                      double snowfall, double wind, double Tcutoff, double air_temp, double net_short, double longwave, double density, double pressure,
                      double vpd, double vp, bool TFALLBACK, IceMeltOut& out) {
-  double DeltaPackCC, DeltaPackSwq, MaxLiquidWater, Qnet, PackRefreezeEnergy, RefrozenWater, SnowFallCC, SurfaceCC, PackCC, SurfaceSwq, PackSwq, PackIce, SnowMelt, IceMelt;
-  double avgcond, SWconducted, deltaCC;
-  double melt_energy = 0.;
-  const double SnowFall = snowfall / 1000.;
-  const double RainFall = rainfall / 1000.;
-  IceMelt = 0.0;
-  RefrozenWater = 0.0;
-  const double InitialSwq = snow.swq;
-  const double OldTSurf = snow.surf_temp;
-  double SnowIce = snow.swq - snow.pack_water - snow.surf_water;
-  double LakeIce = lake.ice_water_eq / lake.areai;
-  const double InitialIce = LakeIce;
-  double Ice = SnowIce + LakeIce;
-  if (Ice > LK_MAX_SURFACE_SWE) SurfaceSwq = LK_MAX_SURFACE_SWE;
-  else SurfaceSwq = Ice;
-  if (SurfaceSwq <= SnowIce) {
-    PackSwq = SnowIce - SurfaceSwq;
-    PackIce = LakeIce;
-  } else {
-    PackSwq = 0.;
-    PackIce = Ice - SurfaceSwq;
-  }
-  SurfaceCC = CH_ICE * SurfaceSwq * snow.surf_temp;
-  PackCC = CH_ICE * (PackSwq + PackIce) * snow.pack_temp;
-  if (air_temp > 0.0) SnowFallCC = 0.0;
-  else SnowFallCC = CH_ICE * SnowFall * air_temp;
-  if (SnowFall > (LK_MAX_SURFACE_SWE - SurfaceSwq)) {
-    DeltaPackSwq = SurfaceSwq + SnowFall - LK_MAX_SURFACE_SWE;
-    if (DeltaPackSwq > SurfaceSwq) DeltaPackCC = SurfaceCC + (SnowFall - LK_MAX_SURFACE_SWE) / SnowFall * SnowFallCC;
-    else DeltaPackCC = DeltaPackSwq / SurfaceSwq * SurfaceCC;
-    SurfaceSwq = LK_MAX_SURFACE_SWE;
-    SurfaceCC += SnowFallCC - DeltaPackCC;
-    PackSwq += DeltaPackSwq;
-    PackCC += DeltaPackCC;
-  } else {
-    SurfaceSwq += SnowFall;
-    SurfaceCC += SnowFallCC;
-    DeltaPackCC = 0;
-  }
-  if (SurfaceSwq > 0.0) snow.surf_temp = SurfaceCC / (CH_ICE * SurfaceSwq);
-  else snow.surf_temp = 0.0;
-  if (PackSwq + PackIce > 0.0) snow.pack_temp = PackCC / (CH_ICE * (PackSwq + PackIce));
-  else snow.pack_temp = 0.0;
-  SnowIce += SnowFall;
-  Ice += SnowFall;
-  snow.surf_water += RainFall;
-  icerad(net_short, lake.hice, SnowIce * RHO_W / LK_RHOSNOW, &avgcond, &SWconducted, &deltaCC);
-  snow.blowing_flux = 0.0;  // (BLOWING branch, ice_melt.c:239-258: not served)
+  const double fall = snowfall / 1000., rain = rainfall / 1000.;  // [m]
+  const double swq0 = sn.swq, T_old = sn.surf_temp;
+  IceSlab s;
+  s.snow = sn.swq - sn.pack_water - sn.surf_water;
+  s.lake = lk.ice_water_eq / lk.areai;
+  const double lake0 = s.lake;
+  s.cut(sn.surf_temp, sn.pack_temp);
+  s.snowfall(fall, air_temp);
+  sn.surf_temp = s.top_temp();
+  sn.pack_temp = s.pack_temp();
+  sn.surf_water += rain;
+
+  double slab_cond, sw_conducted, sw_through;
+  icerad(net_short, lk.hice, s.snow * RHO_W / LK_RHOSNOW, &slab_cond, &sw_conducted, &sw_through);
+  sn.blowing_flux = 0.0;  // (BLOWING branch, ice_melt.c:239-258: not served)
 
   IceEB eb;
   eb.stab.reset();
   eb.Dt = (double)delta_t; eb.Ra = aero_resist; eb.Z = z2; eb.Z0 = Z0; eb.Wind = wind; eb.ShortRad = net_short; eb.LongRadIn = longwave;
   eb.AirDens = density; eb.Lv = latent_heat_Le; eb.Tair = air_temp; eb.Press = pressure * 1000.; eb.Vpd = vpd * 1000.; eb.EactAir = vp * 1000.;
-  eb.Rain = RainFall; eb.SurfaceLiquidWater = snow.surf_water; eb.Tfreeze = Tcutoff; eb.AvgCond = avgcond; eb.SWconducted = SWconducted;
-  eb.vapor_flux = snow.vapor_flux; eb.blowing_flux = snow.blowing_flux; eb.surface_flux = snow.surface_flux;
-  double& RefreezeEnergy = eb.RefreezeEnergy;
-  Qnet = eb(0.0);
-  snow.vapor_flux = eb.vapor_flux;
-  snow.surface_flux = eb.surface_flux;
+  eb.Rain = rain; eb.SurfaceLiquidWater = sn.surf_water; eb.Tfreeze = Tcutoff; eb.AvgCond = slab_cond; eb.SWconducted = sw_conducted;
+  eb.vapor_flux = sn.vapor_flux; eb.blowing_flux = sn.blowing_flux; eb.surface_flux = sn.surface_flux;
+  double& refreeze = eb.RefreezeEnergy;  // [W/m2], left by the last evaluation of the balance
+  double lake_melted = 0.0;
+  const double step_s = delta_t * SECPHOUR;  // (int product, as in the reference)
+
+  double Qnet = eb(0.0);  // the balance with the surface at the melting point
+  sn.vapor_flux = eb.vapor_flux;
+  sn.surface_flux = eb.surface_flux;
   if (Qnet == 0.0) {
-    snow.surf_temp = 0.0;
-    if (RefreezeEnergy >= 0.0) {
-      RefrozenWater = RefreezeEnergy / (Lf * RHO_W) * delta_t * SECPHOUR;
-      if (RefrozenWater > snow.surf_water) {
-        RefrozenWater = snow.surf_water;
-        RefreezeEnergy = RefrozenWater * Lf * RHO_W / (delta_t * SECPHOUR);
+    // ---- surface at 0 C: the residual went into refreezing (>= 0) or melting (< 0), ice_melt.c:292-392
+    sn.surf_temp = 0.0;
+    double melted;
+    if (refreeze >= 0.0) {
+      double refrozen = refreeze / (Lf * RHO_W) * delta_t * SECPHOUR;
+      if (refrozen > sn.surf_water) {
+        refrozen = sn.surf_water;
+        refreeze = refrozen * Lf * RHO_W / step_s;
       }
-      melt_energy += RefreezeEnergy;
-      SurfaceSwq += RefrozenWater;
-      SnowIce += RefrozenWater;
-      Ice += RefrozenWater;
-      snow.surf_water -= RefrozenWater;
-      if (snow.surf_water < 0.0) snow.surf_water = 0.0;
-      SnowMelt = 0.0;
+      s.top += refrozen;
+      s.snow += refrozen;
+      s.all += refrozen;
+      sn.surf_water -= refrozen;
+      if (sn.surf_water < 0.0) sn.surf_water = 0.0;
+      melted = 0.0;
     } else {
-      SnowMelt = fabs(RefreezeEnergy) / (Lf * RHO_W) * delta_t * SECPHOUR;
-      melt_energy += RefreezeEnergy;
+      melted = fabs(refreeze) / (Lf * RHO_W) * delta_t * SECPHOUR;
     }
-    if (snow.surf_water < -(snow.vapor_flux)) {
-      snow.blowing_flux *= -(snow.surf_water) / snow.vapor_flux;
-      snow.vapor_flux = -(snow.surf_water);
-      snow.surface_flux = -(snow.surf_water) - snow.blowing_flux;
-      snow.surf_water = 0.0;
+    // vapour leaves the liquid water first; more than there is cannot leave
+    if (sn.surf_water < -(sn.vapor_flux)) {
+      sn.blowing_flux *= -(sn.surf_water) / sn.vapor_flux;
+      sn.vapor_flux = -(sn.surf_water);
+      sn.surface_flux = -(sn.surf_water) - sn.blowing_flux;
+      sn.surf_water = 0.0;
     } else {
-      snow.surf_water += snow.vapor_flux;
+      sn.surf_water += sn.vapor_flux;
     }
-    if (SnowMelt < Ice) {
-      if (SnowMelt <= PackSwq) {
-        snow.surf_water += SnowMelt;
-        PackSwq -= SnowMelt;
-        Ice -= SnowMelt;
-        SnowIce -= SnowMelt;
-      } else if (SnowMelt <= SnowIce) {
-        snow.surf_water += SnowMelt + snow.pack_water;
-        snow.pack_water = 0.0;
-        SurfaceSwq -= (SnowMelt - PackSwq);
-        PackSwq = 0.0;
-        SnowIce -= SnowMelt;
-        Ice -= SnowMelt;
-      } else {
-        snow.surf_water += SnowIce + snow.pack_water;
-        snow.pack_water = 0.0;
-        PackSwq = 0.0;
-        Ice -= SnowMelt;
-        LakeIce -= SnowMelt - SnowIce;
-        IceMelt = SnowMelt - SnowIce;
-        if (SurfaceSwq > SnowMelt) {
-          SurfaceSwq -= SnowMelt;
+    if (melted < s.all) {
+      if (melted <= s.pack_snow) {  // (the reference takes it out of the pack's snow)
+        sn.surf_water += melted;
+        s.pack_snow -= melted;
+        s.all -= melted;
+        s.snow -= melted;
+      } else if (melted <= s.snow) {  // all of the pack's snow and part of the surface layer
+        sn.surf_water += melted + sn.pack_water;
+        sn.pack_water = 0.0;
+        s.top -= (melted - s.pack_snow);
+        s.pack_snow = 0.0;
+        s.snow -= melted;
+        s.all -= melted;
+      } else {  // all snow and some lake ice
+        sn.surf_water += s.snow + sn.pack_water;
+        sn.pack_water = 0.0;
+        s.pack_snow = 0.0;
+        s.all -= melted;
+        s.lake -= melted - s.snow;
+        lake_melted = melted - s.snow;
+        if (s.top > melted) {
+          s.top -= melted;
         } else {
-          SurfaceSwq = 0.0;
-          PackIce -= (SnowMelt - SurfaceSwq - PackSwq);
+          s.top = 0.0;
+          s.pack_ice -= (melted - s.top - s.pack_snow);
         }
-        SnowIce = 0.0;
+        s.snow = 0.0;
       }
-    } else {
-      snow.surf_water += SnowIce + snow.pack_water;
-      snow.pack_water = 0.0;
-      PackSwq = 0.0;
-      SurfaceSwq = 0.0;
-      SnowIce = 0.0;
-      SnowMelt = Ice;
-      IceMelt = LakeIce;
-      LakeIce = 0.0;
-      PackIce = 0.0;
-      Ice = 0.0;
-      snow.surf_temp = 0.0;
-      snow.pack_temp = 0.0;
-      melt_energy -= RefreezeEnergy;
-      RefreezeEnergy = RefreezeEnergy / fabs(RefreezeEnergy) * SnowMelt * Lf * RHO_W / (delta_t);
-      melt_energy += RefreezeEnergy;
+    } else {  // everything melts
+      sn.surf_water += s.snow + sn.pack_water;
+      sn.pack_water = 0.0;
+      s.pack_snow = 0.0;
+      s.top = 0.0;
+      s.snow = 0.0;
+      melted = s.all;
+      lake_melted = s.lake;
+      s.lake = 0.0;
+      s.pack_ice = 0.0;
+      s.all = 0.0;
+      sn.surf_temp = 0.0;
+      sn.pack_temp = 0.0;
+      refreeze = refreeze / fabs(refreeze) * melted * Lf * RHO_W / (delta_t);
     }
   } else {
-    if (SurfaceSwq > LK_MIN_SWQ_EB_THRES) {
-      snow.surf_temp = root_brent((double)(snow.surf_temp - LK_SNOW_DT), (double)(snow.surf_temp + LK_SNOW_DT), eb);
-      if (snow.surf_temp <= -998) {
-        if (TFALLBACK) {
-          snow.surf_temp = OldTSurf;
-          snow.surf_temp_fbflag = 1;
-          snow.surf_temp_fbcount++;
-        } else {
-          return ERROR_I;
-        }
+    // ---- surface below 0 C: find its temperature (thick enough a layer only), ice_melt.c:394-500
+    if (s.top > LK_MIN_SWQ_EB_THRES) {
+      sn.surf_temp = root_brent((double)(sn.surf_temp - LK_SNOW_DT), (double)(sn.surf_temp + LK_SNOW_DT), eb);
+      if (sn.surf_temp <= -998) {  // RootBrent::resultIsError
+        if (!TFALLBACK) return ERROR_I;
+        sn.surf_temp = T_old;
+        sn.surf_temp_fbflag = 1;
+        sn.surf_temp_fbcount++;
       }
     } else {
-      snow.surf_temp = NAN;  // INVALID
+      sn.surf_temp = NAN;  // INVALID
     }
-    if (snow.surf_temp == snow.surf_temp && !(snow.surf_temp <= -998)) {
-      Qnet = eb(snow.surf_temp);
-      snow.vapor_flux = eb.vapor_flux;
-      snow.surface_flux = eb.surface_flux;
-      SnowMelt = 0.0;
-      IceMelt = 0.0;
-      SnowIce += snow.surf_water;
-      Ice += snow.surf_water;
-      melt_energy += snow.surf_water * Lf * RHO_W / (delta_t * SECPHOUR);
-      RefrozenWater = snow.surf_water;
-      snow.surf_water = 0.0;
-      if (SurfaceSwq < -(snow.vapor_flux)) {
-        if (SurfaceSwq > SnowIce) {
-          snow.blowing_flux *= -(SurfaceSwq) / snow.vapor_flux;
-          snow.vapor_flux = -SurfaceSwq;
-          snow.surface_flux = -SurfaceSwq - snow.blowing_flux;
-          LakeIce -= SurfaceSwq - SnowIce;
-          Ice = PackIce;
-          SnowIce = 0.0;
+    if (sn.surf_temp == sn.surf_temp && !(sn.surf_temp <= -998)) {
+      Qnet = eb(sn.surf_temp);
+      sn.vapor_flux = eb.vapor_flux;
+      sn.surface_flux = eb.surface_flux;
+      // the liquid water of the surface layer freezes
+      s.snow += sn.surf_water;
+      s.all += sn.surf_water;
+      sn.surf_water = 0.0;
+      if (s.top < -(sn.vapor_flux)) {  // sublimation would take more than the surface layer holds
+        sn.blowing_flux *= -(s.top) / sn.vapor_flux;
+        sn.vapor_flux = -s.top;
+        sn.surface_flux = -s.top - sn.blowing_flux;
+        if (s.top > s.snow) {
+          s.lake -= s.top - s.snow;
+          s.all = s.pack_ice;
+          s.snow = 0.0;
         } else {
-          snow.blowing_flux *= -(SurfaceSwq) / snow.vapor_flux;
-          snow.vapor_flux = -SurfaceSwq;
-          snow.surface_flux = -SurfaceSwq - snow.blowing_flux;
-          SurfaceSwq = 0.0;
-          Ice = PackSwq + PackIce;
+          s.top = 0.0;
+          s.all = s.pack_snow + s.pack_ice;
         }
       } else {
-        SurfaceSwq += snow.vapor_flux;
-        if (SnowIce > -(snow.vapor_flux)) SnowIce += snow.vapor_flux;
+        s.top += sn.vapor_flux;
+        if (s.snow > -(sn.vapor_flux)) s.snow += sn.vapor_flux;
         else {
-          LakeIce += (snow.vapor_flux + SnowIce);
-          SnowIce = 0.;
+          s.lake += (sn.vapor_flux + s.snow);
+          s.snow = 0.;
         }
-        Ice += snow.vapor_flux;
+        s.all += sn.vapor_flux;
       }
     } else {
-      snow.surf_temp = NAN;
+      sn.surf_temp = NAN;
     }
   }
-  if (SnowIce > SurfaceSwq) MaxLiquidWater = LK_LIQUID_WATER_CAPACITY * SurfaceSwq;
-  else MaxLiquidWater = LK_LIQUID_WATER_CAPACITY * SnowIce;
-  double melt;
-  if (snow.surf_water > MaxLiquidWater) {
-    melt = snow.surf_water - MaxLiquidWater;
-    snow.surf_water = MaxLiquidWater;
-  } else melt = 0.0;
-  snow.pack_water += melt;
-  PackRefreezeEnergy = snow.pack_water * Lf * RHO_W;
-  if (PackCC < -PackRefreezeEnergy) {
-    PackSwq += snow.pack_water;
-    Ice += snow.pack_water;
-    SnowIce += snow.pack_water;
-    snow.pack_water = 0.0;
-    if (PackSwq + PackIce > 0.0) {
-      PackCC = (PackSwq + PackIce) * CH_ICE * snow.pack_temp + PackRefreezeEnergy;
-      snow.pack_temp = PackCC / (CH_ICE * (PackSwq + PackIce));
-      if (snow.pack_temp > 0.) snow.pack_temp = 0.;
-    } else snow.pack_temp = 0.0;
-  } else {
-    snow.pack_temp = 0.0;
-    DeltaPackSwq = -PackCC / (Lf * RHO_W);
-    snow.pack_water -= DeltaPackSwq;
-    PackSwq += DeltaPackSwq;
-    Ice += DeltaPackSwq;
-    SnowIce += DeltaPackSwq;
+
+  // ---- liquid water: what the surface layer cannot hold drains into the pack, refreezes there or leaves, ice_melt.c:502-560
+  double hold = LK_LIQUID_WATER_CAPACITY * (s.snow > s.top ? s.top : s.snow);
+  double drained = 0.0;
+  if (sn.surf_water > hold) {
+    drained = sn.surf_water - hold;
+    sn.surf_water = hold;
   }
-  MaxLiquidWater = LK_LIQUID_WATER_CAPACITY * PackSwq;
-  if (snow.pack_water > MaxLiquidWater) {
-    melt = snow.pack_water - MaxLiquidWater;
-    snow.pack_water = MaxLiquidWater;
-  } else melt = 0.0;
-  Ice = PackIce + PackSwq + SurfaceSwq;
-  if (Ice > LK_MAX_SURFACE_SWE) {
-    SurfaceCC = CH_ICE * snow.surf_temp * SurfaceSwq;
-    PackCC = CH_ICE * snow.pack_temp * (PackSwq + PackIce);
-    if (SurfaceSwq > LK_MAX_SURFACE_SWE) {
-      PackCC += SurfaceCC * (SurfaceSwq - LK_MAX_SURFACE_SWE) / SurfaceSwq;
-      SurfaceCC -= SurfaceCC * (SurfaceSwq - LK_MAX_SURFACE_SWE) / SurfaceSwq;
-      PackSwq += SurfaceSwq - LK_MAX_SURFACE_SWE;
-      SurfaceSwq -= SurfaceSwq - LK_MAX_SURFACE_SWE;
-    } else if (SurfaceSwq < LK_MAX_SURFACE_SWE) {
-      PackCC -= PackCC * (LK_MAX_SURFACE_SWE - SurfaceSwq) / (PackSwq + PackIce);
-      SurfaceCC += PackCC * (LK_MAX_SURFACE_SWE - SurfaceSwq) / (PackSwq + PackIce);
-      PackSwq -= LK_MAX_SURFACE_SWE - SurfaceSwq;
-      SurfaceSwq += LK_MAX_SURFACE_SWE - SurfaceSwq;
+  sn.pack_water += drained;
+  const double pack_refreeze = sn.pack_water * Lf * RHO_W;
+  if (s.pack_cc < -pack_refreeze) {  // the pack is cold enough to freeze all of it
+    s.pack_snow += sn.pack_water;
+    s.all += sn.pack_water;
+    s.snow += sn.pack_water;
+    sn.pack_water = 0.0;
+    if (s.pack_snow + s.pack_ice > 0.0) {
+      s.pack_cc = (s.pack_snow + s.pack_ice) * CH_ICE * sn.pack_temp + pack_refreeze;
+      sn.pack_temp = s.pack_cc / (CH_ICE * (s.pack_snow + s.pack_ice));
+      if (sn.pack_temp > 0.) sn.pack_temp = 0.;
+    } else sn.pack_temp = 0.0;
+  } else {
+    sn.pack_temp = 0.0;
+    const double frozen = -s.pack_cc / (Lf * RHO_W);
+    sn.pack_water -= frozen;
+    s.pack_snow += frozen;
+    s.all += frozen;
+    s.snow += frozen;
+  }
+  hold = LK_LIQUID_WATER_CAPACITY * s.pack_snow;
+  if (sn.pack_water > hold) {
+    drained = sn.pack_water - hold;
+    sn.pack_water = hold;
+  } else drained = 0.0;
+
+  // ---- bring the surface layer back to its thickness, ice_melt.c:562-600
+  s.all = s.pack_ice + s.pack_snow + s.top;
+  if (s.all > LK_MAX_SURFACE_SWE) {
+    s.top_cc = CH_ICE * sn.surf_temp * s.top;
+    s.pack_cc = CH_ICE * sn.pack_temp * (s.pack_snow + s.pack_ice);
+    if (s.top > LK_MAX_SURFACE_SWE) {
+      s.pack_cc += s.top_cc * (s.top - LK_MAX_SURFACE_SWE) / s.top;
+      s.top_cc -= s.top_cc * (s.top - LK_MAX_SURFACE_SWE) / s.top;
+      s.pack_snow += s.top - LK_MAX_SURFACE_SWE;
+      s.top -= s.top - LK_MAX_SURFACE_SWE;
+    } else if (s.top < LK_MAX_SURFACE_SWE) {
+      s.pack_cc -= s.pack_cc * (LK_MAX_SURFACE_SWE - s.top) / (s.pack_snow + s.pack_ice);
+      s.top_cc += s.pack_cc * (LK_MAX_SURFACE_SWE - s.top) / (s.pack_snow + s.pack_ice);
+      s.pack_snow -= LK_MAX_SURFACE_SWE - s.top;
+      s.top += LK_MAX_SURFACE_SWE - s.top;
     }
-    snow.pack_temp = PackCC / (CH_ICE * (PackSwq + PackIce));
-    snow.surf_temp = SurfaceCC / (CH_ICE * SurfaceSwq);
+    sn.pack_temp = s.pack_cc / (CH_ICE * (s.pack_snow + s.pack_ice));
+    sn.surf_temp = s.top_cc / (CH_ICE * s.top);
   } else {
-    PackSwq = 0.0;
-    PackCC = 0.0;
-    PackIce = 0.0;
-    snow.pack_temp = 0.0;
+    s.pack_snow = 0.0;
+    s.pack_cc = 0.0;
+    s.pack_ice = 0.0;
+    sn.pack_temp = 0.0;
   }
-  snow.swq = SnowIce + snow.surf_water + snow.pack_water;
-  lake.ice_water_eq = LakeIce * lake.areai;
-  lake.volume -= (InitialIce - LakeIce - IceMelt) * lake.areai;
-  if (lake.ice_water_eq <= 0.0) lake.ice_water_eq = 0.0;
-  if (snow.swq > 0) snow.coverage = 1.;
-  else snow.coverage = 0.;
-  const double MassBalanceError = (InitialSwq - snow.swq) + (InitialIce - LakeIce) + (RainFall + SnowFall) - IceMelt - melt + snow.vapor_flux;
-  melt *= 1000.;
-  snow.mass_error = MassBalanceError;
-  snow.coldcontent = SurfaceCC;
-  snow.vapor_flux *= -1.;
+
+  // ---- results, ice_melt.c:602-640
+  sn.swq = s.snow + sn.surf_water + sn.pack_water;
+  lk.ice_water_eq = s.lake * lk.areai;
+  lk.volume -= (lake0 - s.lake - lake_melted) * lk.areai;
+  if (lk.ice_water_eq <= 0.0) lk.ice_water_eq = 0.0;
+  sn.coverage = sn.swq > 0 ? 1. : 0.;
+  sn.mass_error = (swq0 - sn.swq) + (lake0 - s.lake) + (rain + fall) - lake_melted - drained + sn.vapor_flux;
+  sn.coldcontent = s.top_cc;
+  sn.vapor_flux *= -1.;
   out.aero_resist_used = eb.Ra_used;
-  out.melt = melt;
+  out.melt = drained * 1000.;
   out.LWnet = eb.LongRadOut;
   out.advection = eb.AdvectedEnergy;
-  out.deltaCC = deltaCC;
+  out.deltaCC = sw_through;
   out.SnowFlux = eb.qf;
   out.latent = eb.LatentHeat + eb.LatentHeatSub;
   out.sensible = eb.SensibleHeat;
-  out.refreeze_energy = RefreezeEnergy;
+  out.refreeze_energy = refreeze;
   out.Qnet = Qnet;
-  (void)melt_energy; (void)RefrozenWater; (void)DeltaPackCC; (void)SnowMelt;
   return 0;
 }
 
