@@ -137,3 +137,25 @@ def test_reference_physics_behind_the_indexed_loader(tmp_path):
     half = out0.size // 2  # (first output step: uninitialised aggdata in the reference, see above)
     assert out0.size > 0 and np.array_equal(out0[half:], out1[half:], equal_nan=True) and np.array_equal(out0[half:], out2[half:], equal_nan=True)
     assert len(st0) > 1000 and st0 == st1 == st2
+
+
+def test_indexed_lookup_with_lai_lines_in_the_vegetation_file(tmp_path):
+    """VEGPARAM_LAI TRUE: every tile carries a second line of twelve monthly LAI values (read_vegparam.c:104, 200-228), header lines with
+    trailing blanks, blank lines at the end of the file, shuffled records and decoys: identical to the reference's scan"""
+    exe = os.path.join(REF, "readercheck")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (oracle/Makefile)")
+    cfg = dataclasses.replace(synth.CONFIGS["frozen_bands"], ndays=1, extra_global=["VEGPARAM_LAI TRUE", "LAI_SRC LAI_FROM_VEGPARAM"])
+    r = synth.generate(str(tmp_path / "in"), cfg, 6, 7, 5)
+    vp = os.path.join(r["dir"], "vegparam.txt")
+    lines, out, i, rng = open(vp).read().splitlines(), [], 0, np.random.default_rng(1)
+    while i < len(lines):
+        n = int(lines[i].split()[1])
+        out.append(lines[i] + "   ")
+        for k in range(n):
+            out += [lines[i + 1 + k], "  " + " ".join(f"{x:.2f}" for x in rng.uniform(0.5, 5, 12))]
+        i += n + 1
+    open(vp, "w").write("\n".join(out) + "\n\n\n")
+    _shuffle_parameter_files(r["dir"], 3, True)
+    o = subprocess.run([exe, "-g", r["global_file"]], capture_output=True, text=True)
+    assert o.returncode == 0 and "identical" in o.stdout and "ncell 42 " in o.stdout, o.stdout[-2000:]
