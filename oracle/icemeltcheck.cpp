@@ -6,6 +6,7 @@
 // every column is compared bit for bit (NaN, the reference's INVALID, equals NaN).  With -o the inputs and the REFERENCE's outputs
 // are written as a case file: the golden vectors of the GPU operator test (tests/golden/make_ice_melt_golden.py).
 // Usage: icemeltcheck [-n N] [--seed S] [--dt HOURS] [--tfallback 0|1] [-o case.bin]
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -73,6 +74,7 @@ int main(int argc, char** argv) {
     a[ICEIN_ice_water_eq] = a[ICEIN_hice] * a[ICEIN_areai] * 0.917 * U(0.5, 1.0);
     a[ICEIN_volume] = U(1e6, 1e10);
   }
+  const auto t_ref0 = std::chrono::steady_clock::now();
   for (int i = 0; i < n; i++) {
     const double* a = &in[(size_t)i * VICGPU_ICE_NIN];
     double* o = &ref[(size_t)i * VICGPU_ICE_NOUT];
@@ -96,7 +98,10 @@ int main(int argc, char** argv) {
     o[ICEOUT_coverage] = snow.coverage; o[ICEOUT_mass_error] = snow.mass_error; o[ICEOUT_coldcontent] = snow.coldcontent;
     o[ICEOUT_ice_water_eq] = lake.ice_water_eq; o[ICEOUT_volume] = lake.volume;
   }
+  const double t_ref = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_ref0).count();
+  const auto t_port0 = std::chrono::steady_clock::now();
   port_ice_melt(n, dt, tfallback, in.data(), port.data());
+  const double t_port = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_port0).count();
 
   static const char* names[] = {
 #define X(nm) #nm,
@@ -133,6 +138,7 @@ int main(int argc, char** argv) {
   printf("n %d dt %d tfallback %d: balance at 0 C %ld, surface solved %ld, thin pack (INVALID surface) %ld, ERROR returns %ld\n", n, dt, tfallback, melting, solved, invalid, errors);
   for (int k = 0; k < VICGPU_ICE_NOUT; k++)
     if (badcol[k]) printf("  %s: %ld rows differ\n", names[k], badcol[k]);
+  printf("reference ice_melt() %.3f s = %.2f M columns/s on one host thread; host build of vic_lakeice.cuh %.3f s\n", t_ref, n / t_ref / 1e6, t_port);
   printf(bad ? "DIFFERENT (%ld)\n" : "identical\n", bad);
   if (out_path) {
     CaseWriter w(out_path);
