@@ -162,6 +162,12 @@ int main(int argc, char **argv) {
       int64_t dm[1] = {8};
       cw->i32("meta", meta, 1, dm);
     }
+    if (state.options.OUTPUT_FORCE) {  // the disaggregator mode has cells (soil parameters, bands) but no vegetation and no state
+      std::vector<double> cellpar((size_t)ncell * L.cp_stride);
+      for (int c = 0; c < ncell; c++) vicgpu_pack_cellpar(cells[c].soil_con, &L, &cellpar[(size_t)c * L.cp_stride]);
+      int64_t dc[2] = {ncell, L.cp_stride};
+      cw->f64("cellpar", cellpar.data(), 2, dc);
+    }
     if (!state.options.OUTPUT_FORCE) {
       std::vector<double> veglib;
       vicgpu_pack_veglib(&state, &L, veglib);

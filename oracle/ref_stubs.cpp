@@ -8,7 +8,7 @@
 // cell and variable as raw doubles to <RESULT_DIR>/<netCDF output name>.f64 at every
 // output step (the real writer narrows to float32, WriteOutputNetCDF.c:279, useless
 // for bit-level parity): that file is what tests/test_dropin.py compares between the
-// stock vicNl and the GPU drop-in vicNl_gpu.
+// stock vicNl and the GPU drop-in vicNl_gpu (and, for OUTPUT_FORCE runs, <...>.force.f64 written by write_data_one_cell).
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -22,7 +22,18 @@ const char *WriteOutputNetCDF::getDescriptionOfOutputType() { return "oracle-stu
 void WriteOutputNetCDF::initializeFile(const ProgramState *, const OutputData *) {}
 void WriteOutputNetCDF::openFile() {}
 void WriteOutputNetCDF::compressFiles() {}
-void WriteOutputNetCDF::write_data_one_cell(std::vector<OutputData *> &, out_data_file_struct *, const int, const int, const ProgramState *) {}
+// disaggregator mode (OUTPUT_FORCE TRUE, vicNl.c:462-480): the chunk's aggdata of every variable, record by record, appended to
+// <RESULT_DIR>/<netCDF output name>.force.f64 (cells follow each other in the order the run processes them)
+void WriteOutputNetCDF::write_data_one_cell(std::vector<OutputData *> &chunk, out_data_file_struct *, const int, const int num_recs, const ProgramState *state) {
+  static bool first = true;
+  const std::string path = std::string(state->options.NETCDF_FULL_FILE_PATH) + ".force.f64";
+  FILE *f = fopen(path.c_str(), first ? "wb" : "ab");
+  first = false;
+  if (!f) throw std::runtime_error("cannot open " + path);
+  for (int r = 0; r < num_recs; r++)
+    for (int v = 0; v < N_OUTVAR_TYPES; v++) fwrite(chunk[r][v].aggdata, sizeof(double), chunk[r][v].nelem, f);
+  fclose(f);
+}
 void WriteOutputNetCDF::write_data_all_cells(std::vector<OutputData *> &all, out_data_file_struct *, const int output_rec, const ProgramState *state) {
   const std::string path = std::string(state->options.NETCDF_FULL_FILE_PATH) + ".f64";
   FILE *f = fopen(path.c_str(), output_rec == 0 ? "wb" : "ab");

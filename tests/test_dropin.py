@@ -159,3 +159,49 @@ def test_indexed_lookup_with_lai_lines_in_the_vegetation_file(tmp_path):
     _shuffle_parameter_files(r["dir"], 3, True)
     o = subprocess.run([exe, "-g", r["global_file"]], capture_output=True, text=True)
     assert o.returncode == 0 and "identical" in o.stdout and "ncell 42 " in o.stdout, o.stdout[-2000:]
+
+
+# ---- OUTPUT_FORCE TRUE: the meteorological disaggregator (BASELINE configs[4], first half; vicNl.c:445-490) ---------------------------
+def _run_output_force(exe, tmp_path, tag, ndays, seed, extra=()):
+    p = os.path.join(REF, exe)
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not built (oracle/Makefile)")
+    res = tmp_path / f"res_{tag}"
+    res.mkdir()
+    cfg = dataclasses.replace(synth.CONFIGS["disagg"], ndays=ndays, extra_global=list(extra))
+    r = synth.generate(str(tmp_path / f"in_{tag}"), cfg, 2, 3, seed, result_dir=str(res))
+    o = subprocess.run([p, "-g", r["global_file"]], cwd=str(res), capture_output=True, text=True)
+    assert o.returncode == 0, o.stderr[-2000:]
+    return np.fromfile(res / "results.nc.force.f64", dtype=np.float64), o.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndays,seed,extra", [(25, 611, ()), (12, 612, ("DISAGG_WRITE_CHUNK_SIZE 7", "ALMA_OUTPUT TRUE", "LW_TYPE LW_PRATA"))])
+def test_vicNl_gpu_disaggregator_mode_matches_stock_vicNl(ndays, seed, extra, tmp_path):
+    """OUTPUT_FORCE TRUE: the stock vicNl disaggregates every cell's daily forcing on the CPU (initialize_atmos) and writes it through
+    write_forcing_file / write_data_one_cell; vicNl_gpu reads the same files with the reference's reader, disaggregates on the device
+    (vicgpu_disagg) and writes through the same two routines: the written stream (every variable of every record of every cell) is
+    identical byte for byte"""
+    cpu, _ = _run_output_force("vicNl", tmp_path, "cpu", ndays, seed, extra)
+    gpu, err = _run_output_force("vicNl_gpu", tmp_path, "gpu", ndays, seed, extra)
+    assert "Execution time (GPU)" in err
+    assert cpu.size == 6 * ndays * 24 * 204 and cpu.size == gpu.size
+    assert np.array_equal(cpu, gpu, equal_nan=True), np.argwhere(~((cpu == gpu) | ((cpu != cpu) & (gpu != gpu))))[:5]
+
+
+def _out_names():
+    """the 204 output columns (184 variables, the multi-element ones expanded) of a three-layer, one-band configuration"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fe_hourly_winter.npz"))
+    from vic_b200.layout import layout_from_options, parse_options
+    return layout_from_options(parse_options(g["options_raw"])).out_names
+
+
+def test_stock_vicNl_disaggregator_mode_writes_the_forcing_stream(tmp_path):
+    """CPU-only part: the reference's executable in OUTPUT_FORCE mode writes one record of 204 values per cell and hour, and the values
+    are its hourly forcing (air temperature within the day's TMIN..TMAX, precipitation summing to the daily input)"""
+    out, err = _run_output_force("vicNl", tmp_path, "cpu", 10, 613)
+    assert "disaggregated forcings generation done" in err
+    rows = out.reshape(6, 240, 204)
+    names = list(_out_names())
+    prec, tair = rows[:, :, names.index("PREC")], rows[:, :, names.index("AIR_TEMP")]
+    assert np.all(prec >= 0) and prec.sum() > 0 and np.all(np.abs(tair) < 60)

@@ -7,7 +7,7 @@
 // Build (oracle/Makefile target _ref/vicNl_gpu): the reference's objects + this file + -lvicgpu.  vicNl.c is compiled as it is; its
 // own runModel is made a weak symbol (objcopy --weaken-symbol) so that the definition below is the one main() calls.
 //
-// What this driver does not serve: OUTPUT_FORCE runs (vicNl.c:445-490; the disaggregation itself is vicgpu_disagg).  There is no CPU
+// OUTPUT_FORCE runs (the meteorological disaggregator, vicNl.c:445-490) go through vicgpu_disagg: run_output_force() below.  There is no CPU
 // fallback: without a CUDA device, or with an option the device code does not implement, the run stops with the library's message.
 #include <algorithm>
 #include <chrono>
@@ -26,9 +26,107 @@ static void gpu_check(int rc, const char* what) {
   vicerror(msg);
 }
 
+// ---- OUTPUT_FORCE TRUE: the meteorological disaggregator (vicNl.c:420-490) ---------------------------------------------------
+// The reference, per cell: initializeCell() -> initialize_atmos() (read the daily forcing, MTCLIM, hourly arrays), then
+// write_forcing_file() + write_data_one_cell() per record.  Here the cells' daily PREC / TMAX / TMIN / WIND are read with the
+// reference's own read_forcing_data(), a chunk of cells is disaggregated on the device by vicgpu_disagg, and the records go through
+// the reference's own write_forcing_file() / write_data_one_cell() in the reference's order (cell by cell, record by record).
+// Served: what vicgpu_disagg takes -- daily PREC, TMAX, TMIN and WIND from one forcing file per cell (FORCE_DT 24), no ALMA_INPUT.
+static void run_output_force(std::vector<cell_info_struct>& cells, filep_struct filep, filenames_struct filenames,
+                             out_data_file_struct* out_data_files_template, OutputData* out_data_list, dmy_struct* dmy, ProgramState* state) {
+  const int ncell = (int)cells.size(), nrecs = state->global_param.nrecs;
+  for (int t = 0; t < N_FORCING_TYPES; t++) {
+    const bool wanted = t == PREC || t == TMAX || t == TMIN || t == WIND;
+    const int sup = state->param_set.TYPE[t].SUPPLIED;
+    if (wanted != (sup != 0) || (wanted && (sup != 1 || state->param_set.FORCE_DT[0] != 24)))
+      vicerror("vicNl_gpu: OUTPUT_FORCE on the device takes daily PREC, TMAX, TMIN and WIND from the first forcing file (FORCE_DT 24) and nothing else");
+  }
+  if (state->options.ALMA_INPUT) vicerror("vicNl_gpu: OUTPUT_FORCE with ALMA_INPUT is not served");
+  vicgpu_options opt;
+  vicgpu_pack_options(state, &opt);
+  vicgpu_disagg_options dopt;
+  vicgpu_pack_disagg_options(state, dmy, &dopt);
+  vicgpu_handle* h = NULL;
+  const char* dev = getenv("VICGPU_DEVICE");
+  gpu_check(vicgpu_create(&h, &opt, dev ? atoi(dev) : 0), "vicgpu_create");
+  vicgpu_layout L;
+  gpu_check(vicgpu_get_layout(h, &L), "vicgpu_get_layout");
+  {  // the disaggregator mode reads no vegetation (vicNl.c:145-151): placeholder library rows for set_cells' range checks
+    std::vector<double> veglib((size_t)(opt.NVegLibTypes + 4) * L.vl_stride, 0.0);
+    gpu_check(vicgpu_set_veglib(h, opt.NVegLibTypes + 4, veglib.data()), "vicgpu_set_veglib");
+  }
+  // cells per device pass: at most ~512 MB of hourly forcing on the host at a time
+  const size_t per_cell = (size_t)nrecs * L.f_stride * sizeof(double);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ncell, ((size_t)512 << 20) / per_cell));
+  std::vector<OutputData*> current_output_data;
+  for (int i = 0; i < state->global_param.disagg_write_chunk_size; i++) copy_output_data(current_output_data, out_data_list, state);
+  std::vector<double> daily, forcing, cellpar, hrupar;
+  fprintf(stderr, "Disaggregating forcings on the GPU...\n");
+  auto t_start = std::chrono::system_clock::now();
+  for (int c0 = 0; c0 < ncell; c0 += chunk) {
+    const int n = std::min(chunk, ncell - c0);
+    daily.assign((size_t)n * dopt.Ndays * 4, 0.0);
+    cellpar.assign((size_t)n * L.cp_stride, 0.0);
+    hrupar.assign((size_t)n * HP_N, 0.0);
+    for (int c = 0; c < n; c++) {
+      cell_info_struct& cell = cells[c0 + c];
+      make_in_files(&filep, &filenames, &cell.soil_con, state);  // vicNl.c:335-337
+      double** fd = read_forcing_data(filep.forcing, filep.forcing_ncid, state->global_param, &cell.soil_con, state);  // initialize_atmos.c:247
+      const int types[4] = {PREC, TMAX, TMIN, WIND};
+      for (int d = 0; d < dopt.Ndays; d++)
+        for (int k = 0; k < 4; k++) daily[((size_t)c * dopt.Ndays + d) * 4 + k] = fd[types[k]][d];
+      for (int t = 0; t < N_FORCING_TYPES; t++) free(fd[t]);
+      free(fd);
+      if (filep.forcing[0]) fclose(filep.forcing[0]);
+      if (filep.forcing[1]) fclose(filep.forcing[1]);
+      vicgpu_pack_cellpar(cell.soil_con, &L, &cellpar[(size_t)c * L.cp_stride]);
+      hrupar[(size_t)c * HP_N + HP_cell] = c;  // one placeholder HRU per cell (no vegetation in this mode); it is never stepped
+      hrupar[(size_t)c * HP_N + HP_Cv] = 1.0;
+    }
+    gpu_check(vicgpu_set_cells(h, n, cellpar.data(), n, hrupar.data()), "vicgpu_set_cells");
+    forcing.resize((size_t)nrecs * n * L.f_stride);
+    gpu_check(vicgpu_disagg(h, &dopt, daily.data(), forcing.data()), "vicgpu_disagg");
+    for (int c = 0; c < n; c++) {
+      cell_info_struct& cell = cells[c0 + c];
+      cell.atmos = alloc_atmos(nrecs, state->NR);
+      for (int rec = 0; rec < nrecs; rec++) vicgpu_unpack_forcing(cell.atmos[rec], &L, &forcing[((size_t)rec * n + c) * L.f_stride]);
+      copy_data_file_format(out_data_files_template, cell.outputFormat->dataFiles, state);
+      make_out_files(&filep, &filenames, &cell.soil_con, cell.outputFormat, state);
+      // vicNl.c:462-480, unchanged
+      int chunk_step_count = 0, chunk_start_rec = 0;
+      for (int rec = 0; rec < nrecs; rec++) {
+        write_forcing_file(&cell, rec, cell.outputFormat, current_output_data[chunk_step_count], state, dmy);
+        chunk_step_count++;
+        if (rec >= nrecs - 1) {
+          cell.outputFormat->write_data_one_cell(current_output_data, out_data_files_template, chunk_start_rec, nrecs - chunk_start_rec, state);
+        } else if (chunk_step_count >= state->global_param.disagg_write_chunk_size) {
+          cell.outputFormat->write_data_one_cell(current_output_data, out_data_files_template, chunk_start_rec, state->global_param.disagg_write_chunk_size, state);
+          chunk_step_count = 0;
+          chunk_start_rec = rec + 1;
+        }
+      }
+      free_atmos(nrecs, &cell.atmos);
+      delete cell.outputFormat;
+    }
+  }
+  gpu_check(vicgpu_destroy(h), "vicgpu_destroy");
+  std::chrono::duration<double> elapsed = std::chrono::system_clock::now() - t_start;
+  fprintf(stderr, "\nVIC forcing disaggregation done. Execution time (GPU): %.3f seconds\n", elapsed.count());
+  for (int c = 0; c < ncell; c++) {  // vicNl.c:640-652 (no vegetation, no atmos left)
+    free(cells[c].soil_con.AreaFract);
+    free(cells[c].soil_con.BandElev);
+    free(cells[c].soil_con.Tfactor);
+    free(cells[c].soil_con.Pfactor);
+    free(cells[c].soil_con.AboveTreeLine);
+  }
+}
+
 void runModel(std::vector<cell_info_struct>& cell_data_structs, filep_struct filep, filenames_struct filenames,
               out_data_file_struct* out_data_files_template, OutputData* out_data_list, dmy_struct* dmy, ProgramState* state) {
-  if (state->options.OUTPUT_FORCE) vicerror("vicNl_gpu: OUTPUT_FORCE runs are not wired into this driver (the disaggregation itself is vicgpu_disagg)");
+  if (state->options.OUTPUT_FORCE) {
+    run_output_force(cell_data_structs, filep, filenames, out_data_files_template, out_data_list, dmy, state);
+    return;
+  }
   std::vector<OutputData*> current_output_data;
   WriteOutputNetCDF* outputwriter = new WriteOutputNetCDF(state);
   outputwriter->openFile();
