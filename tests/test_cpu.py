@@ -319,3 +319,23 @@ def test_unsupported_options_are_rejected():
         h = ctypes.c_void_p()
         rc = lib.vicgpu_create(ctypes.byref(h), raw.ctypes.data_as(ctypes.c_void_p), 0)
         assert rc in (-3, -2), (key, rc)  # EUNSUPPORTED (or ENODEV when the device check comes first)
+
+
+@pytest.mark.parametrize("seed,startday,extra", [(71, 1, ()), (72, 160, ("LW_TYPE LW_PRATA", "VP_ITER VP_ITER_CONVERGE", "PLAPSE FALSE"))])
+def test_disaggregator_mode_forcing_matches_reference(seed, startday, extra, ref_harness, root, tmp_path):
+    """OUTPUT_FORCE TRUE (BASELINE configs[4], first half): the hourly forcing the reference's initialize_atmos() produces in its
+    meteorological-disaggregator mode (no vegetation, no bands: vicNl.c:335-337) against the host build of vic_disagg.cuh, bit for bit"""
+    import dataclasses
+    from vic_b200 import synth
+    cfg = dataclasses.replace(synth.CONFIGS["disagg"], ndays=40, startday=startday, extra_global=list(extra))
+    r = synth.generate(str(tmp_path / "in"), cfg, 3, 3, seed)
+    case = str(tmp_path / "case.bin")
+    subprocess.run([ref_harness, "-g", r["global_file"], "-o", case], check=True, stdout=subprocess.DEVNULL)
+    c = read_case(case)
+    assert int(c["meta"][7]) == 1 and int(c["meta"][1]) == 0  # OUTPUT_FORCE, no HRUs
+    lat, lng = (c["cellpar"][:, TABLES["cpar"].index(k)] for k in ("CP_lat", "CP_lng"))
+    nd = int(c["disagg_raw"][5])
+    daily = np.stack([np.loadtxt(os.path.join(r["dir"], "forc", f"f_{la:.5f}_{lo:.5f}"))[:nd] for la, lo in zip(lat, lng)])
+    g = {"options_raw": c["options_raw"], "disagg_raw": c["disagg_raw"], "meta": c["meta"], "cellpar": c["cellpar"], "daily": daily}
+    f = _run_port(_port_for("", root, "disaggport"), g, tmp_path, ("options_raw", "disagg_raw", "meta", "cellpar", "daily"))["forcing"]
+    assert f.shape == c["forcing"].shape and np.array_equal(f, c["forcing"])
