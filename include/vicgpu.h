@@ -523,6 +523,38 @@ int vicgpu_nc_dims(vicgpu_ncfile *nc, long long *ntime, long long *nlat, long lo
 int vicgpu_nc_read_slab(vicgpu_ncfile *nc, int nvar, const char *const *varnames, long long t0, long long nt, int ncell,
                         const double *lat, const double *lng, double *out);
 
+/* ---- NetCDF output, one record per output step (stands in for WriteOutputNetCDF::initializeFile / write_data_all_cells,
+ * WriteOutputNetCDF.c:163-299, 386-452) ----------------------------------------------------------------------------------
+ * Host-side and device-free.  Same dimensions (lat, lon, bnds, time, depth), coordinate variables, per-variable attributes, fill
+ * value and cell placement as the reference's file; `time` is the record dimension so that a step's grids of ALL variables are one
+ * contiguous record, filled from the float32 rows vicgpu_step_f32 returns and written with one write.  Container: NetCDF classic
+ * with 64-bit offsets (vic_b200/host/vicgpu_ncwrite.h); no compression. */
+typedef struct vicgpu_ncout vicgpu_ncout;
+typedef struct vicgpu_ncout_var {
+  const char *name;          /* NetCDF variable name (VariableMetaData::name, variable_mapping.c) */
+  int nelem;                 /* OutputData::nelem; > 1: (time, depth, lat, lon), elements beyond nelem stay at the fill value */
+  const char *long_name, *units, *standard_name, *cell_methods, *internal_vic_name, *category;
+} vicgpu_ncout_var;
+typedef struct vicgpu_ncout_spec {
+  int nlat, nlon, depth;     /* gridNumLatDivisions, gridNumLonDivisions, MAX_BANDS */
+  double lat0, dlat, lon0, dlon;   /* gridStartLat, gridStepLat, gridStartLon, gridStepLon */
+  const char *time_units;    /* "hours since Y-M-D H:00" / "days since Y-M-D" (WriteOutputNetCDF.c:221-229) */
+  double time_step;          /* out_dt when out_dt < 24, else 1 (:240-243) */
+  int nvar;
+  const vicgpu_ncout_var *vars;
+  int ntext;                 /* global text attributes (title, institution, source, history, frequency, Conventions ...) */
+  const char *const *text_keys, *const *text_values;
+  int nint;                  /* global integer attributes (model_start_year ... model_end_day) */
+  const char *const *int_keys;
+  const int *int_values;
+  int ncell;                 /* modelled cells, in the order of the rows handed to write_step */
+  const int *lat_index, *lon_index;   /* latitudeToIndex / longitudeToIndex of every cell */
+} vicgpu_ncout_spec;
+int vicgpu_ncout_create(vicgpu_ncout **w, const char *path, const vicgpu_ncout_spec *spec);
+/* rows [ncell][row_stride] float32 (vicgpu_step_f32's out_agg of one output step); col_of_var [nvar]: first column of each variable */
+int vicgpu_ncout_write_step(vicgpu_ncout *w, const float *rows, long long row_stride, const int *col_of_var);
+int vicgpu_ncout_close(vicgpu_ncout *w);
+
 /* ---- lake-ice surface solve as a batch operator ------------------------------------------------------
  * ice_melt() (ice_melt.c:30-585) with its residual IceEnergyBalance::calculate (IceEnergyBalance.c:60-175) and icerad()
  * (lakes.eb.c:1092-1151) for n independent lake-ice columns, one device thread each; bit-identical to the reference's ice_melt().

@@ -205,3 +205,52 @@ def test_stock_vicNl_disaggregator_mode_writes_the_forcing_stream(tmp_path):
     names = list(_out_names())
     prec, tair = rows[:, :, names.index("PREC")], rows[:, :, names.index("AIR_TEMP")]
     assert np.all(prec >= 0) and prec.sum() > 0 and np.all(np.abs(tair) < 60)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfgname,ndays,seed", [("fe_hourly", 4, 521), ("frozen_bands", 2, 522)])
+def test_vicNl_gpu_netcdf_output_holds_the_stock_outputs_narrowed(cfgname, ndays, seed, tmp_path):
+    """VICGPU_NC_OUTPUT: vicNl_gpu writes its daily aggregates through the library's NetCDF writer (float32 rows of vicgpu_step_f32, one
+    record per output step, metadata from the reference's own output_mapping and grid).  Every variable of the file, at every modelled
+    cell and step, is the stock vicNl's aggregate narrowed to float32 (what WriteOutputNetCDF.c:412 stores); coordinates, time axis and
+    the unused depth planes are as the reference's writer lays them out."""
+    from scipy.io import netcdf_file
+    out_cpu, _, _ = _run("vicNl", cfgname, tmp_path, "cpu", ndays, ndays, seed)
+    nc_path = str(tmp_path / "out.nc")
+    os.environ["VICGPU_NC_OUTPUT"] = nc_path
+    try:
+        _, _, err = _run("vicNl_gpu", cfgname, tmp_path, "gpu", ndays, ndays, seed)
+    finally:
+        del os.environ["VICGPU_NC_OUTPUT"]
+    assert "Model execution time (GPU)" in err
+    ncell = 6
+    per_cell = out_cpu.size // (ndays * ncell)
+    ref = out_cpu.reshape(ndays, ncell, per_cell)
+    # the stream's columns: the 184 variables in enum order, multi-element ones expanded (layout of the case's options)
+    import dataclasses as dc
+    from vic_b200.casefile import read_case
+    cfg = dc.replace(synth.CONFIGS[cfgname], ndays=1)
+    r = synth.generate(str(tmp_path / "in_layout"), cfg, 2, 3, seed)
+    case = str(tmp_path / "layout.bin")
+    subprocess.run([os.path.join(REF, "vic_ref_harness"), "-g", r["global_file"], "-o", case, "--no-run"], check=True, stdout=subprocess.DEVNULL)
+    from vic_b200.layout import layout_from_options, parse_options
+    names = list(layout_from_options(parse_options(read_case(case)["options_raw"])).out_names)
+    assert len(names) == per_cell
+    f = netcdf_file(nc_path, "r", mmap=False)
+    assert f.dimensions["time"] is None and f.dimensions["lat"] == 2 and f.dimensions["lon"] == 3 and f.dimensions["depth"] == 30
+    assert np.array_equal(f.variables["time"][:], np.arange(ndays, dtype=np.float32)) and f.variables["time"].units == b"days since 2001-1-1"
+    checked = 0
+    for name, var in f.variables.items():
+        if name in ("lat", "lon", "time", "depth"):
+            continue
+        vic = var.internal_vic_name.decode().replace("OUT_", "", 1)
+        cols = [k for k, n in enumerate(names) if n == vic or n.startswith(vic + "[")]
+        assert cols, vic
+        data = var[:].reshape(ndays, -1, ncell)  # (time, depth or 1, lat * lon): the six cells fill the 2 x 3 grid in order
+        want = ref[:, :, cols].astype(np.float32).transpose(0, 2, 1)
+        assert np.array_equal(data[1:, :len(cols)], want[1:], equal_nan=True), vic  # (first step: uninitialised aggdata in the reference)
+        if data.shape[1] > len(cols):
+            assert np.all(data[:, len(cols):] == np.float32(1e20))
+        checked += 1
+    f.close()
+    assert checked >= 20

@@ -159,3 +159,58 @@ def test_disagg_from_a_netcdf_file_gives_the_reference_forcing(tmp_path):
     f_cm = gp.disagg(g["disagg_raw"], daily)
     gp.close()
     assert np.array_equal(f_tm, g["forcing"]) and np.array_equal(f_cm, g["forcing"])
+
+
+# ---- the output side: vicgpu_ncout_* (WriteOutputNetCDF.c:163-299, 386-452) --------------------------------------------------------
+def test_output_file_holds_the_reference_writers_content(tmp_path):
+    """float32 rows of a few output steps -> one record per step; read back with scipy (an independent reader): dimensions, coordinate
+    values and attributes, per-variable attributes and fill value, every modelled cell's values at its (lat, lon) position, the fill
+    value at the unmodelled grid points and in the unused depth planes, as the reference's writer lays them out"""
+    rng = np.random.default_rng(4)
+    nlat, nlon, ncell, nstep = 5, 7, 23, 4
+    pos = rng.permutation(nlat * nlon)[:ncell]
+    pos.sort()  # cells in grid order, as the soil file must list them (vicNl.c readSoilData)
+    lat_i, lon_i = pos // nlon, pos % nlon
+    variables = [
+        dict(name="RUNOFF", nelem=1, long_name="surface runoff", units="mm", standard_name="runoff_amount", cell_methods="time: sum", internal_vic_name="OUT_RUNOFF", category="fluxes"),
+        dict(name="SOIL_MOIST", nelem=3, long_name="soil moisture", units="mm", standard_name="soil_moisture", cell_methods="time: point", internal_vic_name="OUT_SOIL_MOIST", category="fluxes"),
+        dict(name="SWE", nelem=1, long_name="snow water equivalent", units="mm", standard_name="swe", cell_methods="time: point", internal_vic_name="OUT_SWE", category="snow"),
+    ]
+    columns = [4, 9, 0]  # where each variable starts in a row of 16 values
+    rows = rng.normal(size=(nstep, ncell, 16)).astype(np.float32)
+    path = str(tmp_path / "results.nc")
+    with api.NcOutput(path, nlat, 48.03125, 0.0625, nlon, -121.96875, 0.0625, "hours since 2001-1-1 0:00", 3, variables, columns, lat_i, lon_i, depth=30,
+                      global_text=[("title", "VIC model run output."), ("Conventions", "CF-1.6")], global_int=[("model_start_year", 2001), ("model_end_day", 31)]) as w:
+        for s in range(nstep):
+            w.write_step(rows[s])
+    f = netcdf_file(path, "r", mmap=False)
+    assert f.version_byte == 2
+    assert {k: (v if v is not None else None) for k, v in f.dimensions.items()} == {"lat": nlat, "lon": nlon, "bnds": 2, "time": None, "depth": 30}
+    assert f.title == b"VIC model run output." and f.Conventions == b"CF-1.6" and f.model_start_year == 2001 and f.model_end_day == 31
+    assert np.array_equal(f.variables["lat"][:], 48.03125 + np.arange(nlat) * 0.0625) and f.variables["lat"].units == b"degrees_north"
+    assert np.array_equal(f.variables["lon"][:], -121.96875 + np.arange(nlon) * 0.0625) and f.variables["lon"].axis == b"X"
+    assert np.array_equal(f.variables["depth"][:], np.arange(30, dtype=np.float32))
+    t = f.variables["time"]
+    assert np.array_equal(t[:], np.arange(nstep, dtype=np.float32) * 3) and t.units == b"hours since 2001-1-1 0:00" and t.calendar == b"gregorian"
+    fill = np.float32(1e20)
+    for v, c0 in zip(variables, columns):
+        var = f.variables[v["name"]]
+        assert var.dimensions == (("time", "depth", "lat", "lon") if v["nelem"] > 1 else ("time", "lat", "lon"))
+        assert var.units == v["units"].encode() and var.internal_vic_name == v["internal_vic_name"].encode() and var.category == v["category"].encode()
+        assert np.float32(var._FillValue) == fill
+        data = var[:].reshape(nstep, -1, nlat, nlon)
+        want = np.full(data.shape, fill, dtype=np.float32)
+        for e in range(v["nelem"]):
+            want[:, e, lat_i, lon_i] = rows[:, :, c0 + e]
+        assert np.array_equal(data, want)
+    f.close()
+
+
+def test_output_writer_refuses_bad_requests(tmp_path):
+    ok = dict(name="X", nelem=1)
+    with pytest.raises(api.VicGpuError, match="outside the grid"):
+        api.NcOutput(str(tmp_path / "a.nc"), 2, 0, 1, 2, 0, 1, "days since 2001-1-1", 1, [ok], [0], [2], [0])
+    with pytest.raises(api.VicGpuError, match="nelem outside"):
+        api.NcOutput(str(tmp_path / "b.nc"), 2, 0, 1, 2, 0, 1, "days since 2001-1-1", 1, [dict(name="X", nelem=31)], [0], [0], [0])
+    with pytest.raises(api.VicGpuError, match="cannot create"):
+        api.NcOutput(str(tmp_path / "no_such_dir" / "c.nc"), 2, 0, 1, 2, 0, 1, "days since 2001-1-1", 1, [ok], [0], [0], [0])

@@ -25,8 +25,21 @@ SYMBOLS = [
     "vicgpu_abi_version", "vicgpu_last_error", "vicgpu_create", "vicgpu_destroy", "vicgpu_get_layout",
     "vicgpu_set_veglib", "vicgpu_set_cells", "vicgpu_set_output_spec", "vicgpu_set_cell_status", "vicgpu_set_state",
     "vicgpu_get_state", "vicgpu_set_forcing", "vicgpu_step", "vicgpu_step_f32", "vicgpu_get_cell_status", "vicgpu_get_balance_errors",
-    "vicgpu_get_last_step_timing", "vicgpu_measure_phase_tax", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_disagg_tm", "vicgpu_nc_open", "vicgpu_nc_close", "vicgpu_nc_dims", "vicgpu_nc_read_slab", "vicgpu_ice_melt", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
+    "vicgpu_get_last_step_timing", "vicgpu_measure_phase_tax", "vicgpu_set_profiling", "vicgpu_get_kernel_profile", "vicgpu_disagg", "vicgpu_disagg_tm", "vicgpu_nc_open", "vicgpu_nc_close", "vicgpu_nc_dims", "vicgpu_nc_read_slab", "vicgpu_ncout_create", "vicgpu_ncout_write_step", "vicgpu_ncout_close", "vicgpu_ice_melt", "vicgpu_get_warp_times", "vicgpu_get_glacier_fit", "vicgpu_measure_fp64_peak",
 ]
+
+
+class NcOutVar(C.Structure):  # vicgpu_ncout_var
+    _fields_ = [("name", C.c_char_p), ("nelem", C.c_int), ("long_name", C.c_char_p), ("units", C.c_char_p), ("standard_name", C.c_char_p),
+                ("cell_methods", C.c_char_p), ("internal_vic_name", C.c_char_p), ("category", C.c_char_p)]
+
+
+class NcOutSpec(C.Structure):  # vicgpu_ncout_spec
+    _fields_ = [("nlat", C.c_int), ("nlon", C.c_int), ("depth", C.c_int), ("lat0", C.c_double), ("dlat", C.c_double), ("lon0", C.c_double), ("dlon", C.c_double),
+                ("time_units", C.c_char_p), ("time_step", C.c_double), ("nvar", C.c_int), ("vars", C.POINTER(NcOutVar)),
+                ("ntext", C.c_int), ("text_keys", C.POINTER(C.c_char_p)), ("text_values", C.POINTER(C.c_char_p)),
+                ("nint", C.c_int), ("int_keys", C.POINTER(C.c_char_p)), ("int_values", C.POINTER(C.c_int)),
+                ("ncell", C.c_int), ("lat_index", C.POINTER(C.c_int)), ("lon_index", C.POINTER(C.c_int))]
 
 
 class VicGpuError(RuntimeError):
@@ -69,6 +82,9 @@ def load_library(path=LIB_PATH):
     lib.vicgpu_disagg.argtypes = [vp, vp, dp, dp]
     lib.vicgpu_disagg_tm.argtypes = [vp, vp, dp, dp]
     lib.vicgpu_ice_melt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]
+    lib.vicgpu_ncout_create.argtypes = [C.POINTER(vp), C.c_char_p, C.POINTER(NcOutSpec)]
+    lib.vicgpu_ncout_write_step.argtypes = [vp, C.POINTER(C.c_float), C.c_longlong, ip]
+    lib.vicgpu_ncout_close.argtypes = [vp]
     lib.vicgpu_nc_open.argtypes = [C.POINTER(vp), C.c_char_p]
     lib.vicgpu_nc_close.argtypes = [vp]
     lib.vicgpu_nc_dims.argtypes = [vp] + [C.POINTER(C.c_longlong)] * 3
@@ -375,6 +391,57 @@ class NcForcing:
         if self.h:
             self.lib.vicgpu_nc_close(self.h)
             self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class NcOutput:
+    """The model output as a NetCDF file, one record per output step, through the library's host-side writer (vicgpu_ncout_*,
+    include/vicgpu.h; stands in for WriteOutputNetCDF.c:163-299, 386-452).  No device needed.
+    variables: list of dicts {name, nelem, long_name, units, standard_name, cell_methods, internal_vic_name, category};
+    columns: first column of each variable in the float32 rows handed to write_step."""
+
+    def __init__(self, path, nlat, lat0, dlat, nlon, lon0, dlon, time_units, time_step, variables, columns, lat_index, lon_index, depth=30,
+                 global_text=(), global_int=()):
+        self.lib = load_library()
+        enc = lambda x: (x or "").encode()  # noqa: E731
+        vs = (NcOutVar * len(variables))(*[NcOutVar(enc(v["name"]), int(v.get("nelem", 1)), enc(v.get("long_name")), enc(v.get("units")), enc(v.get("standard_name")),
+                                                     enc(v.get("cell_methods")), enc(v.get("internal_vic_name")), enc(v.get("category"))) for v in variables])
+        tk = (C.c_char_p * max(1, len(global_text)))(*[k.encode() for k, _ in global_text])
+        tv = (C.c_char_p * max(1, len(global_text)))(*[v.encode() for _, v in global_text])
+        ik = (C.c_char_p * max(1, len(global_int)))(*[k.encode() for k, _ in global_int])
+        iv = (C.c_int * max(1, len(global_int)))(*[int(v) for _, v in global_int])
+        li = np.ascontiguousarray(lat_index, dtype=np.int32)
+        lo = np.ascontiguousarray(lon_index, dtype=np.int32)
+        assert li.shape == lo.shape and li.ndim == 1
+        self.ncell = li.shape[0]
+        self.cols = np.ascontiguousarray(columns, dtype=np.int32)
+        assert self.cols.shape == (len(variables),)
+        spec = NcOutSpec(int(nlat), int(nlon), int(depth), float(lat0), float(dlat), float(lon0), float(dlon), time_units.encode(), float(time_step), len(variables), vs,
+                         len(global_text), tk, tv, len(global_int), ik, iv, self.ncell, _iptr(li), _iptr(lo))
+        self.h = C.c_void_p()
+        rc = self.lib.vicgpu_ncout_create(C.byref(self.h), os.fsencode(path), C.byref(spec))
+        if rc != 0:
+            raise VicGpuError(rc, (self.lib.vicgpu_last_error() or b"").decode())
+
+    def write_step(self, rows):
+        """rows: float32 [ncell][row_stride] (one output step of vicgpu_step_f32's out_agg)"""
+        r = np.asarray(rows)
+        assert r.dtype == np.float32 and r.ndim == 2 and r.shape[0] == self.ncell and r.flags["C_CONTIGUOUS"], (r.dtype, r.shape)
+        rc = self.lib.vicgpu_ncout_write_step(self.h, r.ctypes.data_as(C.POINTER(C.c_float)), int(r.shape[1]), _iptr(self.cols))
+        if rc != 0:
+            raise VicGpuError(rc, (self.lib.vicgpu_last_error() or b"").decode())
+
+    def close(self):
+        if self.h:
+            rc = self.lib.vicgpu_ncout_close(self.h)
+            self.h = C.c_void_p()
+            if rc != 0:
+                raise VicGpuError(rc, (self.lib.vicgpu_last_error() or b"").decode())
 
     def __enter__(self):
         return self

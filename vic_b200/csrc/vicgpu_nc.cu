@@ -2,6 +2,7 @@
 #include "vicgpu.h"
 #include "vicgpu_internal.h"
 #include "../host/vicgpu_ncslab.h"
+#include "../host/vicgpu_ncwrite.h"
 
 struct vicgpu_ncfile {
   vicgpu_nc::File file;
@@ -56,4 +57,66 @@ extern "C" int vicgpu_nc_read_slab(vicgpu_ncfile* nc, int nvar, const char* cons
     return nc_error(e);
   }
   return VICGPU_OK;
+}
+
+// ---- output writer -------------------------------------------------------------------------------------------------------------
+struct vicgpu_ncout {
+  vicgpu_nc::Writer* w = nullptr;
+  ~vicgpu_ncout() { delete w; }
+};
+
+extern "C" int vicgpu_ncout_create(vicgpu_ncout** out, const char* path, const vicgpu_ncout_spec* sp) {
+  if (!out || !path || !sp || !sp->vars || !sp->time_units || !sp->lat_index || !sp->lon_index || sp->nvar < 1 || sp->ncell < 0)
+    return vicgpu_fail(VICGPU_EINVAL, "null or empty argument");
+  *out = nullptr;
+  try {
+    auto str = [](const char* s) { return std::string(s ? s : ""); };
+    std::vector<vicgpu_nc::OutVar> vars((size_t)sp->nvar);
+    for (int v = 0; v < sp->nvar; v++) {
+      const vicgpu_ncout_var& a = sp->vars[v];
+      if (!a.name) return vicgpu_fail(VICGPU_EINVAL, "variable without a name");
+      vars[(size_t)v].name = a.name;
+      vars[(size_t)v].nelem = a.nelem;
+      vars[(size_t)v].text_atts = {{"long_name", str(a.long_name)}, {"units", str(a.units)}, {"standard_name", str(a.standard_name)}, {"cell_methods", str(a.cell_methods)},
+                                   {"internal_vic_name", str(a.internal_vic_name)}, {"category", str(a.category)}};
+    }
+    std::vector<std::pair<std::string, std::string>> gtext;
+    for (int k = 0; k < sp->ntext; k++) gtext.emplace_back(str(sp->text_keys[k]), str(sp->text_values[k]));
+    std::vector<std::pair<std::string, int>> gint;
+    for (int k = 0; k < sp->nint; k++) gint.emplace_back(str(sp->int_keys[k]), sp->int_values[k]);
+    std::vector<int> li(sp->lat_index, sp->lat_index + sp->ncell), lo(sp->lon_index, sp->lon_index + sp->ncell);
+    vicgpu_ncout* h = new vicgpu_ncout;
+    try {
+      h->w = new vicgpu_nc::Writer(path, sp->nlat, sp->lat0, sp->dlat, sp->nlon, sp->lon0, sp->dlon, sp->depth, sp->time_units, sp->time_step, vars, gtext, gint, li, lo);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    *out = h;
+  } catch (const std::exception& e) {
+    return vicgpu_fail(VICGPU_EINVAL, e.what());
+  }
+  return VICGPU_OK;
+}
+
+extern "C" int vicgpu_ncout_write_step(vicgpu_ncout* w, const float* rows, long long row_stride, const int* col_of_var) {
+  if (!w || !w->w || !rows || !col_of_var || row_stride < 1) return vicgpu_fail(VICGPU_EINVAL, "bad argument");
+  try {
+    w->w->write_step(rows, (size_t)row_stride, col_of_var);
+  } catch (const std::exception& e) {
+    return vicgpu_fail(VICGPU_EINVAL, e.what());
+  }
+  return VICGPU_OK;
+}
+
+extern "C" int vicgpu_ncout_close(vicgpu_ncout* w) {
+  if (!w) return VICGPU_OK;
+  int rc = VICGPU_OK;
+  try {
+    if (w->w) w->w->close();
+  } catch (const std::exception& e) {
+    rc = vicgpu_fail(VICGPU_EINVAL, e.what());
+  }
+  delete w;
+  return rc;
 }

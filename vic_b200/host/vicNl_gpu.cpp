@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstring>
+#include <string>
 #include <vector>
 #include "vicNl.h"
 #include "WriteOutputNetCDF.h"
@@ -121,6 +123,67 @@ static void run_output_force(std::vector<cell_info_struct>& cells, filep_struct 
   }
 }
 
+// ---- VICGPU_NC_OUTPUT=<file>: the output through the library's own NetCDF writer ------------------------------------------------
+// What WriteOutputNetCDF::initializeFile() and write_data_all_cells() (WriteOutputNetCDF.c:163-299, 386-452) put into the file, taken
+// from the same sources -- the output files' variable lists, ProgramState::output_mapping, the grid of initGrid() and the modelled-cell
+// mask of initCellMask() -- but one record per output step, filled from the float32 rows vicgpu_step_f32 returns (vicgpu_ncwrite.h).
+static vicgpu_ncout* open_nc_output(const char* path, out_data_file_struct* files, OutputData* out_data_list, const vicgpu_layout& L, int ncell,
+                                    const ProgramState* state, std::vector<int>& col_of_var) {
+  const global_param_struct& gp = state->global_param;
+  const int nlat = (int)gp.gridNumLatDivisions, nlon = (int)gp.gridNumLonDivisions;
+  // cell k sits where the k-th set bit of the mask is (WriteOutputNetCDF.c:419-430)
+  std::vector<int> lat_index, lon_index;
+  for (int g = 0; g < nlat * nlon; g++)
+    if (state->modeled_cell_mask[g]) {
+      lat_index.push_back(g / nlon);
+      lon_index.push_back(g % nlon);
+    }
+  if ((int)lat_index.size() != ncell) vicerror("vicNl_gpu: the modelled-cell mask does not hold one grid point per cell");
+  std::vector<std::string> keep;  // owns the strings the spec points to
+  keep.reserve(8 * N_OUTVAR_TYPES + 64);
+  auto own = [&](const std::string& x) { keep.push_back(x); return keep.back().c_str(); };
+  std::vector<vicgpu_ncout_var> vars;
+  col_of_var.clear();
+  for (int f = 0; f < state->options.Noutfiles; f++)
+    for (int v = 0; v < files[f].nvars; v++) {
+      const int id = files[f].varid[v];
+      const std::string varname = out_data_list[id].varname;
+      if (state->output_mapping.find(varname) == state->output_mapping.end()) vicerror("vicNl_gpu: output variable missing from output_mapping");
+      const VariableMetaData& m = state->output_mapping.at(varname);
+      vicgpu_ncout_var a;
+      a.name = own(m.name); a.nelem = out_data_list[id].nelem; a.long_name = own(m.longName); a.units = own(m.units); a.standard_name = own(m.standardName);
+      a.cell_methods = own(m.cellMethods); a.internal_vic_name = own(varname); a.category = own(files[f].prefix);
+      vars.push_back(a);
+      col_of_var.push_back(L.out_off[id]);
+    }
+  std::string units = gp.out_dt < 24 ? "hours since " : "days since ";  // WriteOutputNetCDF.c:221-229
+  units += std::to_string(gp.startyear) + "-" + std::to_string(gp.startmonth) + "-" + std::to_string(gp.startday);
+  if (gp.out_dt < 24) units += " " + std::to_string(gp.starthour) + ":00";
+  std::vector<const char*> tk, tv, ik;
+  std::vector<int> iv;
+  tk.push_back("title"); tv.push_back("VIC model run output.");
+  for (const auto& a : gp.netCDFGlobalAttributes) { tk.push_back(own(a.first)); tv.push_back(own(a.second)); }
+  tk.push_back("source"); tv.push_back("VIC (time loop on libvicgpu)");
+  tk.push_back("frequency"); tv.push_back(own(gp.out_dt < 24 ? std::to_string(gp.out_dt) + " hour" : std::string("day")));
+  tk.push_back("Conventions"); tv.push_back("CF-1.6");
+  const char* inames[] = {"model_start_year", "model_start_month", "model_start_day", "model_start_hour", "model_end_year", "model_end_month", "model_end_day"};
+  const int ivals[] = {gp.startyear, gp.startmonth, gp.startday, gp.starthour, gp.endyear, gp.endmonth, gp.endday};
+  for (int k = 0; k < 7; k++) { ik.push_back(inames[k]); iv.push_back(ivals[k]); }
+  vicgpu_ncout_spec sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.nlat = nlat; sp.nlon = nlon; sp.depth = MAX_BANDS;
+  sp.lat0 = gp.gridStartLat; sp.dlat = gp.gridStepLat; sp.lon0 = gp.gridStartLon; sp.dlon = gp.gridStepLon;
+  sp.time_units = units.c_str();
+  sp.time_step = gp.out_dt < 24 ? gp.out_dt : 1;
+  sp.nvar = (int)vars.size(); sp.vars = vars.data();
+  sp.ntext = (int)tk.size(); sp.text_keys = tk.data(); sp.text_values = tv.data();
+  sp.nint = (int)ik.size(); sp.int_keys = ik.data(); sp.int_values = iv.data();
+  sp.ncell = ncell; sp.lat_index = lat_index.data(); sp.lon_index = lon_index.data();
+  vicgpu_ncout* w = NULL;
+  gpu_check(vicgpu_ncout_create(&w, path, &sp), "vicgpu_ncout_create");
+  return w;
+}
+
 void runModel(std::vector<cell_info_struct>& cell_data_structs, filep_struct filep, filenames_struct filenames,
               out_data_file_struct* out_data_files_template, OutputData* out_data_list, dmy_struct* dmy, ProgramState* state) {
   if (state->options.OUTPUT_FORCE) {
@@ -181,6 +244,12 @@ void runModel(std::vector<cell_info_struct>& cell_data_structs, filep_struct fil
     gpu_check(vicgpu_set_output_spec(h, aggtype.data()), "vicgpu_set_output_spec");
   }
   gpu_check(vicgpu_set_state(h, hrurec.data()), "vicgpu_set_state");
+  // VICGPU_NC_OUTPUT=<file>: float32 rows straight into the library's NetCDF writer instead of OutputData + the reference's writer
+  const char* nc_path = getenv("VICGPU_NC_OUTPUT");
+  vicgpu_ncout* ncout = NULL;
+  std::vector<int> col_of_var;
+  std::vector<float> agg32;
+  if (nc_path && *nc_path) ncout = open_nc_output(nc_path, out_data_files_template, out_data_list, L, ncell, state, col_of_var);
 
   // the record after which the state file is written (vicNl.c:569-577)
   int state_rec = -1;
@@ -215,9 +284,14 @@ void runModel(std::vector<cell_info_struct>& cell_data_structs, filep_struct fil
         state->step_count = 0;
       }
     }
-    agg.resize(std::max<size_t>(1, out_recs.size()) * (size_t)ncell * nout);
     gpu_check(vicgpu_set_forcing(h, rec0, n, forcing.data()), "vicgpu_set_forcing");
-    gpu_check(vicgpu_step(h, rec0, n, dmy5.data(), NULL, out_recs.empty() ? NULL : agg.data()), "vicgpu_step");
+    if (ncout) {
+      agg32.resize(std::max<size_t>(1, out_recs.size()) * (size_t)ncell * nout);
+      gpu_check(vicgpu_step_f32(h, rec0, n, dmy5.data(), NULL, out_recs.empty() ? NULL : agg32.data()), "vicgpu_step_f32");
+    } else {
+      agg.resize(std::max<size_t>(1, out_recs.size()) * (size_t)ncell * nout);
+      gpu_check(vicgpu_step(h, rec0, n, dmy5.data(), NULL, out_recs.empty() ? NULL : agg.data()), "vicgpu_step");
+    }
     // cells the step invalidated (dist_prec would have returned ERROR, vicNl.c:545-559)
     gpu_check(vicgpu_get_cell_status(h, status.data()), "vicgpu_get_cell_status");
     for (int c = 0; c < ncell; c++)
@@ -236,6 +310,10 @@ void runModel(std::vector<cell_info_struct>& cell_data_structs, filep_struct fil
     // the unchanged output writer consumes OutputData::aggdata (vicNl.c:596-598)
     for (size_t s = 0; s < out_recs.size(); s++) {
       if (out_recs[s] < state->global_param.skipyear) continue;
+      if (ncout) {
+        gpu_check(vicgpu_ncout_write_step(ncout, &agg32[s * (size_t)ncell * nout], nout, col_of_var.data()), "vicgpu_ncout_write_step");
+        continue;
+      }
       for (int c = 0; c < ncell; c++) vicgpu_unpack_outdata(current_output_data[c], &L, &agg[(s * ncell + c) * nout], true);
       outputwriter->write_data_all_cells(current_output_data, out_data_files_template, out_recs[s] / state->out_step_ratio, state);
     }
@@ -257,6 +335,7 @@ void runModel(std::vector<cell_info_struct>& cell_data_structs, filep_struct fil
     }
     rec0 += n;
   }
+  if (ncout) gpu_check(vicgpu_ncout_close(ncout), "vicgpu_ncout_close");
   gpu_check(vicgpu_destroy(h), "vicgpu_destroy");
   std::chrono::duration<double> elapsed = std::chrono::system_clock::now() - t_start;
   fprintf(stderr, "\nVIC model run done. Model execution time (GPU): %.3f seconds\n", elapsed.count());
