@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 
-def _run(exe, cfgname, tmp_path, tag, ndays, stateday, seed, extra=()):
+def _run(exe, cfgname, tmp_path, tag, ndays, stateday, seed, extra=(), stream=True):
     p = os.path.join(REF, exe)
     if not os.path.exists(p):
         pytest.skip(f"{p} not built (oracle/Makefile)")
@@ -30,7 +30,7 @@ def _run(exe, cfgname, tmp_path, tag, ndays, stateday, seed, extra=()):
     # "_<yyyy>-<mm>-<dd>" whatever STATENAME says
     o = subprocess.run([p, "-g", r["global_file"]], cwd=str(res), capture_output=True, text=True)
     assert o.returncode == 0, o.stderr[-2000:]
-    out = np.fromfile(res / "results.nc.f64", dtype=np.float64)
+    out = np.fromfile(res / "results.nc.f64", dtype=np.float64) if stream else None
     state = (res / f"_2001-01-{stateday:02d}").read_bytes()
     return out, state, o.stderr
 
@@ -219,7 +219,7 @@ def test_vicNl_gpu_netcdf_output_holds_the_stock_outputs_narrowed(cfgname, ndays
     nc_path = str(tmp_path / "out.nc")
     os.environ["VICGPU_NC_OUTPUT"] = nc_path
     try:
-        _, _, err = _run("vicNl_gpu", cfgname, tmp_path, "gpu", ndays, ndays, seed)
+        _, _, err = _run("vicNl_gpu", cfgname, tmp_path, "gpu", ndays, ndays, seed, stream=False)  # (the stub's stream is not written in this mode)
     finally:
         del os.environ["VICGPU_NC_OUTPUT"]
     assert "Model execution time (GPU)" in err
@@ -247,7 +247,8 @@ def test_vicNl_gpu_netcdf_output_holds_the_stock_outputs_narrowed(cfgname, ndays
         cols = [k for k, n in enumerate(names) if n == vic or n.startswith(vic + "[")]
         assert cols, vic
         data = var[:].reshape(ndays, -1, ncell)  # (time, depth or 1, lat * lon): the six cells fill the 2 x 3 grid in order
-        want = ref[:, :, cols].astype(np.float32).transpose(0, 2, 1)
+        with np.errstate(over="ignore"):  # (unset band slots hold huge doubles: both narrowings give inf)
+            want = ref[:, :, cols].astype(np.float32).transpose(0, 2, 1)
         assert np.array_equal(data[1:, :len(cols)], want[1:], equal_nan=True), vic  # (first step: uninitialised aggdata in the reference)
         if data.shape[1] > len(cols):
             assert np.all(data[:, len(cols):] == np.float32(1e20))
