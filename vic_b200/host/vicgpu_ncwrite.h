@@ -67,22 +67,23 @@ class Writer {
     unsigned char* p = rec_.data();
     put_be(p, (float)(nrec_ * time_step_));  // the time coordinate of this record
     p += 4;
-    uint32_t fill_be;
-    {
-      unsigned char b[4];
-      put_be(b, fill_);
-      memcpy(&fill_be, b, 4);
-    }
-    for (size_t v = 0; v < vars_.size(); v++) {
-      const size_t planes = vars_[v].nelem > 1 ? (size_t)depth_ : 1;
-      uint32_t* g = reinterpret_cast<uint32_t*>(p);
-      for (size_t i = 0; i < planes * grid; i++) g[i] = fill_be;
-      for (int e = 0; e < vars_[v].nelem; e++) {
-        unsigned char* plane = p + (size_t)e * grid * 4;
-        const float* col = rows + col_of_var[v] + e;
-        for (size_t k = 0; k < cell_pos_.size(); k++) put_be(plane + cell_pos_[k] * 4, col[k * row_stride]);
+    // (everything but the modelled cells' positions of the used planes holds the fill value since the record buffer was set up:
+    // the same positions are overwritten at every step)
+    // blocks of cells: a block's rows stay in cache while its values go to the planes of all variables (cells in grid order write
+    // each plane sequentially)
+    const size_t ncell = cell_pos_.size(), block = 512;
+    for (size_t k0 = 0; k0 < ncell; k0 += block) {
+      const size_t k1 = std::min(ncell, k0 + block);
+      unsigned char* pv = p;
+      for (size_t v = 0; v < vars_.size(); v++) {
+        const size_t planes = vars_[v].nelem > 1 ? (size_t)depth_ : 1;
+        for (int e = 0; e < vars_[v].nelem; e++) {
+          unsigned char* plane = pv + (size_t)e * grid * 4;
+          const float* col = rows + col_of_var[v] + e;
+          for (size_t k = k0; k < k1; k++) put_be(plane + cell_pos_[k] * 4, col[k * row_stride]);
+        }
+        pv += planes * grid * 4;
       }
-      p += planes * grid * 4;
     }
     if (fseeko(f_, (off_t)(rec_begin_ + nrec_ * rec_.size()), SEEK_SET) != 0 || fwrite(rec_.data(), 1, rec_.size(), f_) != rec_.size())
       throw std::runtime_error("short write");
@@ -227,6 +228,7 @@ class Writer {
       rec_bytes += d.bytes;
     }
     rec_.assign(rec_bytes, 0);
+    for (size_t i = 4; i + 4 <= rec_bytes; i += 4) put_be(&rec_[i], fill_);  // after the 4 bytes of the time coordinate: grids of fill values
     std::vector<unsigned char> fixed;
     auto push_d = [&](double v) { unsigned char b[8]; put_be(b, v); fixed.insert(fixed.end(), b, b + 8); };
     auto push_f = [&](float v) { unsigned char b[4]; put_be(b, v); fixed.insert(fixed.end(), b, b + 4); };
