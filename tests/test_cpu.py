@@ -339,3 +339,10 @@ def test_disaggregator_mode_forcing_matches_reference(seed, startday, extra, ref
     g = {"options_raw": c["options_raw"], "disagg_raw": c["disagg_raw"], "meta": c["meta"], "cellpar": c["cellpar"], "daily": daily}
     f = _run_port(_port_for("", root, "disaggport"), g, tmp_path, ("options_raw", "disagg_raw", "meta", "cellpar", "daily"))["forcing"]
     assert f.shape == c["forcing"].shape and np.array_equal(f, c["forcing"])
+
+
+def test_parity_fuzzer_draws_are_bit_identical(ref_harness, vicport, root):
+    """tools/parity_fuzz.py (random options, calendars and domain shapes through the reference build and the host build of the kernels'
+    headers, step and disaggregation): a few draws of a fixed seed here, hundreds in profiles/r02b_parity_fuzz.log"""
+    o = subprocess.run([os.sys.executable, os.path.join(root, "tools", "parity_fuzz.py"), "--trials", "4", "--seed", "11", "--jobs", "4"], capture_output=True, text=True)
+    assert o.returncode == 0 and "FAIL" not in o.stdout and "'ok'" in o.stdout, o.stdout[-3000:]

@@ -84,7 +84,7 @@ def draw(rng):
 def run_trial(t):
     idx, base, cfg, seed, nlat, nlon, keep = t
     d = tempfile.mkdtemp(prefix=f"fuzz{idx}_")
-    label = (f"[{d}] " if keep else "") + f"#{idx} {base} {nlat}x{nlon} seed {seed} days {cfg.ndays} start {cfg.startyear}/{cfg.startday} dt {cfg.dt}/{cfg.snow_step} bands {cfg.nbands} tiles {cfg.ntiles} " \
+    label = (f"[{d}] " if keep else "") + ("(binned, roles) " if idx % 2 else "") + f"#{idx} {base} {nlat}x{nlon} seed {seed} days {cfg.ndays} start {cfg.startyear}/{cfg.startday} dt {cfg.dt}/{cfg.snow_step} bands {cfg.nbands} tiles {cfg.ntiles} " \
             f"out_step {cfg.out_step} | " + ", ".join(cfg.extra_global)
     try:
         try:
@@ -95,7 +95,9 @@ def run_trial(t):
         h = subprocess.run([os.path.join(REF, "vic_ref_harness"), "-g", r["global_file"], "-o", case, "--dump-every", "240"], capture_output=True, text=True)
         if h.returncode != 0:
             return label, "skipped", f"the reference refuses the draw (rc {h.returncode})"
-        p = subprocess.run([os.path.join(REF, "vicport"), case, out], capture_output=True, text=True)
+        # every other draw in the device's binned row order with the three-thread cell output emulated (vicport --binned --roles)
+        devlike = ["--binned", "--roles"] if idx % 2 else []
+        p = subprocess.run([os.path.join(REF, "vicport"), case, out, *devlike], capture_output=True, text=True)
         if p.returncode != 0:
             msg = (p.stderr or p.stdout).strip().splitlines()[-1:] or ["?"]
             if "not implemented" in msg[0] or "unsupported" in msg[0].lower():
