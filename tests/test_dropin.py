@@ -255,3 +255,23 @@ def test_vicNl_gpu_netcdf_output_holds_the_stock_outputs_narrowed(cfgname, ndays
         checked += 1
     f.close()
     assert checked >= 20
+
+
+def test_indexed_loader_fails_like_the_reference_when_a_cell_is_missing(tmp_path):
+    """a cell of the soil file without a record in the vegetation file: the indexed lookup falls back to the reference's own scan, which
+    ends the run with its own message and exit code (read_vegparam.c:130-133)"""
+    outs = {}
+    for exe in ("vicNl", "vicNl_fastread"):
+        p = os.path.join(REF, exe)
+        if not os.path.exists(p):
+            pytest.skip(f"{p} not built (oracle/Makefile)")
+        res = tmp_path / f"res_{exe}"
+        res.mkdir()
+        cfg = dataclasses.replace(synth.CONFIGS["fe_hourly"], ndays=1)
+        r = synth.generate(str(tmp_path / f"in_{exe}"), cfg, 2, 2, 77, result_dir=str(res))
+        vp = os.path.join(r["dir"], "vegparam.txt")
+        recs = _records(vp, lambda h: int(h.split()[1]))
+        open(vp, "w").write("".join("".join(rec) for rec in recs[:2] + recs[3:]))  # cell 3 has no record
+        o = subprocess.run([p, "-g", r["global_file"]], cwd=str(res), capture_output=True, text=True)
+        outs[exe] = (o.returncode, [ln for ln in o.stderr.splitlines() if "not found" in ln])
+    assert outs["vicNl"] == outs["vicNl_fastread"] and outs["vicNl"][0] == 99 and outs["vicNl"][1], outs
