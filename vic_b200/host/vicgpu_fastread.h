@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdio>
 #include <map>
+#include <sys/stat.h>
 #include <unordered_map>
 #include <vector>
 #include "vicNl.h"
@@ -35,6 +36,18 @@ namespace vicgpu_fastread {
 
 struct RecordIndex {
   std::unordered_map<int, long> first;  // cell number -> offset of its first record
+  dev_t dev = 0;                        // the file the index was built from: a stream address can be reused by another file
+  ino_t ino = 0;
+  off_t size = -1;
+  time_t mtime = 0;
+  bool built_for(FILE* f) const {
+    struct stat st;
+    return fstat(fileno(f), &st) == 0 && st.st_dev == dev && st.st_ino == ino && st.st_size == size && st.st_mtime == mtime;
+  }
+  void stamp(FILE* f) {
+    struct stat st;
+    if (fstat(fileno(f), &st) == 0) { dev = st.st_dev; ino = st.st_ino; size = st.st_size; mtime = st.st_mtime; }
+  }
 };
 
 inline long& seek_target() {
@@ -60,6 +73,7 @@ inline RecordIndex index_vegparam(FILE* f, int lines_per_tile) {
   }
   clearerr(f);
   fseek(f, keep < 0 ? 0 : keep, SEEK_SET);
+  ix.stamp(f);
   return ix;
 }
 
@@ -78,6 +92,7 @@ inline RecordIndex index_snowband(FILE* f) {
   }
   clearerr(f);
   fseek(f, keep < 0 ? 0 : keep, SEEK_SET);
+  ix.stamp(f);
   return ix;
 }
 
@@ -89,6 +104,10 @@ inline std::map<FILE*, RecordIndex>& indices() {
 // read_vegparam() with the scan replaced by a lookup; same arguments, same results, same messages
 inline int read_vegparam_indexed(FILE* vegparam, cell_info_struct& cell, const ProgramState* state) {
   auto it = indices().find(vegparam);
+  if (it != indices().end() && !it->second.built_for(vegparam)) {  // another (or a changed) file behind the same stream address
+    indices().erase(it);
+    it = indices().end();
+  }
   if (it == indices().end()) it = indices().emplace(vegparam, index_vegparam(vegparam, state->options.VEGPARAM_LAI ? 2 : 1)).first;
   auto rec = it->second.first.find(cell.soil_con.gridcel);
   seek_target() = rec == it->second.first.end() ? -1 : rec->second;
@@ -100,6 +119,10 @@ inline int read_vegparam_indexed(FILE* vegparam, cell_info_struct& cell, const P
 inline void read_snowband_indexed(FILE* snowband, soil_con_struct* soil_con, const int num_elevation_snow_bands) {
   if (num_elevation_snow_bands > 1 && snowband) {
     auto it = indices().find(snowband);
+    if (it != indices().end() && !it->second.built_for(snowband)) {
+      indices().erase(it);
+      it = indices().end();
+    }
     if (it == indices().end()) it = indices().emplace(snowband, index_snowband(snowband)).first;
     auto rec = it->second.first.find(soil_con->gridcel);
     seek_target() = rec == it->second.first.end() ? -1 : rec->second;
