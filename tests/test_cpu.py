@@ -346,3 +346,12 @@ def test_parity_fuzzer_draws_are_bit_identical(ref_harness, vicport, root):
     headers, step and disaggregation): a few draws of a fixed seed here, hundreds in profiles/r02b_parity_fuzz.log"""
     o = subprocess.run([os.sys.executable, os.path.join(root, "tools", "parity_fuzz.py"), "--trials", "4", "--seed", "11", "--jobs", "4"], capture_output=True, text=True)
     assert o.returncode == 0 and "FAIL" not in o.stdout and "'ok'" in o.stdout, o.stdout[-3000:]
+
+
+def test_disaggregation_fuzzer_polar_and_time_zone_draws(ref_harness, root):
+    """tools/disagg_fuzz.py: the reference's disaggregator mode against the host build of vic_disagg.cuh at the polar circles, the poles,
+    the equator and the southern hemisphere, with longitudes hours away from the model's time zone: identical hourly forcing.  (Found this
+    round: the summation order of the hour that holds both ends of the solar day, visible only under the midnight sun.)"""
+    o = subprocess.run([os.sys.executable, os.path.join(root, "tools", "disagg_fuzz.py"), "5", "12"], capture_output=True, text=True)
+    assert o.returncode == 0 and "different 0" in o.stdout, o.stdout[-3000:]
+    assert int(o.stdout.split("compared")[1].split()[0]) >= 10

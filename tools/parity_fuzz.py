@@ -78,17 +78,21 @@ def draw(rng):
     for k in rng.choice(sorted(OPTIONS), size=nopt, replace=False):
         extra.append(f"{k} {rng.choice(OPTIONS[str(k)])}")
     over["extra_global"] = extra
-    return str(base), dataclasses.replace(cfg, **over), int(rng.integers(1, 1 << 30)), int(rng.integers(2, 4)), int(rng.integers(2, 4))
+    # where on the globe: the latitude drives the solar geometry of the disaggregation (68 N: polar night and midnight sun; the southern
+    # hemisphere), the longitude the offset between the forcing's local days and the model's time zone (time_zone_lng -120: -2 .. +2 hours)
+    lat0 = float(rng.choice([48.03125, 48.03125, 35.03125, 60.03125, 68.03125, -35.03125]))
+    lon0 = float(rng.choice([-121.96875, -121.96875, -150.03125, -135.03125, -100.03125, -90.03125]))
+    return str(base), dataclasses.replace(cfg, **over), int(rng.integers(1, 1 << 30)), int(rng.integers(2, 4)), int(rng.integers(2, 4)), lat0, lon0
 
 
 def run_trial(t):
-    idx, base, cfg, seed, nlat, nlon, keep = t
+    idx, base, cfg, seed, nlat, nlon, lat0, lon0, keep = t
     d = tempfile.mkdtemp(prefix=f"fuzz{idx}_")
-    label = (f"[{d}] " if keep else "") + ("(binned, roles) " if idx % 2 else "") + f"#{idx} {base} {nlat}x{nlon} seed {seed} days {cfg.ndays} start {cfg.startyear}/{cfg.startday} dt {cfg.dt}/{cfg.snow_step} bands {cfg.nbands} tiles {cfg.ntiles} " \
+    label = (f"[{d}] " if keep else "") + ("(binned, roles) " if idx % 2 else "") + f"#{idx} {base} {nlat}x{nlon} at {lat0:.2f} {lon0:.2f} seed {seed} days {cfg.ndays} start {cfg.startyear}/{cfg.startday} dt {cfg.dt}/{cfg.snow_step} bands {cfg.nbands} tiles {cfg.ntiles} " \
             f"out_step {cfg.out_step} | " + ", ".join(cfg.extra_global)
     try:
         try:
-            r = synth.generate(os.path.join(d, "in"), cfg, nlat, nlon, seed)
+            r = synth.generate(os.path.join(d, "in"), cfg, nlat, nlon, seed, lat0=lat0, lon0=lon0)
         except Exception as e:
             return label, "skipped", f"generator: {e}"
         case, out, fout = os.path.join(d, "case.bin"), os.path.join(d, "res.bin"), os.path.join(d, "forc.bin")

@@ -196,6 +196,14 @@ VIC_HDI void disagg_solar(const CellPar& cp, const DisaggOpts& d, const DisaggSc
   double hf[24];
   for (int j = 0; j < 24; j++) hf[j] = 0;
   const bool norm = (daylength != 0) && sum_flat_potrad > 0;
+  // The reference sums an hour's 30 s slots in the order of the hour's own index k (mtclim_wrapper.c:240-249: tinystep = j*120 + k -
+  // tiny_offset, wrapped into the day).  When tiny_offset is not a whole number of hours, ONE hour holds both the last slots of the solar
+  // day and its first ones, and the reference adds the last ones first.  This loop meets the first slots of the day first, so the ones of
+  // that hour are set aside and added after the loop.  They are non-zero only when the sun is up at solar midnight (polar day).
+  const int off_in_hour = ((tiny_offset % tinystepsphour) + tinystepsphour) % tinystepsphour;
+  const int n_early = off_in_hour ? tinystepsphour - off_in_hour : 0;  // slots [0, n_early) of the solar day belong to the straddling hour
+  double early[120];
+  int ne = 0;
   int cur = -1;
   double curv = 0;
   for (double h = -hss; h < hss; h += dh) {
@@ -210,7 +218,9 @@ VIC_HDI void disagg_solar(const CellPar& cp, const DisaggOpts& d, const DisaggSc
         int tp = cur + tiny_offset;  // inverse of tinystep = j*120 + k - tiny_offset (with wrap)
         tp %= tinystepspday;
         if (tp < 0) tp += tinystepspday;
-        hf[tp / tinystepsphour] += norm ? curv / sum_flat_potrad : curv;
+        const double frac = norm ? curv / sum_flat_potrad : curv;
+        if (cur < n_early && ne < 120) early[ne++] = frac;
+        else hf[tp / tinystepsphour] += frac;
       }
       cur = tinystep;
     }
@@ -219,7 +229,14 @@ VIC_HDI void disagg_solar(const CellPar& cp, const DisaggOpts& d, const DisaggSc
   if (cur >= 0) {
     int tp = (cur + tiny_offset) % tinystepspday;
     if (tp < 0) tp += tinystepspday;
-    hf[tp / tinystepsphour] += norm ? curv / sum_flat_potrad : curv;
+    const double frac = norm ? curv / sum_flat_potrad : curv;
+    if (cur < n_early && ne < 120) early[ne++] = frac;
+    else hf[tp / tinystepsphour] += frac;
+  }
+  if (ne) {
+    int tp = tiny_offset % tinystepspday;  // the hour that holds slot 0 of the solar day
+    if (tp < 0) tp += tinystepspday;
+    for (int q = 0; q < ne; q++) hf[tp / tinystepsphour] += early[q];
   }
   const int last = (i == 364) ? 2 : 1;  // day 366 repeats day 365 (mtclim_vic.c:1453-1460)
   for (int r = 0; r < last; r++) {
