@@ -214,3 +214,71 @@ def test_output_writer_refuses_bad_requests(tmp_path):
         api.NcOutput(str(tmp_path / "b.nc"), 2, 0, 1, 2, 0, 1, "days since 2001-1-1", 1, [dict(name="X", nelem=31)], [0], [0], [0])
     with pytest.raises(api.VicGpuError, match="cannot create"):
         api.NcOutput(str(tmp_path / "no_such_dir" / "c.nc"), 2, 0, 1, 2, 0, 1, "days since 2001-1-1", 1, [ok], [0], [0], [0])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_reader_on_random_file_structures(seed, tmp_path):
+    """random classic files: both versions, record or fixed time dimension, forcing variables of the three served types created in random order
+    between unrelated variables (other dimensions, characters, bytes, odd sizes that need padding), random grid sizes: the slab is what scipy reads"""
+    rng = np.random.default_rng(100 + seed)
+    nt, nlat, nlon = int(rng.integers(1, 9)), int(rng.integers(1, 7)), int(rng.integers(1, 9))
+    record = bool(rng.integers(0, 2))
+    path = str(tmp_path / "f.nc")
+    f = netcdf_file(path, "w", version=int(rng.choice([1, 2])))
+    f.createDimension("time", None if record else nt)
+    f.createDimension("lat", nlat)
+    f.createDimension("lon", nlon)
+    f.createDimension("odd", 3)
+    f.createDimension("strlen", 5)
+    lat = np.sort(rng.uniform(-80, 80, nlat)).astype(np.float32).astype(np.float64)
+    lon = np.sort(rng.uniform(-170, 170, nlon))
+    makers, expect = [], {}
+
+    def coord(name, vals, typ):
+        def make():
+            v = f.createVariable(name, typ, (name,))
+            v[:] = vals
+        return make
+    makers += [coord("time", np.arange(nt, dtype=np.float64), rng.choice(["d", "f"])), coord("lat", lat, "f"), coord("lon", lon, "d")]
+    for k in range(int(rng.integers(1, 5))):
+        name, typ = f"v{k}", str(rng.choice(["h", "f", "d"]))
+        if typ == "h":
+            data = rng.integers(-30000, 30000, (nt, nlat, nlon)).astype(np.int16)
+            inv = bool(rng.integers(0, 2))
+            scale = np.float32(rng.choice([10.0, 100.0, 0.1, 0.025]))
+            expect[name] = data.astype(np.float64) / np.float64(scale) if inv else data.astype(np.float64) * np.float64(scale)
+        else:
+            data = rng.normal(0, 50, (nt, nlat, nlon)).astype(np.float32 if typ == "f" else np.float64)
+            inv, scale = False, None
+            expect[name] = data.astype(np.float64)
+
+        def make(name=name, typ=typ, data=data, inv=inv, scale=scale):
+            v = f.createVariable(name, typ, ("time", "lat", "lon"))
+            v[:] = data
+            if scale is not None:
+                setattr(v, "inverse_scale_factor" if inv else "scale_factor", scale)
+            v.long_name = "x" * int(rng.integers(0, 9))  # (attribute text of any length: header padding)
+        makers.append(make)
+
+    def junk1():
+        v = f.createVariable("station", "c", ("odd", "strlen"))
+        v[:] = np.array([list("abcde"), list("fghij"), list("klmno")], dtype="S1")
+    def junk2():
+        v = f.createVariable("flags", "b", ("odd",))
+        v[:] = np.array([1, 2, 3], dtype=np.int8)
+    def junk3():
+        v = f.createVariable("perstep", "h", ("time", "odd"))
+        v[:] = rng.integers(0, 9, (nt, 3)).astype(np.int16)
+    makers += [junk1, junk2, junk3]
+    for i in rng.permutation(len(makers)):
+        makers[i]()
+    f.title = "random"
+    f.close()
+    ii, jj = rng.integers(0, nlat, 11), rng.integers(0, nlon, 11)
+    names = sorted(expect)
+    t0 = int(rng.integers(0, nt))
+    with api.NcForcing(path) as nc:
+        assert (nc.ntime, nc.nlat, nc.nlon) == (nt, nlat, nlon)
+        got = nc.read_slab(names, t0, nt - t0, lat[ii], lon[jj])
+    want = np.stack([expect[n][t0:, ii, jj] for n in names], axis=1)
+    assert np.array_equal(got, want)

@@ -82,19 +82,29 @@ def draw(rng):
     # hemisphere), the longitude the offset between the forcing's local days and the model's time zone (time_zone_lng -120: -2 .. +2 hours)
     lat0 = float(rng.choice([48.03125, 48.03125, 35.03125, 60.03125, 68.03125, -35.03125]))
     lon0 = float(rng.choice([-121.96875, -121.96875, -150.03125, -135.03125, -100.03125, -90.03125]))
-    return str(base), dataclasses.replace(cfg, **over), int(rng.integers(1, 1 << 30)), int(rng.integers(2, 4)), int(rng.integers(2, 4)), lat0, lon0
+    # the weather: the generator's mid-latitude climate shifted and scaled (arctic cold, heat, drought, deluge, calm, gale)
+    climate = (float(rng.choice([0.0, 0.0, -25.0, -10.0, 10.0, 20.0])), float(rng.choice([1.0, 1.0, 0.0, 0.2, 5.0])), float(rng.choice([1.0, 1.0, 0.05, 4.0])))
+    return str(base), dataclasses.replace(cfg, **over), int(rng.integers(1, 1 << 30)), int(rng.integers(2, 4)), int(rng.integers(2, 4)), lat0, lon0, climate
 
 
 def run_trial(t):
-    idx, base, cfg, seed, nlat, nlon, lat0, lon0, keep = t
+    idx, base, cfg, seed, nlat, nlon, lat0, lon0, climate, keep = t
     d = tempfile.mkdtemp(prefix=f"fuzz{idx}_")
-    label = (f"[{d}] " if keep else "") + ("(binned, roles) " if idx % 2 else "") + f"#{idx} {base} {nlat}x{nlon} at {lat0:.2f} {lon0:.2f} seed {seed} days {cfg.ndays} start {cfg.startyear}/{cfg.startday} dt {cfg.dt}/{cfg.snow_step} bands {cfg.nbands} tiles {cfg.ntiles} " \
+    label = (f"[{d}] " if keep else "") + ("(binned, roles) " if idx % 2 else "") + f"#{idx} {base} {nlat}x{nlon} at {lat0:.2f} {lon0:.2f} climate {climate[0]:+.0f}C x{climate[1]:g} prec x{climate[2]:g} wind seed {seed} days {cfg.ndays} start {cfg.startyear}/{cfg.startday} dt {cfg.dt}/{cfg.snow_step} bands {cfg.nbands} tiles {cfg.ntiles} " \
             f"out_step {cfg.out_step} | " + ", ".join(cfg.extra_global)
     try:
         try:
             r = synth.generate(os.path.join(d, "in"), cfg, nlat, nlon, seed, lat0=lat0, lon0=lon0)
         except Exception as e:
             return label, "skipped", f"generator: {e}"
+        if climate != (0.0, 1.0, 1.0):  # rewrite the daily forcing files: PREC TMAX TMIN WIND
+            fdir = os.path.join(r["dir"], "forc")
+            for fn in os.listdir(fdir):
+                a = np.loadtxt(os.path.join(fdir, fn), ndmin=2)
+                a[:, 0] *= climate[1]
+                a[:, 1:3] += climate[0]
+                a[:, 3] *= climate[2]
+                np.savetxt(os.path.join(fdir, fn), a, fmt="%.4f")
         case, out, fout = os.path.join(d, "case.bin"), os.path.join(d, "res.bin"), os.path.join(d, "forc.bin")
         h = subprocess.run([os.path.join(REF, "vic_ref_harness"), "-g", r["global_file"], "-o", case, "--dump-every", "240"], capture_output=True, text=True)
         if h.returncode != 0:
