@@ -18,9 +18,10 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 40):
     lon0=float(rng.choice([-150.03125,-142.53125,-135.03125,-127.53125,-121.96875,-112.53125,-100.03125,-90.03125, -120.03125, -119.96875, 10.03125, 179.03125]))
     startday=int(rng.choice([1,80,150,172,182,200,265,330,355]))
     year=int(rng.choice([2001,2004]))
-    dt=int(rng.choice([1,1,3,6]))
+    dt=int(rng.choice([1,1,3,6,24]))
+    snow_step=dt if dt < 24 else int(rng.choice([1,3,6]))  # daily model step: the sub-daily snow step sets the forcing slots (NF = 24 / SNOW_STEP)
     extra=[f"LW_TYPE {rng.choice(['LW_TVA','LW_PRATA','LW_IDSO'])}", f"VP_ITER {rng.choice(['VP_ITER_ALWAYS','VP_ITER_NONE','VP_ITER_CONVERGE','VP_ITER_ANNUAL'])}", f"VP_INTERP {rng.choice(['TRUE','FALSE'])}", f"PLAPSE {rng.choice(['TRUE','FALSE'])}"]
-    cfg=dataclasses.replace(synth.CONFIGS["disagg"], ndays=int(rng.integers(5,40)), startday=startday, startyear=year, dt=dt, snow_step=dt, extra_global=extra)
+    cfg=dataclasses.replace(synth.CONFIGS["disagg"], ndays=int(rng.integers(5,40)), startday=startday, startyear=year, dt=dt, snow_step=snow_step, extra_global=extra)
     d=tempfile.mkdtemp(prefix='polar_')
     try:
         r=synth.generate(d+'/in', cfg, 2, 3, int(rng.integers(1,1<<30)), lat0=lat0, lon0=lon0)
@@ -36,7 +37,7 @@ for trial in range(int(sys.argv[2]) if len(sys.argv)>2 else 40):
         f=read_case(d+'/f.bin')["forcing"]; n+=1
         same=np.array_equal(f,c["forcing"])
         if not same:
-            bad+=1; ne=(f!=c["forcing"]); print("DIFF", lat0, lon0, startday, year, dt, extra, ne.sum(), sorted(set(np.nonzero(ne)[2])))
+            bad+=1; ne=(f!=c["forcing"]); print("DIFF", lat0, lon0, startday, year, dt, snow_step, extra, ne.sum(), sorted(set(np.nonzero(ne)[2])))
     finally:
         shutil.rmtree(d, ignore_errors=True)
 print("compared", n, "different", bad)
