@@ -105,6 +105,19 @@ def run_trial(t):
                 a[:, 1:3] += climate[0]
                 a[:, 3] *= climate[2]
                 np.savetxt(os.path.join(fdir, fn), a, fmt="%.4f")
+        sb = os.path.join(r["dir"], "snowband.txt")
+        if idx % 3 == 0 and os.path.exists(sb):  # every third banded draw: some bands without area (their share goes to the first band)
+            rows = [ln.split() for ln in open(sb).read().splitlines() if ln.strip()]
+            nb = cfg.nbands
+            zr = np.random.default_rng(seed)
+            for row in rows:
+                frac = [float(x) for x in row[1:1 + nb]]
+                for b in range(1, nb):
+                    if zr.random() < 0.35:
+                        frac[0] += frac[b]
+                        frac[b] = 0.0
+                row[1:1 + nb] = [f"{x:.6f}" for x in frac]
+            open(sb, "w").write("\n".join(" ".join(row) for row in rows) + "\n")
         case, out, fout = os.path.join(d, "case.bin"), os.path.join(d, "res.bin"), os.path.join(d, "forc.bin")
         h = subprocess.run([os.path.join(REF, "vic_ref_harness"), "-g", r["global_file"], "-o", case, "--dump-every", "240"], capture_output=True, text=True)
         if h.returncode != 0:
